@@ -670,3 +670,24 @@ void kuqo_run_counts(const kuqo_run *r, uint32_t *taxid, uint64_t *n_reads, uint
   }
   free(tmp);
 }
+
+/* Clade roll-up of TaxReport's constructor (taxdb.hpp:956-973): ReadCounts of the listed taxa summed with
+ * operator+= (readcounts.hpp:76-81 → HLL merge :627-665).  Returns the clade's uniqueKmerCount. */
+uint64_t kuqo_run_clade(const kuqo_run *r, const uint32_t *taxa, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers) {
+  kuqo_hll *acc = kuqo_hll_new();
+  uint64_t reads = 0, kmers = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    for (uint32_t j = 0; j < r->global.n; j++) {
+      if (r->global.e[j].taxid != taxa[i]) continue;
+      reads += r->global.e[j].n_reads;
+      kmers += r->global.e[j].n_kmers;
+      kuqo_hll_merge(acc, r->global.e[j].hll);
+      break;
+    }
+  }
+  uint64_t u = kuqo_hll_cardinality(acc);
+  kuqo_hll_free(acc);
+  if (n_reads) *n_reads = reads;
+  if (n_kmers) *n_kmers = kmers;
+  return u;
+}

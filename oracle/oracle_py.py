@@ -112,6 +112,8 @@ class Oracle:
         L.kuqo_run_n_taxa.restype = C.c_uint32
         L.kuqo_run_n_taxa.argtypes = [C.c_void_p]
         L.kuqo_run_counts.argtypes = [C.c_void_p, u32p, u64p, u64p, u64p, u8p, u8p]
+        L.kuqo_run_clade.restype = C.c_uint64
+        L.kuqo_run_clade.argtypes = [C.c_void_p, u32p, C.c_uint32, u64p, u64p]
 
     # -- scalar helpers -------------------------------------------------------------------------------
     def fmix64(self, x):
@@ -288,6 +290,14 @@ class OracleRun:
         if want_regs:
             out["regs"] = regs
         return out
+
+
+    def clade(self, taxa):
+        """(unique estimate, reads, kmers) of the union of the listed taxa (TaxReport clade roll-up)."""
+        t = np.ascontiguousarray(taxa, np.uint32)
+        r, k = C.c_uint64(0), C.c_uint64(0)
+        u = self.o.L.kuqo_run_clade(self.h, _p(t, u32p), len(t), C.byref(r), C.byref(k))
+        return u, r.value, k.value
 
 
 class RefShim:
