@@ -1,0 +1,223 @@
+/* include/kuq.h — C ABI of libkuq.so: KrakenUniq's per-read classification hot path on one NVIDIA B200 (sm_100a).
+ *
+ * The reference (fbreitwieser/krakenuniq v1.0.4) has no plugin / FFI interface; its drop-in surface is the
+ * `classify` executable and the on-disk formats.  Inside that executable the hot path is one
+ * function, `classify_sequence()` (src/classify.cpp:897-1012), called per read from the work-unit loop of
+ * `process_file()` (src/classify.cpp:487-564) with the global state `KrakenDatabases`, `Parent_map` and
+ * `taxon_counts` (src/classify.cpp:78,109,113).  This header is the boundary a maintainer binds instead of that
+ * loop body: plain pointers and sizes in, plain arrays out, int error codes, no C++ or torch types.
+ * Citations are file:line under the reference's src/.
+ *
+ *   reference object / call                              → entry point here
+ *   ---------------------------------------------------------------------------------------------------------
+ *   QuickFile::open_file + load_file (-M), KrakenDB(ptr),   kuq_stage_db            (HBM takes the place of the
+ *     KrakenDBIndex(ptr)   classify.cpp:176-200,             page cache; krakendb.cpp:60-78,534-544 validation)
+ *   KrakenDB::prepare_chunking / load_chunk (-x)            kuq_stage_db with a minimizer range [bin_lo,bin_hi)
+ *     krakendb.cpp:411-522
+ *   KrakenDB::count_taxons  krakendb.cpp:90-113             kuq_db_taxids           (by-product of staging)
+ *   TaxonomyDB::getParentMap → Parent_map                   kuq_set_taxonomy
+ *     taxdb.hpp:383-398, classify.cpp:217-219
+ *   process_file work-unit loop + classify_sequence         kuq_classify_batch / kuq_submit_batch+kuq_wait_batch
+ *     classify.cpp:506-559, 897-1012                          (host buffers) and kuq_classify_device (HBM buffers)
+ *   classify_sequence_with_db_chunk (per-chunk lookups)     kuq_lookup_device   (per-window taxa of one DB range)
+ *     classify.cpp:1014-1056
+ *   merge + final pass of the chunked mode                  kuq_resolve_device  (calls + counters from merged taxa)
+ *     classify.cpp:390-485, 663-791
+ *   taxon_counts (ReadCounts<HyperLogLogPlusMinus>)         kuq_read_counts / kuq_get_registers / kuq_state_ptrs
+ *     classify.cpp:78, readcounts.hpp:32-129
+ *
+ * Threading: a context is bound to one CUDA device and is thread-compatible (one caller at a time).  Each of
+ * its `n_slots` batch slots owns a CUDA stream plus device and pinned-host staging, so H2D copy, kernels and D2H
+ * copy of consecutive batches overlap when the caller alternates slots.
+ */
+#ifndef KUQ_H
+#define KUQ_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (0 = success).  The reference calls errx()/exit() in these situations. ---------------- */
+#define KUQ_OK 0
+#define KUQ_E_INVALID_ARG (-1)    /* NULL pointer, zero size, bad slot ... */
+#define KUQ_E_CUDA (-2)           /* a CUDA runtime call failed (kuq_last_error has the text) */
+#define KUQ_E_NO_DEVICE (-3)      /* no usable sm_100 device: there is no CPU fallback */
+#define KUQ_E_DB_FORMAT (-4)      /* krakendb.cpp:64-74: not JFLISTDN / val_len != 4; :541: bad index magic */
+#define KUQ_E_UNSUPPORTED_K (-5)  /* only 8-byte keys (k = 29..31; every published KrakenUniq DB is k=31) */
+#define KUQ_E_STATE (-6)          /* call order: DB and taxonomy must be set before classifying, ... */
+#define KUQ_E_CAPACITY (-7)       /* batch larger than the configured slot capacity */
+#define KUQ_E_NOMEM (-8)          /* host or device allocation failed */
+#define KUQ_E_TAXA_OVERFLOW (-9)  /* a read hit more distinct taxa than the on-chip hit list holds */
+#define KUQ_E_TAXONOMY (-10)      /* cyclic parent chain in the taxonomy */
+
+/* per-window code for an ambiguous k-mer ("A:" in the Kraken hit list, classify.cpp:846-848) */
+#define KUQ_CODE_AMBIG 0xFFFFFFFFu
+
+/* HLL mode rule to reproduce */
+#define KUQ_HLL_PRELOAD 0   /* per-work-unit sketches merged into the global map (classify.cpp:525,542-544) */
+#define KUQ_HLL_CHUNKED 1   /* one global sketch per taxon (classify.cpp:719) — the `-x` path */
+#define KUQ_HLL_DENSE_ONLY 2 /* p=12 registers only, no sparse-tier emulation (fastest; estimates = dense Ertl) */
+
+/* flags of the classify calls */
+#define KUQ_F_WANT_CODES 1u     /* also return the per-window codes (4 B per base position) */
+#define KUQ_F_NO_RUNS 2u        /* skip the run-length-encoded hit lists */
+#define KUQ_F_NO_COUNTS 4u      /* do not touch the per-taxon counters / sketches (pure lookups) */
+
+typedef struct kuq_ctx kuq_ctx;
+
+typedef struct kuq_config {
+  int32_t device;                /* CUDA device ordinal */
+  uint32_t n_slots;              /* batch slots (streams) for copy/compute overlap; 0 → 2 */
+  uint32_t max_reads_per_batch;  /* slot capacity in reads; 0 → 1<<20 */
+  uint64_t max_bases_per_batch;  /* slot capacity in bases (bytes of sequence); 0 → 192 MiB */
+  uint64_t work_unit_size;       /* classify -u (classify.cpp:38,1106); 0 → 500000 */
+  uint32_t hll_mode;             /* KUQ_HLL_* */
+  uint32_t reserved0;
+  uint64_t sparse_set_slots;     /* capacity (slots of 8 B) of the device set that backs the sparse HLL tier;
+                                    0 → 1<<26 */
+} kuq_config;
+
+/* One run of the Kraken hit list: `code:count` (classify.cpp:826-861). code = taxid, 0 (miss) or KUQ_CODE_AMBIG */
+typedef struct kuq_run {
+  uint32_t code;
+  uint32_t count;
+} kuq_run;
+
+/* Result of one batch; every pointer refers to pinned host memory owned by the slot and stays valid until the
+ * slot is submitted again. */
+typedef struct kuq_batch_result {
+  uint32_t n_reads;
+  uint32_t reserved0;
+  const uint32_t *call;        /* [n_reads] taxon call (classify.cpp:965; 0 = unclassified) */
+  const uint32_t *n_windows;   /* [n_reads] k-mer windows scanned (0 when the read is shorter than k, :913) */
+  const uint32_t *run_start;   /* [n_reads] first run of the read in `runs` (undefined with KUQ_F_NO_RUNS) */
+  const uint32_t *run_count;   /* [n_reads] number of runs (0 → the reference prints "0:0", :994-995) */
+  const kuq_run *runs;         /* [n_runs] */
+  uint64_t n_runs;
+  const uint32_t *codes;       /* KUQ_F_WANT_CODES: code of window i of read r at codes[read_offsets[r] -
+                                  read_offsets[0] + i]; NULL otherwise */
+  uint64_t n_classified;       /* reads with call != 0 (total_classified, classify.cpp:541) */
+  double kernel_ms;            /* device time of the batch's kernels (CUDA events on the slot's stream) */
+} kuq_batch_result;
+
+/* Device-side view of a slot's outputs after kuq_classify_device / kuq_resolve_device (HBM pointers). */
+typedef struct kuq_device_result {
+  const uint32_t *d_call;      /* [n_reads] raw taxids */
+  const uint32_t *d_n_windows; /* [n_reads] */
+  const uint32_t *d_codes;     /* per window, indexed like the bases; raw taxids / KUQ_CODE_AMBIG */
+  const uint32_t *d_run_start;
+  const uint32_t *d_run_count;
+  const kuq_run *d_runs;
+  const uint64_t *d_n_runs;    /* device scalar */
+} kuq_device_result;
+
+/* Raw device pointers to the per-taxon state, for the cross-GPU merge the caller performs with NCCL
+ * (allreduce MAX over regs, SUM over the counters) when reads or DB ranges are spread over GPUs. */
+typedef struct kuq_state_ptrs {
+  uint8_t *d_regs;             /* [n_sketch][4096] HLL registers, p = 12 (readcounts.hpp:40) */
+  uint64_t regs_bytes;
+  uint64_t *d_n_kmers;         /* [n_sketch] add_kmer count per taxon (readcounts.hpp:71-74) */
+  uint64_t *d_n_reads;         /* [n_taxa]   incrementReadCount per taxon (readcounts.hpp:36) */
+  uint8_t *d_dense_flag;       /* [n_sketch] 1 = some sketch of the taxon converted to dense (mode emulation) */
+  uint32_t n_sketch;
+  uint32_t n_taxa;
+} kuq_state_ptrs;
+
+void kuq_config_default(kuq_config *cfg);
+int kuq_create(const kuq_config *cfg, kuq_ctx **ctx_out);
+void kuq_destroy(kuq_ctx *ctx);
+const char *kuq_strerror(int code);
+const char *kuq_last_error(const kuq_ctx *ctx);
+/* Build identification: "libkuq <version> sm_100a" */
+const char *kuq_version(void);
+
+/* ---- database -------------------------------------------------------------------------------------------- */
+/* Stage (a minimizer range of) the database into HBM.  kdb_image / idx_image are the bytes of database.kdb and
+ * database.idx (mmap'ed files are fine).  Bins [bin_lo, bin_hi) are copied; bin_hi = 0 means "to the end".
+ * Replaces a previously staged range (the `load_chunk` step of the chunked mode, krakendb.cpp:411-425). */
+int kuq_stage_db(kuq_ctx *ctx, const void *kdb_image, uint64_t kdb_bytes, const void *idx_image,
+                 uint64_t idx_bytes, uint64_t bin_lo, uint64_t bin_hi);
+/* Adopt a database that already lives in HBM (records in on-disk layout, values still raw taxids; offsets =
+ * the full 4^nt+1 table or, with bin_lo>0, the slice starting at bin_lo).  The buffers stay owned by the caller
+ * but the record values are rewritten in place (taxid → dense id). */
+int kuq_attach_db_device(kuq_ctx *ctx, void *d_pairs, uint64_t key_ct, const uint64_t *d_offsets, uint32_t k,
+                         uint32_t nt, uint32_t idx_type, uint64_t bin_lo, uint64_t bin_hi);
+/* Distinct taxids stored in the staged records with their record counts — what KrakenDB::count_taxons()
+ * (krakendb.cpp:90-113) computes for database.kdb.counts.  Pass cap = 0 to query *n only. */
+int kuq_db_taxids(kuq_ctx *ctx, uint32_t *taxid, uint64_t *count, uint32_t cap, uint32_t *n);
+/* Optional: the taxids of ALL database records when only a range is staged (other chunks / other GPUs), so that
+ * every participant numbers taxa identically.  Must precede the first classify/lookup call. */
+int kuq_set_db_taxid_universe(kuq_ctx *ctx, const uint32_t *taxid, uint32_t n);
+
+/* ---- taxonomy: Parent_map (taxdb.hpp:383-398): taxid → parent taxid, 0 for the root / unknown parent --------- */
+int kuq_set_taxonomy(kuq_ctx *ctx, const uint32_t *taxid, const uint32_t *parent_taxid, uint32_t n);
+
+/* ---- classification, host buffers (the call a user makes) ----------------------------------------------- */
+/* bases: concatenated sequences exactly as DNASequence::seq holds them (seqreader.hpp:27-32), read r =
+ * bases[read_offsets[r] .. read_offsets[r+1]).  unit_id: work-unit id per read for the HLL mode rule, or NULL to
+ * let the library cut units like process_file does (classify.cpp:514-520, continuing across batches).
+ * kuq_classify_batch = submit + wait on slot 0. */
+int kuq_classify_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                       const uint32_t *unit_id, uint32_t flags, kuq_batch_result *out);
+int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint64_t *read_offsets,
+                     uint32_t n_reads, const uint32_t *unit_id, uint32_t flags);
+int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out);
+/* Pinned host memory for callers that want zero-copy staging of their batches. */
+void *kuq_host_alloc(uint64_t bytes);
+void kuq_host_free(void *p);
+
+/* ---- classification, device buffers (inputs already in HBM) ---------------------------------------------- */
+/* d_bases must be 16-byte aligned with 32 readable bytes of slack after the last base (TMA bulk loads fetch
+ * whole 16-byte blocks); d_read_offsets are relative to d_bases.  Asynchronous on the slot's stream;
+ * kuq_sync_slot() waits.  d_unit_id may be NULL (units cut on the host need the offsets: pass h_read_offsets,
+ * or NULL when hll_mode == KUQ_HLL_DENSE_ONLY / KUQ_HLL_CHUNKED). */
+int kuq_classify_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                        uint32_t n_reads, uint64_t total_bases, const uint32_t *d_unit_id, uint32_t flags);
+/* Stage 1 only (classify_sequence_with_db_chunk): per-window DENSE taxon ids of the staged DB range into
+ * d_codes_out (indexed like the bases; 0 where the range has no hit; KUQ_CODE_AMBIG for ambiguous windows).
+ * d_codes_out may be peer memory of another GPU (NVLink P2P stores) when only_hits != 0: then only hits are
+ * written, so several ranges can be merged into one zero-initialised buffer without a reduction. */
+int kuq_lookup_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                      uint32_t n_reads, uint64_t total_bases, uint32_t *d_codes_out, uint32_t only_hits);
+/* Stage 2 only: calls, hit lists and counters from merged per-window dense ids (the final pass of the chunked
+ * mode, classify.cpp:663-791). */
+int kuq_resolve_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                       uint32_t n_reads, uint64_t total_bases, const uint32_t *d_codes_in,
+                       const uint32_t *d_unit_id, uint32_t flags);
+int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot);
+int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out);
+/* CUDA stream (cudaStream_t) of a slot, so callers can order their own work (e.g. NCCL) against it. */
+void *kuq_slot_stream(kuq_ctx *ctx, uint32_t slot);
+/* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
+uint64_t kuq_launch_count(const kuq_ctx *ctx);
+/* Device time in ms of the most recent batch's dominant (classification) kernel on `slot`. */
+double kuq_last_kernel_ms(kuq_ctx *ctx, uint32_t slot);
+
+/* ---- per-taxon results --------------------------------------------------------------------------------- */
+/* End of input: closes the open work unit (the flush the reference performs when the reader runs dry). */
+int kuq_finish(kuq_ctx *ctx);
+/* Number of taxa with a non-zero counter, then their rows sorted by taxid: reads (readCount), kmers (kmerCount)
+ * and unique (uniqueKmerCount = ertlCardinality under the configured mode rule, hyperloglogplus.cpp:722-753). */
+int kuq_counts_size(kuq_ctx *ctx, uint32_t *n);
+int kuq_read_counts(kuq_ctx *ctx, uint32_t *taxid, uint64_t *n_reads, uint64_t *n_kmers, uint64_t *unique,
+                    uint8_t *is_sparse, uint32_t cap);
+/* Clade roll-up of the report (TaxReport ctor, taxdb.hpp:956-973): sums the counters and merges the sketches
+ * of the listed taxa; returns reads / kmers / unique of the union. */
+int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers,
+                     uint64_t *unique);
+/* The 4096 p=12 registers of one taxon (all zero if it received no k-mer). */
+int kuq_get_registers(kuq_ctx *ctx, uint32_t taxid, uint8_t *regs4096);
+int kuq_state_ptrs_get(kuq_ctx *ctx, kuq_state_ptrs *out);
+/* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
+int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);
+int kuq_reset_counts(kuq_ctx *ctx);
+
+/* Host-side estimator (no device needed): ertlCardinality over 4096 dense registers (hyperloglogplus.cpp:
+ * 730-752) — exported so bindings and tests can call the exact code the report path uses. */
+uint64_t kuq_ertl_dense(const uint8_t *regs4096, uint64_t n_observed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KUQ_H */

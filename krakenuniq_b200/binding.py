@@ -1,0 +1,319 @@
+"""ctypes binding of libkuq.so (include/kuq.h) — the host-side mirror of the reference's classify driver objects.
+
+`Classifier` plays the role of the globals `KrakenDatabases` / `Parent_map` / `taxon_counts` of
+src/classify.cpp:78-113 and of its per-read function `classify_sequence()` (:897-1012): stage a database, set
+the taxonomy, push batches of reads, read per-read calls / hit lists and the per-taxon counters back.
+
+There is no CPU path here: if libkuq.so is missing or no sm_100 device is present this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+AMBIG = 0xFFFFFFFF
+HLL_PRELOAD, HLL_CHUNKED, HLL_DENSE_ONLY = 0, 1, 2
+F_WANT_CODES, F_NO_RUNS, F_NO_COUNTS = 1, 2, 4
+
+u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+
+
+class KuqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libkuq error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_slots", C.c_uint32), ("max_reads_per_batch", C.c_uint32),
+                ("max_bases_per_batch", C.c_uint64), ("work_unit_size", C.c_uint64), ("hll_mode", C.c_uint32),
+                ("reserved0", C.c_uint32), ("sparse_set_slots", C.c_uint64)]
+
+
+class Run(C.Structure):
+    _fields_ = [("code", C.c_uint32), ("count", C.c_uint32)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("reserved0", C.c_uint32), ("call", u32p), ("n_windows", u32p),
+                ("run_start", u32p), ("run_count", u32p), ("runs", C.POINTER(Run)), ("n_runs", C.c_uint64),
+                ("codes", u32p), ("n_classified", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+class DeviceResult(C.Structure):
+    _fields_ = [("d_call", C.c_void_p), ("d_n_windows", C.c_void_p), ("d_codes", C.c_void_p),
+                ("d_run_start", C.c_void_p), ("d_run_count", C.c_void_p), ("d_runs", C.c_void_p),
+                ("d_n_runs", C.c_void_p)]
+
+
+class StatePtrs(C.Structure):
+    _fields_ = [("d_regs", C.c_void_p), ("regs_bytes", C.c_uint64), ("d_n_kmers", C.c_void_p),
+                ("d_n_reads", C.c_void_p), ("d_dense_flag", C.c_void_p), ("n_sketch", C.c_uint32),
+                ("n_taxa", C.c_uint32)]
+
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load_library(rebuild_if_stale: bool = False):
+    """Load libkuq.so; raises if it is not there (no silent fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if rebuild_if_stale:
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise FileNotFoundError(f"{_build.LIB} is missing: run `python -m krakenuniq_b200.build` "
+                                "(the CUDA extension is the only implementation; there is no CPU path)")
+    L = C.CDLL(_build.LIB)
+    vp = C.c_void_p
+    sigs = {
+        "kuq_config_default": (None, [C.POINTER(Config)]),
+        "kuq_create": (C.c_int, [C.POINTER(Config), C.POINTER(vp)]),
+        "kuq_destroy": (None, [vp]),
+        "kuq_strerror": (C.c_char_p, [C.c_int]),
+        "kuq_last_error": (C.c_char_p, [vp]),
+        "kuq_version": (C.c_char_p, []),
+        "kuq_stage_db": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64]),
+        "kuq_attach_db_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                           C.c_uint64]),
+        "kuq_db_taxids": (C.c_int, [vp, u32p, u64p, C.c_uint32, u32p]),
+        "kuq_set_db_taxid_universe": (C.c_int, [vp, u32p, C.c_uint32]),
+        "kuq_set_taxonomy": (C.c_int, [vp, u32p, u32p, C.c_uint32]),
+        "kuq_classify_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, C.c_uint32, C.POINTER(BatchResult)]),
+        "kuq_submit_batch": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint32, u32p, C.c_uint32]),
+        "kuq_wait_batch": (C.c_int, [vp, C.c_uint32, C.POINTER(BatchResult)]),
+        "kuq_host_alloc": (vp, [C.c_uint64]),
+        "kuq_host_free": (None, [vp]),
+        "kuq_classify_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32]),
+        "kuq_lookup_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32]),
+        "kuq_resolve_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, vp, C.c_uint32]),
+        "kuq_sync_slot": (C.c_int, [vp, C.c_uint32]),
+        "kuq_slot_device_result": (C.c_int, [vp, C.c_uint32, C.POINTER(DeviceResult)]),
+        "kuq_slot_stream": (vp, [vp, C.c_uint32]),
+        "kuq_launch_count": (C.c_uint64, [vp]),
+        "kuq_last_kernel_ms": (C.c_double, [vp, C.c_uint32]),
+        "kuq_finish": (C.c_int, [vp]),
+        "kuq_counts_size": (C.c_int, [vp, u32p]),
+        "kuq_read_counts": (C.c_int, [vp, u32p, u64p, u64p, u64p, u8p, C.c_uint32]),
+        "kuq_clade_counts": (C.c_int, [vp, u32p, C.c_uint32, u64p, u64p, u64p]),
+        "kuq_get_registers": (C.c_int, [vp, C.c_uint32, u8p]),
+        "kuq_state_ptrs_get": (C.c_int, [vp, C.POINTER(StatePtrs)]),
+        "kuq_dense_taxids": (C.c_int, [vp, u32p, C.c_uint32, u32p]),
+        "kuq_reset_counts": (C.c_int, [vp]),
+        "kuq_ertl_dense": (C.c_uint64, [u8p, C.c_uint64]),
+    }
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)            # AttributeError here = the library does not export what kuq.h declares
+        f.restype, f.argtypes = res, args
+    _LIB = L
+    return L
+
+
+def exported_symbols():
+    """Names include/kuq.h declares; used by the CPU tests to check the library exports them all."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "kuq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(kuq_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Classifier:
+    """One GPU's classification context (kuq_ctx)."""
+
+    def __init__(self, device=0, n_slots=2, max_reads=1 << 20, max_bases=192 << 20, work_unit_size=500000,
+                 hll_mode=HLL_PRELOAD, sparse_set_slots=1 << 26):
+        self.L = load_library()
+        cfg = Config()
+        self.L.kuq_config_default(C.byref(cfg))
+        cfg.device, cfg.n_slots = device, n_slots
+        cfg.max_reads_per_batch, cfg.max_bases_per_batch = max_reads, max_bases
+        cfg.work_unit_size, cfg.hll_mode, cfg.sparse_set_slots = work_unit_size, hll_mode, sparse_set_slots
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.L.kuq_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise KuqError(rc, self.L.kuq_strerror(rc).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kuq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise KuqError(rc, f"{self.L.kuq_strerror(rc).decode()}: {self.L.kuq_last_error(self.h).decode()}")
+
+    # ---- database / taxonomy -------------------------------------------------------------------------------
+    def stage_db(self, kdb: np.ndarray, idx: np.ndarray, bin_lo=0, bin_hi=0):
+        kdb = np.ascontiguousarray(kdb).view(np.uint8) if not isinstance(kdb, np.memmap) else kdb
+        idx = np.ascontiguousarray(idx).view(np.uint8) if not isinstance(idx, np.memmap) else idx
+        self._ck(self.L.kuq_stage_db(self.h, kdb.ctypes.data, kdb.size, idx.ctypes.data, idx.size, bin_lo, bin_hi))
+
+    def stage_db_files(self, kdb_path, idx_path, bin_lo=0, bin_hi=0):
+        self.stage_db(np.memmap(kdb_path, np.uint8, "r"), np.memmap(idx_path, np.uint8, "r"), bin_lo, bin_hi)
+
+    def attach_db_device(self, d_pairs_ptr, key_ct, d_offsets_ptr, k, nt, idx_type=2, bin_lo=0, bin_hi=0):
+        self._ck(self.L.kuq_attach_db_device(self.h, d_pairs_ptr, key_ct, d_offsets_ptr, k, nt, idx_type, bin_lo,
+                                             bin_hi))
+
+    def db_taxids(self):
+        n = C.c_uint32(0)
+        self._ck(self.L.kuq_db_taxids(self.h, None, None, 0, C.byref(n)))
+        t = np.zeros(n.value, np.uint32)
+        c = np.zeros(n.value, np.uint64)
+        if n.value:
+            self._ck(self.L.kuq_db_taxids(self.h, _p(t, u32p), _p(c, u64p), n.value, C.byref(n)))
+        return t, c
+
+    def set_db_taxid_universe(self, taxids):
+        t = np.ascontiguousarray(taxids, np.uint32)
+        self._ck(self.L.kuq_set_db_taxid_universe(self.h, _p(t, u32p), len(t)))
+
+    def set_taxonomy(self, taxid, parent):
+        t = np.ascontiguousarray(taxid, np.uint32)
+        p = np.ascontiguousarray(parent, np.uint32)
+        self._ck(self.L.kuq_set_taxonomy(self.h, _p(t, u32p), _p(p, u32p), len(t)))
+
+    # ---- host-buffer classification ---------------------------------------------------------------------------
+    def _result(self, res: BatchResult, offsets, copy=True):
+        n = res.n_reads
+        as_np = lambda ptr, cnt, dt: (np.ctypeslib.as_array(ptr, shape=(cnt,)).view(dt) if cnt else np.zeros(0, dt))
+        out = dict(call=as_np(res.call, n, np.uint32), n_windows=as_np(res.n_windows, n, np.uint32),
+                   n_classified=int(res.n_classified), kernel_ms=res.kernel_ms, n_runs=int(res.n_runs))
+        if res.n_runs or res.run_start:
+            out["run_start"] = as_np(res.run_start, n, np.uint32)
+            out["run_count"] = as_np(res.run_count, n, np.uint32)
+            runs = np.ctypeslib.as_array(C.cast(res.runs, u32p), shape=(int(res.n_runs) * 2,)) if res.n_runs else \
+                np.zeros(0, np.uint32)
+            out["runs"] = runs.reshape(-1, 2)
+        if res.codes:
+            total = int(offsets[-1] - offsets[0])
+            out["codes"] = as_np(res.codes, total, np.uint32)
+        if copy:
+            out = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()}
+        return out
+
+    def classify(self, bases: np.ndarray, offsets: np.ndarray, unit_id=None, flags=0):
+        """kuq_classify_batch: returns dict(call, n_windows, run_start, run_count, runs[, codes])."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        u = np.ascontiguousarray(unit_id, np.uint32) if unit_id is not None else None
+        res = BatchResult()
+        self._ck(self.L.kuq_classify_batch(self.h, bases.ctypes.data if bases.size else None, _p(offsets, u64p), n,
+                                           _p(u, u32p) if u is not None else None, flags, C.byref(res)))
+        return self._result(res, offsets)
+
+    def submit(self, slot, bases_ptr, offsets: np.ndarray, unit_id=None, flags=0):
+        n = len(offsets) - 1
+        u = np.ascontiguousarray(unit_id, np.uint32) if unit_id is not None else None
+        self._ck(self.L.kuq_submit_batch(self.h, slot, bases_ptr, _p(offsets, u64p), n,
+                                         _p(u, u32p) if u is not None else None, flags))
+
+    def wait(self, slot, offsets=None, copy=False):
+        res = BatchResult()
+        self._ck(self.L.kuq_wait_batch(self.h, slot, C.byref(res)))
+        return self._result(res, offsets if offsets is not None else np.zeros(2, np.uint64), copy=copy)
+
+    # ---- device-buffer classification ---------------------------------------------------------------------------
+    def classify_device(self, slot, d_bases, d_offsets, n_reads, total_bases, d_unit=None, flags=0):
+        self._ck(self.L.kuq_classify_device(self.h, slot, d_bases, d_offsets, n_reads, total_bases, d_unit, flags))
+
+    def lookup_device(self, slot, d_bases, d_offsets, n_reads, total_bases, d_codes_out, only_hits=0):
+        self._ck(self.L.kuq_lookup_device(self.h, slot, d_bases, d_offsets, n_reads, total_bases, d_codes_out,
+                                          only_hits))
+
+    def resolve_device(self, slot, d_bases, d_offsets, n_reads, total_bases, d_codes_in, d_unit=None, flags=0):
+        self._ck(self.L.kuq_resolve_device(self.h, slot, d_bases, d_offsets, n_reads, total_bases, d_codes_in, d_unit,
+                                           flags))
+
+    def sync(self, slot):
+        self._ck(self.L.kuq_sync_slot(self.h, slot))
+
+    def device_result(self, slot):
+        r = DeviceResult()
+        self._ck(self.L.kuq_slot_device_result(self.h, slot, C.byref(r)))
+        return r
+
+    def slot_stream(self, slot):
+        return self.L.kuq_slot_stream(self.h, slot)
+
+    def launch_count(self):
+        return int(self.L.kuq_launch_count(self.h))
+
+    def last_kernel_ms(self, slot):
+        return float(self.L.kuq_last_kernel_ms(self.h, slot))
+
+    # ---- results ---------------------------------------------------------------------------------------------
+    def finish(self):
+        self._ck(self.L.kuq_finish(self.h))
+
+    def counts(self):
+        n = C.c_uint32(0)
+        self._ck(self.L.kuq_counts_size(self.h, C.byref(n)))
+        m = n.value
+        taxid, nr, nk, un, sp = (np.zeros(m, np.uint32), np.zeros(m, np.uint64), np.zeros(m, np.uint64),
+                                 np.zeros(m, np.uint64), np.zeros(m, np.uint8))
+        if m:
+            self._ck(self.L.kuq_read_counts(self.h, _p(taxid, u32p), _p(nr, u64p), _p(nk, u64p), _p(un, u64p),
+                                            _p(sp, u8p), m))
+        return dict(taxid=taxid, n_reads=nr, n_kmers=nk, unique=un, sparse=sp)
+
+    def clade(self, taxids):
+        t = np.ascontiguousarray(taxids, np.uint32)
+        r, k, u = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.L.kuq_clade_counts(self.h, _p(t, u32p), len(t), C.byref(r), C.byref(k), C.byref(u)))
+        return u.value, r.value, k.value
+
+    def registers(self, taxid):
+        r = np.zeros(4096, np.uint8)
+        self._ck(self.L.kuq_get_registers(self.h, int(taxid), _p(r, u8p)))
+        return r
+
+    def state_ptrs(self):
+        s = StatePtrs()
+        self._ck(self.L.kuq_state_ptrs_get(self.h, C.byref(s)))
+        return s
+
+    def dense_taxids(self):
+        n = C.c_uint32(0)
+        self._ck(self.L.kuq_dense_taxids(self.h, None, 0, C.byref(n)))
+        t = np.zeros(n.value, np.uint32)
+        self._ck(self.L.kuq_dense_taxids(self.h, _p(t, u32p), n.value, C.byref(n)))
+        return t
+
+    def reset_counts(self):
+        self._ck(self.L.kuq_reset_counts(self.h))
+
+
+def ertl_dense(regs: np.ndarray, n_observed: int) -> int:
+    L = load_library()
+    regs = np.ascontiguousarray(regs, np.uint8)
+    return int(L.kuq_ertl_dense(_p(regs, u8p), n_observed))
+
+
+def decode_runs(res, i):
+    """hit list of read i as [(code, count), ...] from a classify() result"""
+    s, c = int(res["run_start"][i]), int(res["run_count"][i])
+    return [(int(a), int(b)) for a, b in res["runs"][s:s + c]]

@@ -1,0 +1,1043 @@
+// kuq_api.cu — host side of libkuq.so: the C ABI declared in include/kuq.h.
+//
+// Owns HBM (database range, taxonomy arrays, per-taxon state), the batch slots (stream + device and pinned
+// host staging) and the host-side pieces of the path that are not data parallel: database header validation
+// (krakendb.cpp:60-78,534-544), dense taxon numbering, work-unit cutting (classify.cpp:514-520) and the
+// double-precision Ertl estimator (hyperloglogplus.cpp:722-753).  There is no CPU classification path: without
+// an sm_100 device kuq_create fails with KUQ_E_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kuq.h"
+#include "kuq_kernels.cuh"
+
+using namespace kuq;
+
+namespace {
+
+constexpr uint64_t INDEX2_XOR_MASK = 0xe37e28c4271b5a2dULL;   // krakendb.cpp:45
+constexpr uint32_t SLACK = 64;                                // bytes readable past the end of a bases buffer
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+  // device
+  char *d_bases = nullptr, *d_clean = nullptr;
+  uint64_t *d_offsets = nullptr;
+  uint32_t *d_unit = nullptr, *d_call = nullptr, *d_nwin = nullptr, *d_codes = nullptr;
+  uint32_t *d_run_start = nullptr, *d_run_count = nullptr;
+  uint2 *d_runs = nullptr;
+  unsigned long long *d_scalars = nullptr;   // [0] run cursor, [1] n_classified, [2] chunk counter(u32) [3] error(u32)
+  // pinned host
+  uint32_t *h_call = nullptr, *h_nwin = nullptr, *h_run_start = nullptr, *h_run_count = nullptr, *h_codes = nullptr;
+  uint32_t *h_unit = nullptr;
+  kuq_run *h_runs = nullptr;
+  uint64_t h_runs_cap = 0;
+  unsigned long long *h_scalars = nullptr;
+  // in-flight batch
+  bool busy = false;
+  uint32_t n_reads = 0, flags = 0;
+  uint64_t total_bases = 0;
+  double kernel_ms = 0;
+  bool external = false;   // inputs are caller-owned device buffers
+  const char *x_bases = nullptr;
+};
+
+}  // namespace
+
+struct kuq_ctx {
+  kuq_config cfg;
+  int device = 0;
+  int n_sm = 148;
+  std::string err;
+  std::vector<Slot> slots;
+  uint64_t launches = 0;
+  cudaStream_t aux = nullptr;
+
+  // database
+  bool db_owned = false;
+  uint8_t *d_pairs = nullptr;
+  uint64_t *d_offsets_owned = nullptr;
+  const uint64_t *d_offsets = nullptr;
+  uint64_t key_ct = 0, rec_base = 0;
+  uint32_t k = 0, nt = 0, idx_type = 0;
+  uint64_t bin_lo = 0, bin_hi = 0;
+  bool db_staged = false, db_remapped = false;
+  std::vector<uint32_t> db_taxids;        // distinct taxids of the staged records (ascending)
+  std::vector<uint64_t> db_taxid_counts;
+  std::vector<uint32_t> universe;         // taxids of all records of the database (optional)
+  // device hash of the staged taxids (keys = taxid + 1)
+  uint32_t *d_tx_keys = nullptr, *d_tx_dense = nullptr;
+  unsigned long long *d_tx_counts = nullptr;
+  uint32_t tx_cap = 0;
+
+  // taxonomy
+  bool tax_set = false, finalized = false;
+  std::vector<uint32_t> tax_ids, tax_parents;
+  std::vector<uint32_t> raw_of_dense;
+  std::unordered_map<uint32_t, uint32_t> dense_of_raw;
+  uint32_t n_taxa = 0, n_sketch = 0;
+  uint32_t *d_parent = nullptr, *d_raw = nullptr;
+  uint16_t *d_depth = nullptr;
+
+  // per-taxon state
+  uint8_t *d_regs = nullptr, *d_dense_flag = nullptr;
+  unsigned long long *d_n_kmers = nullptr, *d_n_reads = nullptr;
+  unsigned long long *d_sparse_slots = nullptr, *d_sparse_used = nullptr;
+  uint32_t *d_sparse_distinct = nullptr;
+  uint64_t sparse_cap = 0;
+
+  // work-unit cutting across batches (classify.cpp:506-521)
+  uint64_t unit_nt = 0;
+  uint32_t unit_next = 0;
+};
+
+namespace {
+
+int fail(kuq_ctx *c, int code, const char *fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(ctx, KUQ_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+cudaError_t dmalloc(T **p, uint64_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+template <typename T>
+cudaError_t hmalloc(T **p, uint64_t n) { return cudaMallocHost((void **)p, n * sizeof(T)); }
+
+void free_slot(Slot &s) {
+  cudaFree(s.d_bases); cudaFree(s.d_clean); cudaFree(s.d_offsets); cudaFree(s.d_unit); cudaFree(s.d_call);
+  cudaFree(s.d_nwin); cudaFree(s.d_codes); cudaFree(s.d_run_start); cudaFree(s.d_run_count); cudaFree(s.d_runs);
+  cudaFree(s.d_scalars);
+  cudaFreeHost(s.h_call); cudaFreeHost(s.h_nwin); cudaFreeHost(s.h_run_start); cudaFreeHost(s.h_run_count);
+  cudaFreeHost(s.h_codes); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_scalars); cudaFreeHost(s.h_unit);
+  if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+  if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Slot();
+}
+
+void free_db(kuq_ctx *ctx) {
+  if (ctx->db_owned) { cudaFree(ctx->d_pairs); cudaFree(ctx->d_offsets_owned); }
+  ctx->d_pairs = nullptr; ctx->d_offsets_owned = nullptr; ctx->d_offsets = nullptr;
+  cudaFree(ctx->d_tx_keys); cudaFree(ctx->d_tx_dense); cudaFree(ctx->d_tx_counts);
+  ctx->d_tx_keys = ctx->d_tx_dense = nullptr; ctx->d_tx_counts = nullptr;
+  ctx->db_staged = false; ctx->db_remapped = false;
+}
+
+void free_tax_state(kuq_ctx *ctx) {
+  cudaFree(ctx->d_parent); cudaFree(ctx->d_raw); cudaFree(ctx->d_depth);
+  cudaFree(ctx->d_regs); cudaFree(ctx->d_dense_flag); cudaFree(ctx->d_n_kmers); cudaFree(ctx->d_n_reads);
+  cudaFree(ctx->d_sparse_slots); cudaFree(ctx->d_sparse_used); cudaFree(ctx->d_sparse_distinct);
+  ctx->d_parent = ctx->d_raw = nullptr; ctx->d_depth = nullptr; ctx->d_regs = ctx->d_dense_flag = nullptr;
+  ctx->d_n_kmers = ctx->d_n_reads = nullptr; ctx->d_sparse_slots = ctx->d_sparse_used = nullptr;
+  ctx->d_sparse_distinct = nullptr;
+  ctx->finalized = false;
+}
+
+// ---- Ertl estimator (hyperloglogplus.cpp:373-422,738-752), same operation order as the reference ----------
+double ertl_sigma(double x) {
+  if (x == 1.0) return INFINITY;
+  double prev, sigma_x = x, y = 1.0;
+  do { prev = sigma_x; x *= x; sigma_x += x * y; y += y; } while (sigma_x != prev);
+  return sigma_x;
+}
+double ertl_tau(double x) {
+  if (x == 0.0 || x == 1.0) return 0.0;
+  double prev, y = 1.0, tau_x = 1 - x;
+  do { prev = tau_x; x = std::sqrt(x); y /= 2.0; tau_x -= std::pow(1 - x, 2) * y; } while (tau_x != prev);
+  return tau_x / 3.0;
+}
+uint64_t ertl_from_hist(const int *C, size_t q, size_t m, uint64_t n_observed) {
+  double est_denominator = m * ertl_tau(1.0 - double(C[q + 1]) / double(m));
+  for (int k = (int)q; k >= 1; --k) { est_denominator += C[k]; est_denominator *= 0.5; }
+  est_denominator += m * ertl_sigma(double(C[0]) / double(m));
+  double m_sq_alpha_inf = (m / (2.0 * std::log(2))) * m;
+  double est = m_sq_alpha_inf / est_denominator;
+  return (double(n_observed) < est) ? n_observed : (uint64_t)std::round(est);
+}
+uint64_t ertl_dense_hist(const uint32_t *hist64, uint64_t n_observed) {
+  int C[66];
+  for (int i = 0; i < 64; i++) C[i] = (int)hist64[i];
+  C[64] = C[65] = 0;
+  return ertl_from_hist(C, 64 - HLL_P, HLL_M, n_observed);
+}
+// getEncodedRank(enc, 25, 12), hyperloglogplus.cpp:152-161
+inline unsigned encoded_rank(uint32_t e) {
+  if (e & 1) return 13 + ((e >> 1) & 0x3F);
+  uint32_t r = e << 12;
+  return (r ? (unsigned)__builtin_clz(r) : 20u) + 1;
+}
+
+int alloc_slot(kuq_ctx *ctx, Slot &s) {
+  const uint64_t mr = ctx->cfg.max_reads_per_batch, mb = ctx->cfg.max_bases_per_batch;
+  CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&s.ev_k0));
+  CU(cudaEventCreate(&s.ev_k1));
+  CU(dmalloc(&s.d_bases, mb + SLACK));
+  CU(dmalloc(&s.d_clean, mb + SLACK));
+  CU(dmalloc(&s.d_offsets, mr + 1));
+  CU(dmalloc(&s.d_unit, mr));
+  CU(dmalloc(&s.d_call, mr));
+  CU(dmalloc(&s.d_nwin, mr));
+  CU(dmalloc(&s.d_codes, mb + SLACK));
+  CU(dmalloc(&s.d_run_start, mr));
+  CU(dmalloc(&s.d_run_count, mr));
+  CU(dmalloc(&s.d_runs, mb + SLACK));
+  CU(dmalloc(&s.d_scalars, 4));
+  CU(hmalloc(&s.h_call, mr));
+  CU(hmalloc(&s.h_nwin, mr));
+  CU(hmalloc(&s.h_run_start, mr));
+  CU(hmalloc(&s.h_run_count, mr));
+  CU(hmalloc(&s.h_unit, mr));
+  CU(hmalloc(&s.h_scalars, 4));
+  s.h_runs_cap = std::max<uint64_t>(mr * 8, 1024);
+  CU(hmalloc(&s.h_runs, s.h_runs_cap));
+  return KUQ_OK;
+}
+
+int check_slot(kuq_ctx *ctx, uint32_t slot) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  if (slot >= ctx->slots.size()) return fail(ctx, KUQ_E_INVALID_ARG, "slot %u out of range (%zu slots)", slot, ctx->slots.size());
+  return KUQ_OK;
+}
+
+// Scan the staged records for their distinct taxids (+counts): count_taxons (krakendb.cpp:90-113) on the GPU.
+int collect_taxids(kuq_ctx *ctx) {
+  uint32_t cap = 1u << 16;
+  for (;;) {
+    cudaFree(ctx->d_tx_keys); cudaFree(ctx->d_tx_counts); cudaFree(ctx->d_tx_dense);
+    ctx->d_tx_keys = ctx->d_tx_dense = nullptr; ctx->d_tx_counts = nullptr;
+    CU(dmalloc(&ctx->d_tx_keys, cap));
+    CU(dmalloc(&ctx->d_tx_counts, cap));
+    CU(dmalloc(&ctx->d_tx_dense, cap));
+    CU(cudaMemsetAsync(ctx->d_tx_keys, 0, cap * 4ull, ctx->aux));
+    CU(cudaMemsetAsync(ctx->d_tx_counts, 0, cap * 8ull, ctx->aux));
+    uint32_t *d_over;
+    CU(dmalloc(&d_over, 1));
+    CU(cudaMemsetAsync(d_over, 0, 4, ctx->aux));
+    launch_collect_taxids(ctx->d_pairs, ctx->key_ct, ctx->d_tx_keys, ctx->d_tx_counts, cap - 1, d_over, ctx->aux);
+    ctx->launches++;
+    uint32_t over = 0;
+    CU(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaStreamSynchronize(ctx->aux));
+    cudaFree(d_over);
+    if (over == 2) return fail(ctx, KUQ_E_DB_FORMAT, "taxid 0xFFFFFFFF is reserved");
+    std::vector<uint32_t> keys(cap);
+    std::vector<unsigned long long> counts(cap);
+    CU(cudaMemcpy(keys.data(), ctx->d_tx_keys, cap * 4ull, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(counts.data(), ctx->d_tx_counts, cap * 8ull, cudaMemcpyDeviceToHost));
+    uint64_t used = 0;
+    for (uint32_t i = 0; i < cap; i++) used += keys[i] != 0;
+    if (over == 1 || used * 2 > cap) {            // too full: the probe chains got long or overflowed
+      if (cap >= (1u << 28)) return fail(ctx, KUQ_E_CAPACITY, "more than 2^27 distinct taxids in the database");
+      cap <<= 2;
+      continue;
+    }
+    std::vector<std::pair<uint32_t, uint64_t>> v;
+    v.reserve(used);
+    for (uint32_t i = 0; i < cap; i++) if (keys[i]) v.emplace_back(keys[i] - 1, counts[i]);
+    std::sort(v.begin(), v.end());
+    ctx->db_taxids.clear(); ctx->db_taxid_counts.clear();
+    for (auto &pr : v) { ctx->db_taxids.push_back(pr.first); ctx->db_taxid_counts.push_back(pr.second); }
+    ctx->tx_cap = cap;
+    return KUQ_OK;
+  }
+}
+
+// Dense numbering: 0 = "no taxon", 1 = taxid 1 (the reference's hard-wired root, krakenutil.cpp:96,106), then every
+// taxid stored in database records (these own HLL sketches), then the remaining taxonomy nodes; each group
+// ascending by taxid.  Builds the flattened Parent_map and uploads everything.
+int finalize(kuq_ctx *ctx) {
+  if (ctx->finalized) return KUQ_OK;
+  if (!ctx->db_staged) return fail(ctx, KUQ_E_STATE, "no database staged");
+  if (!ctx->tax_set) return fail(ctx, KUQ_E_STATE, "no taxonomy set");
+  std::vector<uint32_t> dbt = ctx->universe.empty() ? ctx->db_taxids : ctx->universe;
+  std::sort(dbt.begin(), dbt.end());
+  dbt.erase(std::unique(dbt.begin(), dbt.end()), dbt.end());
+  std::vector<uint32_t> &raw = ctx->raw_of_dense;
+  raw.clear();
+  ctx->dense_of_raw.clear();
+  raw.push_back(0);
+  raw.push_back(1);
+  for (uint32_t t : dbt) if (t > 1) raw.push_back(t);
+  ctx->n_sketch = (uint32_t)raw.size();
+  for (uint32_t i = 0; i < raw.size(); i++) ctx->dense_of_raw[raw[i]] = i;
+  std::vector<uint32_t> rest;
+  for (uint32_t t : ctx->tax_ids) if (!ctx->dense_of_raw.count(t)) rest.push_back(t);
+  for (uint32_t t : ctx->tax_parents) if (t && !ctx->dense_of_raw.count(t)) rest.push_back(t);   // parents without a row
+  std::sort(rest.begin(), rest.end());
+  rest.erase(std::unique(rest.begin(), rest.end()), rest.end());
+  for (uint32_t t : rest) { ctx->dense_of_raw[t] = (uint32_t)raw.size(); raw.push_back(t); }
+  ctx->n_taxa = (uint32_t)raw.size();
+  // staged taxids must all be numbered
+  for (uint32_t t : ctx->db_taxids)
+    if (!ctx->dense_of_raw.count(t) || ctx->dense_of_raw[t] >= ctx->n_sketch)
+      return fail(ctx, KUQ_E_STATE, "staged records hold taxid %u that is not in the declared taxid universe", t);
+
+  // Parent_map (taxdb.hpp:383-398): every taxonomy row has an entry; rows whose parent is themselves / 0 map to
+  // 0.  A parent id WITHOUT a row of its own is still walked to by resolve_tree/lca (then the walk stops:
+  // "No parent for ..." krakenutil.cpp:166-169), so such ids got a dense id above with parent 0.
+  std::vector<uint32_t> parent(ctx->n_taxa, 0);
+  for (size_t i = 0; i < ctx->tax_ids.size(); i++) {
+    uint32_t t = ctx->tax_ids[i], p = ctx->tax_parents[i];
+    if (t == 0) continue;
+    parent[ctx->dense_of_raw[t]] = (p == t || p == 0) ? 0 : ctx->dense_of_raw[p];
+  }
+  // depth = steps until the chain ends at 0 or at dense 1 (lca() stops at taxid 1, krakenutil.cpp:96,106)
+  std::vector<uint16_t> depth(ctx->n_taxa, 0);
+  std::vector<uint8_t> state(ctx->n_taxa, 0);   // 0 new, 1 on stack, 2 done
+  state[0] = state[1] = 2;
+  std::vector<uint32_t> stack;
+  for (uint32_t i = 2; i < ctx->n_taxa; i++) {
+    if (state[i]) continue;
+    uint32_t x = i;
+    stack.clear();
+    while (state[x] == 0) { state[x] = 1; stack.push_back(x); x = parent[x]; }
+    if (state[x] == 1) return fail(ctx, KUQ_E_TAXONOMY, "cycle in the taxonomy at taxid %u", raw[x]);
+    uint32_t d = depth[x];
+    while (!stack.empty()) {
+      uint32_t y = stack.back(); stack.pop_back();
+      d++;
+      if (d > 65000) return fail(ctx, KUQ_E_TAXONOMY, "taxonomy deeper than 65000 levels");
+      depth[y] = (uint16_t)d; state[y] = 2;
+    }
+  }
+  free_tax_state(ctx);
+  CU(dmalloc(&ctx->d_parent, ctx->n_taxa));
+  CU(dmalloc(&ctx->d_raw, ctx->n_taxa));
+  CU(dmalloc(&ctx->d_depth, ctx->n_taxa));
+  CU(cudaMemcpy(ctx->d_parent, parent.data(), ctx->n_taxa * 4ull, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->d_raw, raw.data(), ctx->n_taxa * 4ull, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->d_depth, depth.data(), ctx->n_taxa * 2ull, cudaMemcpyHostToDevice));
+  CU(dmalloc(&ctx->d_regs, (uint64_t)ctx->n_sketch * HLL_M));
+  CU(dmalloc(&ctx->d_dense_flag, ctx->n_sketch));
+  CU(dmalloc(&ctx->d_n_kmers, ctx->n_sketch));
+  CU(dmalloc(&ctx->d_n_reads, ctx->n_taxa));
+  CU(cudaMemset(ctx->d_regs, 0, (uint64_t)ctx->n_sketch * HLL_M));
+  CU(cudaMemset(ctx->d_dense_flag, 0, ctx->n_sketch));
+  CU(cudaMemset(ctx->d_n_kmers, 0, ctx->n_sketch * 8ull));
+  CU(cudaMemset(ctx->d_n_reads, 0, ctx->n_taxa * 8ull));
+  if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
+    ctx->sparse_cap = ctx->cfg.sparse_set_slots;
+    CU(dmalloc(&ctx->d_sparse_slots, ctx->sparse_cap));
+    CU(dmalloc(&ctx->d_sparse_used, 1));
+    CU(dmalloc(&ctx->d_sparse_distinct, ctx->n_sketch));
+    CU(cudaMemset(ctx->d_sparse_slots, 0, ctx->sparse_cap * 8ull));
+    CU(cudaMemset(ctx->d_sparse_used, 0, 8));
+    CU(cudaMemset(ctx->d_sparse_distinct, 0, ctx->n_sketch * 4ull));
+  }
+  ctx->finalized = true;
+  return KUQ_OK;
+}
+
+// rewrite the staged record values taxid → dense id (once per staged range)
+int remap_db(kuq_ctx *ctx) {
+  if (ctx->db_remapped) return KUQ_OK;
+  std::vector<uint32_t> keys(ctx->tx_cap), dense(ctx->tx_cap, 0);
+  CU(cudaMemcpy(keys.data(), ctx->d_tx_keys, ctx->tx_cap * 4ull, cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < ctx->tx_cap; i++)
+    if (keys[i]) {
+      auto it = ctx->dense_of_raw.find(keys[i] - 1);
+      if (it == ctx->dense_of_raw.end() || it->second >= ctx->n_sketch)
+        return fail(ctx, KUQ_E_STATE, "staged records hold taxid %u outside the numbered universe", keys[i] - 1);
+      dense[i] = it->second;
+    }
+  CU(cudaMemcpy(ctx->d_tx_dense, dense.data(), ctx->tx_cap * 4ull, cudaMemcpyHostToDevice));
+  uint32_t *d_missing;
+  CU(dmalloc(&d_missing, 1));
+  CU(cudaMemset(d_missing, 0, 4));
+  launch_remap_values(ctx->d_pairs, ctx->key_ct, ctx->d_tx_keys, ctx->d_tx_dense, ctx->tx_cap - 1, d_missing, ctx->aux);
+  ctx->launches++;
+  uint32_t missing = 0;
+  CU(cudaMemcpyAsync(&missing, d_missing, 4, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  cudaFree(d_missing);
+  if (missing) return fail(ctx, KUQ_E_STATE, "internal: a record value was missing from the taxid table");
+  ctx->db_remapped = true;
+  return KUQ_OK;
+}
+
+int ensure_ready(kuq_ctx *ctx) {
+  int rc = finalize(ctx);
+  if (rc) return rc;
+  return remap_db(ctx);
+}
+
+// process_file's unit cutting (classify.cpp:506-521): reads join the open unit until its length reaches -u.
+void cut_units(kuq_ctx *ctx, const uint64_t *offsets, uint32_t n, uint32_t *unit) {
+  const uint64_t wus = ctx->cfg.work_unit_size;
+  for (uint32_t i = 0; i < n; i++) {
+    unit[i] = ctx->unit_next;
+    ctx->unit_nt += offsets[i + 1] - offsets[i];
+    if (ctx->unit_nt >= wus) { ctx->unit_next++; ctx->unit_nt = 0; }
+  }
+}
+
+void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const uint64_t *d_offsets,
+                 const uint32_t *d_unit, uint32_t n_reads, uint32_t flags) {
+  memset(&p, 0, sizeof p);
+  p.db.pairs = ctx->d_pairs;
+  p.db.offsets = ctx->d_offsets;
+  p.db.rec_base = ctx->rec_base;
+  p.db.key_mask = ctx->k >= 32 ? ~0ull : ((1ull << (2 * ctx->k)) - 1);
+  p.db.bin_lo = (uint32_t)ctx->bin_lo;
+  p.db.bin_hi = (uint32_t)ctx->bin_hi;
+  p.db.k = ctx->k;
+  p.db.nt = ctx->nt;
+  p.db.xor_mask = (uint32_t)((ctx->idx_type == 1 ? 0ull : INDEX2_XOR_MASK) & ((1ull << (2 * ctx->nt)) - 1));
+  p.db.n_mini = ctx->k - ctx->nt + 1;
+  p.tax.parent = ctx->d_parent;
+  p.tax.depth = ctx->d_depth;
+  p.tax.raw = ctx->d_raw;
+  p.tax.n_taxa = ctx->n_taxa;
+  p.tax.n_sketch = ctx->n_sketch;
+  p.bases = d_bases;
+  p.offsets = d_offsets;
+  p.unit_id = d_unit;
+  p.clean = s.d_clean;
+  p.n_reads = n_reads;
+  p.n_chunks = (n_reads + CHUNK_READS - 1) / CHUNK_READS;
+  p.flags = flags;
+  p.hll_mode = ctx->cfg.hll_mode;
+  p.call = s.d_call;
+  p.n_windows = s.d_nwin;
+  p.codes = s.d_codes;
+  p.run_start = s.d_run_start;
+  p.run_count = s.d_run_count;
+  p.runs = s.d_runs;
+  p.run_cursor = s.d_scalars;
+  p.n_classified = s.d_scalars + 1;
+  p.chunk_counter = reinterpret_cast<uint32_t *>(s.d_scalars + 2);
+  p.error_flag = reinterpret_cast<uint32_t *>(s.d_scalars + 3);
+  p.regs = ctx->d_regs;
+  p.n_kmers = ctx->d_n_kmers;
+  p.n_reads_ctr = ctx->d_n_reads;
+  p.dense_flag = ctx->d_dense_flag;
+  p.sparse.slots = ctx->d_sparse_slots;
+  p.sparse.mask = ctx->sparse_cap ? ctx->sparse_cap - 1 : 0;
+  p.sparse.n_used = ctx->d_sparse_used;
+  p.sparse.distinct = ctx->d_sparse_distinct;
+}
+
+int grid_for(kuq_ctx *ctx, uint32_t n_chunks) {
+  int g = ctx->n_sm * 2;     // 2 resident CTAs per SM (launch bounds), persistent
+  if ((uint32_t)g > n_chunks) g = (int)std::max(1u, n_chunks);
+  return g;
+}
+
+int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
+  CU(cudaMemsetAsync(s.d_scalars, 0, 4 * 8, s.stream));
+  CU(cudaEventRecord(s.ev_k0, s.stream));
+  if (p.n_reads) {
+    launch_classify(mode, p, grid_for(ctx, p.n_chunks), s.stream);
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(s.ev_k1, s.stream));
+  CU(cudaGetLastError());
+  return KUQ_OK;
+}
+
+}  // namespace
+
+// ===========================================================================================================
+extern "C" {
+
+const char *kuq_version(void) { return "libkuq 0.1.0 sm_100a"; }
+
+const char *kuq_strerror(int code) {
+  switch (code) {
+    case KUQ_OK: return "ok";
+    case KUQ_E_INVALID_ARG: return "invalid argument";
+    case KUQ_E_CUDA: return "CUDA error";
+    case KUQ_E_NO_DEVICE: return "no sm_100 CUDA device (libkuq has no CPU path)";
+    case KUQ_E_DB_FORMAT: return "database in improper format";
+    case KUQ_E_UNSUPPORTED_K: return "unsupported k (only 8-byte keys: k = 29..31)";
+    case KUQ_E_STATE: return "call order / state error";
+    case KUQ_E_CAPACITY: return "capacity exceeded";
+    case KUQ_E_NOMEM: return "out of memory";
+    case KUQ_E_TAXA_OVERFLOW: return "a read hit more than 32 distinct taxa";
+    case KUQ_E_TAXONOMY: return "malformed taxonomy";
+    default: return "unknown error";
+  }
+}
+
+const char *kuq_last_error(const kuq_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+void kuq_config_default(kuq_config *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->device = 0;
+  cfg->n_slots = 2;
+  cfg->max_reads_per_batch = 1u << 20;
+  cfg->max_bases_per_batch = 192ull << 20;
+  cfg->work_unit_size = 500000;           // DEF_WORK_UNIT_SIZE, classify.cpp:38
+  cfg->hll_mode = KUQ_HLL_PRELOAD;
+  cfg->sparse_set_slots = 1ull << 26;
+}
+
+int kuq_create(const kuq_config *cfg_in, kuq_ctx **out) {
+  if (!out) return KUQ_E_INVALID_ARG;
+  *out = nullptr;
+  kuq_config cfg;
+  kuq_config_default(&cfg);
+  if (cfg_in) {
+    cfg = *cfg_in;
+    kuq_config d;
+    kuq_config_default(&d);
+    if (!cfg.n_slots) cfg.n_slots = d.n_slots;
+    if (!cfg.max_reads_per_batch) cfg.max_reads_per_batch = d.max_reads_per_batch;
+    if (!cfg.max_bases_per_batch) cfg.max_bases_per_batch = d.max_bases_per_batch;
+    if (!cfg.work_unit_size) cfg.work_unit_size = d.work_unit_size;
+    if (!cfg.sparse_set_slots) cfg.sparse_set_slots = d.sparse_set_slots;
+  }
+  if (cfg.hll_mode > KUQ_HLL_DENSE_ONLY || cfg.n_slots > 16) return KUQ_E_INVALID_ARG;
+  // round the sparse set to a power of two
+  uint64_t sc = 1024;
+  while (sc < cfg.sparse_set_slots) sc <<= 1;
+  cfg.sparse_set_slots = sc;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= cfg.device || cfg.device < 0) return KUQ_E_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg.device) != cudaSuccess) return KUQ_E_NO_DEVICE;
+  if (prop.major < 10) return KUQ_E_NO_DEVICE;     // kernels are built for sm_100a only
+  if (cudaSetDevice(cfg.device) != cudaSuccess) return KUQ_E_NO_DEVICE;
+  kuq_ctx *ctx = new kuq_ctx();
+  ctx->cfg = cfg;
+  ctx->device = cfg.device;
+  ctx->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return KUQ_E_CUDA; }
+  ctx->slots.resize(cfg.n_slots);
+  for (auto &s : ctx->slots) {
+    int rc = alloc_slot(ctx, s);
+    if (rc) {
+      fprintf(stderr, "libkuq: %s\n", ctx->err.c_str());
+      kuq_destroy(ctx);
+      return rc == KUQ_E_CUDA ? KUQ_E_NOMEM : rc;
+    }
+  }
+  *out = ctx;
+  return KUQ_OK;
+}
+
+void kuq_destroy(kuq_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto &s : ctx->slots) free_slot(s);
+  free_db(ctx);
+  free_tax_state(ctx);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  delete ctx;
+}
+
+void *kuq_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void kuq_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- database -------------------------------------------------------------------------------------------------
+int kuq_stage_db(kuq_ctx *ctx, const void *kdb_image, uint64_t kdb_bytes, const void *idx_image, uint64_t idx_bytes,
+                 uint64_t bin_lo, uint64_t bin_hi) {
+  if (!ctx || !kdb_image || !idx_image) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const uint8_t *p = (const uint8_t *)kdb_image;
+  if (kdb_bytes < 56 || memcmp(p, "JFLISTDN", 8) != 0)                     // krakendb.cpp:32,67-68
+    return fail(ctx, KUQ_E_DB_FORMAT, "database in improper format");
+  uint64_t key_bits, val_len, key_ct;
+  memcpy(&key_bits, p + 8, 8);
+  memcpy(&val_len, p + 16, 8);
+  memcpy(&key_ct, p + 48, 8);
+  if (val_len != 4) return fail(ctx, KUQ_E_DB_FORMAT, "can only handle 4 byte DB values");   // :73-74
+  uint32_t k = (uint32_t)(key_bits / 2);
+  uint64_t key_len = key_bits / 8 + !!(key_bits % 8);
+  if (key_len != 8 || k > 31)
+    return fail(ctx, KUQ_E_UNSUPPORTED_K, "k = %u (key_len %llu): only 8-byte keys (k = 29..31) are supported", k,
+                (unsigned long long)key_len);
+  uint64_t header = 72 + 2 * (4 + 8 * key_bits);                           // :177
+  if (kdb_bytes < header + key_ct * 12) return fail(ctx, KUQ_E_DB_FORMAT, "database file truncated");
+  const uint8_t *q = (const uint8_t *)idx_image;
+  uint32_t idx_type;
+  if (idx_bytes < 8) return fail(ctx, KUQ_E_DB_FORMAT, "illegal Kraken DB index format");
+  if (memcmp(q, "KRAKIDX", 7) == 0) idx_type = 1;
+  else if (memcmp(q, "KRAKIX2", 7) == 0) idx_type = 2;
+  else return fail(ctx, KUQ_E_DB_FORMAT, "illegal Kraken DB index format");  // :541
+  uint32_t nt = q[7];
+  if (nt < 1 || nt > 15 || nt > k) return fail(ctx, KUQ_E_DB_FORMAT, "index minimizer length %u out of range", nt);
+  uint64_t n_bins = 1ull << (2 * nt);
+  if (idx_bytes < 8 + 8 * (n_bins + 1)) return fail(ctx, KUQ_E_DB_FORMAT, "index file truncated");
+  const uint64_t *offsets = (const uint64_t *)(q + 8);
+  if (bin_hi == 0 || bin_hi > n_bins) bin_hi = n_bins;
+  if (bin_lo >= bin_hi) return fail(ctx, KUQ_E_INVALID_ARG, "empty minimizer range");
+  uint64_t rec_lo = offsets[bin_lo], rec_hi = offsets[bin_hi];
+  if (rec_hi < rec_lo || rec_hi > key_ct) return fail(ctx, KUQ_E_DB_FORMAT, "index offsets inconsistent with key count");
+  // taxonomy numbering survives a re-stage (chunked mode) as long as the new range only holds numbered taxids
+  free_db(ctx);
+  ctx->k = k; ctx->nt = nt; ctx->idx_type = idx_type;
+  ctx->bin_lo = bin_lo; ctx->bin_hi = bin_hi;
+  ctx->rec_base = rec_lo;
+  ctx->key_ct = rec_hi - rec_lo;
+  ctx->db_owned = true;
+  CU(cudaMalloc((void **)&ctx->d_pairs, ctx->key_ct * 12 + SLACK));
+  CU(dmalloc(&ctx->d_offsets_owned, bin_hi - bin_lo + 1));
+  ctx->d_offsets = ctx->d_offsets_owned;
+  // bulk H2D: the images may be pageable / mmap'ed file memory; the driver stages them
+  const uint64_t step = 1ull << 30;
+  const uint8_t *src = p + header + rec_lo * 12;
+  for (uint64_t off = 0; off < ctx->key_ct * 12; off += step) {
+    uint64_t n = std::min(step, ctx->key_ct * 12 - off);
+    CU(cudaMemcpy(ctx->d_pairs + off, src + off, n, cudaMemcpyHostToDevice));
+  }
+  CU(cudaMemcpy(ctx->d_offsets_owned, offsets + bin_lo, (bin_hi - bin_lo + 1) * 8, cudaMemcpyHostToDevice));
+  ctx->db_staged = true;
+  int rc = collect_taxids(ctx);
+  if (rc) return rc;
+  if (ctx->finalized) return remap_db(ctx);
+  return KUQ_OK;
+}
+
+int kuq_attach_db_device(kuq_ctx *ctx, void *d_pairs, uint64_t key_ct, const uint64_t *d_offsets, uint32_t k,
+                         uint32_t nt, uint32_t idx_type, uint64_t bin_lo, uint64_t bin_hi) {
+  if (!ctx || !d_pairs || !d_offsets) return KUQ_E_INVALID_ARG;
+  if (k < 29 || k > 31) return fail(ctx, KUQ_E_UNSUPPORTED_K, "k = %u: only 8-byte keys (k = 29..31)", k);
+  if (nt < 1 || nt > 15 || (idx_type != 1 && idx_type != 2)) return fail(ctx, KUQ_E_INVALID_ARG, "bad index parameters");
+  CU(cudaSetDevice(ctx->device));
+  uint64_t n_bins = 1ull << (2 * nt);
+  if (bin_hi == 0 || bin_hi > n_bins) bin_hi = n_bins;
+  if (bin_lo >= bin_hi) return fail(ctx, KUQ_E_INVALID_ARG, "empty minimizer range");
+  free_db(ctx);
+  ctx->k = k; ctx->nt = nt; ctx->idx_type = idx_type;
+  ctx->bin_lo = bin_lo; ctx->bin_hi = bin_hi;
+  ctx->db_owned = false;
+  ctx->d_pairs = (uint8_t *)d_pairs;
+  ctx->d_offsets = d_offsets;
+  uint64_t first = 0;
+  CU(cudaMemcpy(&first, d_offsets, 8, cudaMemcpyDeviceToHost));
+  ctx->rec_base = first;
+  ctx->key_ct = key_ct;
+  ctx->db_staged = true;
+  int rc = collect_taxids(ctx);
+  if (rc) return rc;
+  if (ctx->finalized) return remap_db(ctx);
+  return KUQ_OK;
+}
+
+int kuq_db_taxids(kuq_ctx *ctx, uint32_t *taxid, uint64_t *count, uint32_t cap, uint32_t *n) {
+  if (!ctx || !n) return KUQ_E_INVALID_ARG;
+  if (!ctx->db_staged) return fail(ctx, KUQ_E_STATE, "no database staged");
+  *n = (uint32_t)ctx->db_taxids.size();
+  if (cap == 0) return KUQ_OK;
+  if (cap < *n) return fail(ctx, KUQ_E_CAPACITY, "need room for %u taxids", *n);
+  for (uint32_t i = 0; i < *n; i++) {
+    if (taxid) taxid[i] = ctx->db_taxids[i];
+    if (count) count[i] = ctx->db_taxid_counts[i];
+  }
+  return KUQ_OK;
+}
+
+int kuq_set_db_taxid_universe(kuq_ctx *ctx, const uint32_t *taxid, uint32_t n) {
+  if (!ctx || (!taxid && n)) return KUQ_E_INVALID_ARG;
+  if (ctx->finalized) return fail(ctx, KUQ_E_STATE, "taxid universe must be declared before the first classification");
+  ctx->universe.assign(taxid, taxid + n);
+  return KUQ_OK;
+}
+
+int kuq_set_taxonomy(kuq_ctx *ctx, const uint32_t *taxid, const uint32_t *parent, uint32_t n) {
+  if (!ctx || ((!taxid || !parent) && n)) return KUQ_E_INVALID_ARG;
+  if (ctx->finalized) return fail(ctx, KUQ_E_STATE, "taxonomy already in use; create a new context to change it");
+  // later rows overwrite earlier ones, like Parent_map[taxid] = parent
+  std::unordered_map<uint32_t, uint32_t> m;
+  for (uint32_t i = 0; i < n; i++) m[taxid[i]] = parent[i];
+  ctx->tax_ids.clear(); ctx->tax_parents.clear();
+  for (auto &kv : m) { ctx->tax_ids.push_back(kv.first); ctx->tax_parents.push_back(kv.second); }
+  ctx->tax_set = true;
+  return KUQ_OK;
+}
+
+// ---- classification -------------------------------------------------------------------------------------------
+int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                     const uint32_t *unit_id, uint32_t flags) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (n_reads && (!bases || !read_offsets)) return fail(ctx, KUQ_E_INVALID_ARG, "NULL batch buffers");
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[slot];
+  if (s.busy) return fail(ctx, KUQ_E_STATE, "slot %u still has an unread batch: call kuq_wait_batch first", slot);
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  if (n_reads > ctx->cfg.max_reads_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%u reads > slot capacity %u", n_reads, ctx->cfg.max_reads_per_batch);
+  const uint64_t base0 = n_reads ? read_offsets[0] : 0;
+  const uint64_t total = n_reads ? read_offsets[n_reads] - base0 : 0;
+  if (total > ctx->cfg.max_bases_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%llu bases > slot capacity %llu", (unsigned long long)total, (unsigned long long)ctx->cfg.max_bases_per_batch);
+  if (total >= (1ull << 32)) return fail(ctx, KUQ_E_CAPACITY, "batches are limited to 4 Gbases");
+  s.n_reads = n_reads; s.flags = flags; s.total_bases = total; s.external = false;
+  // H2D: bases, offsets (rebased to 0 on the device by subtracting base0 in a tiny host loop only when needed)
+  if (n_reads) {
+    CU(cudaMemcpyAsync(s.d_bases, bases + base0, total, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemsetAsync(s.d_bases + total, 'N', SLACK, s.stream));
+    if (base0 == 0) {
+      CU(cudaMemcpyAsync(s.d_offsets, read_offsets, (n_reads + 1ull) * 8, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      std::vector<uint64_t> tmp(n_reads + 1);
+      for (uint32_t i = 0; i <= n_reads; i++) tmp[i] = read_offsets[i] - base0;
+      CU(cudaMemcpy(s.d_offsets, tmp.data(), (n_reads + 1ull) * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  const uint32_t *d_unit = nullptr;
+  if (ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && n_reads) {
+    if (unit_id) memcpy(s.h_unit, unit_id, n_reads * 4ull);
+    else cut_units(ctx, read_offsets, n_reads, s.h_unit);
+    CU(cudaMemcpyAsync(s.d_unit, s.h_unit, n_reads * 4ull, cudaMemcpyHostToDevice, s.stream));
+    d_unit = s.d_unit;
+  }
+  Params p;
+  fill_params(ctx, s, p, s.d_bases, s.d_offsets, d_unit, n_reads, flags);
+  rc = launch_on_slot(ctx, s, MODE_FUSED, p);
+  if (rc) return rc;
+  // D2H of the fixed-size results; the variable-size hit lists follow in kuq_wait_batch
+  if (n_reads) {
+    CU(cudaMemcpyAsync(s.h_call, s.d_call, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(s.h_nwin, s.d_nwin, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    if (!(flags & KUQ_F_NO_RUNS)) {
+      CU(cudaMemcpyAsync(s.h_run_start, s.d_run_start, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+      CU(cudaMemcpyAsync(s.h_run_count, s.d_run_count, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    }
+  }
+  CU(cudaMemcpyAsync(s.h_scalars, s.d_scalars, 4 * 8, cudaMemcpyDeviceToHost, s.stream));
+  s.busy = true;
+  return KUQ_OK;
+}
+
+int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!out) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[slot];
+  if (!s.busy) return fail(ctx, KUQ_E_STATE, "slot %u has no batch in flight", slot);
+  CU(cudaStreamSynchronize(s.stream));
+  s.busy = false;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  s.kernel_ms = ms;
+  const uint32_t err = (uint32_t)(s.h_scalars[3] & 0xFFFFFFFFu);
+  if (err) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  const uint64_t n_runs = (s.flags & KUQ_F_NO_RUNS) ? 0 : s.h_scalars[0];
+  if (n_runs) {
+    if (n_runs > s.h_runs_cap) {
+      cudaFreeHost(s.h_runs);
+      s.h_runs = nullptr;
+      s.h_runs_cap = n_runs + n_runs / 2;
+      CU(hmalloc(&s.h_runs, s.h_runs_cap));
+    }
+    CU(cudaMemcpyAsync(s.h_runs, s.d_runs, n_runs * 8, cudaMemcpyDeviceToHost, s.stream));
+  }
+  if ((s.flags & KUQ_F_WANT_CODES) && s.total_bases) {
+    if (!s.h_codes) CU(hmalloc(&s.h_codes, ctx->cfg.max_bases_per_batch));
+    CU(cudaMemcpyAsync(s.h_codes, s.d_codes, s.total_bases * 4, cudaMemcpyDeviceToHost, s.stream));
+  }
+  CU(cudaStreamSynchronize(s.stream));
+  memset(out, 0, sizeof *out);
+  out->n_reads = s.n_reads;
+  out->call = s.h_call;
+  out->n_windows = s.h_nwin;
+  out->run_start = s.h_run_start;
+  out->run_count = s.h_run_count;
+  out->runs = s.h_runs;
+  out->n_runs = n_runs;
+  out->codes = (s.flags & KUQ_F_WANT_CODES) ? s.h_codes : nullptr;
+  out->n_classified = s.h_scalars[1];
+  out->kernel_ms = s.kernel_ms;
+  return KUQ_OK;
+}
+
+int kuq_classify_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                       const uint32_t *unit_id, uint32_t flags, kuq_batch_result *out) {
+  int rc = kuq_submit_batch(ctx, 0, bases, read_offsets, n_reads, unit_id, flags);
+  if (rc) return rc;
+  return kuq_wait_batch(ctx, 0, out);
+}
+
+static int device_call(kuq_ctx *ctx, uint32_t slot, int mode, const char *d_bases, const uint64_t *d_offsets,
+                       uint32_t n_reads, uint64_t total_bases, const uint32_t *d_unit, uint32_t flags,
+                       uint32_t *d_codes_out, const uint32_t *d_codes_in, uint32_t only_hits) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (n_reads && (!d_bases || !d_offsets)) return fail(ctx, KUQ_E_INVALID_ARG, "NULL device buffers");
+  if ((uintptr_t)d_bases & 15) return fail(ctx, KUQ_E_INVALID_ARG, "d_bases must be 16-byte aligned");
+  CU(cudaSetDevice(ctx->device));
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  Slot &s = ctx->slots[slot];
+  if (n_reads > ctx->cfg.max_reads_per_batch || total_bases > ctx->cfg.max_bases_per_batch)
+    return fail(ctx, KUQ_E_CAPACITY, "batch exceeds the slot capacity");
+  s.n_reads = n_reads; s.flags = flags; s.total_bases = total_bases; s.external = true;
+  Params p;
+  fill_params(ctx, s, p, d_bases, d_offsets, d_unit, n_reads, flags);
+  if (mode == MODE_LOOKUP) { p.codes = d_codes_out; p.only_hits = only_hits; }
+  if (mode == MODE_RESOLVE) p.codes_in = d_codes_in;
+  return launch_on_slot(ctx, s, mode, p);
+}
+
+int kuq_classify_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                        uint32_t n_reads, uint64_t total_bases, const uint32_t *d_unit_id, uint32_t flags) {
+  return device_call(ctx, slot, MODE_FUSED, d_bases, d_read_offsets, n_reads, total_bases, d_unit_id, flags, nullptr, nullptr, 0);
+}
+int kuq_lookup_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                      uint32_t n_reads, uint64_t total_bases, uint32_t *d_codes_out, uint32_t only_hits) {
+  if (!d_codes_out) return KUQ_E_INVALID_ARG;
+  return device_call(ctx, slot, MODE_LOOKUP, d_bases, d_read_offsets, n_reads, total_bases, nullptr, 0, d_codes_out, nullptr, only_hits);
+}
+int kuq_resolve_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                       uint32_t n_reads, uint64_t total_bases, const uint32_t *d_codes_in, const uint32_t *d_unit_id,
+                       uint32_t flags) {
+  if (!d_codes_in) return KUQ_E_INVALID_ARG;
+  return device_call(ctx, slot, MODE_RESOLVE, d_bases, d_read_offsets, n_reads, total_bases, d_unit_id, flags, nullptr, d_codes_in, 0);
+}
+
+int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  Slot &s = ctx->slots[slot];
+  CU(cudaStreamSynchronize(s.stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.kernel_ms = ms;
+  uint32_t err = 0;
+  CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
+  if (err) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  return KUQ_OK;
+}
+
+int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!out) return KUQ_E_INVALID_ARG;
+  Slot &s = ctx->slots[slot];
+  out->d_call = s.d_call;
+  out->d_n_windows = s.d_nwin;
+  out->d_codes = s.d_codes;
+  out->d_run_start = s.d_run_start;
+  out->d_run_count = s.d_run_count;
+  out->d_runs = reinterpret_cast<const kuq_run *>(s.d_runs);
+  out->d_n_runs = reinterpret_cast<const uint64_t *>(s.d_scalars);
+  return KUQ_OK;
+}
+
+void *kuq_slot_stream(kuq_ctx *ctx, uint32_t slot) {
+  if (!ctx || slot >= ctx->slots.size()) return nullptr;
+  return (void *)ctx->slots[slot].stream;
+}
+uint64_t kuq_launch_count(const kuq_ctx *ctx) { return ctx ? ctx->launches : 0; }
+double kuq_last_kernel_ms(kuq_ctx *ctx, uint32_t slot) {
+  if (!ctx || slot >= ctx->slots.size()) return -1;
+  return ctx->slots[slot].kernel_ms;
+}
+
+// ---- per-taxon results ------------------------------------------------------------------------------------------
+int kuq_finish(kuq_ctx *ctx) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  ctx->unit_nt = 0;
+  ctx->unit_next++;
+  return KUQ_OK;
+}
+
+namespace {
+struct CountsHost {
+  std::vector<unsigned long long> n_kmers, n_reads;
+  std::vector<uint32_t> hist;      // [n_sketch][64]
+  std::vector<uint8_t> dense_flag;
+  std::vector<uint32_t> distinct;
+};
+int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
+  if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  h.n_kmers.resize(ctx->n_sketch);
+  h.n_reads.resize(ctx->n_taxa);
+  h.hist.resize((size_t)ctx->n_sketch * 64);
+  h.dense_flag.assign(ctx->n_sketch, 1);
+  h.distinct.assign(ctx->n_sketch, 0);
+  CU(cudaMemcpy(h.n_kmers.data(), ctx->d_n_kmers, ctx->n_sketch * 8ull, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(h.n_reads.data(), ctx->d_n_reads, ctx->n_taxa * 8ull, cudaMemcpyDeviceToHost));
+  uint32_t *d_hist;
+  CU(dmalloc(&d_hist, (uint64_t)ctx->n_sketch * 64));
+  launch_register_histograms(ctx->d_regs, ctx->n_sketch, d_hist, ctx->aux);
+  ctx->launches++;
+  CU(cudaMemcpyAsync(h.hist.data(), d_hist, (uint64_t)ctx->n_sketch * 64 * 4, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  cudaFree(d_hist);
+  if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
+    CU(cudaMemcpy(h.dense_flag.data(), ctx->d_dense_flag, ctx->n_sketch, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h.distinct.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost));
+  }
+  return KUQ_OK;
+}
+}  // namespace
+
+int kuq_counts_size(kuq_ctx *ctx, uint32_t *n) {
+  if (!ctx || !n) return KUQ_E_INVALID_ARG;
+  CountsHost h;
+  int rc = fetch_counts(ctx, h);
+  if (rc) return rc;
+  uint32_t c = 0;
+  for (uint32_t d = 0; d < ctx->n_taxa; d++)
+    if (h.n_reads[d] || (d < ctx->n_sketch && h.n_kmers[d])) c++;
+  *n = c;
+  return KUQ_OK;
+}
+
+int kuq_read_counts(kuq_ctx *ctx, uint32_t *taxid, uint64_t *n_reads, uint64_t *n_kmers, uint64_t *unique,
+                    uint8_t *is_sparse, uint32_t cap) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  CountsHost h;
+  int rc = fetch_counts(ctx, h);
+  if (rc) return rc;
+  std::vector<std::pair<uint32_t, uint32_t>> rows;   // (taxid, dense)
+  for (uint32_t d = 0; d < ctx->n_taxa; d++)
+    if (h.n_reads[d] || (d < ctx->n_sketch && h.n_kmers[d])) rows.emplace_back(ctx->raw_of_dense[d], d);
+  std::sort(rows.begin(), rows.end());
+  if (rows.size() > cap) return fail(ctx, KUQ_E_CAPACITY, "need room for %zu rows", rows.size());
+  for (size_t i = 0; i < rows.size(); i++) {
+    uint32_t d = rows[i].second;
+    uint64_t nk = d < ctx->n_sketch ? h.n_kmers[d] : 0;
+    if (taxid) taxid[i] = rows[i].first;
+    if (n_reads) n_reads[i] = h.n_reads[d];
+    if (n_kmers) n_kmers[i] = nk;
+    // dense tier; the sparse tier (mode emulation) overrides this in kuq_unique_sparse when applicable
+    uint64_t u = (d < ctx->n_sketch && nk) ? ertl_dense_hist(&h.hist[(size_t)d * 64], nk) : 0;
+    if (unique) unique[i] = u;
+    if (is_sparse) is_sparse[i] = 0;
+  }
+  return KUQ_OK;
+}
+
+int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers,
+                     uint64_t *unique) {
+  if (!ctx || (!taxids && n)) return KUQ_E_INVALID_ARG;
+  if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  std::vector<uint32_t> members;
+  uint64_t reads = 0, kmers = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    auto it = ctx->dense_of_raw.find(taxids[i]);
+    if (it == ctx->dense_of_raw.end()) continue;
+    uint32_t d = it->second;
+    unsigned long long r = 0, km = 0;
+    CU(cudaMemcpy(&r, ctx->d_n_reads + d, 8, cudaMemcpyDeviceToHost));
+    if (d < ctx->n_sketch) {
+      CU(cudaMemcpy(&km, ctx->d_n_kmers + d, 8, cudaMemcpyDeviceToHost));
+      if (km) members.push_back(d);
+    }
+    reads += r; kmers += km;
+  }
+  uint64_t u = 0;
+  if (!members.empty()) {
+    uint32_t *d_members; uint8_t *d_out; uint32_t *d_hist;
+    CU(dmalloc(&d_members, members.size()));
+    CU(dmalloc(&d_out, HLL_M));
+    CU(dmalloc(&d_hist, 64));
+    CU(cudaMemcpyAsync(d_members, members.data(), members.size() * 4, cudaMemcpyHostToDevice, ctx->aux));
+    launch_clade_max(ctx->d_regs, d_members, (uint32_t)members.size(), d_out, ctx->aux);
+    launch_register_histograms(d_out, 1, d_hist, ctx->aux);
+    ctx->launches += 2;
+    uint32_t hist[64];
+    CU(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaStreamSynchronize(ctx->aux));
+    cudaFree(d_members); cudaFree(d_out); cudaFree(d_hist);
+    u = ertl_dense_hist(hist, kmers);
+  }
+  if (n_reads) *n_reads = reads;
+  if (n_kmers) *n_kmers = kmers;
+  if (unique) *unique = u;
+  return KUQ_OK;
+}
+
+int kuq_get_registers(kuq_ctx *ctx, uint32_t taxid, uint8_t *regs) {
+  if (!ctx || !regs) return KUQ_E_INVALID_ARG;
+  if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  memset(regs, 0, HLL_M);
+  auto it = ctx->dense_of_raw.find(taxid);
+  if (it == ctx->dense_of_raw.end() || it->second >= ctx->n_sketch) return KUQ_OK;
+  CU(cudaMemcpy(regs, ctx->d_regs + (size_t)it->second * HLL_M, HLL_M, cudaMemcpyDeviceToHost));
+  return KUQ_OK;
+}
+
+int kuq_state_ptrs_get(kuq_ctx *ctx, kuq_state_ptrs *out) {
+  if (!ctx || !out) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  out->d_regs = ctx->d_regs;
+  out->regs_bytes = (uint64_t)ctx->n_sketch * HLL_M;
+  out->d_n_kmers = reinterpret_cast<uint64_t *>(ctx->d_n_kmers);
+  out->d_n_reads = reinterpret_cast<uint64_t *>(ctx->d_n_reads);
+  out->d_dense_flag = ctx->d_dense_flag;
+  out->n_sketch = ctx->n_sketch;
+  out->n_taxa = ctx->n_taxa;
+  return KUQ_OK;
+}
+
+int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n) {
+  if (!ctx || !n) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  *n = ctx->n_taxa;
+  if (cap == 0) return KUQ_OK;
+  if (cap < ctx->n_taxa) return fail(ctx, KUQ_E_CAPACITY, "need room for %u ids", ctx->n_taxa);
+  memcpy(taxid_of_dense, ctx->raw_of_dense.data(), ctx->n_taxa * 4ull);
+  return KUQ_OK;
+}
+
+int kuq_reset_counts(kuq_ctx *ctx) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  if (!ctx->finalized) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  CU(cudaMemset(ctx->d_regs, 0, (uint64_t)ctx->n_sketch * HLL_M));
+  CU(cudaMemset(ctx->d_dense_flag, 0, ctx->n_sketch));
+  CU(cudaMemset(ctx->d_n_kmers, 0, ctx->n_sketch * 8ull));
+  CU(cudaMemset(ctx->d_n_reads, 0, ctx->n_taxa * 8ull));
+  if (ctx->d_sparse_slots) {
+    CU(cudaMemset(ctx->d_sparse_slots, 0, ctx->sparse_cap * 8ull));
+    CU(cudaMemset(ctx->d_sparse_used, 0, 8));
+    CU(cudaMemset(ctx->d_sparse_distinct, 0, ctx->n_sketch * 4ull));
+  }
+  ctx->unit_nt = 0;
+  ctx->unit_next = 0;
+  return KUQ_OK;
+}
+
+uint64_t kuq_ertl_dense(const uint8_t *regs, uint64_t n_observed) {
+  int C[66];
+  memset(C, 0, sizeof C);
+  for (uint32_t i = 0; i < HLL_M; i++) C[regs[i] > 65 ? 65 : regs[i]]++;
+  return ertl_from_hist(C, 64 - HLL_P, HLL_M, n_observed);
+}
+
+}  // extern "C"

@@ -1,0 +1,682 @@
+// kuq_kernels.cu — see kuq_kernels.cuh for the map from kernel stages to reference functions.
+#include "kuq_kernels.cuh"
+
+namespace kuq {
+
+// ------------------------------------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + 1-D TMA bulk copy (global → shared), sm_90+/sm_100a
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// cp.async.bulk: one thread moves `bytes` (multiple of 16, 16-byte aligned on both sides) and signals `bar`.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bit arithmetic
+// ------------------------------------------------------------------------------------------------------
+// KrakenDB::reverse_complement (krakendb.cpp:218-225): reverse the 2-bit groups, complement, shift down.
+__device__ __forceinline__ uint64_t revcomp64(uint64_t x, uint32_t n) {
+  x = __brevll(x);                                                              // reverses bits inside groups too
+  x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);  // ... so swap them back
+  return (~x) >> (64 - 2 * n);
+}
+__device__ __forceinline__ uint32_t revcomp32(uint32_t x, uint32_t n) {   // n <= 15
+  x = __brev(x);
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  return (~x) >> (32 - 2 * n);
+}
+// murmurhash3_finalizer (hyperloglogplus.cpp:830-838)
+__device__ __forceinline__ uint64_t fmix64(uint64_t key) {
+  key += 1;
+  key ^= key >> 33;
+  key *= 0xff51afd7ed558ccdull;
+  key ^= key >> 33;
+  key *= 0xc4ceb9fe1a85ec53ull;
+  key ^= key >> 33;
+  return key;
+}
+
+// 12-byte records are only 4-byte aligned: a key is two 32-bit loads.
+__device__ __forceinline__ uint64_t load_key(const uint8_t *pairs, uint64_t pos, uint64_t key_mask) {
+  const uint32_t *p = reinterpret_cast<const uint32_t *>(pairs + pos * 12);
+  uint32_t lo = __ldg(p), hi = __ldg(p + 1);
+  return (((uint64_t)hi << 32) | lo) & key_mask;                                // krakendb.cpp:283-284
+}
+__device__ __forceinline__ uint32_t load_val(const uint8_t *pairs, uint64_t pos) {
+  return __ldg(reinterpret_cast<const uint32_t *>(pairs + pos * 12) + 2);
+}
+
+// HyperLogLogPlusMinus::insert, dense branch (hyperloglogplus.cpp:514-521): M[idx] = max(M[idx], rank).
+// Registers are bytes; a byte-wide max is a CAS on the enclosing word, reached only when the plain load says the
+// register would grow (after warm-up almost never: P[grow] ~ 1/n).  A stale load can only be too small, which
+// costs a redundant CAS, never a lost update.
+__device__ __forceinline__ void hll_update(uint8_t *regs, uint32_t taxon, uint64_t hash) {
+  uint32_t idx = (uint32_t)(hash >> (64 - HLL_P));
+  uint64_t rest = hash << HLL_P;
+  uint32_t rank = rest ? (uint32_t)__clzll((long long)rest) + 1 : (64 - HLL_P + 1);   // getRank, :140-147
+  uint8_t *reg = regs + (size_t)taxon * HLL_M + idx;
+  if (*reinterpret_cast<volatile uint8_t *>(reg) >= rank) return;
+  uint32_t *word = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(reg) & ~(uintptr_t)3);
+  uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(reg) & 3) * 8;
+  uint32_t old = *reinterpret_cast<volatile uint32_t *>(word);
+  while (((old >> shift) & 0xFF) < rank) {
+    uint32_t upd = (old & ~(0xFFu << shift)) | (rank << shift);
+    uint32_t prev = atomicCAS(word, old, upd);
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
+// encodeHashIn32Bit(h, pPrime=25, p=12), hyperloglogplus.cpp:181-204
+__device__ __forceinline__ uint32_t encode_hash32(uint64_t hash) {
+  uint32_t idx = (uint32_t)((hash >> 39) << 7);
+  if ((idx << 12) == 0) {
+    uint64_t rest = hash << 25;
+    uint32_t add_rank = rest ? (uint32_t)__clzll((long long)rest) + 1 : 40;
+    return idx | (add_rank << 1) | 1;
+  }
+  return idx;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // table hash for the device sets (not reference arithmetic)
+  x ^= x >> 31;
+  x *= 0x7fb5d329728ea185ull;
+  x ^= x >> 27;
+  x *= 0x81dadef4bc2dd44dull;
+  x ^= x >> 33;
+  return x;
+}
+
+// Insert into the (taxon, code) set behind the sparse HLL tier.  Returns true when the key is new.
+__device__ __forceinline__ bool sparse_insert(const SparseSet &s, uint32_t taxon, uint32_t code) {
+  unsigned long long key = ((unsigned long long)(taxon + 1) << 32) | code;
+  uint64_t slot = mix64(key) & s.mask;
+  for (uint32_t probe = 0; probe < 4096; probe++) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(s.slots + slot);
+    if (cur == key) return false;
+    if (cur == 0) {
+      unsigned long long prev = atomicCAS(s.slots + slot, 0ull, key);
+      if (prev == 0) return true;
+      if (prev == key) return false;
+    }
+    slot = (slot + 1) & s.mask;
+  }
+  return false;   // table saturated: the host sees n_used close to capacity and reports KUQ_E_CAPACITY
+}
+
+// ------------------------------------------------------------------------------------------------------
+// taxonomy walks on the flattened parent array
+// ------------------------------------------------------------------------------------------------------
+// lca(), krakenutil.cpp:90-118, in dense ids.  Dense id 1 is ALWAYS the node of taxid 1 (the reference's
+// hard-wired root: loops run `while (a > 1)`), dense id 0 is "no taxon".  depth[] counts the steps of a node's
+// parent chain until it ends (at 0, or at node 1), so both chains can be levelled first.
+__device__ uint32_t lca_dense(const TaxView &t, uint32_t a, uint32_t b) {
+  if (a == 0 || b == 0) return a ? a : b;
+  uint32_t da = a <= 1 ? 0 : t.depth[a], db = b <= 1 ? 0 : t.depth[b];
+  while (da > db) { a = t.parent[a]; da--; }
+  while (db > da) { b = t.parent[b]; db--; }
+  while (a != b && a > 1 && b > 1) {
+    a = t.parent[a];
+    b = t.parent[b];
+  }
+  return (a == b && a > 1) ? a : 1u;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one read, one warp
+// ------------------------------------------------------------------------------------------------------
+struct Block64 {         // 32 bases: 2-bit codes, first base in bits 63:62; amb bit l = base l is not ACGT
+  uint64_t codes;
+  uint32_t amb;
+};
+
+// Convert 32 characters (lane = position) — krakenutil.cpp:253-273.  Positions >= len read as ambiguous.
+__device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uint32_t blk, uint32_t lane) {
+  uint32_t pos = blk * 32 + lane;
+  uint32_t c = pos < len ? (uint32_t)(uint8_t)seq[pos] : (uint32_t)'N';
+  uint32_t uc = c & 0xDFu;                                  // case-insensitive, :254-264
+  bool ok = (uc == 'A') | (uc == 'C') | (uc == 'G') | (uc == 'T');
+  uint32_t code = ok ? (((c >> 1) ^ (c >> 2)) & 3u) : 0u;   // A=0 C=1 G=2 T=3
+  uint32_t sh = 2 * (15 - (lane & 15));
+  uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? code << sh : 0u);
+  uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane >= 16 ? code << sh : 0u);
+  Block64 b;
+  b.codes = ((uint64_t)hi << 32) | lo;
+  b.amb = __ballot_sync(0xFFFFFFFFu, !ok);
+  return b;
+}
+
+template <int MODE>
+__device__ void process_read(const Params &p, uint32_t r, const char *seq, uint32_t len, uint64_t out_base,
+                             uint32_t lane) {
+  const DbView &db = p.db;
+  const uint32_t k = db.k, nt = db.nt;
+  const uint32_t nwin = len >= k ? len - k + 1 : 0;           // classify.cpp:913-914
+  uint32_t my_t = 0, my_c = 0;                                // hit list: lane j holds entry j (dense id, count)
+  uint32_t n_hits = 0, n_miss = 0, n_runs = 0;
+  uint32_t carry_code = 0;                                    // code of the previous slot's last window
+  bool overflow = false;
+  const bool counting = (MODE != MODE_LOOKUP) && !(p.flags & 4u);
+
+  if (nwin > 0) {
+    Block64 A = load_block(seq, len, 0, lane);
+    const uint32_t nslots = (nwin + 31) / 32;
+    // carry of the minimizer run that crosses the slot boundary
+    uint32_t carry_bin = 0xFFFFFFFFu, carry_n = 0;
+    uint64_t carry_lo = 0;
+    for (uint32_t s = 0; s < nslots; s++) {
+      Block64 B = load_block(seq, len, s + 1, lane);
+      const uint32_t i = s * 32 + lane;
+      const bool valid = i < nwin;
+      // ---- k-mer of window i: bases [i, i+k) of the 128-bit string A:B ------------------------------------
+      uint64_t hi = lane ? (A.codes << (2 * lane)) | (B.codes >> (64 - 2 * lane)) : A.codes;
+      uint64_t kmer = hi >> (64 - 2 * k);
+      uint64_t amb64 = ((uint64_t)B.amb << 32) | A.amb;
+      bool amb = ((amb64 >> lane) & ((1ull << k) - 1)) != 0;  // any non-ACGT base in the window, :275,280-282
+      uint32_t taxon = 0;
+      uint64_t canon = 0;
+      bool look = valid && !amb;
+      if (MODE == MODE_RESOLVE) {
+        if (valid) {
+          uint32_t c = p.codes_in[out_base + i];
+          taxon = (c == AMBIG) ? 0 : c;                       // ambiguity is recomputed from the bases
+        }
+        if (look) {
+          uint64_t rc = revcomp64(kmer, k);
+          canon = kmer < rc ? kmer : rc;
+        }
+      } else {
+        // ---- canonical k-mer (krakendb.cpp:238-246) ------------------------------------------------------
+        uint64_t rc = revcomp64(kmer, k);
+        canon = kmer < rc ? kmer : rc;
+        // ---- minimizer = min over the k-nt+1 nt-mers of (xor_mask ^ canonical(nt-mer)) (krakendb.cpp:200-215).
+        // Candidate of position q (0..63 relative to the slot): lane holds q = lane (m0) and q = 32+lane (m1).
+        uint32_t f0 = (uint32_t)(hi >> (64 - 2 * nt));
+        uint32_t r0 = revcomp32(f0, nt);
+        uint32_t m0 = db.xor_mask ^ (f0 < r0 ? f0 : r0);
+        uint32_t f1 = (uint32_t)((B.codes << (2 * lane)) >> (64 - 2 * nt));
+        uint32_t r1 = revcomp32(f1, nt);
+        uint32_t m1 = db.xor_mask ^ (f1 < r1 ? f1 : r1);
+        // sliding-window minimum of width n_mini by doubling: after the loop m0/m1 hold min over [q, q+w)
+        uint32_t w = 1;
+        while (2 * w <= db.n_mini) {
+          uint32_t src = (lane + w) & 31;
+          uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
+          bool wrap = lane + w >= 32;
+          uint32_t a0 = wrap ? x1 : x0;
+          uint32_t a1 = wrap ? 0xFFFFFFFFu : x1;
+          m0 = min(m0, a0);
+          m1 = min(m1, a1);
+          w *= 2;
+        }
+        if (w < db.n_mini) {                                  // [q, q+n_mini) = [q, q+w) ∪ [q+n_mini-w, q+n_mini)
+          uint32_t d = db.n_mini - w;
+          uint32_t src = (lane + d) & 31;
+          uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
+          m0 = min(m0, lane + d >= 32 ? x1 : x0);
+        }
+        const uint32_t bin = m0;
+        // ---- index fetch, once per run of equal minimizers (the reference caches the range the same way,
+        //      krakendb.cpp:261-277) ----------------------------------------------------------------------
+        uint32_t prev_bin = __shfl_up_sync(0xFFFFFFFFu, bin, 1);
+        bool prev_look = __shfl_up_sync(0xFFFFFFFFu, (int)look, 1);
+        if (lane == 0) { prev_bin = carry_bin; prev_look = carry_bin != 0xFFFFFFFFu; }
+        bool head = look && !(prev_look && prev_bin == bin);
+        uint64_t lo = 0;
+        uint32_t n = 0;
+        if (head && !(lane == 0 && carry_bin == bin)) {
+          if (bin >= db.bin_lo && bin < db.bin_hi) {
+            const uint64_t *o = db.offsets + (bin - db.bin_lo);
+            uint64_t o0 = __ldg(o), o1 = __ldg(o + 1);        // KrakenDBIndex::at, krakendb.cpp:586-593
+            lo = o0 - db.rec_base;
+            n = (uint32_t)(o1 - o0);
+          }
+        }
+        uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+        uint32_t below = heads & (0xFFFFFFFFu >> (31 - lane));
+        int hl = below ? 31 - __clz(below) : -1;               // lane of my run's head (-1: run started earlier)
+        uint64_t hlo = __shfl_sync(0xFFFFFFFFu, lo, hl < 0 ? 0 : hl);
+        uint32_t hn = __shfl_sync(0xFFFFFFFFu, n, hl < 0 ? 0 : hl);
+        if (look) {
+          if (hl < 0) { lo = carry_lo; n = carry_n; } else { lo = hlo; n = hn; }
+        }
+        // carry the last looked-up window's range into the next slot
+        uint32_t looks = __ballot_sync(0xFFFFFFFFu, look);
+        if (looks) {
+          int last = 31 - __clz(looks);
+          carry_bin = __shfl_sync(0xFFFFFFFFu, bin, last);
+          carry_lo = __shfl_sync(0xFFFFFFFFu, lo, last);
+          carry_n = __shfl_sync(0xFFFFFFFFu, n, last);
+          if (last != 31) carry_bin = 0xFFFFFFFFu;            // the run is broken by an ambiguous/invalid window
+        } else {
+          carry_bin = 0xFFFFFFFFu;
+        }
+        // ---- bin search (kmer_query, krakendb.cpp:280-299): bisection to a small window, then a scan ------
+        if (look && n > 0) {
+          while (n > (uint32_t)SEARCH_WINDOW) {
+            uint32_t h = n >> 1;
+            uint64_t key = load_key(db.pairs, lo + h, db.key_mask);
+            if (key <= canon) { lo += h; n -= h; } else { n = h; }
+          }
+          uint64_t keys[SEARCH_WINDOW];
+#pragma unroll
+          for (int j = 0; j < SEARCH_WINDOW; j++) keys[j] = load_key(db.pairs, lo + min((uint32_t)j, n - 1), db.key_mask);
+          int hit = -1;
+#pragma unroll
+          for (int j = 0; j < SEARCH_WINDOW; j++)
+            if ((uint32_t)j < n && keys[j] == canon) hit = j;
+          if (hit >= 0) taxon = load_val(db.pairs, lo + hit);  // value = dense id (rewritten at staging)
+        }
+      }
+
+      // ---- per-window code ----------------------------------------------------------------------------------
+      uint32_t code = amb ? AMBIG : taxon;
+      if (MODE == MODE_LOOKUP) {
+        // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
+        // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
+        if (valid && (!p.only_hits || (taxon != 0))) p.codes[out_base + i] = code;
+      } else {
+        uint32_t raw = (look && taxon) ? __ldg(p.tax.raw + taxon) : 0;
+        uint32_t out_code = amb ? AMBIG : raw;
+        if (valid) p.codes[out_base + i] = out_code;
+        // runs of the hit list (classify.cpp:826-861)
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
+        if (lane == 0) prev = carry_code;
+        bool brk = valid && (i == 0 || out_code != prev);
+        n_runs += __popc(__ballot_sync(0xFFFFFFFFu, brk));
+        carry_code = __shfl_sync(0xFFFFFFFFu, out_code, 31);
+
+        // ---- add_kmer: HLL insert into the sketch of `taxon` (0 for misses), classify.cpp:939 -------------
+        if (counting && look) {
+          uint64_t h = fmix64(canon);
+          hll_update(p.regs, taxon, h);
+          if (p.hll_mode != 2u && !p.dense_flag[taxon]) {
+            uint32_t enc = encode_hash32(h);
+            if (sparse_insert(p.sparse, taxon, enc)) {
+              atomicAdd(p.sparse.n_used, 1ull);
+              atomicAdd(p.sparse.distinct + taxon, 1u);
+            }
+          }
+        }
+        // ---- hit_counts[taxon]++ (classify.cpp:941-942), aggregated per distinct taxon of the slot ---------
+        n_miss += __popc(__ballot_sync(0xFFFFFFFFu, look && taxon == 0));
+        uint32_t rem = __ballot_sync(0xFFFFFFFFu, look && taxon != 0);
+        while (rem) {
+          int ldr = __ffs(rem) - 1;
+          uint32_t t = __shfl_sync(0xFFFFFFFFu, taxon, ldr);
+          uint32_t same = __ballot_sync(0xFFFFFFFFu, look && taxon == t) & rem;
+          uint32_t cnt = __popc(same);
+          rem &= ~same;
+          uint32_t pos = __ballot_sync(0xFFFFFFFFu, lane < n_hits && my_t == t);
+          if (pos) {
+            if (lane == (uint32_t)(__ffs(pos) - 1)) my_c += cnt;
+          } else if (n_hits < 32) {
+            if (lane == n_hits) { my_t = t; my_c = cnt; }
+            n_hits++;
+          } else {
+            overflow = true;
+          }
+        }
+      }
+      A = B;
+    }
+  }
+
+  if (MODE == MODE_LOOKUP) {
+    if (lane == 0) p.n_windows[r] = nwin;
+    return;
+  }
+
+  // ---- resolve_tree (krakenutil.cpp:149-200) --------------------------------------------------------------
+  uint32_t call = 0;
+  if (n_hits == 1) {
+    call = __shfl_sync(0xFFFFFFFFu, my_t, 0);                 // a single hit taxon is its own best path
+  } else if (n_hits > 1) {
+    // score(t) = sum of hit counts along t's root path (:156-177); lane j walks entry j
+    uint32_t node = lane < n_hits ? my_t : 0;
+    uint32_t score = 0;
+    while (__any_sync(0xFFFFFFFFu, node != 0)) {
+      for (uint32_t q = 0; q < n_hits; q++) {
+        uint32_t tq = __shfl_sync(0xFFFFFFFFu, my_t, q);
+        uint32_t cq = __shfl_sync(0xFFFFFFFFu, my_c, q);
+        if (node == tq) score += cq;
+      }
+      if (node) node = __ldg(p.tax.parent + node);
+    }
+    uint32_t best = __reduce_max_sync(0xFFFFFFFFu, score);
+    uint32_t tied = __ballot_sync(0xFFFFFFFFu, lane < n_hits && score == best);
+    if (__popc(tied) == 1) {
+      call = __shfl_sync(0xFFFFFFFFu, my_t, __ffs(tied) - 1);
+    } else {
+      // ties → LCA of all tied taxa, folded in ascending taxid order (std::set iteration, :190-196)
+      uint32_t raw = (tied >> lane) & 1 ? __ldg(p.tax.raw + my_t) : 0xFFFFFFFFu;
+      uint32_t acc = 0;
+      uint32_t left = tied;
+      while (left) {
+        // smallest remaining taxid
+        uint32_t cand = (left >> lane) & 1 ? raw : 0xFFFFFFFFu;
+        uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, cand);
+        uint32_t who = __ballot_sync(0xFFFFFFFFu, cand == mn && ((left >> lane) & 1));
+        int src = __ffs(who) - 1;
+        uint32_t t = __shfl_sync(0xFFFFFFFFu, my_t, src);
+        acc = acc ? lca_dense(p.tax, acc, t) : t;             // all lanes compute the same walk
+        left &= ~(1u << src);
+      }
+      call = acc;
+    }
+  }
+
+  const uint32_t call_raw = call ? __ldg(p.tax.raw + call) : 0;
+  if (lane == 0) {
+    p.n_windows[r] = nwin;
+    p.call[r] = call_raw;
+    if (overflow) atomicExch(p.error_flag, 1u);
+  }
+  // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
+  if (counting) {
+    if (lane < n_hits) atomicAdd(p.n_kmers + my_t, (unsigned long long)my_c);
+    if (lane == 0) {
+      if (n_miss) atomicAdd(p.n_kmers, (unsigned long long)n_miss);
+      atomicAdd(p.n_reads_ctr + call, 1ull);
+      if (call) atomicAdd(p.n_classified, 1ull);
+    }
+  }
+  // ---- run-length encoded hit list --------------------------------------------------------------------------
+  if (!(p.flags & 2u)) {
+    uint32_t start = 0;
+    if (lane == 0) {
+      start = n_runs ? (uint32_t)atomicAdd(p.run_cursor, (unsigned long long)n_runs) : 0;
+      p.run_start[r] = start;
+      p.run_count[r] = n_runs;
+    }
+    start = __shfl_sync(0xFFFFFFFFu, start, 0);
+    if (n_runs) {
+      __syncwarp();
+      // walk the slots backwards so that each run knows where the next one starts
+      uint32_t next_start = nwin;     // window index of the first break after the current slot
+      uint32_t later = 0;             // breaks in the slots already visited
+      for (int s = (int)((nwin + 31) / 32) - 1; s >= 0; s--) {
+        uint32_t i = (uint32_t)s * 32 + lane;
+        bool valid = i < nwin;
+        uint32_t c = valid ? p.codes[out_base + i] : 0;
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+        if (lane == 0) prev = (s > 0) ? p.codes[out_base + i - 1] : 0;
+        bool brk = valid && (i == 0 || c != prev);
+        uint32_t bm = __ballot_sync(0xFFFFFFFFu, brk);
+        if (brk) {
+          uint32_t after = lane == 31 ? 0u : (bm >> (lane + 1));
+          uint32_t end = after ? (uint32_t)s * 32 + lane + (uint32_t)__ffs(after) : next_start;
+          uint32_t idx = n_runs - later - (uint32_t)__popc(bm >> lane);
+          p.runs[start + idx] = make_uint2(c, end - i);
+        }
+        if (bm) next_start = (uint32_t)s * 32 + (uint32_t)__ffs(bm) - 1;
+        later += __popc(bm);
+      }
+    }
+  }
+}
+
+// A read that contains '\n' / '\r' (CRLF input): KmerScanner skips those characters without
+// consuming a base (krakenutil.cpp:265-269) and, when they trail the sequence, reads the string terminator as one
+// ambiguous base.  The warp compacts the read into scratch memory and pads it the way the scanner would see it.
+__device__ uint32_t clean_read(const char *seq, uint32_t len, char *dst, uint32_t k, uint32_t lane) {
+  uint32_t n = 0;
+  bool trailing = false;
+  for (uint32_t base = 0; base < len; base += 32) {
+    uint32_t pos = base + lane;
+    char c = pos < len ? seq[pos] : '\n';
+    bool keep = pos < len && c != '\n' && c != '\r';
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (keep) dst[n + __popc(m & ((1u << lane) - 1))] = c;
+    n += __popc(m);
+    if (base + 32 >= len) {
+      uint32_t inrange = len - base >= 32 ? 0xFFFFFFFFu : ((1u << (len - base)) - 1);
+      uint32_t skipped = inrange & ~m;
+      // trailing skip characters exist iff the last in-range position was skipped
+      trailing = (skipped >> (31 - __clz(inrange))) & 1;
+    }
+  }
+  // windows = max(1, n - k + 1 + trailing) for len >= k (see oracle/kuq_oracle.c kuqo_scan): pad with 'N'
+  uint32_t eff = n + (trailing ? 1 : 0);
+  if (len >= k && eff < k) eff = k;
+  for (uint32_t pos = n + lane; pos < eff; pos += 32) dst[pos] = 'N';
+  __syncwarp();
+  return len >= k ? eff : n;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------------------
+struct __align__(16) SharedState {
+  uint64_t bar[N_STAGES];
+  uint32_t chunk[N_STAGES];
+  uint32_t staged[N_STAGES];
+  uint64_t a0[N_STAGES];       // global byte offset the stage starts at
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t *stage_buf = smem;                                                   // N_STAGES x STAGE_BYTES
+  SharedState *ss = reinterpret_cast<SharedState *>(smem + N_STAGES * STAGE_BYTES);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  auto fetch = [&](uint32_t st) {   // thread 0: claim the next chunk and start its bulk copy
+    uint32_t c = atomicAdd(p.chunk_counter, 1u);
+    ss->chunk[st] = c;
+    ss->staged[st] = 0;
+    if (c < p.n_chunks) {
+      uint32_t r0 = c * CHUNK_READS, r1 = min(r0 + CHUNK_READS, p.n_reads);
+      uint64_t b0 = p.offsets[r0], b1 = p.offsets[r1];
+      uint64_t a0 = b0 & ~15ull, a1 = (b1 + 15) & ~15ull;
+      ss->a0[st] = a0;
+      if (a1 - a0 <= (uint64_t)STAGE_BYTES && a1 > a0) {
+        uint32_t bytes = (uint32_t)(a1 - a0);
+        mbar_expect_tx(&ss->bar[st], bytes);
+        tma_load_1d(stage_buf + st * STAGE_BYTES, p.bases + a0, bytes, &ss->bar[st]);
+        ss->staged[st] = 1;
+      }
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < N_STAGES; s++) mbar_init(&ss->bar[s], 1);
+    mbar_fence_init();
+    fetch(0);
+  }
+  __syncthreads();
+  uint32_t phase[N_STAGES] = {0, 0};
+  for (uint32_t it = 0;; it++) {
+    const uint32_t st = it & 1;
+    const uint32_t c = ss->chunk[st];
+    if (c >= p.n_chunks) break;
+    if (tid == 0) fetch(st ^ 1);        // the other stage was released by the barrier that ended the last round
+    const bool staged = ss->staged[st] != 0;
+    const uint64_t a0 = ss->a0[st];
+    if (staged) {
+      mbar_wait(&ss->bar[st], phase[st]);
+      phase[st] ^= 1;
+    }
+    const uint32_t r0 = c * CHUNK_READS, r1 = min(r0 + CHUNK_READS, p.n_reads);
+    for (uint32_t r = r0 + warp; r < r1; r += CTA_WARPS) {
+      const uint64_t b0 = p.offsets[r], b1 = p.offsets[r + 1];
+      uint32_t len = (uint32_t)(b1 - b0);
+      const char *seq = staged ? reinterpret_cast<const char *>(stage_buf + st * STAGE_BYTES + (b0 - a0))
+                               : p.bases + b0;
+      // pre-scan for skipped characters (rare: CRLF input)
+      bool skip = false;
+      for (uint32_t pos = lane; pos < len; pos += 32) {
+        char ch = seq[pos];
+        skip |= (ch == '\n') | (ch == '\r');
+      }
+      if (__any_sync(0xFFFFFFFFu, skip)) {
+        len = clean_read(seq, len, p.clean + b0, p.db.k, lane);
+        seq = p.clean + b0;
+      }
+      process_read<MODE>(p, r, seq, len, b0, lane);
+    }
+    __syncthreads();
+  }
+}
+
+int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedState); }
+
+void launch_classify(int mode, const Params &p, int grid, cudaStream_t stream) {
+  const int smem = classify_smem_bytes();
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_classify<MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_classify<MODE_LOOKUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_classify<MODE_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  switch (mode) {
+    case MODE_FUSED: k_classify<MODE_FUSED><<<grid, CTA_THREADS, smem, stream>>>(p); break;
+    case MODE_LOOKUP: k_classify<MODE_LOOKUP><<<grid, CTA_THREADS, smem, stream>>>(p); break;
+    default: k_classify<MODE_RESOLVE><<<grid, CTA_THREADS, smem, stream>>>(p); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// database staging: distinct taxids + record counts (KrakenDB::count_taxons, krakendb.cpp:90-113) and the
+// in-place rewrite taxid → dense id
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+// keys[] holds taxid + 1 (0 = empty)
+__global__ void k_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t *keys, unsigned long long *counts,
+                                 uint32_t cap_mask, uint32_t *overflow) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_rec;
+       base += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t i = base + lane;
+    bool in = i < n_rec;
+    uint32_t v = in ? load_val(pairs, i) : 0;
+    uint32_t active = __ballot_sync(0xFFFFFFFFu, in);
+    if (!in) continue;
+    uint32_t same = __match_any_sync(active, v);
+    if (lane != (uint32_t)(__ffs(same) - 1)) continue;      // one lane per distinct value
+    uint32_t key = v + 1;
+    if (key == 0) { atomicExch(overflow, 2u); continue; }   // taxid 0xFFFFFFFF is reserved
+    uint32_t slot = hash_u32(v) & cap_mask;
+    for (uint32_t probe = 0; probe <= cap_mask; probe++) {
+      uint32_t cur = keys[slot];
+      if (cur == 0) cur = atomicCAS(keys + slot, 0u, key), cur = cur ? cur : key;
+      if (cur == key) { atomicAdd(counts + slot, (unsigned long long)__popc(same)); break; }
+      slot = (slot + 1) & cap_mask;
+      if (probe == cap_mask) atomicExch(overflow, 1u);
+    }
+  }
+}
+
+__global__ void k_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, const uint32_t *dense,
+                               uint32_t cap_mask, uint32_t *missing) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t *vp = reinterpret_cast<uint32_t *>(pairs + i * 12) + 2;
+    uint32_t v = *vp;
+    uint32_t key = v + 1, slot = hash_u32(v) & cap_mask, d = 0xFFFFFFFFu;
+    for (uint32_t probe = 0; probe <= cap_mask; probe++) {
+      uint32_t cur = keys[slot];
+      if (cur == key) { d = dense[slot]; break; }
+      if (cur == 0) break;
+      slot = (slot + 1) & cap_mask;
+    }
+    if (d == 0xFFFFFFFFu) { atomicExch(missing, 1u); d = 0; }
+    *vp = d;
+  }
+}
+
+// C[taxon][v] = number of registers of the taxon holding v (registerHistogram, hyperloglogplus.cpp:337-354);
+// the double-precision Ertl sum over it runs on the host.
+__global__ void k_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist) {
+  __shared__ uint32_t h[64];
+  for (uint32_t t = blockIdx.x; t < n_sketch; t += gridDim.x) {
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(regs + (size_t)t * HLL_M);
+    for (uint32_t i = threadIdx.x; i < HLL_M / 4; i += blockDim.x) {
+      uint32_t x = w[i];
+      atomicAdd(&h[x & 63], 1u);
+      atomicAdd(&h[(x >> 8) & 63], 1u);
+      atomicAdd(&h[(x >> 16) & 63], 1u);
+      atomicAdd(&h[(x >> 24) & 63], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) hist[(size_t)t * 64 + threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// register-wise max over the sketches of the listed dense ids: the dense∪dense merge of the clade roll-up
+// (hyperloglogplus.cpp:614-620)
+__global__ void k_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_members, uint8_t *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;     // word index 0..1023
+  if (i >= HLL_M / 4) return;
+  uint32_t acc = 0;
+  for (uint32_t m = 0; m < n_members; m++) {
+    uint32_t x = reinterpret_cast<const uint32_t *>(regs + (size_t)members[m] * HLL_M)[i];
+    acc = __vmaxu4(acc, x);
+  }
+  reinterpret_cast<uint32_t *>(out)[i] = acc;
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void launch_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t *keys, unsigned long long *counts,
+                           uint32_t cap_mask, uint32_t *overflow, cudaStream_t stream) {
+  if (!n_rec) return;
+  int grid = (int)min((uint64_t)148 * 8, (n_rec + 255) / 256);
+  k_collect_taxids<<<grid, 256, 0, stream>>>(pairs, n_rec, keys, counts, cap_mask, overflow);
+}
+void launch_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, const uint32_t *dense,
+                         uint32_t cap_mask, uint32_t *missing, cudaStream_t stream) {
+  if (!n_rec) return;
+  int grid = (int)min((uint64_t)148 * 8, (n_rec + 255) / 256);
+  k_remap_values<<<grid, 256, 0, stream>>>(pairs, n_rec, keys, dense, cap_mask, missing);
+}
+void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist, cudaStream_t stream) {
+  if (!n_sketch) return;
+  k_register_histograms<<<min(n_sketch, 148u * 16), 256, 0, stream>>>(regs, n_sketch, hist);
+}
+void launch_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_members, uint8_t *out4096,
+                      cudaStream_t stream) {
+  k_clade_max<<<4, 256, 0, stream>>>(regs, members, n_members, out4096);
+}
+void launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream) {
+  if (!n) return;
+  k_fill_u32<<<(int)min((uint64_t)148 * 8, (n + 255) / 256), 256, 0, stream>>>(p, n, v);
+}
+
+}  // namespace kuq

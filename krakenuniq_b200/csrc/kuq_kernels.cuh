@@ -1,0 +1,122 @@
+// kuq_kernels.cuh — sm_100a kernels of the KrakenUniq classification hot path (device side of libkuq.so).
+//
+// One persistent kernel, k_classify<MODE>, carries the whole per-read path of the reference's
+// classify_sequence() (src/classify.cpp:897-1012):
+//
+//   read blocks --TMA bulk copy--> shared memory            (cp.async.bulk + mbarrier, double buffered)
+//   2-bit packing + ambiguity mask   KmerScanner::next_kmer  src/krakenutil.cpp:239-282
+//   canonical k-mer                  canonical_representation src/krakendb.cpp:238-246
+//   rolling minimizer                bin_key                  src/krakendb.cpp:200-215
+//   index fetch + bin search         kmer_query               src/krakendb.cpp:250-321, :586-593
+//   HLL register update + counters   ReadCounts::add_kmer     src/readcounts.hpp:71-74, hyperloglogplus.cpp:485-523
+//   hit aggregation + tree resolve   resolve_tree / lca       src/krakenutil.cpp:90-118,149-200
+//   run-length hit list              hitlist_string           src/classify.cpp:826-861
+//
+// Work decomposition: a CTA (8 warps) owns a chunk of consecutive reads whose bytes one thread pulls into
+// shared memory with a single 1-D bulk copy while the warps still work on the previous chunk; a warp owns a
+// read and walks it in slots of 32 consecutive k-mer windows (lane = window), so that windows sharing a
+// minimizer sit in neighbouring lanes: their index fetches and bin probes coalesce into the same sectors.
+// No tensor cores: the path is integer compares on randomly addressed HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kuq {
+
+constexpr uint32_t AMBIG = 0xFFFFFFFFu;
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+constexpr int CHUNK_READS = 64;            // reads per CTA work item
+constexpr int STAGE_BYTES = 24 * 1024;     // bytes of read text per shared-memory stage
+constexpr int N_STAGES = 2;
+constexpr uint32_t HLL_P = 12;
+constexpr uint32_t HLL_M = 4096;
+constexpr int SEARCH_WINDOW = 8;           // records scanned linearly once the bisection window is this small
+
+enum Mode { MODE_FUSED = 0, MODE_LOOKUP = 1, MODE_RESOLVE = 2 };
+
+struct DbView {
+  const uint8_t *pairs;      // records of the staged range, on-disk layout: {u64 key, u32 value} packed to 12 B
+  const uint64_t *offsets;   // offsets[b - bin_lo] = absolute record index of the first record of bin b
+  uint64_t rec_base;         // absolute record index of pairs[0]
+  uint64_t key_mask;         // (1 << 2k) - 1
+  uint32_t bin_lo, bin_hi;   // staged minimizer range [bin_lo, bin_hi)
+  uint32_t k, nt;
+  uint32_t xor_mask;         // INDEX2_XOR_MASK & (4^nt - 1) for KRAKIX2, 0 for KRAKIDX (krakendb.cpp:45,203-206)
+  uint32_t n_mini;           // k - nt + 1 minimizer candidates per k-mer (krakendb.cpp:208)
+};
+
+struct TaxView {
+  const uint32_t *parent;    // dense id → dense id of the parent (0 = none), Parent_map of taxdb.hpp:383-398
+  const uint16_t *depth;     // dense id → steps to the end of its parent chain (0 or the node of taxid 1)
+  const uint32_t *raw;       // dense id → taxid
+  uint32_t n_taxa;
+  uint32_t n_sketch;         // dense ids < n_sketch own HLL registers / k-mer counters
+};
+
+struct SparseSet {           // device set of (dense taxon, encoded hash) pairs: the sparse HLL tier
+  unsigned long long *slots; // 0 = empty; key = (taxon + 1) << 32 | code
+  uint64_t mask;             // capacity - 1 (power of two)
+  unsigned long long *n_used;
+  uint32_t *distinct;        // [n_sketch] distinct codes inserted per taxon
+};
+
+struct UnitSet {             // per-batch set of (unit, taxon, code) triples: distinct codes per work-unit sketch
+  unsigned long long *slots; // two words per entry: {unit<<32|taxon+1, code}; slot i → words 2i, 2i+1
+  uint64_t mask;
+  uint32_t *map_keys_lo;     // per-batch (unit,taxon) → counter map
+  unsigned long long *map_keys;
+  uint32_t *map_distinct;
+  uint32_t *map_inserts;
+  uint64_t map_mask;
+};
+
+struct Params {
+  DbView db;
+  TaxView tax;
+  // batch
+  const char *bases;            // 16-byte aligned, >= 32 bytes of slack after the last base
+  const uint64_t *offsets;      // [n_reads + 1], relative to bases
+  const uint32_t *unit_id;      // [n_reads] or nullptr
+  char *clean;                  // scratch of the same size as bases for reads containing '\n' / '\r'
+  uint32_t n_reads;
+  uint32_t n_chunks;
+  uint32_t flags;
+  uint32_t hll_mode;
+  // outputs
+  uint32_t *call;               // [n_reads] taxid
+  uint32_t *n_windows;          // [n_reads]
+  uint32_t *codes;              // per window, indexed like bases
+  const uint32_t *codes_in;     // MODE_RESOLVE: merged dense ids
+  uint32_t *run_start;
+  uint32_t *run_count;
+  uint2 *runs;
+  unsigned long long *run_cursor;
+  unsigned long long *n_classified;
+  uint32_t *chunk_counter;      // dynamic chunk scheduler
+  uint32_t *error_flag;
+  uint32_t only_hits;           // MODE_LOOKUP: write hits only (peer-memory merge)
+  // per-taxon state
+  uint8_t *regs;                // [n_sketch][4096]
+  unsigned long long *n_kmers;  // [n_sketch]
+  unsigned long long *n_reads_ctr; // [n_taxa]
+  uint8_t *dense_flag;          // [n_sketch]
+  SparseSet sparse;
+  UnitSet units;
+};
+
+void launch_classify(int mode, const Params &p, int grid, cudaStream_t stream);
+int classify_smem_bytes();
+
+// database staging helpers
+void launch_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t *keys, unsigned long long *counts,
+                           uint32_t cap_mask, uint32_t *overflow, cudaStream_t stream);
+void launch_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, const uint32_t *dense,
+                         uint32_t cap_mask, uint32_t *missing, cudaStream_t stream);
+void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist /*[n_sketch][64]*/,
+                                cudaStream_t stream);
+void launch_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_members, uint8_t *out4096,
+                      cudaStream_t stream);
+void launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream);
+
+}  // namespace kuq

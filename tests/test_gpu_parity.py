@@ -1,0 +1,182 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libkuq.so), against the oracle on the same
+seeded inputs and against the golden outputs of the unmodified reference.  Bit-exact: calls, per-window codes,
+hit lists, per-taxon read/k-mer counters and HLL registers."""
+import os
+
+import numpy as np
+import pytest
+
+from krakenuniq_b200 import binding, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+K = 31
+
+
+def _classifier(**kw):
+    kw.setdefault("max_reads", 1 << 16)
+    kw.setdefault("max_bases", 16 << 20)
+    kw.setdefault("sparse_set_slots", 1 << 22)
+    return binding.Classifier(**kw)
+
+
+def _runs_to_codes(res, i):
+    out = []
+    for code, cnt in binding.decode_runs(res, i):
+        out += [code] * cnt
+    return np.array(out, np.uint32)
+
+
+def _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_DENSE_ONLY, unit=500000,
+                          oracle_mode=0):
+    db = oracle.open_db(kdb, idx)
+    pm = oracle.parent_map(*tax.parent_map())
+    run = oracle.run(db, pm, unit, oracle_mode)
+    calls, codes, code_off = run.classify(bases, offs)
+    run.finish()
+    want = run.counts(want_regs=True)
+
+    clf = _classifier(hll_mode=hll_mode, work_unit_size=unit)
+    clf.stage_db(kdb, idx)
+    clf.set_taxonomy(*tax.parent_map())
+    res = clf.classify(bases, offs, flags=binding.F_WANT_CODES)
+    clf.finish()
+    n = len(offs) - 1
+    assert np.array_equal(res["call"], calls)
+    nwin = np.diff(code_off).astype(np.uint32)
+    assert np.array_equal(res["n_windows"], nwin)
+    base0 = int(offs[0])
+    for i in range(n):
+        w = codes[int(code_off[i]):int(code_off[i + 1])]
+        o = int(offs[i]) - base0
+        got = res["codes"][o:o + len(w)]
+        assert np.array_equal(got, w), f"read {i}"
+        assert np.array_equal(_runs_to_codes(res, i), w), f"runs of read {i}"
+    assert res["n_classified"] == int((calls != 0).sum())
+    got = clf.counts()
+    assert np.array_equal(got["taxid"], want["taxid"])
+    assert np.array_equal(got["n_reads"], want["n_reads"])
+    assert np.array_equal(got["n_kmers"], want["n_kmers"])
+    for j, t in enumerate(want["taxid"]):
+        assert np.array_equal(clf.registers(int(t)), want["regs"][j]), f"registers of taxon {t}"
+    return clf, got, want
+
+
+def _synthetic(seed, nt, idx_type, n_genomes=5, glen=2500, n_reads=800, read_len=150, n_frac=0.2):
+    rng = np.random.default_rng(seed)
+    tax = synth.make_taxonomy(n_genomes)
+    sp = synth.species_ids(tax)
+    genomes = synth.random_genomes(rng, n_genomes, glen, shared_frac=0.25)
+    km, tx = synth.label_kmers(genomes, sp, tax, K)
+    kdb, idx = synth.build_db_images(km, tx, K, nt, idx_type)
+    bases, offs = synth.sample_reads(rng, genomes, n_reads, read_len, 0.01, n_frac, 0.2)
+    return tax, genomes, kdb, idx, bases, offs
+
+
+@pytest.mark.parametrize("nt,idx_type", [(8, 2), (6, 1), (11, 2), (15, 2)])
+def test_synthetic_db_matches_oracle(oracle, nt, idx_type):
+    tax, genomes, kdb, idx, bases, offs = _synthetic(100 + nt, nt, idx_type)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs)
+
+
+def test_edge_reads_match_oracle(oracle):
+    tax, genomes, kdb, idx, _, _ = _synthetic(7, 8, 2)
+    g = [synth.decode(x).tobytes() for x in genomes]
+    rng = np.random.default_rng(3)
+    long_read = b"".join(g[int(rng.integers(0, 5))][s:s + 97] for s in rng.integers(0, 2300, 40).tolist())
+    seqs = [b"", b"A", b"ACGT" * 7 + b"AC", b"ACGT" * 7 + b"ACG", g[0][:31], g[0][:32], g[0][5:36].lower(),
+            b"N" * 31, b"N" * 200, g[1][100:163], g[1][100:164], g[1][100:165], g[1][0:95], g[1][0:96], g[1][0:97],
+            g[2][10:130] + b"N" + g[3][10:130], g[2][10:40] + b"R" + g[2][41:200], long_read, g[4][:2500],
+            g[0][50:200] + b"\r", g[0][50:110] + b"\r" + g[0][110:170] + b"\r", g[0][50:80] + b"\r",
+            g[0][50:79] + b"\n\r", b"\r" * 40, g[3][7:38] + b"\r\r\r", g[0][100:131] + b"acgtnACGT" * 10]
+    seqs += [g[i % 5][s:s + ln] for i, (s, ln) in enumerate(zip(rng.integers(0, 2000, 200).tolist(),
+                                                                rng.integers(1, 400, 200).tolist()))]
+    bases, offs = synth.pack_reads(seqs)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs)
+
+
+def test_orphan_taxa_ties_and_forest(oracle):
+    """taxids stored in the DB but absent from taxDB, several roots, ties → LCA"""
+    rng = np.random.default_rng(11)
+    rows = [(1, 1, "root", "no rank"), (10, 1, "a", "genus"), (11, 10, "a1", "species"), (12, 10, "a2", "species"),
+            (20, 1, "b", "genus"), (21, 20, "b1", "species"), (500, 500, "other root", "no rank"),
+            (501, 500, "c1", "species"), (600, 999, "dangling parent", "species")]
+    tax = synth.Taxonomy(rows)
+    labels = [11, 12, 21, 501, 600, 4242, 77]          # 4242 and 77 are not in taxDB
+    genomes = [rng.integers(0, 4, 1200, dtype=np.uint8) for _ in labels]
+    ks, ts = [], []
+    for gseq, t in zip(genomes, labels):
+        km, ok = synth.forward_kmers(gseq, K)
+        c = np.unique(synth.canonical(km[ok], K))
+        ks.append(c); ts.append(np.full(len(c), t, np.uint32))
+    km, first = np.unique(np.concatenate(ks), return_index=True)
+    tx = np.concatenate(ts)[first]
+    kdb, idx = synth.build_db_images(km, tx, K, 7, 2)
+    g = [synth.decode(x).tobytes() for x in genomes]
+    seqs = []
+    for a in range(len(g)):
+        for b in range(len(g)):
+            for la, lb in [(45, 45), (45, 46), (60, 40)]:
+                seqs.append(g[a][100:100 + la] + b"N" + g[b][300:300 + lb])
+    seqs += [g[0][0:50] + b"N" + g[1][0:50] + b"N" + g[2][0:50] + b"N" + g[3][0:50] + b"N" + g[5][0:50]]
+    bases, offs = synth.pack_reads(seqs)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs)
+
+
+@pytest.mark.parametrize("tag,reads", [("preload", "reads.fa"), ("fastq", "reads_300.fq"), ("crlf", "reads_crlf_60.fa")])
+def test_golden_reference_outputs(oracle, tag, reads):
+    """Kraken lines byte-identical to the unmodified reference's `classify -M -t 1` output."""
+    kdb = np.fromfile(os.path.join(util.GOLDEN, "database.kdb"), np.uint8)
+    idx = np.fromfile(os.path.join(util.GOLDEN, "database.idx"), np.uint8)
+    tax = synth.Taxonomy.read(os.path.join(util.GOLDEN, "taxDB"))
+    path = os.path.join(util.GOLDEN, reads)
+    ids, seqs = util.read_fastq(path) if reads.endswith(".fq") else util.read_fasta(path)
+    bases, offs = synth.pack_reads(seqs)
+    clf = _classifier(hll_mode=binding.HLL_DENSE_ONLY)
+    clf.stage_db(kdb, idx)
+    clf.set_taxonomy(*tax.parent_map())
+    res = clf.classify(bases, offs)
+    lines = []
+    for i, (rid, s) in enumerate(zip(ids, seqs)):
+        runs = binding.decode_runs(res, i)
+        hl = " ".join(("A" if c == binding.AMBIG else str(c)) + ":" + str(n) for c, n in runs) if runs else "0:0"
+        call = int(res["call"][i])
+        lines.append(f"{'C' if call else 'U'}\t{rid}\t{call}\t{len(s)}\t{hl}\n")
+    assert "".join(lines) == open(os.path.join(util.GOLDEN, f"{tag}.kraken")).read()
+    # per-taxon read counts = taxReads column of the reference's report
+    rep = util.parse_report(os.path.join(util.GOLDEN, f"{tag}.report.tsv"))
+    cnt = clf.counts()
+    by_tax = dict(zip(cnt["taxid"].tolist(), cnt["n_reads"].tolist()))
+    for t, row in rep.items():
+        assert row["taxReads"] == by_tax.get(t, 0)
+    # the database scan reproduces database.kdb.counts (KrakenDB::count_taxons)
+    t, c = clf.db_taxids()
+    want = [tuple(int(x) for x in l.split()) for l in open(os.path.join(util.GOLDEN, "database.kdb.counts"))]
+    assert list(zip(t.tolist(), c.tolist())) == want
+
+
+def test_batches_and_slots_are_equivalent(oracle):
+    """Splitting the input over batches / slots changes nothing (counters are order independent)."""
+    tax, genomes, kdb, idx, bases, offs = _synthetic(21, 9, 2, n_reads=1000)
+    clf1, got1, _ = _check_against_oracle(oracle, kdb, idx, tax, bases, offs)
+    clf = _classifier(hll_mode=binding.HLL_DENSE_ONLY, n_slots=3)
+    clf.stage_db(kdb, idx)
+    clf.set_taxonomy(*tax.parent_map())
+    calls = []
+    cuts = [0, 1, 130, 131, 700, 1000]
+    pending = []
+    for j in range(len(cuts) - 1):
+        o = np.ascontiguousarray(offs[cuts[j]:cuts[j + 1] + 1])
+        slot = j % 3
+        if len(pending) == 3:
+            s0, o0 = pending.pop(0)
+            calls.append(clf.wait(s0, o0, copy=True)["call"])
+        clf.submit(slot, bases.ctypes.data, o)
+        pending.append((slot, o))
+    for s0, o0 in pending:
+        calls.append(clf.wait(s0, o0, copy=True)["call"])
+    clf.finish()
+    assert np.array_equal(np.concatenate(calls), clf1.classify(bases, offs)["call"])
+    got = clf.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "unique"):
+        assert np.array_equal(got[key], got1[key]), key
