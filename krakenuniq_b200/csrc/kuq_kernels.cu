@@ -155,12 +155,15 @@ __device__ uint32_t lca_dense(const TaxView &t, uint32_t a, uint32_t b) {
 struct Block64 {         // 32 bases: 2-bit codes, first base in bits 63:62; amb bit l = base l is not ACGT
   uint64_t codes;
   uint32_t amb;
+  uint32_t mark;         // bit l = a window ENDS at base l (only for cleaned reads, see clean_read)
 };
 
 // Convert 32 characters (lane = position) — krakenutil.cpp:253-273.  Positions >= len read as ambiguous.
-__device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uint32_t blk, uint32_t lane) {
+__device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uint32_t blk, uint32_t lane, bool marks) {
   uint32_t pos = blk * 32 + lane;
   uint32_t c = pos < len ? (uint32_t)(uint8_t)seq[pos] : (uint32_t)'N';
+  uint32_t mk = 0;
+  if (marks) { mk = c >> 7; c &= 0x7Fu; }
   uint32_t uc = c & 0xDFu;                                  // case-insensitive, :254-264
   bool ok = (uc == 'A') | (uc == 'C') | (uc == 'G') | (uc == 'T');
   uint32_t code = ok ? (((c >> 1) ^ (c >> 2)) & 3u) : 0u;   // A=0 C=1 G=2 T=3
@@ -170,15 +173,19 @@ __device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uin
   Block64 b;
   b.codes = ((uint64_t)hi << 32) | lo;
   b.amb = __ballot_sync(0xFFFFFFFFu, !ok);
+  b.mark = marks ? __ballot_sync(0xFFFFFFFFu, mk != 0) : 0u;
   return b;
 }
 
 template <int MODE>
 __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint32_t len, uint64_t out_base,
-                             uint32_t lane) {
+                             uint32_t lane, bool marks) {
   const DbView &db = p.db;
   const uint32_t k = db.k, nt = db.nt;
+  // candidate windows; every one of them is a scanner window unless the read was cleaned (marks), in which case
+  // only the marked ones are (the scanner drops a window per skipped character, see clean_read)
   const uint32_t nwin = len >= k ? len - k + 1 : 0;           // classify.cpp:913-914
+  uint32_t n_out = 0;                                         // windows emitted so far
   uint32_t my_t = 0, my_c = 0;                                // hit list: lane j holds entry j (dense id, count)
   uint32_t n_hits = 0, n_miss = 0, n_runs = 0;
   uint32_t carry_code = 0;                                    // code of the previous slot's last window
@@ -186,15 +193,19 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
   const bool counting = (MODE != MODE_LOOKUP) && !(p.flags & 4u);
 
   if (nwin > 0) {
-    Block64 A = load_block(seq, len, 0, lane);
+    Block64 A = load_block(seq, len, 0, lane, marks);
     const uint32_t nslots = (nwin + 31) / 32;
     // carry of the minimizer run that crosses the slot boundary
     uint32_t carry_bin = 0xFFFFFFFFu, carry_n = 0;
     uint64_t carry_lo = 0;
     for (uint32_t s = 0; s < nslots; s++) {
-      Block64 B = load_block(seq, len, s + 1, lane);
+      Block64 B = load_block(seq, len, s + 1, lane, marks);
       const uint32_t i = s * 32 + lane;
-      const bool valid = i < nwin;
+      bool valid = i < nwin;
+      if (marks) valid = valid && (((((uint64_t)B.mark << 32) | A.mark) >> (lane + k - 1)) & 1);
+      const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+      const uint32_t oi = n_out + __popc(vmask & ((1u << lane) - 1));   // output slot of this window
+      n_out += __popc(vmask);
       // ---- k-mer of window i: bases [i, i+k) of the 128-bit string A:B ------------------------------------
       uint64_t hi = lane ? (A.codes << (2 * lane)) | (B.codes >> (64 - 2 * lane)) : A.codes;
       uint64_t kmer = hi >> (64 - 2 * k);
@@ -205,7 +216,7 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
       bool look = valid && !amb;
       if (MODE == MODE_RESOLVE) {
         if (valid) {
-          uint32_t c = p.codes_in[out_base + i];
+          uint32_t c = p.codes_in[out_base + oi];
           taxon = (c == AMBIG) ? 0 : c;                       // ambiguity is recomputed from the bases
         }
         if (look) {
@@ -301,12 +312,12 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
       if (MODE == MODE_LOOKUP) {
         // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
         // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
-        if (valid && (!p.only_hits || (taxon != 0))) p.codes[out_base + i] = code;
+        if (valid && (!p.only_hits || (taxon != 0))) p.codes[out_base + oi] = code;
       } else {
         uint32_t raw = (look && taxon) ? __ldg(p.tax.raw + taxon) : 0;
         uint32_t out_code = amb ? AMBIG : raw;
-        if (valid) p.codes[out_base + i] = out_code;
-        // runs of the hit list (classify.cpp:826-861)
+        if (valid) p.codes[out_base + oi] = out_code;
+        // runs of the hit list (classify.cpp:826-861); cleaned reads count theirs after the loop
         uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
         if (lane == 0) prev = carry_code;
         bool brk = valid && (i == 0 || out_code != prev);
@@ -350,8 +361,17 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
   }
 
   if (MODE == MODE_LOOKUP) {
-    if (lane == 0) p.n_windows[r] = nwin;
+    if (lane == 0) p.n_windows[r] = n_out;
     return;
+  }
+  if (marks && !(p.flags & 2u)) {   // runs over the compacted codes of a cleaned read
+    __syncwarp();
+    n_runs = 0;
+    for (uint32_t base = 0; base < n_out; base += 32) {
+      uint32_t i = base + lane;
+      bool brk = i < n_out && (i == 0 || p.codes[out_base + i] != p.codes[out_base + i - 1]);
+      n_runs += __popc(__ballot_sync(0xFFFFFFFFu, brk));
+    }
   }
 
   // ---- resolve_tree (krakenutil.cpp:149-200) --------------------------------------------------------------
@@ -395,7 +415,7 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
 
   const uint32_t call_raw = call ? __ldg(p.tax.raw + call) : 0;
   if (lane == 0) {
-    p.n_windows[r] = nwin;
+    p.n_windows[r] = n_out;
     p.call[r] = call_raw;
     if (overflow) atomicExch(p.error_flag, 1u);
   }
@@ -420,11 +440,11 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
     if (n_runs) {
       __syncwarp();
       // walk the slots backwards so that each run knows where the next one starts
-      uint32_t next_start = nwin;     // window index of the first break after the current slot
+      uint32_t next_start = n_out;    // window index of the first break after the current slot
       uint32_t later = 0;             // breaks in the slots already visited
-      for (int s = (int)((nwin + 31) / 32) - 1; s >= 0; s--) {
+      for (int s = (int)((n_out + 31) / 32) - 1; s >= 0; s--) {
         uint32_t i = (uint32_t)s * 32 + lane;
-        bool valid = i < nwin;
+        bool valid = i < n_out;
         uint32_t c = valid ? p.codes[out_base + i] : 0;
         uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, c, 1);
         if (lane == 0) prev = (s > 0) ? p.codes[out_base + i - 1] : 0;
@@ -443,32 +463,44 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
   }
 }
 
-// A read that contains '\n' / '\r' (CRLF input): KmerScanner skips those characters without
-// consuming a base (krakenutil.cpp:265-269) and, when they trail the sequence, reads the string terminator as one
-// ambiguous base.  The warp compacts the read into scratch memory and pads it the way the scanner would see it.
+// A read that contains '\n' / '\r' (CRLF input).  KmerScanner::next_kmer (krakenutil.cpp:239-278)
+// "skips" such a character by undoing the loaded_nt increment (:265-269), but the base that follows a skipped
+// character is then loaded WITHOUT being counted (skip_pos, :246-247), and every further skipped character of a
+// run decrements loaded_nt once more.  Net effect: each skipped character makes the scanner swallow one extra
+// base, i.e. one k-mer window is never produced.  If the text ends while a call is still loading, the scanner
+// reads the string terminator as an ambiguous base and produces one last (ambiguous) window.
+// The warp's lane 0 replays that automaton once (rare path) and writes the cleaned bases to scratch, setting bit 7
+// of the base each produced window ENDS at; process_read then only keeps the marked windows.
 __device__ uint32_t clean_read(const char *seq, uint32_t len, char *dst, uint32_t k, uint32_t lane) {
   uint32_t n = 0;
-  bool trailing = false;
-  for (uint32_t base = 0; base < len; base += 32) {
-    uint32_t pos = base + lane;
-    char c = pos < len ? seq[pos] : '\n';
-    bool keep = pos < len && c != '\n' && c != '\r';
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, keep);
-    if (keep) dst[n + __popc(m & ((1u << lane) - 1))] = c;
-    n += __popc(m);
-    if (base + 32 >= len) {
-      uint32_t inrange = len - base >= 32 ? 0xFFFFFFFFu : ((1u << (len - base)) - 1);
-      uint32_t skipped = inrange & ~m;
-      // trailing skip characters exist iff the last in-range position was skipped
-      trailing = (skipped >> (31 - __clz(inrange))) & 1;
+  if (lane == 0) {
+    int loaded = 0;
+    bool skipflag = false;
+    int64_t last_emit = -1;
+    for (uint32_t i = 0; i < len; i++) {
+      char c = seq[i];
+      if (c == '\n' || c == '\r') {
+        if (skipflag) loaded--;
+        skipflag = true;
+      } else {
+        uint8_t o = ((uint8_t)c & 0x80) ? (uint8_t)'N' : (uint8_t)c;   // bit 7 is the window mark
+        if (!skipflag) {
+          loaded++;
+          if (loaded == (int)k) { o |= 0x80; loaded = (int)k - 1; last_emit = i; }
+        }
+        skipflag = false;
+        dst[n++] = (char)o;
+      }
+    }
+    if (len >= k && last_emit + 1 < (int64_t)len) {     // a call is still loading: one last, ambiguous window
+      uint32_t target = n + 1 > k ? n + 1 : k;          // <= len because at least one character was skipped
+      while (n < target) dst[n++] = 'N';
+      dst[n - 1] = (char)((uint8_t)'N' | 0x80);
     }
   }
-  // windows = max(1, n - k + 1 + trailing) for len >= k (see oracle/kuq_oracle.c kuqo_scan): pad with 'N'
-  uint32_t eff = n + (trailing ? 1 : 0);
-  if (len >= k && eff < k) eff = k;
-  for (uint32_t pos = n + lane; pos < eff; pos += 32) dst[pos] = 'N';
+  n = __shfl_sync(0xFFFFFFFFu, n, 0);
   __syncwarp();
-  return len >= k ? eff : n;
+  return n;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -536,11 +568,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_consta
         char ch = seq[pos];
         skip |= (ch == '\n') | (ch == '\r');
       }
+      bool marks = false;
       if (__any_sync(0xFFFFFFFFu, skip)) {
         len = clean_read(seq, len, p.clean + b0, p.db.k, lane);
         seq = p.clean + b0;
+        marks = true;
       }
-      process_read<MODE>(p, r, seq, len, b0, lane);
+      process_read<MODE>(p, r, seq, len, b0, lane, marks);
     }
     __syncthreads();
   }
