@@ -63,6 +63,7 @@ extern "C" {
 #define KUQ_F_WANT_CODES 1u     /* also return the per-window codes (4 B per base position) */
 #define KUQ_F_NO_RUNS 2u        /* skip the run-length-encoded hit lists */
 #define KUQ_F_NO_COUNTS 4u      /* do not touch the per-taxon counters / sketches (pure lookups) */
+#define KUQ_F_STATS 8u          /* measurement aid: accumulate the algorithmic probe counts (kuq_slot_stats) */
 
 typedef struct kuq_ctx kuq_ctx;
 
@@ -187,6 +188,9 @@ int kuq_resolve_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const u
                        const uint32_t *d_unit_id, uint32_t flags);
 int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot);
 int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out);
+/* With KUQ_F_STATS: number of non-ambiguous windows looked up by the slot's last batch and the sum over them of
+ * ceil(log2(bin size + 1)) — the textbook probe count SURVEY.md §8(d) defines the algorithmic bytes with. */
+int kuq_slot_stats(kuq_ctx *ctx, uint32_t slot, uint64_t *n_lookups, uint64_t *sum_probes);
 /* CUDA stream (cudaStream_t) of a slot, so callers can order their own work (e.g. NCCL) against it. */
 void *kuq_slot_stream(kuq_ctx *ctx, uint32_t slot);
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */

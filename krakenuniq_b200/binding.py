@@ -17,7 +17,7 @@ from . import build as _build
 
 AMBIG = 0xFFFFFFFF
 HLL_PRELOAD, HLL_CHUNKED, HLL_DENSE_ONLY = 0, 1, 2
-F_WANT_CODES, F_NO_RUNS, F_NO_COUNTS = 1, 2, 4
+F_WANT_CODES, F_NO_RUNS, F_NO_COUNTS, F_STATS = 1, 2, 4, 8
 
 u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 
@@ -99,6 +99,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_sync_slot": (C.c_int, [vp, C.c_uint32]),
         "kuq_slot_device_result": (C.c_int, [vp, C.c_uint32, C.POINTER(DeviceResult)]),
         "kuq_slot_stream": (vp, [vp, C.c_uint32]),
+        "kuq_slot_stats": (C.c_int, [vp, C.c_uint32, u64p, u64p]),
         "kuq_launch_count": (C.c_uint64, [vp]),
         "kuq_last_kernel_ms": (C.c_double, [vp, C.c_uint32]),
         "kuq_finish": (C.c_int, [vp]),
@@ -255,6 +256,11 @@ class Classifier:
         r = DeviceResult()
         self._ck(self.L.kuq_slot_device_result(self.h, slot, C.byref(r)))
         return r
+
+    def slot_stats(self, slot):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.L.kuq_slot_stats(self.h, slot, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def slot_stream(self, slot):
         return self.L.kuq_slot_stream(self.h, slot)

@@ -204,13 +204,13 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(dmalloc(&s.d_run_start, mr));
   CU(dmalloc(&s.d_run_count, mr));
   CU(dmalloc(&s.d_runs, mb + SLACK));
-  CU(dmalloc(&s.d_scalars, 4));
+  CU(dmalloc(&s.d_scalars, 8));
   CU(hmalloc(&s.h_call, mr));
   CU(hmalloc(&s.h_nwin, mr));
   CU(hmalloc(&s.h_run_start, mr));
   CU(hmalloc(&s.h_run_count, mr));
   CU(hmalloc(&s.h_unit, mr));
-  CU(hmalloc(&s.h_scalars, 4));
+  CU(hmalloc(&s.h_scalars, 8));
   s.h_runs_cap = std::max<uint64_t>(mr * 8, 1024);
   CU(hmalloc(&s.h_runs, s.h_runs_cap));
   return KUQ_OK;
@@ -430,6 +430,7 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.n_classified = s.d_scalars + 1;
   p.chunk_counter = reinterpret_cast<uint32_t *>(s.d_scalars + 2);
   p.error_flag = reinterpret_cast<uint32_t *>(s.d_scalars + 3);
+  p.stats = s.d_scalars + 4;
   p.regs = ctx->d_regs;
   p.n_kmers = ctx->d_n_kmers;
   p.n_reads_ctr = ctx->d_n_reads;
@@ -447,7 +448,7 @@ int grid_for(kuq_ctx *ctx, uint32_t n_chunks) {
 }
 
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
-  CU(cudaMemsetAsync(s.d_scalars, 0, 4 * 8, s.stream));
+  CU(cudaMemsetAsync(s.d_scalars, 0, 8 * 8, s.stream));
   CU(cudaEventRecord(s.ev_k0, s.stream));
   if (p.n_reads) {
     launch_classify(mode, p, grid_for(ctx, p.n_chunks), s.stream);
@@ -725,7 +726,7 @@ int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint6
       CU(cudaMemcpyAsync(s.h_run_count, s.d_run_count, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
     }
   }
-  CU(cudaMemcpyAsync(s.h_scalars, s.d_scalars, 4 * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaMemcpyAsync(s.h_scalars, s.d_scalars, 8 * 8, cudaMemcpyDeviceToHost, s.stream));
   s.busy = true;
   return KUQ_OK;
 }
@@ -842,6 +843,18 @@ int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out) 
   out->d_run_count = s.d_run_count;
   out->d_runs = reinterpret_cast<const kuq_run *>(s.d_runs);
   out->d_n_runs = reinterpret_cast<const uint64_t *>(s.d_scalars);
+  return KUQ_OK;
+}
+
+int kuq_slot_stats(kuq_ctx *ctx, uint32_t slot, uint64_t *n_lookups, uint64_t *sum_probes) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  Slot &s = ctx->slots[slot];
+  CU(cudaStreamSynchronize(s.stream));
+  unsigned long long v[2];
+  CU(cudaMemcpy(v, s.d_scalars + 4, 16, cudaMemcpyDeviceToHost));
+  if (n_lookups) *n_lookups = v[0];
+  if (sum_probes) *sum_probes = v[1];
   return KUQ_OK;
 }
 

@@ -289,6 +289,12 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
         } else {
           carry_bin = 0xFFFFFFFFu;
         }
+        if (p.flags & 8u) {   // measurement aid: algorithmic probe count of SURVEY.md §8(d)
+          uint32_t probes = (look && n) ? 32 - __clz(n) : 0;
+          uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, probes);
+          uint32_t nl = __popc(__ballot_sync(0xFFFFFFFFu, look));
+          if (lane == 0) { atomicAdd(p.stats, (unsigned long long)nl); atomicAdd(p.stats + 1, (unsigned long long)tot); }
+        }
         // ---- bin search (kmer_query, krakendb.cpp:280-299): bisection to a small window, then a scan ------
         if (look && n > 0) {
           while (n > (uint32_t)SEARCH_WINDOW) {

@@ -96,6 +96,7 @@ struct Params {
   uint32_t *chunk_counter;      // dynamic chunk scheduler
   uint32_t *error_flag;
   uint32_t only_hits;           // MODE_LOOKUP: write hits only (peer-memory merge)
+  unsigned long long *stats;    // flag 8: [0] += looked-up windows, [1] += sum of ceil(log2(bin size + 1))
   // per-taxon state
   uint8_t *regs;                // [n_sketch][4096]
   unsigned long long *n_kmers;  // [n_sketch]

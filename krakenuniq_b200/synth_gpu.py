@@ -1,0 +1,185 @@
+"""Large synthetic KrakenUniq workloads generated ON the GPU with torch (BASELINE.json configs[1..]: an "8 GB
+synthetic KrakenDB (k=31)" and 150 bp reads).  Workload generation only — torch is plumbing here; nothing in this
+file is on the classification path.  Layouts are the on-disk ones, validated against the
+reference's db_sort at small scale by tests/test_synth_gpu.py.
+
+Recipe: one long uniform-random sequence cut into `n_genomes` equal "genomes" under a
+4-level taxonomy; every canonical k-mer of the sequence becomes one record labelled with the taxid of the genome
+it starts in; records sorted by (bin_key, key); reads sampled from the sequence (substitutions, reverse
+complement) plus a fraction of unrelated random reads.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+INDEX2_XOR_MASK = 0xE37E28C4271B5A2D
+
+
+def _lsr(x: torch.Tensor, s: int) -> torch.Tensor:
+    """logical shift right on int64"""
+    return (x >> s) & ((1 << (64 - s)) - 1)
+
+
+def revcomp(x: torch.Tensor, n: int) -> torch.Tensor:
+    """krakendb.cpp:218-225 on int64 tensors holding unsigned 2n-bit values"""
+    x = ((x >> 2) & 0x3333333333333333) | ((x & 0x3333333333333333) << 2)
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0F) | ((x & 0x0F0F0F0F0F0F0F0F) << 4)
+    x = ((x >> 8) & 0x00FF00FF00FF00FF) | ((x & 0x00FF00FF00FF00FF) << 8)
+    x = ((x >> 16) & 0x0000FFFF0000FFFF) | ((x & 0x0000FFFF0000FFFF) << 16)
+    x = ((x >> 32) & 0xFFFFFFFF) | (x << 32)
+    return _lsr(~x, 64 - 2 * n)
+
+
+def canonical(x: torch.Tensor, n: int) -> torch.Tensor:
+    return torch.minimum(x, revcomp(x, n))
+
+
+def bin_key(kmers: torch.Tensor, k: int, nt: int, idx_type: int = 2) -> torch.Tensor:
+    """krakendb.cpp:200-215 (int64 in, int64 out)"""
+    mask = (1 << (2 * nt)) - 1
+    xor = (0 if idx_type == 1 else INDEX2_XOR_MASK) & mask
+    x = kmers.clone()
+    best = torch.full_like(x, (1 << 62))
+    for _ in range(k - nt + 1):
+        best = torch.minimum(best, canonical(x & mask, nt) ^ xor)
+        x >>= 2
+    return best
+
+
+def forward_kmers(codes: torch.Tensor, start: int, count: int, k: int) -> torch.Tensor:
+    """k-mers of windows [start, start+count) of a uint8 code tensor (first base most significant)"""
+    km = torch.zeros(count, dtype=torch.int64, device=codes.device)
+    for j in range(k):
+        km = (km << 2) | codes[start + j:start + j + count].to(torch.int64)
+    return km
+
+
+def make_taxonomy_rows(n_genomes: int, first_id: int = 100):
+    """root(1) → families → genera → species(genomes); returns (rows, species_taxids)"""
+    n_gen = max(1, n_genomes // 20)
+    n_fam = max(1, n_gen // 10)
+    rows = [(1, 1, "root", "no rank")]
+    nid = first_id
+    fam = list(range(nid, nid + n_fam)); nid += n_fam
+    gen = list(range(nid, nid + n_gen)); nid += n_gen
+    sp = list(range(nid, nid + n_genomes))
+    rows += [(f, 1, f"family{i}", "family") for i, f in enumerate(fam)]
+    rows += [(g, fam[i % n_fam], f"genus{i}", "genus") for i, g in enumerate(gen)]
+    rows += [(s, gen[i % n_gen], f"species{i}", "species") for i, s in enumerate(sp)]
+    return rows, sp
+
+
+class GpuDatabase:
+    """A synthetic database resident in HBM in the on-disk layout."""
+
+    def __init__(self, n_records: int, n_genomes: int = 2000, k: int = 31, nt: int = 15, idx_type: int = 2,
+                 seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26):
+        self.k, self.nt, self.idx_type = k, nt, idx_type
+        dev = torch.device(device)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        n_pos = n_records                       # one window per position (duplicates are removed below)
+        self.genome = torch.randint(0, 4, (n_pos + k - 1,), dtype=torch.uint8, device=dev, generator=gen)
+        self.rows, self.species = make_taxonomy_rows(n_genomes)
+        self.genome_len = (n_pos + n_genomes - 1) // n_genomes
+        sp = torch.tensor(self.species, dtype=torch.int32, device=dev)
+        keys = torch.empty(n_pos, dtype=torch.int64, device=dev)
+        bins = torch.empty(n_pos, dtype=torch.int32, device=dev)
+        for a in range(0, n_pos, chunk):
+            c = min(chunk, n_pos - a)
+            km = canonical(forward_kmers(self.genome, a, c, k), k)
+            keys[a:a + c] = km
+            bins[a:a + c] = bin_key(km, k, nt, idx_type).to(torch.int32)
+            del km
+        # sort by (bin, key): key sort, then a stable bin sort
+        keys, order = torch.sort(keys)
+        bins = bins[order]
+        taxa = sp[(order // self.genome_len).to(torch.int64)]
+        del order
+        # drop duplicate keys (same k-mer at two positions / palindromes): keep the first owner
+        keep = torch.ones(n_pos, dtype=torch.bool, device=dev)
+        keep[1:] = keys[1:] != keys[:-1]
+        if not bool(keep.all()):
+            keys, bins, taxa = keys[keep], bins[keep], taxa[keep]
+        del keep
+        bins, order = torch.sort(bins, stable=True)
+        keys = keys[order]
+        taxa = taxa[order]
+        del order
+        n = keys.numel()
+        self.key_ct = n
+        rec = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        rec[:, 0] = (keys & 0xFFFFFFFF).to(torch.int32)          # wraps to the same 32 bits
+        rec[:, 1] = (keys >> 32).to(torch.int32)
+        rec[:, 2] = taxa
+        self.records = rec                                       # (n, 3) int32 == packed 12-byte records
+        del keys, taxa
+        counts = torch.bincount(bins.to(torch.int64), minlength=1 << (2 * nt))
+        del bins
+        off = torch.zeros((1 << (2 * nt)) + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=off[1:])
+        del counts
+        self.offsets = off
+        torch.cuda.empty_cache()
+
+    # ---- host images (for the reference binary / the oracle) --------------------------------------------------
+    def kdb_header(self) -> np.ndarray:
+        from . import synth
+        return synth.kdb_header(self.k, self.key_ct)
+
+    def write_files(self, kdb_path: str, idx_path: str, chunk: int = 1 << 26):
+        with open(kdb_path, "wb") as f:
+            f.write(self.kdb_header().tobytes())
+            for a in range(0, self.key_ct, chunk):
+                f.write(self.records[a:a + chunk].cpu().numpy().tobytes())
+        with open(idx_path, "wb") as f:
+            f.write(b"KRAKIDX" if self.idx_type == 1 else b"KRAKIX2")
+            f.write(bytes([self.nt]))
+            n = self.offsets.numel()
+            for a in range(0, n, chunk):
+                f.write(self.offsets[a:a + chunk].cpu().numpy().tobytes())
+
+    def images(self):
+        kdb = np.concatenate([self.kdb_header(), self.records.cpu().numpy().view(np.uint8).reshape(-1)])
+        idx = np.concatenate([np.frombuffer(b"KRAKIDX" if self.idx_type == 1 else b"KRAKIX2", np.uint8),
+                              np.array([self.nt], np.uint8), self.offsets.cpu().numpy().view(np.uint8)])
+        return kdb, idx
+
+    def parent_map(self):
+        taxid = np.array([r[0] for r in self.rows], np.uint32)
+        parent = np.array([0 if r[1] == r[0] else r[1] for r in self.rows], np.uint32)
+        return taxid, parent
+
+    def write_taxdb(self, path):
+        with open(path, "w") as f:
+            for t, p, name, rank in self.rows:
+                f.write(f"{t}\t{p}\t{name}\t{rank}\n")
+
+    # ---- reads --------------------------------------------------------------------------------------------------
+    def sample_reads(self, n_reads: int, read_len: int = 150, seed: int = 3, random_frac: float = 0.2,
+                     sub_rate: float = 0.01, chunk: int = 1 << 20):
+        """→ (bases uint8 [n_reads*read_len + 64 slack] ASCII on the GPU, offsets int64 [n_reads+1] on the GPU)"""
+        dev = self.genome.device
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        out = torch.full((n_reads * read_len + 64,), ord("N"), dtype=torch.uint8, device=dev)
+        lut = torch.tensor([ord(c) for c in "ACGT"], dtype=torch.uint8, device=dev)
+        ar = torch.arange(read_len, device=dev)
+        max_start = self.genome.numel() - read_len
+        for a in range(0, n_reads, chunk):
+            c = min(chunk, n_reads - a)
+            start = torch.randint(0, max_start, (c,), device=dev, generator=gen)
+            codes = self.genome[(start[:, None] + ar[None, :])]
+            sub = torch.rand((c, read_len), device=dev, generator=gen) < sub_rate
+            delta = torch.randint(1, 4, (c, read_len), device=dev, generator=gen, dtype=torch.uint8)
+            codes = torch.where(sub, (codes + delta) & 3, codes)
+            rc = torch.rand((c,), device=dev, generator=gen) < 0.5
+            codes = torch.where(rc[:, None], (3 - codes).flip(1), codes)
+            rnd = torch.rand((c,), device=dev, generator=gen) < random_frac
+            noise = torch.randint(0, 4, (c, read_len), device=dev, generator=gen, dtype=torch.uint8)
+            codes = torch.where(rnd[:, None], noise, codes)
+            out[a * read_len:(a + c) * read_len] = lut[codes.to(torch.int64)].reshape(-1)
+            del codes, sub, delta, noise
+        offsets = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * read_len
+        return out, offsets
