@@ -246,7 +246,7 @@ def main():
     clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2)
     clf.set_taxonomy(*db.parent_map())
 
-    d_offsets = (torch.arange(B + 1, dtype=torch.int64, device=dev) * READ_LEN)
+    d_offsets = (torch.arange(B + 2, dtype=torch.int64, device=dev) * READ_LEN)   # +1: slices are copied in 16-byte units
     host_offsets = (np.arange(B + 1, dtype=np.uint64) * READ_LEN)
 
     def batch_ptr(i):

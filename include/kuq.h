@@ -170,7 +170,7 @@ void kuq_host_free(void *p);
 
 /* ---- classification, device buffers (inputs already in HBM) ---------------------------------------------- */
 /* d_bases must be 16-byte aligned with 32 readable bytes of slack after the last base (TMA bulk loads fetch
- * whole 16-byte blocks); d_read_offsets are relative to d_bases.  Asynchronous on the slot's stream;
+ * whole 16-byte blocks); d_read_offsets (16-byte aligned, n_reads + 2 entries readable) are relative to d_bases.  Asynchronous on the slot's stream;
  * kuq_sync_slot() waits.  d_unit_id may be NULL (units cut on the host need the offsets: pass h_read_offsets,
  * or NULL when hll_mode == KUQ_HLL_DENSE_ONLY / KUQ_HLL_CHUNKED). */
 int kuq_classify_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,

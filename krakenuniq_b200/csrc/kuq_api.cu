@@ -196,7 +196,7 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(cudaEventCreate(&s.ev_k1));
   CU(dmalloc(&s.d_bases, mb + SLACK));
   CU(dmalloc(&s.d_clean, mb + SLACK));
-  CU(dmalloc(&s.d_offsets, mr + 1));
+  CU(dmalloc(&s.d_offsets, mr + 4));   // + slack: offsets slices are bulk-copied in 16-byte units
   CU(dmalloc(&s.d_unit, mr));
   CU(dmalloc(&s.d_call, mr));
   CU(dmalloc(&s.d_nwin, mr));

@@ -193,176 +193,256 @@ __device__ void process_read(const Params &p, uint32_t r, const char *seq, uint3
   const bool counting = (MODE != MODE_LOOKUP) && !(p.flags & 4u);
 
   if (nwin > 0) {
-    Block64 A = load_block(seq, len, 0, lane, marks);
+    // The read is walked NS slots (NS*32 windows) at a time; everything below is unrolled over the NS slots so
+    // that their index fetches, bin probes and sketch loads are in flight together (the path is bound by the
+    // latency of dependent random HBM accesses, not by arithmetic).
+    constexpr int NS = 4;
     const uint32_t nslots = (nwin + 31) / 32;
-    // carry of the minimizer run that crosses the slot boundary
-    uint32_t carry_bin = 0xFFFFFFFFu, carry_n = 0;
+    Block64 blk[NS + 1];
+    blk[0] = load_block(seq, len, 0, lane, marks);
+    uint32_t carry_bin = 0xFFFFFFFFu, carry_n = 0;            // minimizer run crossing a pass boundary
     uint64_t carry_lo = 0;
-    for (uint32_t s = 0; s < nslots; s++) {
-      Block64 B = load_block(seq, len, s + 1, lane, marks);
-      const uint32_t i = s * 32 + lane;
-      bool valid = i < nwin;
-      if (marks) valid = valid && (((((uint64_t)B.mark << 32) | A.mark) >> (lane + k - 1)) & 1);
-      const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
-      const uint32_t oi = n_out + __popc(vmask & ((1u << lane) - 1));   // output slot of this window
-      n_out += __popc(vmask);
-      // ---- k-mer of window i: bases [i, i+k) of the 128-bit string A:B ------------------------------------
-      uint64_t hi = lane ? (A.codes << (2 * lane)) | (B.codes >> (64 - 2 * lane)) : A.codes;
-      uint64_t kmer = hi >> (64 - 2 * k);
-      uint64_t amb64 = ((uint64_t)B.amb << 32) | A.amb;
-      bool amb = ((amb64 >> lane) & ((1ull << k) - 1)) != 0;  // any non-ACGT base in the window, :275,280-282
-      uint32_t taxon = 0;
-      uint64_t canon = 0;
-      bool look = valid && !amb;
+    const uint32_t hi_mask = (uint32_t)(db.key_mask >> 32);
+    for (uint32_t s0 = 0; s0 < nslots; s0 += NS) {
+#pragma unroll
+      for (int j = 0; j < NS; j++) blk[j + 1] = load_block(seq, len, s0 + j + 1, lane, marks);
+
+      bool valid[NS], look[NS], amb[NS];
+      uint32_t oi[NS], taxon[NS];
+      uint64_t canon[NS];
+      uint32_t cand[NS + 1];                                  // minimizer candidate of position 32*(s0+j)+lane
+#pragma unroll
+      for (int j = 0; j < NS; j++) {
+        const uint32_t i = (s0 + j) * 32 + lane;
+        // k-mer of window i: bases [i, i+k) of the 128-bit string blk[j]:blk[j+1]
+        uint64_t hi = lane ? (blk[j].codes << (2 * lane)) | (blk[j + 1].codes >> (64 - 2 * lane)) : blk[j].codes;
+        uint64_t kmer = hi >> (64 - 2 * k);
+        uint64_t amb64 = ((uint64_t)blk[j + 1].amb << 32) | blk[j].amb;
+        amb[j] = ((amb64 >> lane) & ((1ull << k) - 1)) != 0;  // any non-ACGT base in the window, :275,280-282
+        bool v = i < nwin;
+        if (marks) v = v && (((((uint64_t)blk[j + 1].mark << 32) | blk[j].mark) >> (lane + k - 1)) & 1);
+        valid[j] = v;
+        const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, v);
+        oi[j] = n_out + __popc(vmask & ((1u << lane) - 1));   // output slot of this window
+        n_out += __popc(vmask);
+        look[j] = v && !amb[j];
+        uint64_t rc = revcomp64(kmer, k);                     // canonical k-mer (krakendb.cpp:238-246)
+        canon[j] = kmer < rc ? kmer : rc;
+        taxon[j] = 0;
+        uint32_t f = (uint32_t)(hi >> (64 - 2 * nt));
+        uint32_t rf = revcomp32(f, nt);
+        cand[j] = db.xor_mask ^ (f < rf ? f : rf);
+      }
       if (MODE == MODE_RESOLVE) {
-        if (valid) {
-          uint32_t c = p.codes_in[out_base + oi];
-          taxon = (c == AMBIG) ? 0 : c;                       // ambiguity is recomputed from the bases
-        }
-        if (look) {
-          uint64_t rc = revcomp64(kmer, k);
-          canon = kmer < rc ? kmer : rc;
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          if (valid[j]) {
+            uint32_t c = p.codes_in[out_base + oi[j]];
+            taxon[j] = (c == AMBIG) ? 0 : c;                  // ambiguity is recomputed from the bases
+          }
         }
       } else {
-        // ---- canonical k-mer (krakendb.cpp:238-246) ------------------------------------------------------
-        uint64_t rc = revcomp64(kmer, k);
-        canon = kmer < rc ? kmer : rc;
-        // ---- minimizer = min over the k-nt+1 nt-mers of (xor_mask ^ canonical(nt-mer)) (krakendb.cpp:200-215).
-        // Candidate of position q (0..63 relative to the slot): lane holds q = lane (m0) and q = 32+lane (m1).
-        uint32_t f0 = (uint32_t)(hi >> (64 - 2 * nt));
-        uint32_t r0 = revcomp32(f0, nt);
-        uint32_t m0 = db.xor_mask ^ (f0 < r0 ? f0 : r0);
-        uint32_t f1 = (uint32_t)((B.codes << (2 * lane)) >> (64 - 2 * nt));
-        uint32_t r1 = revcomp32(f1, nt);
-        uint32_t m1 = db.xor_mask ^ (f1 < r1 ? f1 : r1);
-        // sliding-window minimum of width n_mini by doubling: after the loop m0/m1 hold min over [q, q+w)
+        {
+          uint32_t f = (uint32_t)((blk[NS].codes << (2 * lane)) >> (64 - 2 * nt));
+          uint32_t rf = revcomp32(f, nt);
+          cand[NS] = db.xor_mask ^ (f < rf ? f : rf);
+        }
+        // ---- minimizer = min over the k-nt+1 nt-mers of (xor_mask ^ canonical(nt-mer)) (krakendb.cpp:200-215):
+        //      sliding-window minimum of width n_mini over the candidates, by doubling --------------------------
         uint32_t w = 1;
         while (2 * w <= db.n_mini) {
-          uint32_t src = (lane + w) & 31;
-          uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
-          bool wrap = lane + w >= 32;
-          uint32_t a0 = wrap ? x1 : x0;
-          uint32_t a1 = wrap ? 0xFFFFFFFFu : x1;
-          m0 = min(m0, a0);
-          m1 = min(m1, a1);
+          const uint32_t src = (lane + w) & 31;
+          const bool wrap = lane + w >= 32;
+          uint32_t x[NS + 1];
+#pragma unroll
+          for (int j = 0; j <= NS; j++) x[j] = __shfl_sync(0xFFFFFFFFu, cand[j], src);
+#pragma unroll
+          for (int j = 0; j < NS; j++) cand[j] = min(cand[j], wrap ? x[j + 1] : x[j]);
+          cand[NS] = min(cand[NS], wrap ? 0xFFFFFFFFu : x[NS]);
           w *= 2;
         }
-        if (w < db.n_mini) {                                  // [q, q+n_mini) = [q, q+w) ∪ [q+n_mini-w, q+n_mini)
-          uint32_t d = db.n_mini - w;
-          uint32_t src = (lane + d) & 31;
-          uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
-          m0 = min(m0, lane + d >= 32 ? x1 : x0);
+        if (w < db.n_mini) {                                  // [q, q+n_mini) = [q, q+w) U [q+n_mini-w, q+n_mini)
+          const uint32_t d = db.n_mini - w;
+          const uint32_t src = (lane + d) & 31;
+          const bool wrap = lane + d >= 32;
+          uint32_t x[NS + 1];
+#pragma unroll
+          for (int j = 0; j <= NS; j++) x[j] = __shfl_sync(0xFFFFFFFFu, cand[j], src);
+#pragma unroll
+          for (int j = 0; j < NS; j++) cand[j] = min(cand[j], wrap ? x[j + 1] : x[j]);
         }
-        const uint32_t bin = m0;
+        // cand[j] is now the bin of window (s0+j)*32+lane
+
         // ---- index fetch, once per run of equal minimizers (the reference caches the range the same way,
-        //      krakendb.cpp:261-277) ----------------------------------------------------------------------
-        uint32_t prev_bin = __shfl_up_sync(0xFFFFFFFFu, bin, 1);
-        bool prev_look = __shfl_up_sync(0xFFFFFFFFu, (int)look, 1);
-        if (lane == 0) { prev_bin = carry_bin; prev_look = carry_bin != 0xFFFFFFFFu; }
-        bool head = look && !(prev_look && prev_bin == bin);
-        uint64_t lo = 0;
-        uint32_t n = 0;
-        if (head && !(lane == 0 && carry_bin == bin)) {
-          if (bin >= db.bin_lo && bin < db.bin_hi) {
-            const uint64_t *o = db.offsets + (bin - db.bin_lo);
-            uint64_t o0 = __ldg(o), o1 = __ldg(o + 1);        // KrakenDBIndex::at, krakendb.cpp:586-593
-            lo = o0 - db.rec_base;
-            n = (uint32_t)(o1 - o0);
+        //      krakendb.cpp:261-277).  All heads of the pass load before anyone consumes. -------------------
+        bool head[NS];
+        uint64_t lo[NS];
+        uint32_t n[NS];
+        uint32_t pbin = carry_bin;                            // bin of the window just before this slot's lane 0
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, cand[j], 1);
+          uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)look[j], 1);
+          if (lane == 0) { pb = pbin; pl = pbin != 0xFFFFFFFFu; }
+          head[j] = look[j] && !(pl && pb == cand[j]);
+          uint32_t lb = __shfl_sync(0xFFFFFFFFu, cand[j], 31);
+          uint32_t ll = __shfl_sync(0xFFFFFFFFu, (uint32_t)look[j], 31);
+          pbin = ll ? lb : 0xFFFFFFFFu;
+          lo[j] = 0;
+          n[j] = 0;
+        }
+        uint64_t o0[NS], o1[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          o0[j] = o1[j] = 0;
+          if (head[j] && cand[j] >= db.bin_lo && cand[j] < db.bin_hi) {
+            const uint64_t *o = db.offsets + (cand[j] - db.bin_lo);
+            o0[j] = __ldg(o);                                 // KrakenDBIndex::at, krakendb.cpp:586-593
+            o1[j] = __ldg(o + 1);
           }
         }
-        uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
-        uint32_t below = heads & (0xFFFFFFFFu >> (31 - lane));
-        int hl = below ? 31 - __clz(below) : -1;               // lane of my run's head (-1: run started earlier)
-        uint64_t hlo = __shfl_sync(0xFFFFFFFFu, lo, hl < 0 ? 0 : hl);
-        uint32_t hn = __shfl_sync(0xFFFFFFFFu, n, hl < 0 ? 0 : hl);
-        if (look) {
-          if (hl < 0) { lo = carry_lo; n = carry_n; } else { lo = hlo; n = hn; }
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          uint64_t l = o0[j] - db.rec_base;
+          uint32_t c = (uint32_t)(o1[j] - o0[j]);
+          const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head[j]);
+          const uint32_t below = heads & (0xFFFFFFFFu >> (31 - lane));
+          const int hl = below ? 31 - __clz(below) : 0;
+          uint64_t hlo = __shfl_sync(0xFFFFFFFFu, l, hl);
+          uint32_t hn = __shfl_sync(0xFFFFFFFFu, c, hl);
+          if (!below) { hlo = carry_lo; hn = carry_n; }       // the run started in an earlier slot
+          lo[j] = hlo;
+          n[j] = look[j] ? hn : 0;
+          carry_lo = __shfl_sync(0xFFFFFFFFu, hlo, 31);
+          carry_n = __shfl_sync(0xFFFFFFFFu, hn, 31);
         }
-        // carry the last looked-up window's range into the next slot
-        uint32_t looks = __ballot_sync(0xFFFFFFFFu, look);
-        if (looks) {
-          int last = 31 - __clz(looks);
-          carry_bin = __shfl_sync(0xFFFFFFFFu, bin, last);
-          carry_lo = __shfl_sync(0xFFFFFFFFu, lo, last);
-          carry_n = __shfl_sync(0xFFFFFFFFu, n, last);
-          if (last != 31) carry_bin = 0xFFFFFFFFu;            // the run is broken by an ambiguous/invalid window
-        } else {
-          carry_bin = 0xFFFFFFFFu;
-        }
+        carry_bin = pbin;
         if (p.flags & 8u) {   // measurement aid: algorithmic probe count of SURVEY.md §8(d)
-          uint32_t probes = (look && n) ? 32 - __clz(n) : 0;
-          uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, probes);
-          uint32_t nl = __popc(__ballot_sync(0xFFFFFFFFu, look));
-          if (lane == 0) { atomicAdd(p.stats, (unsigned long long)nl); atomicAdd(p.stats + 1, (unsigned long long)tot); }
+          uint32_t probes = 0, nl = 0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) { probes += (look[j] && n[j]) ? 32 - __clz(n[j]) : 0; nl += look[j]; }
+          probes = __reduce_add_sync(0xFFFFFFFFu, probes);
+          nl = __reduce_add_sync(0xFFFFFFFFu, nl);
+          if (lane == 0) { atomicAdd(p.stats, (unsigned long long)nl); atomicAdd(p.stats + 1, (unsigned long long)probes); }
         }
-        // ---- bin search (kmer_query, krakendb.cpp:280-299): bisection to a small window, then a scan ------
-        if (look && n > 0) {
-          while (n > (uint32_t)SEARCH_WINDOW) {
-            uint32_t h = n >> 1;
-            uint64_t key = load_key(db.pairs, lo + h, db.key_mask);
-            if (key <= canon) { lo += h; n -= h; } else { n = h; }
+        // ---- bin search (kmer_query, krakendb.cpp:280-299): 4-ary narrowing rounds, then a scan of <= 8 records.
+        //      The three pivots of a round are independent loads; the NS slots run their rounds together. -------
+        for (;;) {
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < NS; j++) any |= n[j] > (uint32_t)SEARCH_WINDOW;
+          if (!__any_sync(0xFFFFFFFFu, any)) break;
+          uint64_t k1[NS], k2[NS], k3[NS];
+#pragma unroll
+          for (int j = 0; j < NS; j++) {
+            if (n[j] > (uint32_t)SEARCH_WINDOW) {
+              const uint32_t q = n[j] >> 2;
+              k1[j] = load_key(db.pairs, lo[j] + q, db.key_mask);
+              k2[j] = load_key(db.pairs, lo[j] + 2 * q, db.key_mask);
+              k3[j] = load_key(db.pairs, lo[j] + 3 * q, db.key_mask);
+            }
           }
-          uint64_t keys[SEARCH_WINDOW];
 #pragma unroll
-          for (int j = 0; j < SEARCH_WINDOW; j++) keys[j] = load_key(db.pairs, lo + min((uint32_t)j, n - 1), db.key_mask);
-          int hit = -1;
-#pragma unroll
-          for (int j = 0; j < SEARCH_WINDOW; j++)
-            if ((uint32_t)j < n && keys[j] == canon) hit = j;
-          if (hit >= 0) taxon = load_val(db.pairs, lo + hit);  // value = dense id (rewritten at staging)
-        }
-      }
-
-      // ---- per-window code ----------------------------------------------------------------------------------
-      uint32_t code = amb ? AMBIG : taxon;
-      if (MODE == MODE_LOOKUP) {
-        // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
-        // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
-        if (valid && (!p.only_hits || (taxon != 0))) p.codes[out_base + oi] = code;
-      } else {
-        uint32_t raw = (look && taxon) ? __ldg(p.tax.raw + taxon) : 0;
-        uint32_t out_code = amb ? AMBIG : raw;
-        if (valid) p.codes[out_base + oi] = out_code;
-        // runs of the hit list (classify.cpp:826-861); cleaned reads count theirs after the loop
-        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
-        if (lane == 0) prev = carry_code;
-        bool brk = valid && (i == 0 || out_code != prev);
-        n_runs += __popc(__ballot_sync(0xFFFFFFFFu, brk));
-        carry_code = __shfl_sync(0xFFFFFFFFu, out_code, 31);
-
-        // ---- add_kmer: HLL insert into the sketch of `taxon` (0 for misses), classify.cpp:939 -------------
-        if (counting && look) {
-          uint64_t h = fmix64(canon);
-          hll_update(p.regs, taxon, h);
-          if (p.hll_mode != 2u && !p.dense_flag[taxon]) {
-            uint32_t enc = encode_hash32(h);
-            if (sparse_insert(p.sparse, taxon, enc)) {
-              atomicAdd(p.sparse.n_used, 1ull);
-              atomicAdd(p.sparse.distinct + taxon, 1u);
+          for (int j = 0; j < NS; j++) {
+            if (n[j] > (uint32_t)SEARCH_WINDOW) {
+              const uint32_t q = n[j] >> 2;
+              const uint64_t c = canon[j];
+              if (c >= k3[j]) { lo[j] += 3 * q; n[j] -= 3 * q; }
+              else if (c >= k2[j]) { lo[j] += 2 * q; n[j] = q; }
+              else if (c >= k1[j]) { lo[j] += q; n[j] = q; }
+              else { n[j] = q; }
             }
           }
         }
-        // ---- hit_counts[taxon]++ (classify.cpp:941-942), aggregated per distinct taxon of the slot ---------
-        n_miss += __popc(__ballot_sync(0xFFFFFFFFu, look && taxon == 0));
-        uint32_t rem = __ballot_sync(0xFFFFFFFFu, look && taxon != 0);
-        while (rem) {
-          int ldr = __ffs(rem) - 1;
-          uint32_t t = __shfl_sync(0xFFFFFFFFu, taxon, ldr);
-          uint32_t same = __ballot_sync(0xFFFFFFFFu, look && taxon == t) & rem;
-          uint32_t cnt = __popc(same);
-          rem &= ~same;
-          uint32_t pos = __ballot_sync(0xFFFFFFFFu, lane < n_hits && my_t == t);
-          if (pos) {
-            if (lane == (uint32_t)(__ffs(pos) - 1)) my_c += cnt;
-          } else if (n_hits < 32) {
-            if (lane == n_hits) { my_t = t; my_c = cnt; }
-            n_hits++;
-          } else {
-            overflow = true;
+        // scan: compare the low key words of the window first, confirm the (rare) matches on the high word
+        uint32_t lw[NS][SEARCH_WINDOW];
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          const uint32_t *b = reinterpret_cast<const uint32_t *>(db.pairs + lo[j] * 12);
+#pragma unroll
+          for (int t = 0; t < SEARCH_WINDOW; t++) lw[j][t] = ((uint32_t)t < n[j]) ? __ldg(b + 3 * t) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          const uint32_t clo = (uint32_t)canon[j], chi = (uint32_t)(canon[j] >> 32);
+          uint32_t m = 0;
+#pragma unroll
+          for (int t = 0; t < SEARCH_WINDOW; t++) m |= ((uint32_t)t < n[j] && lw[j][t] == clo) ? (1u << t) : 0u;
+          while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t *b = reinterpret_cast<const uint32_t *>(db.pairs + (lo[j] + t) * 12);
+            if ((__ldg(b + 1) & hi_mask) == chi) { taxon[j] = __ldg(b + 2); m = 0; }   // value = dense id
           }
         }
       }
-      A = B;
+
+      // ---- per-window code, sketches, hit aggregation --------------------------------------------------------
+#pragma unroll
+      for (int j = 0; j < NS; j++) {
+        const uint32_t i = (s0 + j) * 32 + lane;
+        const uint32_t code = amb[j] ? AMBIG : taxon[j];
+        if (MODE == MODE_LOOKUP) {
+          // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
+          // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
+          if (valid[j] && (!p.only_hits || (taxon[j] != 0))) p.codes[out_base + oi[j]] = code;
+        } else {
+          const uint32_t raw = (look[j] && taxon[j]) ? __ldg(p.tax.raw + taxon[j]) : 0;
+          const uint32_t out_code = amb[j] ? AMBIG : raw;
+          if (valid[j]) p.codes[out_base + oi[j]] = out_code;
+          // runs of the hit list (classify.cpp:826-861); cleaned reads count theirs after the loop
+          uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
+          if (lane == 0) prev = carry_code;
+          const bool brk = valid[j] && (i == 0 || out_code != prev);
+          n_runs += __popc(__ballot_sync(0xFFFFFFFFu, brk));
+          carry_code = __shfl_sync(0xFFFFFFFFu, out_code, 31);
+        }
+      }
+      if (MODE != MODE_LOOKUP) {
+        // ---- add_kmer: HLL insert into the sketch of `taxon` (0 for misses), classify.cpp:939 -----------------
+        if (counting) {
+          uint64_t h[NS];
+#pragma unroll
+          for (int j = 0; j < NS; j++) h[j] = fmix64(canon[j]);
+#pragma unroll
+          for (int j = 0; j < NS; j++)
+            if (look[j]) hll_update(p.regs, taxon[j], h[j]);
+          if (p.hll_mode != 2u) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+              if (look[j] && !p.dense_flag[taxon[j]]) {
+                if (sparse_insert(p.sparse, taxon[j], encode_hash32(h[j]))) {
+                  atomicAdd(p.sparse.n_used, 1ull);
+                  atomicAdd(p.sparse.distinct + taxon[j], 1u);
+                }
+              }
+            }
+          }
+        }
+        // ---- hit_counts[taxon]++ (classify.cpp:941-942), aggregated per distinct taxon of the slot -------------
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          n_miss += __popc(__ballot_sync(0xFFFFFFFFu, look[j] && taxon[j] == 0));
+          uint32_t rem = __ballot_sync(0xFFFFFFFFu, look[j] && taxon[j] != 0);
+          while (rem) {
+            const int ldr = __ffs(rem) - 1;
+            const uint32_t t = __shfl_sync(0xFFFFFFFFu, taxon[j], ldr);
+            const uint32_t same = __ballot_sync(0xFFFFFFFFu, look[j] && taxon[j] == t) & rem;
+            const uint32_t cnt = __popc(same);
+            rem &= ~same;
+            const uint32_t pos = __ballot_sync(0xFFFFFFFFu, lane < n_hits && my_t == t);
+            if (pos) {
+              if (lane == (uint32_t)(__ffs(pos) - 1)) my_c += cnt;
+            } else if (n_hits < 32) {
+              if (lane == n_hits) { my_t = t; my_c = cnt; }
+              n_hits++;
+            } else {
+              overflow = true;
+            }
+          }
+        }
+      }
+      blk[0] = blk[NS];
     }
   }
 
@@ -513,10 +593,12 @@ __device__ uint32_t clean_read(const char *seq, uint32_t len, char *dst, uint32_
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------------
 struct __align__(16) SharedState {
+  uint64_t off[N_STAGES][CHUNK_READS + 2];   // read offsets of the chunk (bulk-copied with the bases)
   uint64_t bar[N_STAGES];
+  uint64_t a0[N_STAGES];                     // global byte offset the stage's text starts at
   uint32_t chunk[N_STAGES];
   uint32_t staged[N_STAGES];
-  uint64_t a0[N_STAGES];       // global byte offset the stage starts at
+  uint32_t next_read[N_STAGES];              // warps take the reads of a chunk from this counter
 };
 
 template <int MODE>
@@ -524,21 +606,27 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_consta
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *stage_buf = smem;                                                   // N_STAGES x STAGE_BYTES
   SharedState *ss = reinterpret_cast<SharedState *>(smem + N_STAGES * STAGE_BYTES);
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
 
-  auto fetch = [&](uint32_t st) {   // thread 0: claim the next chunk and start its bulk copy
+  // thread 0: claim the next chunk and start the bulk copies of its offsets slice and of its read text
+  auto fetch = [&](uint32_t st) {
     uint32_t c = atomicAdd(p.chunk_counter, 1u);
     ss->chunk[st] = c;
     ss->staged[st] = 0;
+    ss->next_read[st] = 0;
     if (c < p.n_chunks) {
-      uint32_t r0 = c * CHUNK_READS, r1 = min(r0 + CHUNK_READS, p.n_reads);
-      uint64_t b0 = p.offsets[r0], b1 = p.offsets[r1];
-      uint64_t a0 = b0 & ~15ull, a1 = (b1 + 15) & ~15ull;
+      const uint32_t r0 = c * CHUNK_READS, r1 = min(r0 + CHUNK_READS, p.n_reads);
+      const uint32_t n_off = (r1 - r0 + 2) & ~1u;                  // even count → multiple of 16 bytes
+      const uint64_t b0 = p.offsets[r0], b1 = p.offsets[r1];
+      const uint64_t a0 = b0 & ~15ull, a1 = (b1 + 15) & ~15ull;
       ss->a0[st] = a0;
-      if (a1 - a0 <= (uint64_t)STAGE_BYTES && a1 > a0) {
-        uint32_t bytes = (uint32_t)(a1 - a0);
-        mbar_expect_tx(&ss->bar[st], bytes);
-        tma_load_1d(stage_buf + st * STAGE_BYTES, p.bases + a0, bytes, &ss->bar[st]);
+      uint32_t bytes = n_off * 8;
+      const bool text = a1 - a0 <= (uint64_t)STAGE_BYTES && a1 > a0;
+      if (text) bytes += (uint32_t)(a1 - a0);
+      mbar_expect_tx(&ss->bar[st], bytes);
+      tma_load_1d(&ss->off[st][0], p.offsets + r0, n_off * 8, &ss->bar[st]);
+      if (text) {
+        tma_load_1d(stage_buf + st * STAGE_BYTES, p.bases + a0, (uint32_t)(a1 - a0), &ss->bar[st]);
         ss->staged[st] = 1;
       }
     }
@@ -558,13 +646,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_consta
     if (tid == 0) fetch(st ^ 1);        // the other stage was released by the barrier that ended the last round
     const bool staged = ss->staged[st] != 0;
     const uint64_t a0 = ss->a0[st];
-    if (staged) {
-      mbar_wait(&ss->bar[st], phase[st]);
-      phase[st] ^= 1;
-    }
+    mbar_wait(&ss->bar[st], phase[st]);
+    phase[st] ^= 1;
     const uint32_t r0 = c * CHUNK_READS, r1 = min(r0 + CHUNK_READS, p.n_reads);
-    for (uint32_t r = r0 + warp; r < r1; r += CTA_WARPS) {
-      const uint64_t b0 = p.offsets[r], b1 = p.offsets[r + 1];
+    for (;;) {
+      uint32_t q = 0;
+      if (lane == 0) q = atomicAdd(&ss->next_read[st], 1u);
+      q = __shfl_sync(0xFFFFFFFFu, q, 0);
+      const uint32_t r = r0 + q;
+      if (r >= r1) break;
+      const uint64_t b0 = ss->off[st][q], b1 = ss->off[st][q + 1];
       uint32_t len = (uint32_t)(b1 - b0);
       const char *seq = staged ? reinterpret_cast<const char *>(stage_buf + st * STAGE_BYTES + (b0 - a0))
                                : p.bases + b0;
