@@ -71,7 +71,7 @@ typedef struct kuq_config {
   int32_t device;                /* CUDA device ordinal */
   uint32_t n_slots;              /* batch slots (streams) for copy/compute overlap; 0 → 2 */
   uint32_t max_reads_per_batch;  /* slot capacity in reads; 0 → 1<<20 */
-  uint64_t max_bases_per_batch;  /* slot capacity in bases (bytes of sequence); 0 → 192 MiB */
+  uint64_t max_bases_per_batch;  /* slot capacity in bases (bytes of sequence); 0 → 160 MiB */
   uint64_t work_unit_size;       /* classify -u (classify.cpp:38,1106); 0 → 500000 */
   uint32_t hll_mode;             /* KUQ_HLL_* */
   uint32_t reserved0;
@@ -106,7 +106,7 @@ typedef struct kuq_batch_result {
 typedef struct kuq_device_result {
   const uint32_t *d_call;      /* [n_reads] raw taxids */
   const uint32_t *d_n_windows; /* [n_reads] */
-  const uint32_t *d_codes;     /* per window, indexed like the bases; raw taxids / KUQ_CODE_AMBIG */
+  const uint32_t *d_codes;     /* per window, indexed like the bases; taxids / KUQ_CODE_AMBIG (KUQ_F_WANT_CODES) */
   const uint32_t *d_run_start;
   const uint32_t *d_run_count;
   const kuq_run *d_runs;
@@ -195,8 +195,11 @@ int kuq_slot_stats(kuq_ctx *ctx, uint32_t slot, uint64_t *n_lookups, uint64_t *s
 void *kuq_slot_stream(kuq_ctx *ctx, uint32_t slot);
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
 uint64_t kuq_launch_count(const kuq_ctx *ctx);
-/* Device time in ms of the most recent batch's dominant (classification) kernel on `slot`. */
+/* Device time in ms of the most recent batch's kernels on `slot` (all stages). */
 double kuq_last_kernel_ms(kuq_ctx *ctx, uint32_t slot);
+/* Device time in ms of the three stages of the slot's last batch: ms3[0] k_scan (k-mers + minimizers),
+ * ms3[1] k_lookup (index + bin search + HLL), ms3[2] k_resolve (hit lists, tree resolution, counters). */
+int kuq_last_stage_ms(kuq_ctx *ctx, uint32_t slot, double *ms3);
 
 /* ---- per-taxon results --------------------------------------------------------------------------------- */
 /* End of input: closes the open work unit (the flush the reference performs when the reader runs dry). */

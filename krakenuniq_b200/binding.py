@@ -102,6 +102,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_slot_stats": (C.c_int, [vp, C.c_uint32, u64p, u64p]),
         "kuq_launch_count": (C.c_uint64, [vp]),
         "kuq_last_kernel_ms": (C.c_double, [vp, C.c_uint32]),
+        "kuq_last_stage_ms": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_double)]),
         "kuq_finish": (C.c_int, [vp]),
         "kuq_counts_size": (C.c_int, [vp, u32p]),
         "kuq_read_counts": (C.c_int, [vp, u32p, u64p, u64p, u64p, u8p, C.c_uint32]),
@@ -270,6 +271,11 @@ class Classifier:
 
     def last_kernel_ms(self, slot):
         return float(self.L.kuq_last_kernel_ms(self.h, slot))
+
+    def last_stage_ms(self, slot):
+        a = (C.c_double * 3)()
+        self._ck(self.L.kuq_last_stage_ms(self.h, slot, a))
+        return [a[0], a[1], a[2]]
 
     # ---- results ---------------------------------------------------------------------------------------------
     def finish(self):

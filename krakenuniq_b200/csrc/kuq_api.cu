@@ -27,11 +27,14 @@ constexpr uint32_t SLACK = 64;                                // bytes readable 
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_stage[2] = {nullptr, nullptr};
+  double stage_ms[3] = {0, 0, 0};
   // device
   char *d_bases = nullptr, *d_clean = nullptr;
   uint64_t *d_offsets = nullptr;
   uint32_t *d_unit = nullptr, *d_call = nullptr, *d_nwin = nullptr, *d_codes = nullptr;
+  uint64_t *d_canon = nullptr;                 // scratch between the stages
+  uint32_t *d_bins = nullptr, *d_dense = nullptr;
   uint32_t *d_run_start = nullptr, *d_run_count = nullptr;
   uint2 *d_runs = nullptr;
   unsigned long long *d_scalars = nullptr;   // [0] run cursor, [1] n_classified, [2] chunk counter(u32) [3] error(u32)
@@ -128,11 +131,13 @@ cudaError_t hmalloc(T **p, uint64_t n) { return cudaMallocHost((void **)p, n * s
 void free_slot(Slot &s) {
   cudaFree(s.d_bases); cudaFree(s.d_clean); cudaFree(s.d_offsets); cudaFree(s.d_unit); cudaFree(s.d_call);
   cudaFree(s.d_nwin); cudaFree(s.d_codes); cudaFree(s.d_run_start); cudaFree(s.d_run_count); cudaFree(s.d_runs);
-  cudaFree(s.d_scalars);
+  cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense);
   cudaFreeHost(s.h_call); cudaFreeHost(s.h_nwin); cudaFreeHost(s.h_run_start); cudaFreeHost(s.h_run_count);
   cudaFreeHost(s.h_codes); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_scalars); cudaFreeHost(s.h_unit);
   if (s.ev_k0) cudaEventDestroy(s.ev_k0);
   if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+  if (s.ev_stage[0]) cudaEventDestroy(s.ev_stage[0]);
+  if (s.ev_stage[1]) cudaEventDestroy(s.ev_stage[1]);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
 }
@@ -194,6 +199,8 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&s.ev_k0));
   CU(cudaEventCreate(&s.ev_k1));
+  CU(cudaEventCreate(&s.ev_stage[0]));
+  CU(cudaEventCreate(&s.ev_stage[1]));
   CU(dmalloc(&s.d_bases, mb + SLACK));
   CU(dmalloc(&s.d_clean, mb + SLACK));
   CU(dmalloc(&s.d_offsets, mr + 4));   // + slack: offsets slices are bulk-copied in 16-byte units
@@ -201,9 +208,13 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(dmalloc(&s.d_call, mr));
   CU(dmalloc(&s.d_nwin, mr));
   CU(dmalloc(&s.d_codes, mb + SLACK));
+  CU(dmalloc(&s.d_canon, mb + SLACK));
+  CU(dmalloc(&s.d_bins, mb + SLACK));
+  CU(dmalloc(&s.d_dense, mb + SLACK));
   CU(dmalloc(&s.d_run_start, mr));
   CU(dmalloc(&s.d_run_count, mr));
-  CU(dmalloc(&s.d_runs, mb + SLACK));
+  // every resolving warp may leave one partly used block of 256 run slots behind (k_resolve)
+  CU(dmalloc(&s.d_runs, mb + SLACK + 256ull * (uint64_t)ctx->n_sm * 64));
   CU(dmalloc(&s.d_scalars, 8));
   CU(hmalloc(&s.h_call, mr));
   CU(hmalloc(&s.h_nwin, mr));
@@ -423,6 +434,10 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.call = s.d_call;
   p.n_windows = s.d_nwin;
   p.codes = s.d_codes;
+  p.total_bases = s.total_bases;
+  p.canon = s.d_canon;
+  p.bins = s.d_bins;
+  p.codes_dense = s.d_dense;
   p.run_start = s.d_run_start;
   p.run_count = s.d_run_count;
   p.runs = s.d_runs;
@@ -441,19 +456,12 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.sparse.distinct = ctx->d_sparse_distinct;
 }
 
-int grid_for(kuq_ctx *ctx, uint32_t n_chunks) {
-  int g = ctx->n_sm * 2;     // 2 resident CTAs per SM (launch bounds), persistent
-  if ((uint32_t)g > n_chunks) g = (int)std::max(1u, n_chunks);
-  return g;
-}
-
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   CU(cudaMemsetAsync(s.d_scalars, 0, 8 * 8, s.stream));
   CU(cudaEventRecord(s.ev_k0, s.stream));
-  if (p.n_reads) {
-    launch_classify(mode, p, grid_for(ctx, p.n_chunks), s.stream);
-    ctx->launches++;
-  }
+  CU(cudaEventRecord(s.ev_stage[0], s.stream));
+  CU(cudaEventRecord(s.ev_stage[1], s.stream));
+  if (p.n_reads) ctx->launches += launch_classify(mode, p, ctx->n_sm, s.stream, s.ev_stage);
   CU(cudaEventRecord(s.ev_k1, s.stream));
   CU(cudaGetLastError());
   return KUQ_OK;
@@ -491,7 +499,7 @@ void kuq_config_default(kuq_config *cfg) {
   cfg->device = 0;
   cfg->n_slots = 2;
   cfg->max_reads_per_batch = 1u << 20;
-  cfg->max_bases_per_batch = 192ull << 20;
+  cfg->max_bases_per_batch = 160ull << 20;
   cfg->work_unit_size = 500000;           // DEF_WORK_UNIT_SIZE, classify.cpp:38
   cfg->hll_mode = KUQ_HLL_PRELOAD;
   cfg->sparse_set_slots = 1ull << 26;
@@ -797,7 +805,7 @@ static int device_call(kuq_ctx *ctx, uint32_t slot, int mode, const char *d_base
   s.n_reads = n_reads; s.flags = flags; s.total_bases = total_bases; s.external = true;
   Params p;
   fill_params(ctx, s, p, d_bases, d_offsets, d_unit, n_reads, flags);
-  if (mode == MODE_LOOKUP) { p.codes = d_codes_out; p.only_hits = only_hits; }
+  if (mode == MODE_LOOKUP) { p.codes_dense = d_codes_out; p.only_hits = only_hits; }
   if (mode == MODE_RESOLVE) p.codes_in = d_codes_in;
   return launch_on_slot(ctx, s, mode, p);
 }
@@ -866,6 +874,19 @@ uint64_t kuq_launch_count(const kuq_ctx *ctx) { return ctx ? ctx->launches : 0; 
 double kuq_last_kernel_ms(kuq_ctx *ctx, uint32_t slot) {
   if (!ctx || slot >= ctx->slots.size()) return -1;
   return ctx->slots[slot].kernel_ms;
+}
+int kuq_last_stage_ms(kuq_ctx *ctx, uint32_t slot, double *ms3) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!ms3) return KUQ_E_INVALID_ARG;
+  Slot &s = ctx->slots[slot];
+  CU(cudaStreamSynchronize(s.stream));
+  float a = 0, b = 0, c = 0;
+  cudaEventElapsedTime(&a, s.ev_k0, s.ev_stage[0]);
+  cudaEventElapsedTime(&b, s.ev_stage[0], s.ev_stage[1]);
+  cudaEventElapsedTime(&c, s.ev_stage[1], s.ev_k1);
+  ms3[0] = a; ms3[1] = b; ms3[2] = c;
+  return KUQ_OK;
 }
 
 // ---- per-taxon results ------------------------------------------------------------------------------------------

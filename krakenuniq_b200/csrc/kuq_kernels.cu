@@ -1,4 +1,7 @@
 // kuq_kernels.cu — see kuq_kernels.cuh for the map from kernel stages to reference functions.
+// Design history: round 1 first fused all stages into one persistent warp-per-read kernel; at 128 registers it ran
+// at 25 % occupancy and was bound by exposed latency (profiles/README.md), so the path is now three kernels that
+// each keep a small register footprint and hand windows over through HBM scratch (12 B per window, streamed).
 #include "kuq_kernels.cuh"
 
 namespace kuq {
@@ -177,376 +180,71 @@ __device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uin
   return b;
 }
 
-template <int MODE>
-__device__ void process_read(const Params &p, uint32_t r, const char *seq, uint32_t len, uint64_t out_base,
-                             uint32_t lane, bool marks) {
+constexpr uint32_t BIN_NONE = 0xFFFFFFFFu;    // scratch marker: no window at this position
+constexpr uint32_t BIN_AMBIG = 0xFFFFFFFEu;   // scratch marker: window with a non-ACGT base
+
+// Stage 1 for one read (one warp, one slot of 32 windows at a time): canonical k-mer and minimizer bin of every
+// window → scratch.  Pure ALU + shuffles, no dependent memory access.
+__device__ void scan_read(const Params &p, uint32_t r, const char *seq, uint32_t len, uint32_t raw_len,
+                          uint64_t out_base, uint32_t lane, bool marks) {
   const DbView &db = p.db;
   const uint32_t k = db.k, nt = db.nt;
   // candidate windows; every one of them is a scanner window unless the read was cleaned (marks), in which case
   // only the marked ones are (the scanner drops a window per skipped character, see clean_read)
   const uint32_t nwin = len >= k ? len - k + 1 : 0;           // classify.cpp:913-914
   uint32_t n_out = 0;                                         // windows emitted so far
-  uint32_t my_t = 0, my_c = 0;                                // hit list: lane j holds entry j (dense id, count)
-  uint32_t n_hits = 0, n_miss = 0, n_runs = 0;
-  uint32_t carry_code = 0;                                    // code of the previous slot's last window
-  bool overflow = false;
-  const bool counting = (MODE != MODE_LOOKUP) && !(p.flags & 4u);
-
   if (nwin > 0) {
-    // The read is walked NS slots (NS*32 windows) at a time; everything below is unrolled over the NS slots so
-    // that their index fetches, bin probes and sketch loads are in flight together (the path is bound by the
-    // latency of dependent random HBM accesses, not by arithmetic).
-    constexpr int NS = 4;
+    Block64 A = load_block(seq, len, 0, lane, marks);
     const uint32_t nslots = (nwin + 31) / 32;
-    Block64 blk[NS + 1];
-    blk[0] = load_block(seq, len, 0, lane, marks);
-    uint32_t carry_bin = 0xFFFFFFFFu, carry_n = 0;            // minimizer run crossing a pass boundary
-    uint64_t carry_lo = 0;
-    const uint32_t hi_mask = (uint32_t)(db.key_mask >> 32);
-    for (uint32_t s0 = 0; s0 < nslots; s0 += NS) {
-#pragma unroll
-      for (int j = 0; j < NS; j++) blk[j + 1] = load_block(seq, len, s0 + j + 1, lane, marks);
-
-      bool valid[NS], look[NS], amb[NS];
-      uint32_t oi[NS], taxon[NS];
-      uint64_t canon[NS];
-      uint32_t cand[NS + 1];                                  // minimizer candidate of position 32*(s0+j)+lane
-#pragma unroll
-      for (int j = 0; j < NS; j++) {
-        const uint32_t i = (s0 + j) * 32 + lane;
-        // k-mer of window i: bases [i, i+k) of the 128-bit string blk[j]:blk[j+1]
-        uint64_t hi = lane ? (blk[j].codes << (2 * lane)) | (blk[j + 1].codes >> (64 - 2 * lane)) : blk[j].codes;
-        uint64_t kmer = hi >> (64 - 2 * k);
-        uint64_t amb64 = ((uint64_t)blk[j + 1].amb << 32) | blk[j].amb;
-        amb[j] = ((amb64 >> lane) & ((1ull << k) - 1)) != 0;  // any non-ACGT base in the window, :275,280-282
-        bool v = i < nwin;
-        if (marks) v = v && (((((uint64_t)blk[j + 1].mark << 32) | blk[j].mark) >> (lane + k - 1)) & 1);
-        valid[j] = v;
-        const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, v);
-        oi[j] = n_out + __popc(vmask & ((1u << lane) - 1));   // output slot of this window
-        n_out += __popc(vmask);
-        look[j] = v && !amb[j];
-        uint64_t rc = revcomp64(kmer, k);                     // canonical k-mer (krakendb.cpp:238-246)
-        canon[j] = kmer < rc ? kmer : rc;
-        taxon[j] = 0;
-        uint32_t f = (uint32_t)(hi >> (64 - 2 * nt));
-        uint32_t rf = revcomp32(f, nt);
-        cand[j] = db.xor_mask ^ (f < rf ? f : rf);
+    for (uint32_t s = 0; s < nslots; s++) {
+      Block64 B = load_block(seq, len, s + 1, lane, marks);
+      const uint32_t i = s * 32 + lane;
+      bool valid = i < nwin;
+      if (marks) valid = valid && (((((uint64_t)B.mark << 32) | A.mark) >> (lane + k - 1)) & 1);
+      const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+      const uint32_t oi = n_out + __popc(vmask & ((1u << lane) - 1));   // output slot of this window
+      n_out += __popc(vmask);
+      // k-mer of window i: bases [i, i+k) of the 128-bit string A:B
+      uint64_t hi = lane ? (A.codes << (2 * lane)) | (B.codes >> (64 - 2 * lane)) : A.codes;
+      uint64_t kmer = hi >> (64 - 2 * k);
+      uint64_t amb64 = ((uint64_t)B.amb << 32) | A.amb;
+      bool amb = ((amb64 >> lane) & ((1ull << k) - 1)) != 0;  // any non-ACGT base in the window, :275,280-282
+      uint64_t rc = revcomp64(kmer, k);                       // canonical k-mer (krakendb.cpp:238-246)
+      uint64_t canon = kmer < rc ? kmer : rc;
+      // minimizer = min over the k-nt+1 nt-mers of (xor_mask ^ canonical(nt-mer)) (krakendb.cpp:200-215).
+      // Candidate of position q (0..63 relative to the slot): lane holds q = lane (m0) and q = 32+lane (m1).
+      uint32_t f0 = (uint32_t)(hi >> (64 - 2 * nt));
+      uint32_t r0 = revcomp32(f0, nt);
+      uint32_t m0 = db.xor_mask ^ (f0 < r0 ? f0 : r0);
+      uint32_t f1 = (uint32_t)((B.codes << (2 * lane)) >> (64 - 2 * nt));
+      uint32_t r1 = revcomp32(f1, nt);
+      uint32_t m1 = db.xor_mask ^ (f1 < r1 ? f1 : r1);
+      // sliding-window minimum of width n_mini by doubling: after the loop m0 holds min over [q, q+n_mini)
+      uint32_t w = 1;
+      while (2 * w <= db.n_mini) {
+        uint32_t src = (lane + w) & 31;
+        uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
+        bool wrap = lane + w >= 32;
+        m0 = min(m0, wrap ? x1 : x0);
+        m1 = min(m1, wrap ? 0xFFFFFFFFu : x1);
+        w *= 2;
       }
-      if (MODE == MODE_RESOLVE) {
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          if (valid[j]) {
-            uint32_t c = p.codes_in[out_base + oi[j]];
-            taxon[j] = (c == AMBIG) ? 0 : c;                  // ambiguity is recomputed from the bases
-          }
-        }
-      } else {
-        {
-          uint32_t f = (uint32_t)((blk[NS].codes << (2 * lane)) >> (64 - 2 * nt));
-          uint32_t rf = revcomp32(f, nt);
-          cand[NS] = db.xor_mask ^ (f < rf ? f : rf);
-        }
-        // ---- minimizer = min over the k-nt+1 nt-mers of (xor_mask ^ canonical(nt-mer)) (krakendb.cpp:200-215):
-        //      sliding-window minimum of width n_mini over the candidates, by doubling --------------------------
-        uint32_t w = 1;
-        while (2 * w <= db.n_mini) {
-          const uint32_t src = (lane + w) & 31;
-          const bool wrap = lane + w >= 32;
-          uint32_t x[NS + 1];
-#pragma unroll
-          for (int j = 0; j <= NS; j++) x[j] = __shfl_sync(0xFFFFFFFFu, cand[j], src);
-#pragma unroll
-          for (int j = 0; j < NS; j++) cand[j] = min(cand[j], wrap ? x[j + 1] : x[j]);
-          cand[NS] = min(cand[NS], wrap ? 0xFFFFFFFFu : x[NS]);
-          w *= 2;
-        }
-        if (w < db.n_mini) {                                  // [q, q+n_mini) = [q, q+w) U [q+n_mini-w, q+n_mini)
-          const uint32_t d = db.n_mini - w;
-          const uint32_t src = (lane + d) & 31;
-          const bool wrap = lane + d >= 32;
-          uint32_t x[NS + 1];
-#pragma unroll
-          for (int j = 0; j <= NS; j++) x[j] = __shfl_sync(0xFFFFFFFFu, cand[j], src);
-#pragma unroll
-          for (int j = 0; j < NS; j++) cand[j] = min(cand[j], wrap ? x[j + 1] : x[j]);
-        }
-        // cand[j] is now the bin of window (s0+j)*32+lane
-
-        // ---- index fetch, once per run of equal minimizers (the reference caches the range the same way,
-        //      krakendb.cpp:261-277).  All heads of the pass load before anyone consumes. -------------------
-        bool head[NS];
-        uint64_t lo[NS];
-        uint32_t n[NS];
-        uint32_t pbin = carry_bin;                            // bin of the window just before this slot's lane 0
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, cand[j], 1);
-          uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)look[j], 1);
-          if (lane == 0) { pb = pbin; pl = pbin != 0xFFFFFFFFu; }
-          head[j] = look[j] && !(pl && pb == cand[j]);
-          uint32_t lb = __shfl_sync(0xFFFFFFFFu, cand[j], 31);
-          uint32_t ll = __shfl_sync(0xFFFFFFFFu, (uint32_t)look[j], 31);
-          pbin = ll ? lb : 0xFFFFFFFFu;
-          lo[j] = 0;
-          n[j] = 0;
-        }
-        uint64_t o0[NS], o1[NS];
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          o0[j] = o1[j] = 0;
-          if (head[j] && cand[j] >= db.bin_lo && cand[j] < db.bin_hi) {
-            const uint64_t *o = db.offsets + (cand[j] - db.bin_lo);
-            o0[j] = __ldg(o);                                 // KrakenDBIndex::at, krakendb.cpp:586-593
-            o1[j] = __ldg(o + 1);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          uint64_t l = o0[j] - db.rec_base;
-          uint32_t c = (uint32_t)(o1[j] - o0[j]);
-          const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head[j]);
-          const uint32_t below = heads & (0xFFFFFFFFu >> (31 - lane));
-          const int hl = below ? 31 - __clz(below) : 0;
-          uint64_t hlo = __shfl_sync(0xFFFFFFFFu, l, hl);
-          uint32_t hn = __shfl_sync(0xFFFFFFFFu, c, hl);
-          if (!below) { hlo = carry_lo; hn = carry_n; }       // the run started in an earlier slot
-          lo[j] = hlo;
-          n[j] = look[j] ? hn : 0;
-          carry_lo = __shfl_sync(0xFFFFFFFFu, hlo, 31);
-          carry_n = __shfl_sync(0xFFFFFFFFu, hn, 31);
-        }
-        carry_bin = pbin;
-        if (p.flags & 8u) {   // measurement aid: algorithmic probe count of SURVEY.md §8(d)
-          uint32_t probes = 0, nl = 0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) { probes += (look[j] && n[j]) ? 32 - __clz(n[j]) : 0; nl += look[j]; }
-          probes = __reduce_add_sync(0xFFFFFFFFu, probes);
-          nl = __reduce_add_sync(0xFFFFFFFFu, nl);
-          if (lane == 0) { atomicAdd(p.stats, (unsigned long long)nl); atomicAdd(p.stats + 1, (unsigned long long)probes); }
-        }
-        // ---- bin search (kmer_query, krakendb.cpp:280-299): 4-ary narrowing rounds, then a scan of <= 8 records.
-        //      The three pivots of a round are independent loads; the NS slots run their rounds together. -------
-        for (;;) {
-          bool any = false;
-#pragma unroll
-          for (int j = 0; j < NS; j++) any |= n[j] > (uint32_t)SEARCH_WINDOW;
-          if (!__any_sync(0xFFFFFFFFu, any)) break;
-          uint64_t k1[NS], k2[NS], k3[NS];
-#pragma unroll
-          for (int j = 0; j < NS; j++) {
-            if (n[j] > (uint32_t)SEARCH_WINDOW) {
-              const uint32_t q = n[j] >> 2;
-              k1[j] = load_key(db.pairs, lo[j] + q, db.key_mask);
-              k2[j] = load_key(db.pairs, lo[j] + 2 * q, db.key_mask);
-              k3[j] = load_key(db.pairs, lo[j] + 3 * q, db.key_mask);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < NS; j++) {
-            if (n[j] > (uint32_t)SEARCH_WINDOW) {
-              const uint32_t q = n[j] >> 2;
-              const uint64_t c = canon[j];
-              if (c >= k3[j]) { lo[j] += 3 * q; n[j] -= 3 * q; }
-              else if (c >= k2[j]) { lo[j] += 2 * q; n[j] = q; }
-              else if (c >= k1[j]) { lo[j] += q; n[j] = q; }
-              else { n[j] = q; }
-            }
-          }
-        }
-        // scan: compare the low key words of the window first, confirm the (rare) matches on the high word
-        uint32_t lw[NS][SEARCH_WINDOW];
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          const uint32_t *b = reinterpret_cast<const uint32_t *>(db.pairs + lo[j] * 12);
-#pragma unroll
-          for (int t = 0; t < SEARCH_WINDOW; t++) lw[j][t] = ((uint32_t)t < n[j]) ? __ldg(b + 3 * t) : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          const uint32_t clo = (uint32_t)canon[j], chi = (uint32_t)(canon[j] >> 32);
-          uint32_t m = 0;
-#pragma unroll
-          for (int t = 0; t < SEARCH_WINDOW; t++) m |= ((uint32_t)t < n[j] && lw[j][t] == clo) ? (1u << t) : 0u;
-          while (m) {
-            const int t = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t *b = reinterpret_cast<const uint32_t *>(db.pairs + (lo[j] + t) * 12);
-            if ((__ldg(b + 1) & hi_mask) == chi) { taxon[j] = __ldg(b + 2); m = 0; }   // value = dense id
-          }
-        }
+      if (w < db.n_mini) {                                    // [q, q+n_mini) = [q, q+w) U [q+n_mini-w, q+n_mini)
+        uint32_t d = db.n_mini - w;
+        uint32_t src = (lane + d) & 31;
+        uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
+        m0 = min(m0, lane + d >= 32 ? x1 : x0);
       }
-
-      // ---- per-window code, sketches, hit aggregation --------------------------------------------------------
-#pragma unroll
-      for (int j = 0; j < NS; j++) {
-        const uint32_t i = (s0 + j) * 32 + lane;
-        const uint32_t code = amb[j] ? AMBIG : taxon[j];
-        if (MODE == MODE_LOOKUP) {
-          // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
-          // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
-          if (valid[j] && (!p.only_hits || (taxon[j] != 0))) p.codes[out_base + oi[j]] = code;
-        } else {
-          const uint32_t raw = (look[j] && taxon[j]) ? __ldg(p.tax.raw + taxon[j]) : 0;
-          const uint32_t out_code = amb[j] ? AMBIG : raw;
-          if (valid[j]) p.codes[out_base + oi[j]] = out_code;
-          // runs of the hit list (classify.cpp:826-861); cleaned reads count theirs after the loop
-          uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
-          if (lane == 0) prev = carry_code;
-          const bool brk = valid[j] && (i == 0 || out_code != prev);
-          n_runs += __popc(__ballot_sync(0xFFFFFFFFu, brk));
-          carry_code = __shfl_sync(0xFFFFFFFFu, out_code, 31);
-        }
+      if (valid) {
+        p.bins[out_base + oi] = amb ? BIN_AMBIG : m0;
+        p.canon[out_base + oi] = canon;
       }
-      if (MODE != MODE_LOOKUP) {
-        // ---- add_kmer: HLL insert into the sketch of `taxon` (0 for misses), classify.cpp:939 -----------------
-        if (counting) {
-          uint64_t h[NS];
-#pragma unroll
-          for (int j = 0; j < NS; j++) h[j] = fmix64(canon[j]);
-#pragma unroll
-          for (int j = 0; j < NS; j++)
-            if (look[j]) hll_update(p.regs, taxon[j], h[j]);
-          if (p.hll_mode != 2u) {
-#pragma unroll
-            for (int j = 0; j < NS; j++) {
-              if (look[j] && !p.dense_flag[taxon[j]]) {
-                if (sparse_insert(p.sparse, taxon[j], encode_hash32(h[j]))) {
-                  atomicAdd(p.sparse.n_used, 1ull);
-                  atomicAdd(p.sparse.distinct + taxon[j], 1u);
-                }
-              }
-            }
-          }
-        }
-        // ---- hit_counts[taxon]++ (classify.cpp:941-942), aggregated per distinct taxon of the slot -------------
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          n_miss += __popc(__ballot_sync(0xFFFFFFFFu, look[j] && taxon[j] == 0));
-          uint32_t rem = __ballot_sync(0xFFFFFFFFu, look[j] && taxon[j] != 0);
-          while (rem) {
-            const int ldr = __ffs(rem) - 1;
-            const uint32_t t = __shfl_sync(0xFFFFFFFFu, taxon[j], ldr);
-            const uint32_t same = __ballot_sync(0xFFFFFFFFu, look[j] && taxon[j] == t) & rem;
-            const uint32_t cnt = __popc(same);
-            rem &= ~same;
-            const uint32_t pos = __ballot_sync(0xFFFFFFFFu, lane < n_hits && my_t == t);
-            if (pos) {
-              if (lane == (uint32_t)(__ffs(pos) - 1)) my_c += cnt;
-            } else if (n_hits < 32) {
-              if (lane == n_hits) { my_t = t; my_c = cnt; }
-              n_hits++;
-            } else {
-              overflow = true;
-            }
-          }
-        }
-      }
-      blk[0] = blk[NS];
+      A = B;
     }
   }
-
-  if (MODE == MODE_LOOKUP) {
-    if (lane == 0) p.n_windows[r] = n_out;
-    return;
-  }
-  if (marks && !(p.flags & 2u)) {   // runs over the compacted codes of a cleaned read
-    __syncwarp();
-    n_runs = 0;
-    for (uint32_t base = 0; base < n_out; base += 32) {
-      uint32_t i = base + lane;
-      bool brk = i < n_out && (i == 0 || p.codes[out_base + i] != p.codes[out_base + i - 1]);
-      n_runs += __popc(__ballot_sync(0xFFFFFFFFu, brk));
-    }
-  }
-
-  // ---- resolve_tree (krakenutil.cpp:149-200) --------------------------------------------------------------
-  uint32_t call = 0;
-  if (n_hits == 1) {
-    call = __shfl_sync(0xFFFFFFFFu, my_t, 0);                 // a single hit taxon is its own best path
-  } else if (n_hits > 1) {
-    // score(t) = sum of hit counts along t's root path (:156-177); lane j walks entry j
-    uint32_t node = lane < n_hits ? my_t : 0;
-    uint32_t score = 0;
-    while (__any_sync(0xFFFFFFFFu, node != 0)) {
-      for (uint32_t q = 0; q < n_hits; q++) {
-        uint32_t tq = __shfl_sync(0xFFFFFFFFu, my_t, q);
-        uint32_t cq = __shfl_sync(0xFFFFFFFFu, my_c, q);
-        if (node == tq) score += cq;
-      }
-      if (node) node = __ldg(p.tax.parent + node);
-    }
-    uint32_t best = __reduce_max_sync(0xFFFFFFFFu, score);
-    uint32_t tied = __ballot_sync(0xFFFFFFFFu, lane < n_hits && score == best);
-    if (__popc(tied) == 1) {
-      call = __shfl_sync(0xFFFFFFFFu, my_t, __ffs(tied) - 1);
-    } else {
-      // ties → LCA of all tied taxa, folded in ascending taxid order (std::set iteration, :190-196)
-      uint32_t raw = (tied >> lane) & 1 ? __ldg(p.tax.raw + my_t) : 0xFFFFFFFFu;
-      uint32_t acc = 0;
-      uint32_t left = tied;
-      while (left) {
-        // smallest remaining taxid
-        uint32_t cand = (left >> lane) & 1 ? raw : 0xFFFFFFFFu;
-        uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, cand);
-        uint32_t who = __ballot_sync(0xFFFFFFFFu, cand == mn && ((left >> lane) & 1));
-        int src = __ffs(who) - 1;
-        uint32_t t = __shfl_sync(0xFFFFFFFFu, my_t, src);
-        acc = acc ? lca_dense(p.tax, acc, t) : t;             // all lanes compute the same walk
-        left &= ~(1u << src);
-      }
-      call = acc;
-    }
-  }
-
-  const uint32_t call_raw = call ? __ldg(p.tax.raw + call) : 0;
-  if (lane == 0) {
-    p.n_windows[r] = n_out;
-    p.call[r] = call_raw;
-    if (overflow) atomicExch(p.error_flag, 1u);
-  }
-  // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
-  if (counting) {
-    if (lane < n_hits) atomicAdd(p.n_kmers + my_t, (unsigned long long)my_c);
-    if (lane == 0) {
-      if (n_miss) atomicAdd(p.n_kmers, (unsigned long long)n_miss);
-      atomicAdd(p.n_reads_ctr + call, 1ull);
-      if (call) atomicAdd(p.n_classified, 1ull);
-    }
-  }
-  // ---- run-length encoded hit list --------------------------------------------------------------------------
-  if (!(p.flags & 2u)) {
-    uint32_t start = 0;
-    if (lane == 0) {
-      start = n_runs ? (uint32_t)atomicAdd(p.run_cursor, (unsigned long long)n_runs) : 0;
-      p.run_start[r] = start;
-      p.run_count[r] = n_runs;
-    }
-    start = __shfl_sync(0xFFFFFFFFu, start, 0);
-    if (n_runs) {
-      __syncwarp();
-      // walk the slots backwards so that each run knows where the next one starts
-      uint32_t next_start = n_out;    // window index of the first break after the current slot
-      uint32_t later = 0;             // breaks in the slots already visited
-      for (int s = (int)((n_out + 31) / 32) - 1; s >= 0; s--) {
-        uint32_t i = (uint32_t)s * 32 + lane;
-        bool valid = i < n_out;
-        uint32_t c = valid ? p.codes[out_base + i] : 0;
-        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, c, 1);
-        if (lane == 0) prev = (s > 0) ? p.codes[out_base + i - 1] : 0;
-        bool brk = valid && (i == 0 || c != prev);
-        uint32_t bm = __ballot_sync(0xFFFFFFFFu, brk);
-        if (brk) {
-          uint32_t after = lane == 31 ? 0u : (bm >> (lane + 1));
-          uint32_t end = after ? (uint32_t)s * 32 + lane + (uint32_t)__ffs(after) : next_start;
-          uint32_t idx = n_runs - later - (uint32_t)__popc(bm >> lane);
-          p.runs[start + idx] = make_uint2(c, end - i);
-        }
-        if (bm) next_start = (uint32_t)s * 32 + (uint32_t)__ffs(bm) - 1;
-        later += __popc(bm);
-      }
-    }
-  }
+  // positions of the read's text that carry no window
+  for (uint32_t q = n_out + lane; q < raw_len; q += 32) p.bins[out_base + q] = BIN_NONE;
+  if (lane == 0) p.n_windows[r] = n_out;
 }
 
 // A read that contains '\n' / '\r' (CRLF input).  KmerScanner::next_kmer (krakenutil.cpp:239-278)
@@ -601,14 +299,14 @@ struct __align__(16) SharedState {
   uint32_t next_read[N_STAGES];              // warps take the reads of a chunk from this counter
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_constant__ Params p) {
+// Stage 1: persistent CTAs; one thread pulls the next chunk of reads (offsets slice + text) into shared memory
+// with TMA bulk copies while the warps still scan the previous chunk.
+__global__ void __launch_bounds__(CTA_THREADS, 4) k_scan(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *stage_buf = smem;                                                   // N_STAGES x STAGE_BYTES
   SharedState *ss = reinterpret_cast<SharedState *>(smem + N_STAGES * STAGE_BYTES);
   const uint32_t tid = threadIdx.x, lane = tid & 31;
 
-  // thread 0: claim the next chunk and start the bulk copies of its offsets slice and of its read text
   auto fetch = [&](uint32_t st) {
     uint32_t c = atomicAdd(p.chunk_counter, 1u);
     ss->chunk[st] = c;
@@ -656,7 +354,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_consta
       const uint32_t r = r0 + q;
       if (r >= r1) break;
       const uint64_t b0 = ss->off[st][q], b1 = ss->off[st][q + 1];
-      uint32_t len = (uint32_t)(b1 - b0);
+      const uint32_t raw_len = (uint32_t)(b1 - b0);
+      uint32_t len = raw_len;
       const char *seq = staged ? reinterpret_cast<const char *>(stage_buf + st * STAGE_BYTES + (b0 - a0))
                                : p.bases + b0;
       // pre-scan for skipped characters (rare: CRLF input)
@@ -671,28 +370,297 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_classify(const __grid_consta
         seq = p.clean + b0;
         marks = true;
       }
-      process_read<MODE>(p, r, seq, len, b0, lane, marks);
+      scan_read(p, r, seq, len, raw_len, b0, lane, marks);
     }
     __syncthreads();
   }
 }
 
+// Stage 2: one thread per text position.  Index fetch (KrakenDBIndex::at, krakendb.cpp:586-593), bin search
+// (kmer_query, :280-299: 4-ary narrowing while the bin is large, then a scan of <= 8 records) and — unless the
+// lookups belong to one range of a sharded database — the HLL insert of ReadCounts::add_kmer (classify.cpp:939).
+// Threads of a warp hold consecutive windows of a read: windows that share a minimizer read the same index
+// sector and the same pivots, which the load unit coalesces.
+template <int MODE>
+__global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Params p) {
+  const DbView &db = p.db;
+  const uint32_t hi_mask = (uint32_t)(db.key_mask >> 32);
+  const bool counting = (MODE == MODE_FUSED) && !(p.flags & 4u);
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.total_bases;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t bin = __ldg(p.bins + g);
+    if (bin == BIN_NONE) continue;
+    if (bin == BIN_AMBIG) {
+      if (!p.only_hits) p.codes_dense[g] = AMBIG;
+      continue;
+    }
+    const uint64_t canon = __ldg(p.canon + g);
+    uint32_t taxon = 0;
+    if (MODE == MODE_RESOLVE) {
+      taxon = p.codes_in[g];                                 // merged dense ids of all database ranges
+    } else if (bin >= db.bin_lo && bin < db.bin_hi) {
+      const uint64_t *o = db.offsets + (bin - db.bin_lo);
+      const uint64_t o0 = __ldg(o), o1 = __ldg(o + 1);
+      uint64_t lo = o0 - db.rec_base;
+      uint32_t n = (uint32_t)(o1 - o0);
+      if (p.flags & 8u) {   // measurement aid: algorithmic probe count of SURVEY.md §8(d)
+        atomicAdd(p.stats, 1ull);
+        atomicAdd(p.stats + 1, (unsigned long long)(n ? 32 - __clz(n) : 0));
+      }
+      while (n > (uint32_t)SEARCH_WINDOW) {
+        const uint32_t q = n >> 2;
+        const uint64_t k1 = load_key(db.pairs, lo + q, db.key_mask);
+        const uint64_t k2 = load_key(db.pairs, lo + 2 * q, db.key_mask);
+        const uint64_t k3 = load_key(db.pairs, lo + 3 * q, db.key_mask);
+        if (canon >= k3) { lo += 3 * q; n -= 3 * q; }
+        else if (canon >= k2) { lo += 2 * q; n = q; }
+        else if (canon >= k1) { lo += q; n = q; }
+        else { n = q; }
+      }
+      if (n) {
+        // compare the low key words of the window first, confirm the (rare) matches on the high word
+        const uint32_t *b = reinterpret_cast<const uint32_t *>(db.pairs + lo * 12);
+        const uint32_t clo = (uint32_t)canon, chi = (uint32_t)(canon >> 32);
+        uint32_t lw[SEARCH_WINDOW];
+#pragma unroll
+        for (int t = 0; t < SEARCH_WINDOW; t++) lw[t] = ((uint32_t)t < n) ? __ldg(b + 3 * t) : 0;
+        uint32_t m = 0;
+#pragma unroll
+        for (int t = 0; t < SEARCH_WINDOW; t++) m |= ((uint32_t)t < n && lw[t] == clo) ? (1u << t) : 0u;
+        while (m) {
+          const int t = __ffs(m) - 1;
+          m &= m - 1;
+          if ((__ldg(b + 3 * t + 1) & hi_mask) == chi) { taxon = __ldg(b + 3 * t + 2); m = 0; }   // value = dense id
+        }
+      }
+    } else if (p.flags & 8u) {
+      atomicAdd(p.stats, 1ull);
+    }
+    // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
+    // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
+    if (MODE == MODE_RESOLVE || !p.only_hits || taxon != 0) p.codes_dense[g] = taxon;
+    if (counting || (MODE == MODE_RESOLVE && !(p.flags & 4u))) {
+      const uint64_t h = fmix64(canon);
+      hll_update(p.regs, taxon, h);
+      if (p.hll_mode != 2u && !p.dense_flag[taxon]) {
+        if (sparse_insert(p.sparse, taxon, encode_hash32(h))) {
+          atomicAdd(p.sparse.n_used, 1ull);
+          atomicAdd(p.sparse.distinct + taxon, 1u);
+        }
+      }
+    }
+  }
+}
+
+// Stage 3: one warp per read.  hit_counts (classify.cpp:941-942), resolve_tree / lca (krakenutil.cpp:90-118,
+// 149-200), the per-taxon counters (classify.cpp:939,968) and the run-length encoded hit list (:826-861).
+constexpr int RUN_BUF = 96;      // runs buffered per warp before they are flushed to global memory
+constexpr uint32_t RUN_BLOCK = 256;   // run slots a warp takes from the global cursor at a time
+
+__global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Params p) {
+  __shared__ uint2 s_runs[CTA_WARPS][RUN_BUF];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warps_total = gridDim.x * CTA_WARPS;
+  const bool counting = !(p.flags & 4u);
+  const bool want_runs = !(p.flags & 2u);
+  const uint32_t *codes_src = p.codes_dense;
+  // Same-address atomics serialise in L2 (about one per few cycles): a million reads per batch must not each hit
+  // the run cursor, n_kmers[0] and n_reads[0].  Each warp therefore allocates run slots in blocks of RUN_BLOCK
+  // and keeps the hot counters in registers until it is done.
+  uint32_t blk_next = 0, blk_end = 0;                           // this warp's block of run slots
+  uint32_t acc_miss = 0, acc_unclassified = 0, acc_classified = 0;
+  for (uint32_t r = blockIdx.x * CTA_WARPS + warp; r < p.n_reads; r += warps_total) {
+    const uint64_t out_base = p.offsets[r];
+    const uint32_t nwin = p.n_windows[r];
+    uint32_t my_t = 0, my_c = 0;                                // hit list: lane j holds entry j (dense id, count)
+    uint32_t n_hits = 0, n_miss = 0, n_runs = 0;
+    uint32_t carry_code = 0;
+    bool overflow = false;
+    const uint32_t nslots = (nwin + 31) / 32;
+    for (uint32_t s = 0; s < nslots; s++) {
+      const uint32_t i = s * 32 + lane;
+      const bool valid = i < nwin;
+      const uint32_t c = valid ? codes_src[out_base + i] : 0;
+      const bool amb = valid && c == AMBIG;
+      const bool look = valid && !amb;
+      const uint32_t taxon = look ? c : 0;
+      const uint32_t raw = taxon ? __ldg(p.tax.raw + taxon) : 0;
+      const uint32_t out_code = amb ? AMBIG : raw;
+      if (valid && (p.flags & 1u)) p.codes[out_base + i] = out_code;
+      // runs of the hit list
+      uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
+      if (lane == 0) prev = carry_code;
+      const bool brk = valid && (i == 0 || out_code != prev);
+      const uint32_t bm = __ballot_sync(0xFFFFFFFFu, brk);
+      if (want_runs && brk) {
+        const uint32_t idx = n_runs + __popc(bm & ((1u << lane) - 1));
+        if (idx < RUN_BUF) s_runs[warp][idx] = make_uint2(out_code, i);   // (code, start); lengths at flush
+      }
+      n_runs += __popc(bm);
+      carry_code = __shfl_sync(0xFFFFFFFFu, out_code, 31);
+      // hit_counts[taxon]++, aggregated per distinct taxon of the slot
+      n_miss += __popc(__ballot_sync(0xFFFFFFFFu, look && taxon == 0));
+      uint32_t rem = __ballot_sync(0xFFFFFFFFu, look && taxon != 0);
+      while (rem) {
+        const int ldr = __ffs(rem) - 1;
+        const uint32_t t = __shfl_sync(0xFFFFFFFFu, taxon, ldr);
+        const uint32_t same = __ballot_sync(0xFFFFFFFFu, look && taxon == t) & rem;
+        const uint32_t cnt = __popc(same);
+        rem &= ~same;
+        const uint32_t pos = __ballot_sync(0xFFFFFFFFu, lane < n_hits && my_t == t);
+        if (pos) {
+          if (lane == (uint32_t)(__ffs(pos) - 1)) my_c += cnt;
+        } else if (n_hits < 32) {
+          if (lane == n_hits) { my_t = t; my_c = cnt; }
+          n_hits++;
+        } else {
+          overflow = true;
+        }
+      }
+    }
+
+    // ---- resolve_tree (krakenutil.cpp:149-200) ------------------------------------------------------------
+    uint32_t call = 0;
+    if (n_hits == 1) {
+      call = __shfl_sync(0xFFFFFFFFu, my_t, 0);                 // a single hit taxon is its own best path
+    } else if (n_hits > 1) {
+      // score(t) = sum of hit counts along t's root path (:156-177); lane j walks entry j
+      uint32_t node = lane < n_hits ? my_t : 0;
+      uint32_t score = 0;
+      while (__any_sync(0xFFFFFFFFu, node != 0)) {
+        for (uint32_t q = 0; q < n_hits; q++) {
+          uint32_t tq = __shfl_sync(0xFFFFFFFFu, my_t, q);
+          uint32_t cq = __shfl_sync(0xFFFFFFFFu, my_c, q);
+          if (node == tq) score += cq;
+        }
+        if (node) node = __ldg(p.tax.parent + node);
+      }
+      uint32_t best = __reduce_max_sync(0xFFFFFFFFu, score);
+      uint32_t tied = __ballot_sync(0xFFFFFFFFu, lane < n_hits && score == best);
+      if (__popc(tied) == 1) {
+        call = __shfl_sync(0xFFFFFFFFu, my_t, __ffs(tied) - 1);
+      } else {
+        // ties → LCA of all tied taxa, folded in ascending taxid order (std::set iteration, :190-196)
+        uint32_t raw = (tied >> lane) & 1 ? __ldg(p.tax.raw + my_t) : 0xFFFFFFFFu;
+        uint32_t acc = 0;
+        uint32_t left = tied;
+        while (left) {
+          uint32_t cand = (left >> lane) & 1 ? raw : 0xFFFFFFFFu;
+          uint32_t mn = __reduce_min_sync(0xFFFFFFFFu, cand);
+          uint32_t who = __ballot_sync(0xFFFFFFFFu, cand == mn && ((left >> lane) & 1));
+          int src = __ffs(who) - 1;
+          uint32_t t = __shfl_sync(0xFFFFFFFFu, my_t, src);
+          acc = acc ? lca_dense(p.tax, acc, t) : t;             // all lanes compute the same walk
+          left &= ~(1u << src);
+        }
+        call = acc;
+      }
+    }
+    const uint32_t call_raw = call ? __ldg(p.tax.raw + call) : 0;
+    if (lane == 0) {
+      p.call[r] = call_raw;
+      if (overflow) atomicExch(p.error_flag, 1u);
+    }
+    // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
+    if (counting) {
+      if (lane < n_hits) atomicAdd(p.n_kmers + my_t, (unsigned long long)my_c);
+      acc_miss += n_miss;
+      if (call) {
+        acc_classified++;
+        if (lane == 0) atomicAdd(p.n_reads_ctr + call, 1ull);
+      } else {
+        acc_unclassified++;
+      }
+    }
+    // ---- run-length encoded hit list ----------------------------------------------------------------------
+    if (want_runs) {
+      uint32_t start = 0;
+      if (lane == 0) {
+        if (n_runs > blk_end - blk_next) {                      // take a fresh block (the old tail stays a hole)
+          const uint32_t take = n_runs > RUN_BLOCK ? n_runs : RUN_BLOCK;
+          blk_next = (uint32_t)atomicAdd(p.run_cursor, (unsigned long long)take);
+          blk_end = blk_next + take;
+        }
+        start = blk_next;
+        blk_next += n_runs;
+        p.run_start[r] = start;
+        p.run_count[r] = n_runs;
+      }
+      start = __shfl_sync(0xFFFFFFFFu, start, 0);
+      __syncwarp();
+      if (n_runs <= RUN_BUF) {
+        for (uint32_t j = lane; j < n_runs; j += 32) {
+          const uint2 a = s_runs[warp][j];
+          const uint32_t end = j + 1 < n_runs ? s_runs[warp][j + 1].y : nwin;
+          p.runs[start + j] = make_uint2(a.x, end - a.y);
+        }
+      } else {
+        // long hit list (long read): recompute from the codes, walking the slots backwards so that each run
+        // knows where the next one starts
+        uint32_t next_start = nwin, later = 0;
+        for (int s = (int)nslots - 1; s >= 0; s--) {
+          uint32_t i = (uint32_t)s * 32 + lane;
+          bool valid = i < nwin;
+          auto code_at = [&](uint32_t w) {
+            uint32_t c = codes_src[out_base + w];
+            return c == AMBIG ? AMBIG : (c ? __ldg(p.tax.raw + c) : 0u);
+          };
+          uint32_t c = valid ? code_at(i) : 0;
+          uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+          if (lane == 0) prev = (s > 0) ? code_at(i - 1) : 0;
+          bool brk = valid && (i == 0 || c != prev);
+          uint32_t bm = __ballot_sync(0xFFFFFFFFu, brk);
+          if (brk) {
+            uint32_t after = lane == 31 ? 0u : (bm >> (lane + 1));
+            uint32_t end = after ? (uint32_t)s * 32 + lane + (uint32_t)__ffs(after) : next_start;
+            uint32_t idx = n_runs - later - (uint32_t)__popc(bm >> lane);
+            p.runs[start + idx] = make_uint2(c, end - i);
+          }
+          if (bm) next_start = (uint32_t)s * 32 + (uint32_t)__ffs(bm) - 1;
+          later += __popc(bm);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (counting && lane == 0) {
+    if (acc_miss) atomicAdd(p.n_kmers, (unsigned long long)acc_miss);
+    if (acc_unclassified) atomicAdd(p.n_reads_ctr, (unsigned long long)acc_unclassified);
+    if (acc_classified) atomicAdd(p.n_classified, (unsigned long long)acc_classified);
+  }
+}
+
 int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedState); }
 
-void launch_classify(int mode, const Params &p, int grid, cudaStream_t stream) {
+// mode MODE_FUSED : scan → lookup (+HLL) → resolve            (whole database on this GPU)
+//      MODE_LOOKUP: scan → lookup into p.codes_dense            (one range of a sharded / chunked database)
+//      MODE_RESOLVE: scan → HLL from merged codes → resolve    (owner of the reads after the merge)
+int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cudaEvent_t *stage_events) {
   const int smem = classify_smem_bytes();
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_classify<MODE_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_classify<MODE_LOOKUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(k_classify<MODE_RESOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
-  switch (mode) {
-    case MODE_FUSED: k_classify<MODE_FUSED><<<grid, CTA_THREADS, smem, stream>>>(p); break;
-    case MODE_LOOKUP: k_classify<MODE_LOOKUP><<<grid, CTA_THREADS, smem, stream>>>(p); break;
-    default: k_classify<MODE_RESOLVE><<<grid, CTA_THREADS, smem, stream>>>(p); break;
+  int launches = 0;
+  if (p.n_reads == 0) return 0;
+  int grid = n_sm * 4;
+  if ((uint32_t)grid > p.n_chunks) grid = (int)p.n_chunks;
+  k_scan<<<grid, CTA_THREADS, smem, stream>>>(p);
+  launches++;
+  if (stage_events) cudaEventRecord(stage_events[0], stream);
+  const int lgrid = (int)min((uint64_t)n_sm * 8 * 8, (p.total_bases + 255) / 256);
+  if (mode == MODE_FUSED) k_lookup<MODE_FUSED><<<lgrid, 256, 0, stream>>>(p);
+  else if (mode == MODE_LOOKUP) k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(p);
+  else k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(p);
+  launches++;
+  if (stage_events) cudaEventRecord(stage_events[1], stream);
+  if (mode != MODE_LOOKUP) {
+    const int rgrid = (int)min((uint32_t)n_sm * 4 * 2, (p.n_reads + CTA_WARPS - 1) / CTA_WARPS);
+    k_resolve<<<rgrid, 256, 0, stream>>>(p);
+    launches++;
   }
+  return launches;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -1,22 +1,26 @@
 // kuq_kernels.cuh — sm_100a kernels of the KrakenUniq classification hot path (device side of libkuq.so).
 //
-// One persistent kernel, k_classify<MODE>, carries the whole per-read path of the reference's
-// classify_sequence() (src/classify.cpp:897-1012):
+// The per-read path of the reference's classify_sequence() (src/classify.cpp:897-1012) as three kernels:
 //
-//   read blocks --TMA bulk copy--> shared memory            (cp.async.bulk + mbarrier, double buffered)
-//   2-bit packing + ambiguity mask   KmerScanner::next_kmer  src/krakenutil.cpp:239-282
-//   canonical k-mer                  canonical_representation src/krakendb.cpp:238-246
-//   rolling minimizer                bin_key                  src/krakendb.cpp:200-215
-//   index fetch + bin search         kmer_query               src/krakendb.cpp:250-321, :586-593
-//   HLL register update + counters   ReadCounts::add_kmer     src/readcounts.hpp:71-74, hyperloglogplus.cpp:485-523
-//   hit aggregation + tree resolve   resolve_tree / lca       src/krakenutil.cpp:90-118,149-200
-//   run-length hit list              hitlist_string           src/classify.cpp:826-861
+//  k_scan     read blocks --TMA bulk copy--> shared memory    (cp.async.bulk + mbarrier, double buffered)
+//   (warp     2-bit packing + ambiguity mask   KmerScanner::next_kmer   src/krakenutil.cpp:239-282
+//    per      canonical k-mer                  canonical_representation src/krakendb.cpp:238-246
+//    read)    rolling minimizer                bin_key                  src/krakendb.cpp:200-215
+//             → scratch: canonical k-mer + bin per window (12 B, coalesced)
+//  k_lookup   index fetch + bin search         kmer_query               src/krakendb.cpp:250-321, :586-593
+//   (thread   HLL register update              ReadCounts::add_kmer     src/readcounts.hpp:71-74,
+//    per                                                                 hyperloglogplus.cpp:485-523
+//    window)  → scratch: dense taxon id per window
+//  k_resolve  hit aggregation + tree resolve   resolve_tree / lca       src/krakenutil.cpp:90-118,149-200
+//   (warp     per-taxon counters               classify.cpp:939,968
+//    per      run-length hit list              hitlist_string           src/classify.cpp:826-861
+//    read)
 //
-// Work decomposition: a CTA (8 warps) owns a chunk of consecutive reads whose bytes one thread pulls into
-// shared memory with a single 1-D bulk copy while the warps still work on the previous chunk; a warp owns a
-// read and walks it in slots of 32 consecutive k-mer windows (lane = window), so that windows sharing a
-// minimizer sit in neighbouring lanes: their index fetches and bin probes coalesce into the same sectors.
-// No tensor cores: the path is integer compares on randomly addressed HBM.
+// k_scan is ALU/shuffle work with no dependent memory access; k_lookup is the random-HBM stage and is written
+// thread-per-window with a small register footprint so that ~48 warps per SM keep enough probes in flight;
+// consecutive threads hold consecutive windows of a read, so windows sharing a minimizer touch the same index
+// sector and the same pivots (coalesced by the load unit).  No tensor cores: the path is integer compares on
+// randomly addressed HBM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -86,7 +90,12 @@ struct Params {
   // outputs
   uint32_t *call;               // [n_reads] taxid
   uint32_t *n_windows;          // [n_reads]
-  uint32_t *codes;              // per window, indexed like bases
+  uint32_t *codes;              // per window, indexed like bases (taxids; only with flag 1)
+  uint64_t total_bases;
+  // scratch between the stages (indexed like bases)
+  uint64_t *canon;              // canonical k-mer of the window
+  uint32_t *bins;               // minimizer bin, or BIN_AMBIG / BIN_NONE
+  uint32_t *codes_dense;        // dense taxon id of the window (0 = miss) or AMBIG
   const uint32_t *codes_in;     // MODE_RESOLVE: merged dense ids
   uint32_t *run_start;
   uint32_t *run_count;
@@ -106,7 +115,8 @@ struct Params {
   UnitSet units;
 };
 
-void launch_classify(int mode, const Params &p, int grid, cudaStream_t stream);
+// returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup
+int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cudaEvent_t *stage_events);
 int classify_smem_bytes();
 
 // database staging helpers
