@@ -24,6 +24,8 @@ namespace {
 
 constexpr uint64_t INDEX2_XOR_MASK = 0xe37e28c4271b5a2dULL;   // krakendb.cpp:45
 constexpr uint32_t SLACK = 64;                                // bytes readable past the end of a bases buffer
+constexpr uint32_t UMAP_CAP = 1u << 21;                       // (unit, taxon) pairs per batch
+constexpr uint32_t USET_CAP = 1u << 22;                       // distinct (pair, code) entries per batch
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -33,6 +35,10 @@ struct Slot {
   char *d_bases = nullptr, *d_clean = nullptr;
   uint64_t *d_offsets = nullptr;
   uint32_t *d_unit = nullptr, *d_call = nullptr, *d_nwin = nullptr, *d_codes = nullptr;
+  // HLL mode rule bookkeeping (KUQ_HLL_PRELOAD), allocated on first use
+  unsigned long long *u_keys = nullptr, *u_last = nullptr, *u_set_keys = nullptr;
+  uint32_t *u_inserts = nullptr, *u_distinct = nullptr, *u_set_count = nullptr, *u_ncand = nullptr;
+  uint8_t *u_cand = nullptr, *u_taxon_cand = nullptr;
   uint64_t *d_canon = nullptr;                 // scratch between the stages
   uint32_t *d_bins = nullptr, *d_dense = nullptr;
   uint32_t *d_run_start = nullptr, *d_run_count = nullptr;
@@ -132,6 +138,8 @@ void free_slot(Slot &s) {
   cudaFree(s.d_bases); cudaFree(s.d_clean); cudaFree(s.d_offsets); cudaFree(s.d_unit); cudaFree(s.d_call);
   cudaFree(s.d_nwin); cudaFree(s.d_codes); cudaFree(s.d_run_start); cudaFree(s.d_run_count); cudaFree(s.d_runs);
   cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense);
+  cudaFree(s.u_keys); cudaFree(s.u_last); cudaFree(s.u_set_keys); cudaFree(s.u_inserts); cudaFree(s.u_distinct);
+  cudaFree(s.u_set_count); cudaFree(s.u_ncand); cudaFree(s.u_cand); cudaFree(s.u_taxon_cand);
   cudaFreeHost(s.h_call); cudaFreeHost(s.h_nwin); cudaFreeHost(s.h_run_start); cudaFreeHost(s.h_run_count);
   cudaFreeHost(s.h_codes); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_scalars); cudaFreeHost(s.h_unit);
   if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -187,11 +195,15 @@ uint64_t ertl_dense_hist(const uint32_t *hist64, uint64_t n_observed) {
   C[64] = C[65] = 0;
   return ertl_from_hist(C, 64 - HLL_P, HLL_M, n_observed);
 }
-// getEncodedRank(enc, 25, 12), hyperloglogplus.cpp:152-161
-inline unsigned encoded_rank(uint32_t e) {
-  if (e & 1) return 13 + ((e >> 1) & 0x3F);
-  uint32_t r = e << 12;
-  return (r ? (unsigned)__builtin_clz(r) : 20u) + 1;
+// ertlCardinality of a sparse sketch (hyperloglogplus.cpp:726-729): q = 64 - 25, m = 2^25, C from
+// sparseRegisterHistogram (:356-366): hist64[r] = distinct codes of encoded rank r, C[0] = m - |S|.
+uint64_t ertl_sparse_hist(const uint32_t *hist64, uint64_t n_codes, uint64_t n_observed) {
+  int C[66];
+  memset(C, 0, sizeof C);
+  for (int i = 1; i <= 40; i++) C[i] = (int)hist64[i];
+  const size_t m = 1u << 25;
+  C[0] = (int)(m - n_codes);
+  return ertl_from_hist(C, 64 - 25, m, n_observed);
 }
 
 int alloc_slot(kuq_ctx *ctx, Slot &s) {
@@ -224,6 +236,17 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(hmalloc(&s.h_scalars, 8));
   s.h_runs_cap = std::max<uint64_t>(mr * 8, 1024);
   CU(hmalloc(&s.h_runs, s.h_runs_cap));
+  return KUQ_OK;
+}
+
+// the (taxon, code) set behind the sparse tier must stay well below its capacity (open addressing)
+int check_sparse_fill(kuq_ctx *ctx) {
+  if (!ctx->d_sparse_used) return KUQ_OK;
+  unsigned long long used = 0;
+  CU(cudaMemcpy(&used, ctx->d_sparse_used, 8, cudaMemcpyDeviceToHost));
+  if (used * 10 > ctx->sparse_cap * 8)
+    return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set is %llu / %llu full: raise kuq_config.sparse_set_slots", used,
+                (unsigned long long)ctx->sparse_cap);
   return KUQ_OK;
 }
 
@@ -395,6 +418,31 @@ int ensure_ready(kuq_ctx *ctx) {
   return remap_db(ctx);
 }
 
+int prepare_unit_map(kuq_ctx *ctx, Slot &s) {
+  if (ctx->cfg.hll_mode != KUQ_HLL_PRELOAD) return KUQ_OK;
+  if (!s.u_keys) {
+    CU(dmalloc(&s.u_keys, UMAP_CAP));
+    CU(dmalloc(&s.u_last, UMAP_CAP));
+    CU(dmalloc(&s.u_inserts, UMAP_CAP));
+    CU(dmalloc(&s.u_distinct, UMAP_CAP));
+    CU(dmalloc(&s.u_cand, UMAP_CAP));
+    CU(dmalloc(&s.u_taxon_cand, ctx->n_sketch));
+    CU(dmalloc(&s.u_ncand, 1));
+    CU(dmalloc(&s.u_set_keys, USET_CAP));
+    CU(dmalloc(&s.u_set_count, USET_CAP));
+  }
+  CU(cudaMemsetAsync(s.u_keys, 0, UMAP_CAP * 8ull, s.stream));
+  CU(cudaMemsetAsync(s.u_last, 0, UMAP_CAP * 8ull, s.stream));
+  CU(cudaMemsetAsync(s.u_inserts, 0, UMAP_CAP * 4ull, s.stream));
+  CU(cudaMemsetAsync(s.u_distinct, 0, UMAP_CAP * 4ull, s.stream));
+  CU(cudaMemsetAsync(s.u_cand, 0, UMAP_CAP, s.stream));
+  CU(cudaMemsetAsync(s.u_taxon_cand, 0, ctx->n_sketch, s.stream));
+  CU(cudaMemsetAsync(s.u_ncand, 0, 4, s.stream));
+  CU(cudaMemsetAsync(s.u_set_keys, 0, USET_CAP * 8ull, s.stream));
+  CU(cudaMemsetAsync(s.u_set_count, 0, USET_CAP * 4ull, s.stream));
+  return KUQ_OK;
+}
+
 // process_file's unit cutting (classify.cpp:506-521): reads join the open unit until its length reaches -u.
 void cut_units(kuq_ctx *ctx, const uint64_t *offsets, uint32_t n, uint32_t *unit) {
   const uint64_t wus = ctx->cfg.work_unit_size;
@@ -403,6 +451,20 @@ void cut_units(kuq_ctx *ctx, const uint64_t *offsets, uint32_t n, uint32_t *unit
     ctx->unit_nt += offsets[i + 1] - offsets[i];
     if (ctx->unit_nt >= wus) { ctx->unit_next++; ctx->unit_nt = 0; }
   }
+}
+
+void set_unit_ptrs(Params &p, Slot &s) {
+  p.units.keys = s.u_keys;
+  p.units.inserts = s.u_inserts;
+  p.units.distinct = s.u_distinct;
+  p.units.last = s.u_last;
+  p.units.cand = s.u_cand;
+  p.units.mask = UMAP_CAP - 1;
+  p.units.taxon_cand = s.u_taxon_cand;
+  p.units.n_cand = s.u_ncand;
+  p.units.set_keys = s.u_set_keys;
+  p.units.set_count = s.u_set_count;
+  p.units.set_mask = USET_CAP - 1;
 }
 
 void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const uint64_t *d_offsets,
@@ -454,15 +516,32 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.sparse.mask = ctx->sparse_cap ? ctx->sparse_cap - 1 : 0;
   p.sparse.n_used = ctx->d_sparse_used;
   p.sparse.distinct = ctx->d_sparse_distinct;
+  set_unit_ptrs(p, s);
 }
 
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
+  const bool units = mode != MODE_LOOKUP && ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && p.unit_id && !(p.flags & 4u);
+  if (units) {
+    int rc = prepare_unit_map(ctx, s);
+    if (rc) return rc;
+    set_unit_ptrs(p, s);                 // the map is allocated on first use
+  } else if (ctx->cfg.hll_mode == KUQ_HLL_PRELOAD) {
+    p.unit_id = nullptr;                 // no per-unit bookkeeping for this call
+  }
   CU(cudaMemsetAsync(s.d_scalars, 0, 8 * 8, s.stream));
   CU(cudaEventRecord(s.ev_k0, s.stream));
   CU(cudaEventRecord(s.ev_stage[0], s.stream));
   CU(cudaEventRecord(s.ev_stage[1], s.stream));
   if (p.n_reads) ctx->launches += launch_classify(mode, p, ctx->n_sm, s.stream, s.ev_stage);
   CU(cudaEventRecord(s.ev_k1, s.stream));
+  // HLL mode rule: which taxa have a sketch that converted to dense
+  if (p.n_reads && mode != MODE_LOOKUP && !(p.flags & 4u)) {
+    if (units) ctx->launches += launch_unit_accounting(p, ctx->n_sm, s.stream);
+    else if (ctx->cfg.hll_mode == KUQ_HLL_CHUNKED) {
+      launch_flag_dense_global(ctx->d_sparse_distinct, ctx->d_dense_flag, ctx->n_sketch, s.stream);
+      ctx->launches++;
+    }
+  }
   CU(cudaGetLastError());
   return KUQ_OK;
 }
@@ -752,7 +831,10 @@ int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
   s.kernel_ms = ms;
   const uint32_t err = (uint32_t)(s.h_scalars[3] & 0xFFFFFFFFu);
-  if (err) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
+  int rc2 = check_sparse_fill(ctx);
+  if (rc2) return rc2;
   const uint64_t n_runs = (s.flags & KUQ_F_NO_RUNS) ? 0 : s.h_scalars[0];
   if (n_runs) {
     if (n_runs > s.h_runs_cap) {
@@ -835,8 +917,9 @@ int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.kernel_ms = ms;
   uint32_t err = 0;
   CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
-  if (err) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
-  return KUQ_OK;
+  if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
+  return check_sparse_fill(ctx);
 }
 
 int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out) {
@@ -905,6 +988,7 @@ struct CountsHost {
   std::vector<uint32_t> hist;      // [n_sketch][64]
   std::vector<uint8_t> dense_flag;
   std::vector<uint32_t> distinct;
+  std::vector<uint32_t> sparse_hist;   // [n_sketch][64] rank histogram of the sparse tier
 };
 int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
   if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
@@ -925,8 +1009,21 @@ int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
   CU(cudaStreamSynchronize(ctx->aux));
   cudaFree(d_hist);
   if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
-    CU(cudaMemcpy(h.dense_flag.data(), ctx->d_dense_flag, ctx->n_sketch, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(h.distinct.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost));
+    if (ctx->cfg.hll_mode == KUQ_HLL_CHUNKED) {
+      launch_flag_dense_global(ctx->d_sparse_distinct, ctx->d_dense_flag, ctx->n_sketch, ctx->aux);
+      ctx->launches++;
+    }
+    uint32_t *d_sh;
+    CU(dmalloc(&d_sh, (uint64_t)ctx->n_sketch * 64));
+    CU(cudaMemsetAsync(d_sh, 0, (uint64_t)ctx->n_sketch * 64 * 4, ctx->aux));
+    launch_sparse_histograms(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, d_sh, ctx->aux);
+    ctx->launches++;
+    h.sparse_hist.resize((size_t)ctx->n_sketch * 64);
+    CU(cudaMemcpyAsync(h.sparse_hist.data(), d_sh, (uint64_t)ctx->n_sketch * 64 * 4, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaMemcpyAsync(h.dense_flag.data(), ctx->d_dense_flag, ctx->n_sketch, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaMemcpyAsync(h.distinct.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaStreamSynchronize(ctx->aux));
+    cudaFree(d_sh);
   }
   return KUQ_OK;
 }
@@ -961,10 +1058,15 @@ int kuq_read_counts(kuq_ctx *ctx, uint32_t *taxid, uint64_t *n_reads, uint64_t *
     if (taxid) taxid[i] = rows[i].first;
     if (n_reads) n_reads[i] = h.n_reads[d];
     if (n_kmers) n_kmers[i] = nk;
-    // dense tier; the sparse tier (mode emulation) overrides this in kuq_unique_sparse when applicable
-    uint64_t u = (d < ctx->n_sketch && nk) ? ertl_dense_hist(&h.hist[(size_t)d * 64], nk) : 0;
+    // the sketch the reference would hold: dense registers if some per-unit (or the global) sketch converted,
+    // else the union of the encoded hashes (sparse tier)
+    const bool sparse = d < ctx->n_sketch && ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY && !h.dense_flag[d];
+    uint64_t u = 0;
+    if (d < ctx->n_sketch && nk)
+      u = sparse ? ertl_sparse_hist(&h.sparse_hist[(size_t)d * 64], h.distinct[d], nk)
+                 : ertl_dense_hist(&h.hist[(size_t)d * 64], nk);
     if (unique) unique[i] = u;
-    if (is_sparse) is_sparse[i] = 0;
+    if (is_sparse) is_sparse[i] = sparse ? 1 : 0;
   }
   return KUQ_OK;
 }
@@ -990,7 +1092,46 @@ int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t 
     reads += r; kmers += km;
   }
   uint64_t u = 0;
-  if (!members.empty()) {
+  // clade sketch = merge of the members' sketches: dense as soon as one member is dense
+  // (hyperloglogplus.cpp:604-621), else the union of the sparse sets (:600-603)
+  bool any_dense = ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY;
+  uint64_t sum_distinct = 0;
+  if (!any_dense && !members.empty()) {
+    if (ctx->cfg.hll_mode == KUQ_HLL_CHUNKED) {
+      launch_flag_dense_global(ctx->d_sparse_distinct, ctx->d_dense_flag, ctx->n_sketch, ctx->aux);
+      CU(cudaStreamSynchronize(ctx->aux));
+    }
+    for (uint32_t d : members) {
+      uint8_t f = 0; uint32_t dc = 0;
+      CU(cudaMemcpy(&f, ctx->d_dense_flag + d, 1, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(&dc, ctx->d_sparse_distinct + d, 4, cudaMemcpyDeviceToHost));
+      any_dense |= f != 0;
+      sum_distinct += dc;
+    }
+  }
+  if (!members.empty() && !any_dense) {
+    std::vector<uint8_t> member(ctx->n_sketch, 0);
+    for (uint32_t d : members) member[d] = 1;
+    uint64_t cap = 1024;
+    while (cap < 2 * sum_distinct + 16) cap <<= 1;
+    uint8_t *d_member; unsigned long long *d_set; uint32_t *d_hist;
+    CU(dmalloc(&d_member, ctx->n_sketch));
+    CU(dmalloc(&d_set, cap));
+    CU(dmalloc(&d_hist, 65));
+    CU(cudaMemcpyAsync(d_member, member.data(), ctx->n_sketch, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemsetAsync(d_set, 0, cap * 8, ctx->aux));
+    CU(cudaMemsetAsync(d_hist, 0, 65 * 4, ctx->aux));
+    launch_sparse_union(ctx->d_sparse_slots, ctx->sparse_cap, d_member, d_set, cap - 1, d_hist, d_hist + 64, ctx->aux);
+    ctx->launches++;
+    uint32_t hist[65];
+    CU(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaStreamSynchronize(ctx->aux));
+    cudaFree(d_member); cudaFree(d_set); cudaFree(d_hist);
+    if (hist[64]) return fail(ctx, KUQ_E_CAPACITY, "internal: clade union scratch overflow");
+    uint64_t n_codes = 0;
+    for (int i = 0; i < 64; i++) n_codes += hist[i];
+    u = ertl_sparse_hist(hist, n_codes, kmers);
+  } else if (!members.empty()) {
     uint32_t *d_members; uint8_t *d_out; uint32_t *d_hist;
     CU(dmalloc(&d_members, members.size()));
     CU(dmalloc(&d_out, HLL_M));

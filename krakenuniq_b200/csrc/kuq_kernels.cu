@@ -452,6 +452,23 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
   }
 }
 
+// ---- per-batch (unit, taxon) map ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t umap_slot(const UnitMap &u, uint32_t unit, uint32_t taxon, bool insert) {
+  const unsigned long long key = ((unsigned long long)(unit + 1) << 32) | taxon;
+  uint32_t slot = (uint32_t)mix64(key) & u.mask;
+  for (uint32_t probe = 0; probe <= u.mask; probe++) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(u.keys + slot);
+    if (cur == key) return slot;
+    if (cur == 0) {
+      if (!insert) return 0xFFFFFFFFu;
+      unsigned long long prev = atomicCAS(u.keys + slot, 0ull, key);
+      if (prev == 0 || prev == key) return slot;
+    }
+    slot = (slot + 1) & u.mask;
+  }
+  return 0xFFFFFFFFu;
+}
+
 // Stage 3: one warp per read.  hit_counts (classify.cpp:941-942), resolve_tree / lca (krakenutil.cpp:90-118,
 // 149-200), the per-taxon counters (classify.cpp:939,968) and the run-length encoded hit list (:826-861).
 constexpr int RUN_BUF = 96;      // runs buffered per warp before they are flushed to global memory
@@ -562,6 +579,20 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       if (overflow) atomicExch(p.error_flag, 1u);
     }
     // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
+    if (counting && p.hll_mode == 0u && p.unit_id) {
+      // inserts per (work unit, taxon): the necessary condition for a per-unit sketch to convert
+      const uint32_t unit = p.unit_id[r];
+      if (lane < n_hits) {
+        uint32_t sl = umap_slot(p.units, unit, my_t, true);
+        if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
+        else atomicAdd(p.units.inserts + sl, my_c);
+      }
+      if (lane == 0 && n_miss) {
+        uint32_t sl = umap_slot(p.units, unit, 0, true);
+        if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
+        else atomicAdd(p.units.inserts + sl, n_miss);
+      }
+    }
     if (counting) {
       if (lane < n_hits) atomicAdd(p.n_kmers + my_t, (unsigned long long)my_c);
       acc_miss += n_miss;
@@ -628,6 +659,153 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
     if (acc_unclassified) atomicAdd(p.n_reads_ctr, (unsigned long long)acc_unclassified);
     if (acc_classified) atomicAdd(p.n_classified, (unsigned long long)acc_classified);
   }
+}
+
+// ---- HLL mode rule ------------------------------------------------------------------------
+__global__ void k_unit_mark(const __grid_constant__ Params p) {
+  const UnitMap &u = p.units;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= u.mask; s += gridDim.x * blockDim.x) {
+    const unsigned long long key = u.keys[s];
+    if (!key) continue;
+    const uint32_t taxon = (uint32_t)key;
+    if (u.inserts[s] >= 1025u && !p.dense_flag[taxon]) {
+      u.cand[s] = 1;
+      u.taxon_cand[taxon] = 1;
+      atomicAdd(u.n_cand, 1u);
+    }
+  }
+}
+
+// warp per read; only windows of candidate (unit, taxon) pairs do any work
+__global__ void __launch_bounds__(256) k_unit_distinct(const __grid_constant__ Params p) {
+  const UnitMap &u = p.units;
+  if (*reinterpret_cast<volatile uint32_t *>(u.n_cand) == 0) return;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + warp; r < p.n_reads; r += warps_total) {
+    const uint64_t base = p.offsets[r];
+    const uint32_t nwin = p.n_windows[r];
+    const uint32_t unit = p.unit_id[r];
+    for (uint32_t i = lane; i < nwin; i += 32) {
+      const uint32_t t = p.codes_dense[base + i];
+      if (t == AMBIG || !u.taxon_cand[t]) continue;
+      const uint32_t sl = umap_slot(u, unit, t, false);
+      if (sl == 0xFFFFFFFFu || !u.cand[sl]) continue;
+      atomicMax(u.last + sl, ((unsigned long long)r << 32) | i);
+      if (*reinterpret_cast<volatile uint32_t *>(u.distinct + sl) >= 1025u) continue;   // decided already
+      const uint32_t code = encode_hash32(fmix64(p.canon[base + i]));
+      const unsigned long long key = ((unsigned long long)(sl + 1) << 32) | code;
+      uint32_t q = (uint32_t)mix64(key) & u.set_mask;
+      for (uint32_t probe = 0; probe <= u.set_mask; probe++) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(u.set_keys + q);
+        if (cur == 0) {
+          cur = atomicCAS(u.set_keys + q, 0ull, key);
+          if (cur == 0) { atomicAdd(u.distinct + sl, 1u); cur = key; }
+        }
+        if (cur == key) { atomicAdd(u.set_count + q, 1u); break; }
+        q = (q + 1) & u.set_mask;
+        if (probe == u.set_mask) atomicExch(p.error_flag, 3u);
+      }
+    }
+  }
+}
+
+// A (unit, taxon) sketch receiving inserts x_1..x_N converts iff D >= 1025, or D == 1024 and the 1024th distinct
+// code arrives before the last insert: i.e. the last insert repeats a code seen earlier.
+__global__ void k_unit_apply(const __grid_constant__ Params p) {
+  const UnitMap &u = p.units;
+  if (*reinterpret_cast<volatile uint32_t *>(u.n_cand) == 0) return;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= u.mask; s += gridDim.x * blockDim.x) {
+    if (!u.cand[s]) continue;
+    const uint32_t taxon = (uint32_t)u.keys[s];
+    const uint32_t d = u.distinct[s];
+    bool conv = d >= 1025u;
+    if (!conv && d == 1024u) {
+      const unsigned long long lp = u.last[s];
+      const uint32_t r = (uint32_t)(lp >> 32), i = (uint32_t)lp;
+      const uint32_t code = encode_hash32(fmix64(p.canon[p.offsets[r] + i]));
+      const unsigned long long key = ((unsigned long long)(s + 1) << 32) | code;
+      uint32_t q = (uint32_t)mix64(key) & u.set_mask;
+      for (uint32_t probe = 0; probe <= u.set_mask; probe++) {
+        unsigned long long cur = u.set_keys[q];
+        if (cur == key) { conv = u.set_count[q] >= 2u; break; }
+        if (cur == 0) break;
+        q = (q + 1) & u.set_mask;
+      }
+    }
+    if (conv) p.dense_flag[taxon] = 1;
+  }
+}
+
+int launch_unit_accounting(const Params &p, int n_sm, cudaStream_t stream) {
+  if (p.n_reads == 0) return 0;
+  k_unit_mark<<<n_sm * 4, 256, 0, stream>>>(p);
+  const int rgrid = (int)min((uint32_t)n_sm * 8, (p.n_reads + 7) / 8);
+  k_unit_distinct<<<rgrid, 256, 0, stream>>>(p);
+  k_unit_apply<<<n_sm * 4, 256, 0, stream>>>(p);
+  return 3;
+}
+
+__global__ void k_flag_dense_global(const uint32_t *distinct, uint8_t *dense_flag, uint32_t n_sketch) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_sketch && distinct[t] >= 1025u) dense_flag[t] = 1;
+}
+void launch_flag_dense_global(const uint32_t *distinct, uint8_t *dense_flag, uint32_t n_sketch, cudaStream_t stream) {
+  if (n_sketch) k_flag_dense_global<<<(n_sketch + 255) / 256, 256, 0, stream>>>(distinct, dense_flag, n_sketch);
+}
+
+// getEncodedRank(enc, 25, 12), hyperloglogplus.cpp:152-161
+__device__ __forceinline__ uint32_t encoded_rank_dev(uint32_t e) {
+  if (e & 1) return 13 + ((e >> 1) & 0x3F);
+  uint32_t r = e << 12;
+  return (r ? (uint32_t)__clz(r) : 20u) + 1;
+}
+
+// sparseRegisterHistogram (hyperloglogplus.cpp:356-366) for every taxon that stayed sparse: C[t][rank]++ over the
+// distinct codes of t (the host derives C[0] = 2^25 - |S_t|)
+__global__ void k_sparse_histograms(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
+                                    uint32_t *hist) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = slots[i];
+    if (!key) continue;
+    const uint32_t taxon = (uint32_t)(key >> 32) - 1;
+    if (dense_flag[taxon]) continue;
+    atomicAdd(hist + (size_t)taxon * 64 + min(encoded_rank_dev((uint32_t)key), 63u), 1u);
+  }
+}
+void launch_sparse_histograms(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
+                              uint32_t *hist, cudaStream_t stream) {
+  if (cap) k_sparse_histograms<<<148 * 16, 256, 0, stream>>>(slots, cap, dense_flag, hist);
+}
+
+// union of the sparse code sets of the member taxa (sparse ∪ sparse merge, hyperloglogplus.cpp:600-603)
+__global__ void k_sparse_union(const unsigned long long *slots, uint64_t cap, const uint8_t *member,
+                               unsigned long long *scratch, uint64_t smask, uint32_t *hist64, uint32_t *overflow) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = slots[i];
+    if (!key) continue;
+    const uint32_t taxon = (uint32_t)(key >> 32) - 1;
+    if (!member[taxon]) continue;
+    const uint32_t code = (uint32_t)key;
+    const unsigned long long k2 = (1ull << 32) | code;
+    uint64_t q = mix64(k2) & smask;
+    for (uint64_t probe = 0; probe <= smask; probe++) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(scratch + q);
+      if (cur == k2) break;
+      if (cur == 0) {
+        cur = atomicCAS(scratch + q, 0ull, k2);
+        if (cur == 0) { atomicAdd(hist64 + min(encoded_rank_dev(code), 63u), 1u); break; }
+        if (cur == k2) break;
+      }
+      q = (q + 1) & smask;
+      if (probe == smask) atomicExch(overflow, 1u);
+    }
+  }
+}
+void launch_sparse_union(const unsigned long long *slots, uint64_t cap, const uint8_t *member,
+                         unsigned long long *scratch_set, uint64_t scratch_mask, uint32_t *hist64, uint32_t *overflow,
+                         cudaStream_t stream) {
+  if (cap) k_sparse_union<<<148 * 16, 256, 0, stream>>>(slots, cap, member, scratch_set, scratch_mask, hist64, overflow);
 }
 
 int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedState); }

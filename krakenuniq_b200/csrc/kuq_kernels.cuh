@@ -65,14 +65,21 @@ struct SparseSet {           // device set of (dense taxon, encoded hash) pairs:
   uint32_t *distinct;        // [n_sketch] distinct codes inserted per taxon
 };
 
-struct UnitSet {             // per-batch set of (unit, taxon, code) triples: distinct codes per work-unit sketch
-  unsigned long long *slots; // two words per entry: {unit<<32|taxon+1, code}; slot i → words 2i, 2i+1
-  uint64_t mask;
-  uint32_t *map_keys_lo;     // per-batch (unit,taxon) → counter map
-  unsigned long long *map_keys;
-  uint32_t *map_distinct;
-  uint32_t *map_inserts;
-  uint64_t map_mask;
+// Per-batch bookkeeping of the reference's per-work-unit sketches (classify.cpp:525: one ReadCounts map per work
+// unit).  A (unit, taxon) sketch converts from sparse to dense iff an insert finds >= 1024 distinct encoded hashes
+// already stored (hyperloglogplus.cpp:496-498), so only pairs with > 1024 inserts need their distinct count.
+struct UnitMap {
+  unsigned long long *keys;   // 0 = empty; (unit + 1) << 32 | taxon   (open addressing, per batch)
+  uint32_t *inserts;          // N(unit, taxon): add_kmer calls
+  uint32_t *distinct;         // D(unit, taxon): distinct encoded hashes (only counted for candidates, saturating)
+  unsigned long long *last;   // (read << 32 | window) of the last insert of the pair
+  uint8_t *cand;              // 1 = candidate (N >= 1025 and the taxon is not already known dense)
+  uint32_t mask;              // capacity - 1
+  uint8_t *taxon_cand;        // [n_sketch] some unit of this batch makes the taxon a candidate
+  uint32_t *n_cand;           // number of candidate pairs of the batch
+  unsigned long long *set_keys;  // distinct (pair slot, code): 0 = empty; (slot + 1) << 32 | code
+  uint32_t *set_count;           // occurrences of the key
+  uint32_t set_mask;
 };
 
 struct Params {
@@ -112,7 +119,7 @@ struct Params {
   unsigned long long *n_reads_ctr; // [n_taxa]
   uint8_t *dense_flag;          // [n_sketch]
   SparseSet sparse;
-  UnitSet units;
+  UnitMap units;
 };
 
 // returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup
@@ -129,5 +136,16 @@ void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t
 void launch_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_members, uint8_t *out4096,
                       cudaStream_t stream);
 void launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream);
+// HLL mode rule, per batch: mark candidate (unit, taxon) pairs, count their distinct codes, flag dense taxa
+int launch_unit_accounting(const Params &p, int n_sm, cudaStream_t stream);
+// chunked rule: one global sketch per taxon converts once it holds >= 1025 distinct codes
+void launch_flag_dense_global(const uint32_t *distinct, uint8_t *dense_flag, uint32_t n_sketch, cudaStream_t stream);
+// histogram of encoded ranks over the sparse set, per taxon: hist[t][64] (+ hist[t][63] unused)
+void launch_sparse_histograms(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
+                              uint32_t *hist, cudaStream_t stream);
+// distinct codes of the union of the member taxa (member[t] != 0): rank histogram hist64 via a scratch set
+void launch_sparse_union(const unsigned long long *slots, uint64_t cap, const uint8_t *member,
+                         unsigned long long *scratch_set, uint64_t scratch_mask, uint32_t *hist64, uint32_t *overflow,
+                         cudaStream_t stream);
 
 }  // namespace kuq

@@ -31,11 +31,16 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 H = {h: i for i, h in enumerate(hdr)}
-data = []
-for r in rows[2:]:
-    if r and r[0] == "Kernel Name" and data:
-        break
-    if len(r) > 10 and r[0].startswith("0x"):
+kname = sys.argv[3] if len(sys.argv) > 3 else "k_lookupILi0"
+short = re.sub(r"ILi\d+.*", "", kname)
+data, active = [], False
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        if data:
+            break
+        active = short in r[1]
+        continue
+    if active and len(r) > 10 and r[0].startswith("0x"):
         data.append(r)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = {s: sum(int(r[H[s]] or 0) for r in data) for s in stalls}
@@ -46,7 +51,6 @@ tmp = "/tmp/kuq_cub"
 os.makedirs(tmp, exist_ok=True)
 subprocess.run(f"cd {tmp} && rm -f *.cubin && cuobjdump -xelf all {so} >/dev/null 2>&1", shell=True)
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "kuq_kernels.sm_100a.cubin")], capture_output=True, text=True).stdout.split("\n")
-kname = "k_classifyILi0"
 start = [i for i, l in enumerate(sass) if ".text." in l and kname in l][0]
 cur, m = None, {}
 for l in sass[start + 1:]:

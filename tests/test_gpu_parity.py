@@ -59,6 +59,10 @@ def _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.H
     assert np.array_equal(got["n_kmers"], want["n_kmers"])
     for j, t in enumerate(want["taxid"]):
         assert np.array_equal(clf.registers(int(t)), want["regs"][j]), f"registers of taxon {t}"
+    if hll_mode != binding.HLL_DENSE_ONLY:
+        # the reference's sparse→dense mode rule reproduced exactly: same tier, same estimate
+        assert np.array_equal(got["sparse"], want["sparse"]), (got["sparse"], want["sparse"])
+        assert np.array_equal(got["unique"], want["unique"]), (got["unique"], want["unique"])
     return clf, got, want
 
 
@@ -180,3 +184,58 @@ def test_batches_and_slots_are_equivalent(oracle):
     got = clf.counts()
     for key in ("taxid", "n_reads", "n_kmers", "unique"):
         assert np.array_equal(got[key], got1[key]), key
+
+
+@pytest.mark.parametrize("unit,mode", [(500000, 0), (1350, 0), (1500, 0), (2000, 0), (4000, 0), (20000, 0),
+                                       (500000, 1)])
+def test_hll_mode_rule_matches_oracle(oracle, unit, mode):
+    """uniqueKmerCount under the reference's sparse/dense rule: per-work-unit sketches (preload)
+    and one global sketch (chunked).  Small units put many (unit, taxon) pairs right around the 1024 threshold."""
+    tax, genomes, kdb, idx, bases, offs = _synthetic(300 + unit % 97, 8, 2, n_genomes=3, glen=1600, n_reads=1500,
+                                                     n_frac=0.05)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs,
+                          hll_mode=binding.HLL_PRELOAD if mode == 0 else binding.HLL_CHUNKED, unit=unit,
+                          oracle_mode=mode)
+
+
+def test_hll_threshold_corner(oracle):
+    """D == 1024 exactly: the sketch converts only if the last insert repeats an earlier code."""
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 4, 1024 + 30, dtype=np.uint8)          # 1024 windows → (almost surely) 1024 distinct codes
+    tax = synth.make_taxonomy(1)
+    sp = synth.species_ids(tax)
+    km, tx = synth.label_kmers([g], sp, tax, K)
+    kdb, idx = synth.build_db_images(km, tx, K, 7, 2)
+    whole = synth.decode(g).tobytes()
+    for tail in (whole[:60], whole[-60:], whole[500:560]):
+        # one unit: all 1024 distinct k-mers, then one more read that only repeats k-mers
+        seqs = [whole, tail]
+        bases, offs = synth.pack_reads(seqs)
+        _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_PRELOAD, unit=10 ** 9)
+    # the last read introduces the 1024th distinct code as the very last insert: stays sparse
+    seqs = [whole[:1024 + 29], whole[-31:]]
+    bases, offs = synth.pack_reads(seqs)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_PRELOAD, unit=10 ** 9)
+
+
+@pytest.mark.parametrize("tag,unit,mode", [("preload", 500000, binding.HLL_PRELOAD),
+                                           ("preload_u20000", 20000, binding.HLL_PRELOAD),
+                                           ("chunked", 500000, binding.HLL_CHUNKED)])
+def test_golden_report_kmers_column(tag, unit, mode):
+    """reads / kmers / dup columns of the unmodified reference's report, for every clade, exactly."""
+    kdb = np.fromfile(os.path.join(util.GOLDEN, "database.kdb"), np.uint8)
+    idx = np.fromfile(os.path.join(util.GOLDEN, "database.idx"), np.uint8)
+    tax = synth.Taxonomy.read(os.path.join(util.GOLDEN, "taxDB"))
+    ids, seqs = util.read_fasta(os.path.join(util.GOLDEN, "reads.fa"))
+    bases, offs = synth.pack_reads(seqs)
+    clf = _classifier(hll_mode=mode, work_unit_size=unit)
+    clf.stage_db(kdb, idx)
+    clf.set_taxonomy(*tax.parent_map())
+    clf.classify(bases, offs)
+    clf.finish()
+    cnt = clf.counts()
+    rep = util.parse_report(os.path.join(util.GOLDEN, f"{tag}.report.tsv"))
+    members = util.clade_members(tax.rows, cnt["taxid"])
+    for taxid, row in rep.items():
+        u, r, k = clf.clade(members[taxid])
+        assert (row["reads"], row["kmers"]) == (r, u), (taxid, row, r, u, k)
