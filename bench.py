@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--batch-reads", type=int, default=1_000_000, help="reads per step")
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hll-mode", type=int, default=2, help="0 preload rule (reference default), 1 chunked, 2 dense only")
+    ap.add_argument("--hll-mode", type=int, default=0, help="0 preload rule (reference default), 1 chunked, 2 dense only")
     ap.add_argument("--cache-dir", default=os.environ.get("KUQ_BENCH_CACHE", "/dev/shm"))
     return ap.parse_args()
 
@@ -247,6 +247,23 @@ def main():
     clf.set_taxonomy(*db.parent_map())
 
     d_offsets = (torch.arange(B + 2, dtype=torch.int64, device=dev) * READ_LEN)   # +1: slices are copied in 16-byte units
+    # work units as process_file cuts them (classify.cpp:514-520): reads join a unit until it holds >= 500000 nt;
+    # every batch starts a fresh unit (a batch = one input file of the reference)
+    per_unit = -(-500000 // READ_LEN)
+    units_per_batch = -(-B // per_unit)
+    unit_local = (torch.arange(B, dtype=torch.int64, device=dev) // per_unit).to(torch.int32)
+    host_unit_local = (np.arange(B, dtype=np.int64) // per_unit).astype(np.uint32)
+    unit_bufs = {}
+
+    def d_units(step_idx):
+        if args.hll_mode != 0:
+            return None
+        t = unit_local + step_idx * units_per_batch
+        unit_bufs[step_idx % 4] = t              # keep alive until the kernels have run
+        return t.data_ptr()
+
+    def h_units(step_idx):
+        return (host_unit_local + np.uint32(step_idx * units_per_batch)) if args.hll_mode == 0 else None
     host_offsets = (np.arange(B + 1, dtype=np.uint64) * READ_LEN)
 
     def batch_ptr(i):
@@ -278,7 +295,7 @@ def main():
     # ---- value: device-resident inputs ----------------------------------------------------------------------------
     step = 0
     for _ in range(args.warmup):
-        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN); step += 1
+        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
     clf.sync(0)
     barrier()
     launches0 = clf.launch_count()
@@ -288,7 +305,7 @@ def main():
     with torch.cuda.stream(stream):
         ev0.record(stream)
     for _ in range(args.steps):
-        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN); step += 1
+        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
     with torch.cuda.stream(stream):
         ev1.record(stream)
     clf.sync(0)
@@ -310,14 +327,14 @@ def main():
     value = world * B * args.steps / (dev_ms / 1e3) / 1e6
 
     # per-launch duration of the dominant kernel + algorithmic bytes (one extra, untimed, instrumented step)
-    clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, flags=binding.F_STATS); step += 1
+    clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step), flags=binding.F_STATS); step += 1
     clf.sync(0)
     n_lookups, sum_probes = clf.slot_stats(0)
     # B_kmer = 16 + 12*P(n_b) + 1 per non-ambiguous k-mer, B_read = L + 4 + 4*(L-30) per read
     algo_bytes = 17 * n_lookups + 12 * sum_probes + B * (READ_LEN + 4 + 4 * (READ_LEN - 30))
     k_ms, st_ms = [], []
     for _ in range(3):
-        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN); step += 1
+        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
         clf.sync(0)
         k_ms.append(clf.last_kernel_ms(0))
         st_ms.append(clf.last_stage_ms(0))
@@ -346,6 +363,7 @@ def main():
         host_bufs.append((p, hb))
     n_slots = 3
     d2h_bytes = [0]
+    e2e_step = [step]
 
     def run_e2e(n_steps):
         inflight = []
@@ -354,7 +372,7 @@ def main():
             if len(inflight) == n_slots:
                 res = clf.wait(inflight.pop(0))
                 d2h_bytes[0] = 4 * B * 4 + 8 * res["n_runs"] + 64
-            clf.submit(slot, host_bufs[s % n_host][0], host_offsets)
+            clf.submit(slot, host_bufs[s % n_host][0], host_offsets, h_units(e2e_step[0])); e2e_step[0] += 1
             inflight.append(slot)
         for slot in inflight:
             res = clf.wait(slot)

@@ -241,12 +241,7 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
 
 // the (taxon, code) set behind the sparse tier must stay well below its capacity (open addressing)
 int check_sparse_fill(kuq_ctx *ctx) {
-  if (!ctx->d_sparse_used) return KUQ_OK;
-  unsigned long long used = 0;
-  CU(cudaMemcpy(&used, ctx->d_sparse_used, 8, cudaMemcpyDeviceToHost));
-  if (used * 10 > ctx->sparse_cap * 8)
-    return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set is %llu / %llu full: raise kuq_config.sparse_set_slots", used,
-                (unsigned long long)ctx->sparse_cap);
+  (void)ctx;   // saturation is reported by the kernels through the slot's error flag (code 4)
   return KUQ_OK;
 }
 
@@ -832,6 +827,7 @@ int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
   s.kernel_ms = ms;
   const uint32_t err = (uint32_t)(s.h_scalars[3] & 0xFFFFFFFFu);
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
   int rc2 = check_sparse_fill(ctx);
   if (rc2) return rc2;
@@ -918,6 +914,7 @@ int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   uint32_t err = 0;
   CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
   return check_sparse_fill(ctx);
 }

@@ -117,21 +117,22 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {   // table hash for the 
   return x;
 }
 
-// Insert into the (taxon, code) set behind the sparse HLL tier.  Returns true when the key is new.
-__device__ __forceinline__ bool sparse_insert(const SparseSet &s, uint32_t taxon, uint32_t code) {
+// Insert into the (taxon, code) set behind the sparse HLL tier.  Returns 1 when the key is new, 0 when it was
+// there already, -1 when the table is saturated (the host turns that into KUQ_E_CAPACITY).
+__device__ __forceinline__ int sparse_insert(const SparseSet &s, uint32_t taxon, uint32_t code) {
   unsigned long long key = ((unsigned long long)(taxon + 1) << 32) | code;
   uint64_t slot = mix64(key) & s.mask;
-  for (uint32_t probe = 0; probe < 4096; probe++) {
+  for (uint32_t probe = 0; probe < 512; probe++) {
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(s.slots + slot);
-    if (cur == key) return false;
+    if (cur == key) return 0;
     if (cur == 0) {
       unsigned long long prev = atomicCAS(s.slots + slot, 0ull, key);
-      if (prev == 0) return true;
-      if (prev == key) return false;
+      if (prev == 0) return 1;
+      if (prev == key) return 0;
     }
     slot = (slot + 1) & s.mask;
   }
-  return false;   // table saturated: the host sees n_used close to capacity and reports KUQ_E_CAPACITY
+  return -1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -443,10 +444,9 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
       const uint64_t h = fmix64(canon);
       hll_update(p.regs, taxon, h);
       if (p.hll_mode != 2u && !p.dense_flag[taxon]) {
-        if (sparse_insert(p.sparse, taxon, encode_hash32(h))) {
-          atomicAdd(p.sparse.n_used, 1ull);
-          atomicAdd(p.sparse.distinct + taxon, 1u);
-        }
+        const int ins = sparse_insert(p.sparse, taxon, encode_hash32(h));
+        if (ins > 0) atomicAdd(p.sparse.distinct + taxon, 1u);
+        else if (ins < 0) atomicExch(p.error_flag, 4u);       // set saturated
       }
     }
   }
@@ -486,7 +486,21 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
   // and keeps the hot counters in registers until it is done.
   uint32_t blk_next = 0, blk_end = 0;                           // this warp's block of run slots
   uint32_t acc_miss = 0, acc_unclassified = 0, acc_classified = 0;
-  for (uint32_t r = blockIdx.x * CTA_WARPS + warp; r < p.n_reads; r += warps_total) {
+  uint32_t unit_cur = 0xFFFFFFFFu, unit_miss = 0;               // misses of the current work unit, not yet booked
+  const bool units = counting && p.hll_mode == 0u && p.unit_id;
+  auto flush_unit = [&]() {
+    if (lane == 0 && unit_miss) {
+      uint32_t sl = umap_slot(p.units, unit_cur, 0, true);
+      if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
+      else atomicAdd(p.units.inserts + sl, unit_miss);
+    }
+    unit_miss = 0;
+  };
+  // each warp takes a contiguous range of reads: consecutive reads share their work unit and their run block
+  const uint32_t per_warp = (p.n_reads + warps_total - 1) / warps_total;
+  const uint32_t r_begin = (blockIdx.x * CTA_WARPS + warp) * per_warp;
+  const uint32_t r_end = min(r_begin + per_warp, p.n_reads);
+  for (uint32_t r = r_begin; r < r_end; r++) {
     const uint64_t out_base = p.offsets[r];
     const uint32_t nwin = p.n_windows[r];
     uint32_t my_t = 0, my_c = 0;                                // hit list: lane j holds entry j (dense id, count)
@@ -579,18 +593,15 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       if (overflow) atomicExch(p.error_flag, 1u);
     }
     // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
-    if (counting && p.hll_mode == 0u && p.unit_id) {
+    if (units) {
       // inserts per (work unit, taxon): the necessary condition for a per-unit sketch to convert
       const uint32_t unit = p.unit_id[r];
+      if (unit != unit_cur) { flush_unit(); unit_cur = unit; }
+      unit_miss += n_miss;
       if (lane < n_hits) {
         uint32_t sl = umap_slot(p.units, unit, my_t, true);
         if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
         else atomicAdd(p.units.inserts + sl, my_c);
-      }
-      if (lane == 0 && n_miss) {
-        uint32_t sl = umap_slot(p.units, unit, 0, true);
-        if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
-        else atomicAdd(p.units.inserts + sl, n_miss);
       }
     }
     if (counting) {
@@ -654,6 +665,7 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       __syncwarp();
     }
   }
+  if (units) flush_unit();
   if (counting && lane == 0) {
     if (acc_miss) atomicAdd(p.n_kmers, (unsigned long long)acc_miss);
     if (acc_unclassified) atomicAdd(p.n_reads_ctr, (unsigned long long)acc_unclassified);
