@@ -281,16 +281,10 @@ def main():
         torch.cuda.synchronize()
 
     def merge_state():
-        """end-of-run merge across replicas"""
-        if not dist:
-            return
-        sp = clf.state_ptrs()
-        regs = _as_tensor(sp.d_regs, sp.regs_bytes, torch.uint8, dev)
-        nk = _as_tensor(sp.d_n_kmers, sp.n_sketch * 8, torch.int64, dev)
-        nr = _as_tensor(sp.d_n_reads, sp.n_taxa * 8, torch.int64, dev)
-        dist.all_reduce(regs, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nk, op=dist.ReduceOp.SUM)
-        dist.all_reduce(nr, op=dist.ReduceOp.SUM)
+        """end-of-run merge across replicas: NCCL allreduce MAX/SUM + sparse-tier union"""
+        if dist:
+            from krakenuniq_b200 import dist as kdist
+            kdist.merge_classifier_state(clf, dev)
 
     # ---- value: device-resident inputs ----------------------------------------------------------------------------
     step = 0
@@ -422,20 +416,6 @@ def main():
     if dist:
         dist.destroy_process_group()
     return 0
-
-
-def _as_tensor(ptr, nbytes, dtype, dev):
-    """torch view of library-owned device memory (for the NCCL collectives only)"""
-    import torch
-
-    class _Holder:
-        pass
-    h = _Holder()
-    itemsize = torch.tensor([], dtype=dtype).element_size()
-    typestr = {torch.uint8: "|u1", torch.int64: "<i8", torch.int32: "<i4"}[dtype]
-    h.__cuda_array_interface__ = {"shape": (int(nbytes // itemsize),), "typestr": typestr, "data": (int(ptr), False),
-                                  "version": 3}
-    return torch.as_tensor(h, device=dev)
 
 
 if __name__ == "__main__":

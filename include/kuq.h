@@ -216,6 +216,12 @@ int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t 
 /* The 4096 p=12 registers of one taxon (all zero if it received no k-mer). */
 int kuq_get_registers(kuq_ctx *ctx, uint32_t taxid, uint8_t *regs4096);
 int kuq_state_ptrs_get(kuq_ctx *ctx, kuq_state_ptrs *out);
+/* Sparse tier across GPUs (replicas / shards with the exact HLL rule): export the (taxon, encoded hash) keys of the
+ * taxa that are still sparse into d_keys_out (HBM; pass NULL / cap 0 to query *n), all-gather them, and import the
+ * peers' keys; together with allreduce(MAX) on d_dense_flag / d_regs and SUM on the counters this is the merge
+ * `taxon_counts[t] += ...` of classify.cpp:542-544 across processes. */
+int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t *n);
+int kuq_sparse_import(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n);
 /* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);
 int kuq_reset_counts(kuq_ctx *ctx);

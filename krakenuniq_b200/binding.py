@@ -110,6 +110,8 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_get_registers": (C.c_int, [vp, C.c_uint32, u8p]),
         "kuq_state_ptrs_get": (C.c_int, [vp, C.POINTER(StatePtrs)]),
         "kuq_dense_taxids": (C.c_int, [vp, u32p, C.c_uint32, u32p]),
+        "kuq_sparse_export": (C.c_int, [vp, vp, C.c_uint64, u64p]),
+        "kuq_sparse_import": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_reset_counts": (C.c_int, [vp]),
         "kuq_ertl_dense": (C.c_uint64, [u8p, C.c_uint64]),
     }
@@ -314,6 +316,14 @@ class Classifier:
         t = np.zeros(n.value, np.uint32)
         self._ck(self.L.kuq_dense_taxids(self.h, _p(t, u32p), n.value, C.byref(n)))
         return t
+
+    def sparse_export(self, d_out=None, cap=0):
+        n = C.c_uint64(0)
+        self._ck(self.L.kuq_sparse_export(self.h, d_out, cap, C.byref(n)))
+        return n.value
+
+    def sparse_import(self, d_keys, n):
+        self._ck(self.L.kuq_sparse_import(self.h, d_keys, n))
 
     def reset_counts(self):
         self._ck(self.L.kuq_reset_counts(self.h))

@@ -1175,6 +1175,52 @@ int kuq_state_ptrs_get(kuq_ctx *ctx, kuq_state_ptrs *out) {
   return KUQ_OK;
 }
 
+int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t *n) {
+  if (!ctx || !n) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  *n = 0;
+  if (!ctx->d_sparse_slots) return KUQ_OK;                    // KUQ_HLL_DENSE_ONLY: no sparse tier
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  unsigned long long *d_n;
+  CU(dmalloc(&d_n, 1));
+  CU(cudaMemsetAsync(d_n, 0, 8, ctx->aux));
+  launch_sparse_export(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag,
+                       reinterpret_cast<unsigned long long *>(d_keys_out), d_keys_out ? cap : 0, d_n, ctx->aux);
+  ctx->launches++;
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, d_n, 8, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  cudaFree(d_n);
+  *n = cnt;
+  if (d_keys_out && cnt > cap) return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", cnt);
+  return KUQ_OK;
+}
+
+int kuq_sparse_import(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
+  if (!ctx || (!d_keys && n)) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  if (!ctx->d_sparse_slots || !n) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  SparseSet ss;
+  ss.slots = ctx->d_sparse_slots; ss.mask = ctx->sparse_cap - 1; ss.n_used = ctx->d_sparse_used;
+  ss.distinct = ctx->d_sparse_distinct;
+  uint32_t *d_err;
+  CU(dmalloc(&d_err, 1));
+  CU(cudaMemsetAsync(d_err, 0, 4, ctx->aux));
+  launch_sparse_import(reinterpret_cast<const unsigned long long *>(d_keys), n, ss, ctx->d_dense_flag, d_err, ctx->aux);
+  ctx->launches++;
+  uint32_t err = 0;
+  CU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  cudaFree(d_err);
+  if (err) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated while importing");
+  return KUQ_OK;
+}
+
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n) {
   if (!ctx || !n) return KUQ_E_INVALID_ARG;
   int rc = ensure_ready(ctx);

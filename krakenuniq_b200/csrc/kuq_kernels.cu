@@ -820,6 +820,44 @@ void launch_sparse_union(const unsigned long long *slots, uint64_t cap, const ui
   if (cap) k_sparse_union<<<148 * 16, 256, 0, stream>>>(slots, cap, member, scratch_set, scratch_mask, hist64, overflow);
 }
 
+// export / import of the sparse tier (cross-GPU union of the (taxon, code) sets)
+__global__ void k_sparse_export(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
+                                unsigned long long *out, uint64_t out_cap, unsigned long long *n_out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = slots[i];
+    const bool keep = key && !dense_flag[(uint32_t)(key >> 32) - 1];
+    const uint32_t m = __ballot_sync(__activemask(), keep);
+    if (!keep) continue;
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned long long pos = base + __popc(m & ((1u << lane) - 1));
+    if (pos < out_cap) out[pos] = key;
+  }
+}
+__global__ void k_sparse_import(const unsigned long long *keys, uint64_t n, SparseSet s, const uint8_t *dense_flag,
+                                uint32_t *error_flag) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[i];
+    if (!key) continue;
+    const uint32_t taxon = (uint32_t)(key >> 32) - 1;
+    if (dense_flag[taxon]) continue;
+    const int ins = sparse_insert(s, taxon, (uint32_t)key);
+    if (ins > 0) atomicAdd(s.distinct + taxon, 1u);
+    else if (ins < 0) atomicExch(error_flag, 4u);
+  }
+}
+void launch_sparse_export(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
+                          unsigned long long *out, uint64_t out_cap, unsigned long long *n_out, cudaStream_t stream) {
+  if (cap) k_sparse_export<<<148 * 16, 256, 0, stream>>>(slots, cap, dense_flag, out, out_cap, n_out);
+}
+void launch_sparse_import(const unsigned long long *keys, uint64_t n, const SparseSet &s, const uint8_t *dense_flag,
+                          uint32_t *error_flag, cudaStream_t stream) {
+  if (n) k_sparse_import<<<(int)min((uint64_t)148 * 16, (n + 255) / 256), 256, 0, stream>>>(keys, n, s, dense_flag, error_flag);
+}
+
 int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedState); }
 
 // mode MODE_FUSED : scan → lookup (+HLL) → resolve            (whole database on this GPU)

@@ -148,4 +148,9 @@ void launch_sparse_union(const unsigned long long *slots, uint64_t cap, const ui
                          unsigned long long *scratch_set, uint64_t scratch_mask, uint32_t *hist64, uint32_t *overflow,
                          cudaStream_t stream);
 
+void launch_sparse_export(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
+                          unsigned long long *out, uint64_t out_cap, unsigned long long *n_out, cudaStream_t stream);
+void launch_sparse_import(const unsigned long long *keys, uint64_t n, const SparseSet &s, const uint8_t *dense_flag,
+                          uint32_t *error_flag, cudaStream_t stream);
+
 }  // namespace kuq

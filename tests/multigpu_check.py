@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run with torchrun, one rank per GPU):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py
+Replicas: every rank stages the whole database, classifies its contiguous share of the reads; after the NCCL merge
+(krakenuniq_b200.dist.merge_classifier_state) every rank must hold exactly the per-taxon state of a single-GPU run
+over all reads — counters, HLL registers, sparse/dense tier and estimates — which is also checked against the oracle.
+Shards: each rank stages one minimizer range, all ranks look the whole batch up (`only_hits`), rank r's hits are
+merged by an NCCL MAX all-reduce (a key lives in one range), and the owner resolves: same final state again."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from krakenuniq_b200 import binding, synth  # noqa: E402
+from krakenuniq_b200 import dist as kdist  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+    rng = np.random.default_rng(17)
+    tax = synth.make_taxonomy(6)
+    genomes = synth.random_genomes(rng, 6, 3000, 0.2)
+    km, tx = synth.label_kmers(genomes, synth.species_ids(tax), tax, 31)
+    kdb, idx = synth.build_db_images(km, tx, 31, 9, 2)
+    bases, offs = synth.sample_reads(rng, genomes, 6000, 150, 0.01, 0.1, 0.2)
+    n = len(offs) - 1
+    unit = 30000          # small work units so that some taxa convert to dense and others stay sparse
+
+    def fresh(**kw):
+        c = binding.Classifier(device=local, max_reads=1 << 14, max_bases=4 << 20, sparse_set_slots=1 << 22,
+                               work_unit_size=unit, **kw)
+        c.set_taxonomy(*tax.parent_map())
+        return c
+
+    # reference state: one GPU, all reads (unit ids given explicitly so that every variant cuts the same units)
+    units, _, _ = synth.work_unit_ids(offs, unit)
+    single = fresh()
+    single.stage_db(kdb, idx)
+    want_res = single.classify(bases, offs, unit_id=units)
+    single.finish()
+    want = single.counts()
+
+    # ---- replicas -------------------------------------------------------------------------------------------
+    lo, hi = kdist.partition(n, world, rank)
+    # keep whole work units together: move the cut to the next unit boundary
+    while lo > 0 and lo < n and units[lo] == units[lo - 1]:
+        lo += 1
+    while hi < n and hi > 0 and units[hi] == units[hi - 1]:
+        hi += 1
+    rep = fresh()
+    rep.stage_db(kdb, idx)
+    o = np.ascontiguousarray(offs[lo:hi + 1])
+    got_res = rep.classify(bases, o, unit_id=units[lo:hi]) if hi > lo else None
+    rep.finish()
+    if got_res is not None:
+        assert np.array_equal(got_res["call"], want_res["call"][lo:hi])
+    kdist.merge_classifier_state(rep, dev)
+    got = rep.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        assert np.array_equal(got[key], want[key]), (rank, "replicas", key, got[key], want[key])
+    for t in want["taxid"].tolist():
+        assert np.array_equal(rep.registers(t), single.registers(t))
+
+    # ---- minimizer-range shards ----------------------------------------------------------------------------------
+    n_bins = 1 << 18
+    idx_off = np.frombuffer(idx[8:].tobytes(), np.uint64)
+    # byte-balanced cut points like prepare_chunking (krakendb.cpp:463-522): by record count
+    targets = [idx_off[-1] * r // world for r in range(world + 1)]
+    cuts = [int(np.searchsorted(idx_off, t, side="left")) for t in targets]
+    cuts[0], cuts[-1] = 0, n_bins
+    sh = fresh()
+    all_t, _ = single.db_taxids()
+    sh.set_db_taxid_universe(all_t)
+    sh.stage_db(kdb, idx, cuts[rank], cuts[rank + 1])
+    d_bases = torch.from_numpy(np.concatenate([bases, np.full(64, ord("N"), np.uint8)])).to(dev)
+    d_offs = torch.from_numpy(np.concatenate([offs, offs[-1:]]).astype(np.int64)).to(dev)
+    codes = torch.zeros(int(offs[-1]) + 64, dtype=torch.int32, device=dev)
+    sh.lookup_device(0, d_bases.data_ptr(), d_offs.data_ptr(), n, int(offs[-1]), codes.data_ptr(), only_hits=1)
+    sh.sync(0)
+    dist.all_reduce(codes, op=dist.ReduceOp.MAX)            # a key hits in at most one range (classify.cpp:447)
+    # every rank resolves its own share of the reads from the merged codes
+    d_units = torch.from_numpy(units.astype(np.int32)).to(dev)
+    if hi > lo:
+        sub_offs = d_offs[lo:hi + 2].contiguous()
+        # offsets stay relative to d_bases; the slice must be 16-byte aligned for the bulk copy
+        assert sub_offs.data_ptr() % 16 == 0
+        sh.resolve_device(0, d_bases.data_ptr(), sub_offs.data_ptr(), hi - lo, int(offs[-1]), codes.data_ptr(),
+                          d_units[lo:hi].contiguous().data_ptr())
+        sh.sync(0)
+    sh.finish()
+    kdist.merge_classifier_state(sh, dev)
+    got = sh.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        assert np.array_equal(got[key], want[key]), (rank, "shards", key, got[key], want[key])
+
+    # and against the oracle (rank 0)
+    if rank == 0:
+        from oracle.oracle_py import Oracle
+        o_ = Oracle()
+        run = o_.run(o_.open_db(kdb, idx), o_.parent_map(*tax.parent_map()), unit, 0)
+        calls, _, _ = run.classify(bases, offs, want_codes=False)
+        run.finish()
+        oc = run.counts()
+        assert np.array_equal(calls, want_res["call"])
+        for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+            assert np.array_equal(oc[key], want[key]), ("oracle", key)
+        print(f"multigpu_check OK on {world} GPUs: replicas and minimizer-range shards reproduce the single-GPU state "
+              f"({len(want['taxid'])} taxa, {int(want['sparse'].sum())} sparse)")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
