@@ -46,5 +46,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLASSIFY = os.path.join(PKG, "bin", "classify")
+
+
+def build_classify(force: bool = False) -> str:
+    """The drop-in `classify` executable (host C++ over libkuq.so)."""
+    src = os.path.join(CSRC, "classify_main.cpp")
+    build(force=force)
+    if not force and os.path.exists(CLASSIFY) and os.path.getmtime(CLASSIFY) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return CLASSIFY
+    os.makedirs(os.path.dirname(CLASSIFY), exist_ok=True)
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", src, "-o", CLASSIFY, "-L" + os.path.dirname(LIB), "-lkuq", "-lz",
+           "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building classify")
+    return CLASSIFY
+
+
 if __name__ == "__main__":
+    build_classify(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,668 @@
+// classify_main.cpp — drop-in `classify` executable over libkuq.so.
+//
+// Same argv, file formats and text outputs as the reference driver (src/classify.cpp:150-346,1068-1189), so that
+// scripts/krakenuniq:240-248 can call it unchanged; the per-read work (classify_sequence, :897-1012) happens on the
+// GPU behind include/kuq.h.  Host-side pieces restated here, each citing what it mirrors:
+//   FASTA/FASTQ readers            src/seqreader.cpp:34-129 (gz through zlib instead of bxzstr)
+//   work-unit loop                 src/classify.cpp:506-559 (batches hold whole work units)
+//   Kraken output lines            src/classify.cpp:980-1010, hitlist_string :826-861
+//   stats / progress lines         src/classify.cpp:361-375, 555-558
+//   taxDB reader, genome sizes     src/taxdb.hpp:563-605, 850-885
+//   report (clades, sorting, cols) src/taxdb.hpp:928-1123, src/classify.cpp:286-328
+// Not supported (exit with a message): -q/-m quick mode, -I uid mapping, several -d databases, databases larger
+// than HBM with -x (the range driver is next-round work; -x with a database that fits runs the chunked HLL rule).
+#include <fcntl.h>
+#include <getopt.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <sysexits.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kuq.h"
+
+using namespace std;
+
+static vector<string> DB_filenames, Index_filenames;
+static bool Quick_mode = false, Print_classified = false, Print_unclassified = false, Print_kraken = true;
+static bool Populate_memory = false, Only_classified_kraken_output = false, Print_sequence = false, Map_UIDs = false;
+static uint64_t Populate_memory_size = 0;
+static string Classified_output_file, Unclassified_output_file, Kraken_output_file, Report_output_file, TaxDB_file;
+static size_t Work_unit_size = 500000;      // DEF_WORK_UNIT_SIZE, classify.cpp:38
+static int HLL_PRECISION = 14;              // readcounts.hpp:29 (only selects report columns, classify.cpp:289)
+static unsigned long long total_classified = 0, total_sequences = 0, total_bases = 0;
+
+[[noreturn]] static void die(int code, const string &msg) {
+  cerr << "classify: " << msg << endl;
+  exit(code);
+}
+
+static void usage(int exit_code = EX_USAGE) {
+  cerr << "Usage: classify [options] <fasta/fastq file(s)>" << endl
+       << endl
+       << "Options: (*mandatory)" << endl
+       << "* -d filename      Kraken DB filename" << endl
+       << "* -i filename      Kraken DB index filename" << endl
+       << "  -o filename      Output file for Kraken output" << endl
+       << "  -r filename      Output file for Kraken report output" << endl
+       << "  -a filename      TaxDB" << endl
+       << "  -I filename      UID to TaxId map" << endl
+       << "  -p #             Precision for unique k-mer counting, between 10 and 18" << endl
+       << "  -t #             Number of threads" << endl
+       << "  -u #             Thread work unit size (in bp)" << endl
+       << "  -q               Quick operation" << endl
+       << "  -m #             Minimum hit count (ignored w/o -q)" << endl
+       << "  -C filename      Print classified sequences" << endl
+       << "  -U filename      Print unclassified sequences" << endl
+       << "  -c               Only include classified reads in output" << endl
+       << "  -M               Preload database files" << endl
+       << "  -x size          Preload database files using x amount of RAM (e.g. 10G)" << endl
+       << "  -s               Print read sequence in Kraken output" << endl
+       << "  -h               Print this message" << endl
+       << endl
+       << "Kraken output is to standard output by default." << endl;
+  exit(exit_code);
+}
+
+// parse_human_readable_size, krakenutil.cpp:30-55
+static uint64_t parse_human_readable_size(const char *s) {
+  char *endp = NULL;
+  errno = 0;
+  uint64_t x = strtoumax(s, &endp, 10);
+  if (errno || endp == s) return 0;
+  int sh;
+  switch (*endp) {
+    case 'k': case 'K': sh = 10; break;
+    case 'm': case 'M': sh = 20; break;
+    case 'g': case 'G': sh = 30; break;
+    case 0: sh = 0; break;
+    default: return 0;
+  }
+  if (x > SIZE_MAX >> sh) return 0;
+  return x << sh;
+}
+
+static void parse_command_line(int argc, char **argv) {
+  int opt;
+  long long sig;
+  if (argc > 1 && strcmp(argv[1], "-h") == 0) usage(0);
+  while ((opt = getopt(argc, argv, "d:i:t:u:n:m:o:qcC:U:Ma:r:sI:p:x:")) != -1) {
+    switch (opt) {
+      case 'd': DB_filenames.push_back(optarg); break;
+      case 'i': Index_filenames.push_back(optarg); break;
+      case 't':
+        sig = atoll(optarg);
+        if (sig <= 0) die(EX_USAGE, "can't use nonpositive thread count");
+        break;                                   // host threads are not the engine here; accepted for compatibility
+      case 'p': HLL_PRECISION = atoi(optarg); break;
+      case 'q': Quick_mode = true; break;
+      case 'm':
+        sig = atoll(optarg);
+        if (sig <= 0) die(EX_USAGE, "can't use nonpositive minimum hit count");
+        break;
+      case 'c': Only_classified_kraken_output = true; break;
+      case 'C': Print_classified = true; Classified_output_file = optarg; break;
+      case 'U': Print_unclassified = true; Unclassified_output_file = optarg; break;
+      case 'o': Kraken_output_file = optarg; break;
+      case 'r': Report_output_file = optarg; break;
+      case 's': Print_sequence = true; break;
+      case 'a': TaxDB_file = optarg; break;
+      case 'u':
+        sig = atoll(optarg);
+        if (sig <= 0) die(EX_USAGE, "can't use nonpositive work unit size");
+        Work_unit_size = sig;
+        break;
+      case 'M': Populate_memory = true; break;
+      case 'x': Populate_memory = true; Populate_memory_size = parse_human_readable_size(optarg); break;
+      case 'I': Map_UIDs = true; break;
+      default: usage(); break;
+    }
+  }
+  if (DB_filenames.empty()) { cerr << "Missing mandatory option -d" << endl; usage(); }
+  if (Index_filenames.empty()) { cerr << "Missing mandatory option -i" << endl; usage(); }
+  if (optind == argc && !Populate_memory) cerr << "No sequence data files specified" << endl;
+}
+
+// ---- output streams: plain file, ".gz" → gzip, "-" → stdout (cout_or_file, classify.cpp:133-148) ---------------
+struct OutStream {
+  FILE *f = NULL;
+  gzFile gz = NULL;
+  bool is_stdout = false;
+  void open(const string &path, bool append = false) {
+    if (path == "-") { f = stdout; is_stdout = true; return; }
+    if (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0) {
+      gz = gzopen(path.c_str(), "wb");
+      if (!gz) die(EX_CANTCREAT, "can't open " + path);
+    } else {
+      f = fopen(path.c_str(), append ? "ab" : "wb");
+      if (!f) die(EX_CANTCREAT, "can't open " + path);
+    }
+  }
+  void write(const char *p, size_t n) {
+    if (gz) gzwrite(gz, p, (unsigned)n);
+    else if (f) fwrite(p, 1, n, f);
+  }
+  void write(const string &s) { write(s.data(), s.size()); }
+  void close() {
+    if (gz) gzclose(gz);
+    else if (f && !is_stdout) fclose(f);
+    else if (f) fflush(f);
+    f = NULL; gz = NULL;
+  }
+};
+
+// ---- input: FASTA / FASTQ through zlib (plain or gzip), semantics of src/seqreader.cpp -------------------------
+struct Read {
+  string id, header_line, quals;
+  uint64_t seq_off, seq_len;          // into the batch's bases buffer
+};
+
+struct LineReader {     // std::ifstream + std::getline state semantics (eofbit / failbit), over zlib
+  gzFile gz = NULL;
+  vector<char> buf;
+  size_t pos = 0, end = 0;
+  bool eofbit = false, failbit = false;
+  bool open(const char *path) {
+    gz = gzopen(path, "rb");
+    if (!gz) return false;
+    gzbuffer(gz, 1 << 20);
+    buf.resize(8 << 20);
+    return true;
+  }
+  void close() { if (gz) gzclose(gz); gz = NULL; }
+  bool fill() {           // false at end of data
+    int n = gzread(gz, buf.data(), (unsigned)buf.size());
+    if (n <= 0) return false;
+    pos = 0; end = (size_t)n;
+    return true;
+  }
+  bool good() const { return !eofbit && !failbit; }
+  // std::getline: extracts up to '\n'; hitting the end of the data sets eofbit, extracting nothing sets failbit
+  bool getline(string &line) {
+    line.clear();
+    if (!good()) { failbit = true; return false; }
+    bool extracted = false;
+    for (;;) {
+      if (pos == end && !fill()) {
+        eofbit = true;
+        if (!extracted) failbit = true;
+        return extracted;
+      }
+      char *nl = (char *)memchr(buf.data() + pos, '\n', end - pos);
+      if (nl) {
+        line.append(buf.data() + pos, nl - (buf.data() + pos));
+        pos = (nl - buf.data()) + 1;
+        return true;
+      }
+      line.append(buf.data() + pos, end - pos);
+      extracted = extracted || end > pos;
+      pos = end;
+    }
+  }
+  int peek() {
+    if (pos == end && !fill()) return -1;
+    return (unsigned char)buf[pos];
+  }
+};
+
+static string first_token(const string &s) {            // istringstream >> id
+  size_t a = 0;
+  while (a < s.size() && isspace((unsigned char)s[a])) a++;
+  size_t b = a;
+  while (b < s.size() && !isspace((unsigned char)s[b])) b++;
+  return s.substr(a, b - a);
+}
+
+struct SeqReader {
+  LineReader in;
+  bool fastq = false, valid = true;
+  string linebuffer;
+  bool have_linebuffer = false;
+  // next_sequence(): FASTA seqreader.cpp:34-79, FASTQ :93-129.  Appends the sequence to `bases`.
+  bool next(Read &r, string &bases) {
+    r.quals.clear();
+    if (fastq) {
+      if (!valid || !in.good()) { valid = false; return false; }
+      string line;
+      in.getline(line);
+      if (line.empty()) { valid = false; return false; }            // :101-104
+      if (line[0] != '@') {
+        if (line[0] != '\r') fprintf(stderr, "classify: malformed fastq file - sequence header (%s)\n", line.c_str());
+        valid = false;
+        return false;
+      }
+      r.header_line = line.substr(1);
+      r.id = first_token(r.header_line);
+      string seq;
+      in.getline(seq);
+      in.getline(line);
+      if (line.empty() || line[0] != '+') {
+        if (line.empty() || line[0] != '\r') fprintf(stderr, "classify: malformed fastq file - quality header (%s)\n", line.c_str());
+        valid = false;
+        return false;
+      }
+      in.getline(r.quals);
+      r.seq_off = bases.size();
+      r.seq_len = seq.size();
+      bases += seq;
+      return true;
+    }
+    if (!in.good()) { valid = false; return false; }                 // seqreader.cpp:37-40
+    string line;
+    if (have_linebuffer) { line = linebuffer; have_linebuffer = false; }
+    else in.getline(line);
+    if (line.empty() || line[0] != '>') {
+      fprintf(stderr, "classify: malformed fasta file - expected header char > not found\n");
+      valid = false;
+      return false;
+    }
+    r.header_line = line.substr(1);
+    r.id = first_token(r.header_line);
+    r.seq_off = bases.size();
+    while (in.good()) {
+      in.getline(line);
+      if (!line.empty() && line[0] == '>') { linebuffer = line; have_linebuffer = true; break; }
+      bases += line;
+    }
+    r.seq_len = bases.size() - r.seq_off;
+    return true;
+  }
+};
+
+// ---- taxonomy (taxdb.hpp:563-605) + report (taxdb.hpp:928-1123) ------------------------------------------------
+struct TaxEntry {
+  uint32_t id = 0;
+  int parent = -1;                    // index into entries, -1 = NULL
+  string name, rank;
+  vector<int> children;
+  uint64_t genomeSize = 0, genomeSizeOfChildren = 0;
+};
+struct TaxDB {
+  vector<TaxEntry> e;
+  unordered_map<uint32_t, int> idx;
+  void read(const string &path) {
+    ifstream in(path);
+    if (!in.is_open()) die(EX_NOINPUT, "unable to open taxonomy index file " + path);
+    vector<uint32_t> parents;
+    string line;
+    while (getline(in, line)) {
+      if (line.empty()) continue;
+      size_t a = line.find('\t'), b = a == string::npos ? a : line.find('\t', a + 1);
+      if (a == string::npos || b == string::npos) continue;
+      size_t c = line.find('\t', b + 1);
+      TaxEntry t;
+      t.id = (uint32_t)strtoul(line.substr(0, a).c_str(), NULL, 10);
+      uint32_t par = (uint32_t)strtoul(line.substr(a + 1, b - a - 1).c_str(), NULL, 10);
+      if (t.id > 1 && t.id == par) die(1, "ERROR: the parent of " + to_string(t.id) + " is itself. Should not happend for taxa other than the root.");
+      t.name = line.substr(b + 1, c == string::npos ? string::npos : c - b - 1);
+      t.rank = c == string::npos ? "" : line.substr(c + 1);
+      if (idx.count(t.id)) continue;                                // entries.insert keeps the first
+      idx[t.id] = (int)e.size();
+      e.push_back(t);
+      parents.push_back(par);
+    }
+    if (!idx.count(0)) {                                            // taxdb.hpp:596
+      TaxEntry z; z.id = 0; z.name = "unclassified"; z.rank = "no rank";
+      idx[0] = (int)e.size(); e.push_back(z); parents.push_back(0);
+    }
+    for (size_t i = 0; i < e.size(); i++) {                          // createPointers, :411-433
+      if (e[i].id == parents[i]) continue;
+      auto it = idx.find(parents[i]);
+      if (it == idx.end()) continue;
+      e[i].parent = it->second;
+      e[it->second].children.push_back((int)i);
+    }
+  }
+  // getParentMap, :383-398
+  void parent_map(vector<uint32_t> &ids, vector<uint32_t> &parents) const {
+    for (auto &t : e) {
+      if (t.id == 0) continue;
+      ids.push_back(t.id);
+      parents.push_back(t.parent < 0 ? 0 : e[t.parent].id);
+    }
+  }
+  void set_genome_size(uint32_t taxid, uint64_t size) {               // :850-866
+    auto it = idx.find(taxid);
+    if (it == idx.end()) { cerr << "No taxonomy entry for " << taxid << "!!" << endl; return; }
+    int i = it->second;
+    e[i].genomeSize += size;
+    while (e[i].parent >= 0) { i = e[i].parent; e[i].genomeSizeOfChildren += size; }
+  }
+};
+
+struct Clade { uint64_t reads = 0, kmers = 0, unique = 0; };
+
+static void print_report(kuq_ctx *ctx, TaxDB &tax, ostream &out) {
+  uint32_t n = 0;
+  if (kuq_counts_size(ctx, &n)) die(EX_SOFTWARE, kuq_last_error(ctx));
+  vector<uint32_t> t(n);
+  vector<uint64_t> nr(n), nk(n), uq(n);
+  if (n && kuq_read_counts(ctx, t.data(), nr.data(), nk.data(), uq.data(), NULL, n)) die(EX_SOFTWARE, kuq_last_error(ctx));
+  unordered_map<uint32_t, size_t> row;
+  for (uint32_t i = 0; i < n; i++) row[t[i]] = i;
+  // TaxReport ctor (:928-982): every counted taxon with an entry is a member of each ancestor's clade
+  cerr << "Setting values in the taxonomy tree ...";
+  map<int, vector<uint32_t>> members;
+  for (uint32_t i = 0; i < n; i++) {
+    auto it = tax.idx.find(t[i]);
+    if (it == tax.idx.end()) { cerr << "No entry for " << t[i] << " in database!" << endl; continue; }
+    for (int x = it->second; x >= 0; x = tax.e[x].parent) members[x].push_back(t[i]);
+  }
+  unordered_map<int, Clade> clade;
+  for (auto &kv : members) {
+    Clade c;
+    if (kuq_clade_counts(ctx, kv.second.data(), (uint32_t)kv.second.size(), &c.reads, &c.kmers, &c.unique))
+      die(EX_SOFTWARE, kuq_last_error(ctx));
+    clade[kv.first] = c;
+  }
+  cerr << " done" << endl;
+  cerr << "Printing classification report ... ";
+  uint64_t total = 0;
+  for (uint32_t root : {0u, 1u, 0xFFFFFFFFu}) {
+    auto it = tax.idx.find(root);
+    if (it != tax.idx.end() && clade.count(it->second)) total += clade[it->second].reads;
+  }
+  if (total == 0) { cerr << "total number of reads is zero - not creating a report!" << endl; return; }
+  const bool hll_cols = HLL_PRECISION > 0;
+  out << (hll_cols ? "%\treads\ttaxReads\tkmers\tdup\tcov\ttaxID\trank\ttaxName\n" : "%\treads\ttaxReads\ttaxID\trank\ttaxName\n");
+  // printReport(tax, depth), :1040-1076 (explicit stack instead of recursion)
+  struct Item { int node; unsigned depth; };
+  for (uint32_t root : {0u, 1u, 0xFFFFFFFFu}) {
+    auto rit = tax.idx.find(root);
+    if (rit == tax.idx.end()) continue;
+    vector<Item> stack{{rit->second, 0}};
+    while (!stack.empty()) {
+      Item it = stack.back();
+      stack.pop_back();
+      auto cit = clade.find(it.node);
+      if (cit == clade.end() || cit->second.reads == 0) continue;
+      const TaxEntry &e = tax.e[it.node];
+      const Clade &c = cit->second;
+      auto r = row.find(e.id);
+      // printLine, :1078-1123
+      out << setprecision(4) << 100.0 * c.reads / total << '\t' << c.reads << '\t' << (r != row.end() ? nr[r->second] : 0) << '\t';
+      if (hll_cols) {
+        double genome_size = double(e.genomeSize + e.genomeSizeOfChildren);
+        out << c.unique << '\t' << setprecision(3) << (double(c.kmers) / c.unique) << '\t';
+        if (genome_size == 0) out << "NA"; else out << setprecision(4) << (c.unique / genome_size);
+        out << '\t';
+      }
+      out << (e.id == 0xFFFFFFFFu ? -1 : (int32_t)e.id) << '\t' << e.rank << '\t' << string(2 * it.depth, ' ') + e.name << '\n';
+      // children that have a clade, sorted descending by (reads, kmers) — ReadCounts::operator<, readcounts.hpp:90-98
+      vector<int> ch;
+      for (int k : e.children) if (clade.count(k)) ch.push_back(k);
+      stable_sort(ch.begin(), ch.end(), [&](int a, int b) {
+        const Clade &x = clade[a], &y = clade[b];
+        return y.reads < x.reads || (y.reads == x.reads && y.kmers < x.kmers);
+      });
+      for (auto k = ch.rbegin(); k != ch.rend(); ++k) stack.push_back({*k, it.depth + 1});
+    }
+  }
+  cerr << " done" << endl;
+}
+
+// ---- mmap helper ----------------------------------------------------------------------------------------------
+struct Mapped {
+  void *p = NULL;
+  size_t size = 0;
+  void open(const string &path) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) die(EX_OSERR, "unable to open " + path);
+    struct stat sb;
+    if (fstat(fd, &sb) < 0) die(EX_OSERR, "unable to fstat " + path);
+    size = sb.st_size;
+    p = mmap(0, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p == MAP_FAILED) die(EX_OSERR, "unable to mmap " + path);
+    madvise(p, size, MADV_SEQUENTIAL);
+    ::close(fd);
+  }
+};
+
+static double get_seconds(struct timeval a, struct timeval b) {
+  return (b.tv_sec - a.tv_sec) + (b.tv_usec - a.tv_usec) / 1e6;
+}
+
+// ---- the work-unit loop ---------------------------------------------------------------------------------------
+struct Batch {
+  string bases;
+  vector<uint64_t> offs{0};
+  vector<Read> reads;
+  void clear() { bases.clear(); offs.assign(1, 0); reads.clear(); }
+};
+
+static OutStream Kraken_out, Classified_out, Unclassified_out;
+static bool Fastq_input = false;
+
+static void print_sequence(OutStream &o, const Read &r, const string &bases) {   // classify.cpp:794-805
+  string s;
+  if (Fastq_input) {
+    s = "@" + r.header_line + "\n";
+    s.append(bases, r.seq_off, r.seq_len);
+    s += "\n+\n" + r.quals + "\n";
+  } else {
+    s = ">" + r.header_line + "\n";
+    s.append(bases, r.seq_off, r.seq_len);
+    s += "\n";
+  }
+  o.write(s);
+}
+
+static void emit_results(const Batch &b, const kuq_batch_result &res) {
+  string out;
+  out.reserve(b.reads.size() * 64);
+  char num[32];
+  for (size_t i = 0; i < b.reads.size(); i++) {
+    const Read &r = b.reads[i];
+    uint32_t call = res.call[i];
+    if (Print_unclassified && !call) print_sequence(Unclassified_out, r, b.bases);
+    if (Print_classified && call) print_sequence(Classified_out, r, b.bases);
+    if (!Print_kraken) continue;
+    if (!call && Only_classified_kraken_output) continue;           // :986-988
+    out += call ? "C\t" : "U\t";
+    out += r.id;
+    out += '\t';
+    snprintf(num, sizeof num, "%u", call); out += num;
+    out += '\t';
+    snprintf(num, sizeof num, "%" PRIu64, r.seq_len); out += num;
+    out += '\t';
+    if (res.run_count[i] == 0) out += "0:0";                         // :994-995
+    for (uint32_t j = 0; j < res.run_count[i]; j++) {               // hitlist_string, :826-861
+      const kuq_run &run = res.runs[res.run_start[i] + j];
+      if (j) out += ' ';
+      if (run.code == KUQ_CODE_AMBIG) snprintf(num, sizeof num, "A:%u", run.count);
+      else snprintf(num, sizeof num, "%u:%u", run.code, run.count);
+      out += num;
+    }
+    if (Print_sequence) { out += '\t'; out.append(b.bases, r.seq_off, r.seq_len); }
+    out += '\n';
+  }
+  if (Print_kraken) Kraken_out.write(out);
+}
+
+static void process_file(kuq_ctx *ctx, const char *filename) {
+  SeqReader reader;
+  if (!reader.in.open(filename)) die(EX_NOINPUT, string("can't open ") + filename);
+  Fastq_input = reader.fastq = reader.in.peek() == '@';            // determine_input_file_type, :377-388
+  const uint64_t BATCH_NT = 96ull << 20;
+  Batch batches[2];
+  int cur = 0, inflight = -1;
+  uint64_t unit_nt = 0;
+  size_t unit_first_read = 0;       // first read of the open work unit inside the current batch
+  auto wait_emit = [&](int which) {
+    kuq_batch_result res;
+    if (kuq_wait_batch(ctx, (uint32_t)which, &res)) die(EX_SOFTWARE, kuq_last_error(ctx));
+    emit_results(batches[which], res);
+    total_classified += res.n_classified;
+    total_sequences += batches[which].reads.size();
+    total_bases += batches[which].bases.size();
+    fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences,
+            total_classified * 100.0 / total_sequences);
+    batches[which].clear();
+  };
+  auto submit = [&](int which) {
+    Batch &b = batches[which];
+    if (b.reads.empty()) return;
+    if (kuq_submit_batch(ctx, (uint32_t)which, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), NULL, 0))
+      die(EX_SOFTWARE, kuq_last_error(ctx));
+    if (inflight >= 0) wait_emit(inflight);
+    inflight = which;
+  };
+  Read r;
+  while (reader.valid) {
+    Batch &b = batches[cur];
+    if (!reader.next(r, b.bases)) break;
+    b.reads.push_back(r);
+    b.offs.push_back(b.bases.size());
+    unit_nt += r.seq_len;
+    if (unit_nt >= Work_unit_size) {                                 // the unit closes (classify.cpp:514-520)
+      unit_nt = 0;
+      unit_first_read = b.reads.size();
+      if (b.bases.size() >= BATCH_NT || b.reads.size() >= (1u << 20) - 4096) {
+        submit(cur);
+        cur ^= 1;
+        unit_first_read = 0;
+      }
+    } else if (b.reads.size() >= (1u << 20) - 1 || b.bases.size() >= (150ull << 20)) {
+      // a single work unit larger than a slot (huge -u): cut here; the unit is then counted as two
+      submit(cur);
+      cur ^= 1;
+      unit_first_read = 0;
+    }
+  }
+  // end of file: a last work unit whose total length is 0 is dropped by the reference (classify.cpp:523-524)
+  {
+    Batch &b = batches[cur];
+    if (unit_nt == 0 && unit_first_read < b.reads.size()) {
+      b.reads.resize(unit_first_read);
+      b.offs.resize(unit_first_read + 1);
+    }
+    submit(cur);
+  }
+  if (inflight >= 0) wait_emit(inflight);
+  if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));     // work units do not span input files
+  reader.in.close();
+}
+
+int main(int argc, char **argv) {
+  parse_command_line(argc, argv);
+  if (Map_UIDs) die(EX_USAGE, "-I (UID mapping) is not supported by the GPU classify");
+  if (Quick_mode) die(EX_USAGE, "-q (quick mode) is not supported by the GPU classify");
+  if (DB_filenames.size() > 1) die(EX_USAGE, "only one database (-d) is supported by the GPU classify");
+  if (Populate_memory && Populate_memory_size == 0) cerr << "Loading database(s)... " << endl;
+  cerr << " Database " << DB_filenames[0] << endl;
+  Mapped kdb, idx;
+  kdb.open(DB_filenames[0]);
+  idx.open(Index_filenames[0]);
+  if (optind == argc) {                                            // `-M` without inputs: page-cache warm-up idiom
+    if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;
+    return 0;
+  }
+  if (TaxDB_file.empty()) { cerr << "TaxDB argument is required!" << endl; return 1; }
+
+  kuq_config cfg;
+  kuq_config_default(&cfg);
+  cfg.n_slots = 2;
+  cfg.work_unit_size = Work_unit_size;
+  cfg.hll_mode = Populate_memory_size > 0 ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;   // -x vs -M / mmap (classify.cpp:250-255)
+  if (getenv("KUQ_SPARSE_SLOTS")) cfg.sparse_set_slots = strtoull(getenv("KUQ_SPARSE_SLOTS"), NULL, 10);
+  if (getenv("KUQ_DEVICE")) cfg.device = atoi(getenv("KUQ_DEVICE"));
+  kuq_ctx *ctx = NULL;
+  int rc = kuq_create(&cfg, &ctx);
+  if (rc) die(EX_UNAVAILABLE, string("libkuq: ") + kuq_strerror(rc));
+  rc = kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, 0, 0);
+  if (rc) die(EX_DATAERR, kuq_last_error(ctx));
+  if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;
+
+  TaxDB tax;
+  cerr << "Reading taxonomy index from " << TaxDB_file;
+  tax.read(TaxDB_file);
+  cerr << ". Done.\n";
+  {
+    vector<uint32_t> ids, parents;
+    tax.parent_map(ids, parents);
+    if (kuq_set_taxonomy(ctx, ids.data(), parents.data(), (uint32_t)ids.size())) die(EX_SOFTWARE, kuq_last_error(ctx));
+  }
+  if (Print_classified) Classified_out.open(Classified_output_file);
+  if (Print_unclassified) Unclassified_out.open(Unclassified_output_file);
+  if (!Kraken_output_file.empty()) {
+    if (Kraken_output_file == "off" || Kraken_output_file == "-") Print_kraken = false;   // classify.cpp:233-235
+    else { cerr << "Writing Kraken output to " << Kraken_output_file << endl; Kraken_out.open(Kraken_output_file); }
+  } else {
+    Kraken_out.open("-");
+  }
+
+  struct timeval tv1, tv2;
+  gettimeofday(&tv1, NULL);
+  for (int i = optind; i < argc; i++) process_file(ctx, argv[i]);
+  gettimeofday(&tv2, NULL);
+  {                                                                 // report_stats, classify.cpp:361-375
+    double seconds = get_seconds(tv1, tv2);
+    cerr << "\r";
+    fprintf(stderr, "%llu sequences (%.2f Mbp) processed in %.3fs (%.1f Kseq/m, %.2f Mbp/m).\n", total_sequences,
+            total_bases / 1.0e6, seconds, total_sequences / 1.0e3 / (seconds / 60), total_bases / 1.0e6 / (seconds / 60));
+    fprintf(stderr, "  %llu sequences classified (%.2f%%)\n", total_classified, total_classified * 100.0 / total_sequences);
+    fprintf(stderr, "  %llu sequences unclassified (%.2f%%)\n", total_sequences - total_classified,
+            (total_sequences - total_classified) * 100.0 / total_sequences);
+  }
+
+  if (!Report_output_file.empty() && Report_output_file != "off") {
+    gettimeofday(&tv1, NULL);
+    cerr << "Writing report file to " << Report_output_file << "  ..\n";
+    const string fname = DB_filenames[0] + ".counts";
+    bool counts_ok = false;
+    {
+      ifstream ifs(fname);
+      if (ifs.good()) {
+        if (ifs.peek() == ifstream::traits_type::eof()) cerr << "Kmer counts file is empty - trying to regenerate ..." << endl;
+        else counts_ok = true;
+      }
+    }
+    if (!counts_ok) {                                               // classify.cpp:275-284 via kuq_db_taxids
+      cerr << "Writing kmer counts to " << fname << "... [only once for this database, may take a while] " << endl;
+      uint32_t m = 0;
+      kuq_db_taxids(ctx, NULL, NULL, 0, &m);
+      vector<uint32_t> tt(m);
+      vector<uint64_t> cc(m);
+      if (m) kuq_db_taxids(ctx, tt.data(), cc.data(), m, &m);
+      ofstream ofs(fname);
+      for (uint32_t i = 0; i < m; i++) ofs << tt[i] << '\t' << cc[i] << '\n';
+    }
+    {
+      cerr << "Reading genome sizes from " << fname << " ...";
+      ifstream in(fname);
+      uint32_t taxid;
+      uint64_t size;
+      while (in >> taxid >> size) tax.set_genome_size(taxid, size);
+      cerr << " done" << endl;
+    }
+    ostringstream rep;
+    print_report(ctx, tax, rep);
+    OutStream ro;
+    ro.open(Report_output_file, true);                              // appended to the wrapper's 2 header lines
+    ro.write(rep.str());
+    ro.close();
+    gettimeofday(&tv2, NULL);
+    fprintf(stderr, "Report finished in %.3f seconds.\n", get_seconds(tv1, tv2));
+  }
+  cerr << "Finishing up ..." << endl;
+  Kraken_out.close();
+  Classified_out.close();
+  Unclassified_out.close();
+  kuq_destroy(ctx);
+  return 0;
+}

@@ -1,0 +1,84 @@
+"""The drop-in `classify` executable (krakenuniq_b200/bin/classify) against the golden outputs of the unmodified
+reference `classify`: Kraken output byte-identical, report rows identical column by column."""
+import os
+import subprocess
+
+import pytest
+
+from krakenuniq_b200 import build
+from tests import util
+
+pytestmark = pytest.mark.gpu
+G = util.GOLDEN
+
+
+def _run(tmp_path, tag, extra, reads):
+    exe = build.build_classify()
+    out, rep = tmp_path / f"{tag}.kraken", tmp_path / f"{tag}.report.tsv"
+    cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
+           os.path.join(G, "taxDB"), "-t", "1", "-r", str(rep), "-o", str(out)] + extra + [os.path.join(G, reads)]
+    env = dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22))
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return out, rep, r
+
+
+def _report_lines(path):
+    rows = {}
+    for line in open(path):
+        if line.startswith("#") or line.startswith("%"):
+            continue
+        f = line.rstrip("\n").split("\t")
+        rows[f[6]] = f
+    return rows
+
+
+@pytest.mark.parametrize("tag,extra,reads", [
+    ("preload", ["-M"], "reads.fa"),
+    ("preload_u20000", ["-M", "-u", "20000"], "reads.fa"),
+    ("chunked", ["-x", "40K"], "reads.fa"),
+    ("fastq", ["-M"], "reads_300.fq"),
+    ("crlf", ["-M"], "reads_crlf_60.fa"),
+])
+def test_cli_matches_reference_outputs(tmp_path, tag, extra, reads):
+    out, rep, r = _run(tmp_path, tag, extra, reads)
+    assert open(out).read() == open(os.path.join(G, f"{tag}.kraken")).read()
+    got, want = _report_lines(rep), _report_lines(os.path.join(G, f"{tag}.report.tsv"))
+    assert got == want
+    # the stats lines of classify.cpp:361-375 (time-dependent numbers masked)
+    want_err = open(os.path.join(G, f"{tag}.stderr.txt")).read().split("\n")
+    n_seq = want_err[0].split(" sequences")[0]
+    assert f"{n_seq} sequences (" in r.stderr
+    assert want_err[1].strip() in r.stderr and want_err[2].strip() in r.stderr
+
+
+def test_cli_flags(tmp_path):
+    exe = build.build_classify()
+    base = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
+            os.path.join(G, "taxDB")]
+    env = dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22))
+    reads = os.path.join(G, "reads_300.fq")
+    # -c: only classified lines; -s: sequence column; stdout by default
+    r = subprocess.run(base + ["-M", "-c", "-s", reads], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-1000:]
+    want = [l for l in open(os.path.join(G, "fastq.kraken")) if l.startswith("C")]
+    got = r.stdout.splitlines(keepends=True)
+    assert len(got) == len(want)
+    ids, seqs = util.read_fastq(reads)
+    seq_of = dict(zip(ids, seqs))
+    for g, w in zip(got, want):
+        assert g.rstrip("\n").rsplit("\t", 1)[0] == w.rstrip("\n")
+        assert g.rstrip("\n").rsplit("\t", 1)[1] == seq_of[w.split("\t")[1]].decode()
+    # -C / -U echo the records; `-o -` prints nothing (classify.cpp:233-235); .gz output
+    c, u, gz = tmp_path / "c.fq", tmp_path / "u.fq", tmp_path / "o.kraken.gz"
+    r = subprocess.run(base + ["-M", "-C", str(c), "-U", str(u), "-o", "-", reads], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and r.stdout == ""
+    n_c = sum(1 for l in open(os.path.join(G, "fastq.kraken")) if l.startswith("C"))
+    assert open(c).read().count("\n+\n") == n_c and open(u).read().count("\n+\n") == len(ids) - n_c
+    r = subprocess.run(base + ["-M", "-o", str(gz), reads], capture_output=True, text=True, env=env)
+    import gzip
+    assert gzip.open(gz, "rt").read() == open(os.path.join(G, "fastq.kraken")).read()
+    # -M without input files is the page-cache warm-up idiom: a no-op that succeeds
+    assert subprocess.run(base + ["-M"], capture_output=True, env=env).returncode == 0
+    # unsupported modes fail loudly
+    assert subprocess.run(base + ["-q", reads], capture_output=True, env=env).returncode != 0
