@@ -645,9 +645,15 @@ int main(int argc, char **argv) {
     {
       cerr << "Reading genome sizes from " << fname << " ...";
       ifstream in(fname);
-      uint32_t taxid;
-      uint64_t size;
-      while (in >> taxid >> size) tax.set_genome_size(taxid, size);
+      // readGenomeSizes, taxdb.hpp:868-885, loop kept literally: `while (!eof) { in >> id >> size; set(...) }` counts
+      // the last line of a newline-terminated file twice (the failed extraction leaves the variables unchanged);
+      // the reference's `cov` column depends on it, so the drop-in reproduces it.
+      uint32_t taxid = 0;
+      uint64_t size = 0;
+      while (!in.eof()) {
+        in >> taxid >> size;
+        tax.set_genome_size(taxid, size);
+      }
       cerr << " done" << endl;
     }
     ostringstream rep;
