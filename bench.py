@@ -52,7 +52,8 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=2000)
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads in the pool")
     ap.add_argument("--batch-reads", type=int, default=1_000_000, help="reads per step")
-    ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=250_000, help="reads per CPU-reference step")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the reference (0 = all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hll-mode", type=int, default=0, help="0 preload rule (reference default), 1 chunked, 2 dense only")
     ap.add_argument("--cache-dir", default=os.environ.get("KUQ_BENCH_CACHE", "/dev/shm"))
@@ -161,7 +162,9 @@ def run_reference_classify(d, fq_files, threads):
     return int(m.group(1)), float(m.group(3))
 
 
-def host_threads():
+def host_threads(args=None):
+    if args is not None and getattr(args, "cpu_threads", 0) > 0:
+        return args.cpu_threads
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
@@ -203,7 +206,7 @@ def main():
 
     # ---------------- reference arm: the unmodified reference on the host cores ------------------------------
     if args.impl == "reference":
-        threads = host_threads()
+        threads = host_threads(args)
         sample = pool_bases[:args.cpu_sample_reads * READ_LEN].cpu().numpy()
         d, fq = ensure_files(args, db, sample)
         del db, pool_bases
@@ -230,7 +233,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "classify")):
         try:
-            threads = host_threads()
+            threads = host_threads(args)
             sample = pool_bases[:args.cpu_sample_reads * READ_LEN].cpu().numpy()
             d, fq = ensure_files(args, db, sample)                 # must precede attach (values still raw taxids)
             run_reference_classify(d, [fq], threads)               # warm-up

@@ -164,6 +164,16 @@ int kuq_classify_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_off
 int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint64_t *read_offsets,
                      uint32_t n_reads, const uint32_t *unit_id, uint32_t flags);
 int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out);
+/* The two halves with host buffers, for databases staged range by range (classify -x, classify.cpp:566-791):
+ * kuq_lookup_batch    = classify_sequence_with_db_chunk (:1014-1056): per-window DENSE taxon ids of the staged range
+ *                       into codes_out (host; indexed like the bases; 0 = no hit in this range, KUQ_CODE_AMBIG for
+ *                       ambiguous windows, 0 at positions without a window).  Ranges are merged by the caller with
+ *                       an element-wise max (a key hits in at most one range, :447).
+ * kuq_resolve_batch   = the final pass (:663-791): calls, hit lists and counters from the merged ids. */
+int kuq_lookup_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                     uint32_t *codes_out, uint32_t *n_windows_out);
+int kuq_resolve_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                      const uint32_t *codes_in, const uint32_t *unit_id, uint32_t flags, kuq_batch_result *out);
 /* Pinned host memory for callers that want zero-copy staging of their batches. */
 void *kuq_host_alloc(uint64_t bytes);
 void kuq_host_free(void *p);

@@ -91,6 +91,8 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_classify_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, C.c_uint32, C.POINTER(BatchResult)]),
         "kuq_submit_batch": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint32, u32p, C.c_uint32]),
         "kuq_wait_batch": (C.c_int, [vp, C.c_uint32, C.POINTER(BatchResult)]),
+        "kuq_lookup_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, u32p]),
+        "kuq_resolve_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, u32p, C.c_uint32, C.POINTER(BatchResult)]),
         "kuq_host_alloc": (vp, [C.c_uint64]),
         "kuq_host_free": (None, [vp]),
         "kuq_classify_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32]),
@@ -227,6 +229,30 @@ class Classifier:
         res = BatchResult()
         self._ck(self.L.kuq_classify_batch(self.h, bases.ctypes.data if bases.size else None, _p(offsets, u64p), n,
                                            _p(u, u32p) if u is not None else None, flags, C.byref(res)))
+        return self._result(res, offsets)
+
+    def lookup(self, bases: np.ndarray, offsets: np.ndarray):
+        """kuq_lookup_batch: per-window dense ids of the staged range (host arrays) + window counts"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        total = int(offsets[-1] - offsets[0])
+        codes = np.zeros(max(total, 1), np.uint32)
+        nwin = np.zeros(max(n, 1), np.uint32)
+        self._ck(self.L.kuq_lookup_batch(self.h, bases.ctypes.data if bases.size else None, _p(offsets, u64p), n,
+                                         _p(codes, u32p), _p(nwin, u32p)))
+        return codes[:total], nwin[:n]
+
+    def resolve(self, bases: np.ndarray, offsets: np.ndarray, codes: np.ndarray, unit_id=None, flags=0):
+        """kuq_resolve_batch: calls / hit lists / counters from merged per-window dense ids"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        codes = np.ascontiguousarray(codes, np.uint32)
+        n = len(offsets) - 1
+        u = np.ascontiguousarray(unit_id, np.uint32) if unit_id is not None else None
+        res = BatchResult()
+        self._ck(self.L.kuq_resolve_batch(self.h, bases.ctypes.data if bases.size else None, _p(offsets, u64p), n,
+                                          _p(codes, u32p), _p(u, u32p) if u is not None else None, flags, C.byref(res)))
         return self._result(res, offsets)
 
     def submit(self, slot, bases_ptr, offsets: np.ndarray, unit_id=None, flags=0):

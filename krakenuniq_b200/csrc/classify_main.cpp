@@ -442,7 +442,9 @@ struct Batch {
   string bases;
   vector<uint64_t> offs{0};
   vector<Read> reads;
-  void clear() { bases.clear(); offs.assign(1, 0); reads.clear(); }
+  vector<uint32_t> codes;             // chunked mode: per-window dense ids merged over the database ranges
+  bool fastq = false;
+  void clear() { bases.clear(); offs.assign(1, 0); reads.clear(); codes.clear(); }
 };
 
 static OutStream Kraken_out, Classified_out, Unclassified_out;
@@ -558,6 +560,103 @@ static void process_file(kuq_ctx *ctx, const char *filename) {
   reader.in.close();
 }
 
+// ---- chunked mode: `-x size` with a database that does not fit (process_file_with_db_chunk, classify.cpp:566-791) --
+// Ranges of minimizer bins whose records + index slice fit the budget (prepare_chunking / upper_bound,
+// krakendb.cpp:430-522).  Any byte-balanced partition gives the same results (a key lives in one bin).
+static vector<pair<uint64_t, uint64_t>> plan_ranges(const uint64_t *offsets, uint64_t n_bins, uint64_t budget) {
+  vector<pair<uint64_t, uint64_t>> ranges;
+  uint64_t first = 0;
+  while (first < n_bins) {
+    uint64_t lo = first, hi = n_bins;                 // largest `end` in (first, n_bins] that still fits
+    auto fits = [&](uint64_t end) { return (end - first + 1) * 8 + (offsets[end] - offsets[first]) * 12 + 8 <= budget; };
+    if (!fits(first + 1)) die(EX_SOFTWARE, "a single minimizer bin exceeds the chunk budget; raise -x");
+    lo = first + 1;
+    while (lo < hi) {
+      uint64_t mid = lo + (hi - lo + 1) / 2;
+      if (fits(mid)) lo = mid; else hi = mid - 1;
+    }
+    if (offsets[lo] > offsets[first]) ranges.emplace_back(first, lo);   // skip ranges without records (:496-499)
+    first = lo;
+  }
+  return ranges;
+}
+
+static void load_file_batches(const char *filename, vector<Batch> &out) {
+  SeqReader reader;
+  if (!reader.in.open(filename)) die(EX_NOINPUT, string("can't open ") + filename);
+  bool fq = reader.fastq = reader.in.peek() == '@';
+  const uint64_t BATCH_NT = 96ull << 20;
+  out.emplace_back();
+  out.back().fastq = fq;
+  Read r;
+  while (reader.valid) {
+    Batch &b = out.back();
+    if (!reader.next(r, b.bases)) break;
+    b.reads.push_back(r);
+    b.offs.push_back(b.bases.size());
+    if (b.bases.size() >= BATCH_NT || b.reads.size() >= (1u << 20) - 1) { out.emplace_back(); out.back().fastq = fq; }
+  }
+  if (out.back().reads.empty()) out.pop_back();
+  reader.in.close();
+}
+
+static void run_chunked(kuq_ctx *ctx, const Mapped &kdb, const Mapped &idx, uint64_t budget, int argc, char **argv,
+                        map<uint32_t, uint64_t> &db_counts) {
+  const uint8_t *q = (const uint8_t *)idx.p;
+  const uint32_t nt = q[7];
+  const uint64_t n_bins = 1ull << (2 * nt);
+  const uint64_t *offsets = (const uint64_t *)(q + 8);
+  vector<pair<uint64_t, uint64_t>> ranges = plan_ranges(offsets, n_bins, budget);
+  cerr << "Database split into " << ranges.size() << " chunks" << endl;
+  // pass 0: the taxids of all records, so that every range numbers taxa identically (also database.kdb.counts)
+  for (auto &rg : ranges) {
+    if (kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, rg.first, rg.second)) die(EX_DATAERR, kuq_last_error(ctx));
+    uint32_t m = 0;
+    kuq_db_taxids(ctx, NULL, NULL, 0, &m);
+    vector<uint32_t> tt(m);
+    vector<uint64_t> cc(m);
+    if (m) kuq_db_taxids(ctx, tt.data(), cc.data(), m, &m);
+    for (uint32_t i = 0; i < m; i++) db_counts[tt[i]] += cc[i];
+  }
+  {
+    vector<uint32_t> all;
+    for (auto &kv : db_counts) all.push_back(kv.first);
+    if (kuq_set_db_taxid_universe(ctx, all.data(), (uint32_t)all.size())) die(EX_SOFTWARE, kuq_last_error(ctx));
+  }
+  vector<Batch> batches;
+  for (int i = optind; i < argc; i++) load_file_batches(argv[i], batches);
+  for (auto &b : batches) b.codes.assign(b.bases.size() + 1, 0);
+  vector<uint32_t> tmp;
+  for (size_t c = 0; c < ranges.size(); c++) {
+    // with one range staged in pass 0 last, re-staging it is skipped
+    if (!(ranges.size() == 1))
+      if (kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, ranges[c].first, ranges[c].second)) die(EX_DATAERR, kuq_last_error(ctx));
+    uint64_t seqs = 0;
+    for (auto &b : batches) {
+      tmp.assign(b.bases.size() + 1, 0);
+      if (kuq_lookup_batch(ctx, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), tmp.data(), NULL))
+        die(EX_SOFTWARE, kuq_last_error(ctx));
+      for (size_t j = 0; j < b.bases.size(); j++) if (tmp[j] > b.codes[j]) b.codes[j] = tmp[j];   // merge, :390-485
+      seqs += b.reads.size();
+      fprintf(stderr, "\r Processed %llu sequences (database chunk %zu of %zu)", (unsigned long long)seqs, c + 1, ranges.size());
+    }
+    fprintf(stderr, "\r Processed %llu sequences\n", (unsigned long long)seqs);
+  }
+  // final pass: classify from the merged taxa (classify.cpp:663-791)
+  for (auto &b : batches) {
+    kuq_batch_result res;
+    if (kuq_resolve_batch(ctx, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), b.codes.data(), NULL, 0, &res))
+      die(EX_SOFTWARE, kuq_last_error(ctx));
+    Fastq_input = b.fastq;
+    emit_results(b, res);
+    total_classified += res.n_classified;
+    total_sequences += b.reads.size();
+    total_bases += b.bases.size();
+    fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
+  }
+  if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
+}
+
 int main(int argc, char **argv) {
   parse_command_line(argc, argv);
   if (Map_UIDs) die(EX_USAGE, "-I (UID mapping) is not supported by the GPU classify");
@@ -574,18 +673,32 @@ int main(int argc, char **argv) {
   }
   if (TaxDB_file.empty()) { cerr << "TaxDB argument is required!" << endl; return 1; }
 
+  // -x: the reference cuts the database into chunks of that many bytes (prepare_chunking).  HBM, not host RAM, is
+  // what limits us: the database is split only when it does not fit the HBM budget (or KUQ_FORCE_CHUNKS=1 asks for
+  // the reference's exact chunk size); either way -x selects the chunked HLL rule.
+  uint64_t hbm_budget = 150ull << 30;
+  if (getenv("KUQ_HBM_BUDGET")) hbm_budget = strtoull(getenv("KUQ_HBM_BUDGET"), NULL, 10);
+  uint64_t chunk_budget = 0;
+  if (kdb.size + idx.size > hbm_budget) chunk_budget = hbm_budget;
+  if (Populate_memory_size > 0 && getenv("KUQ_FORCE_CHUNKS")) chunk_budget = Populate_memory_size;
   kuq_config cfg;
   kuq_config_default(&cfg);
   cfg.n_slots = 2;
   cfg.work_unit_size = Work_unit_size;
-  cfg.hll_mode = Populate_memory_size > 0 ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;   // -x vs -M / mmap (classify.cpp:250-255)
+  // -x (or a database that has to be split) → one global sketch per taxon (classify.cpp:719); else per work unit
+  cfg.hll_mode = (Populate_memory_size > 0 || chunk_budget) ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;
+  if (chunk_budget && !Populate_memory_size)
+    cerr << "classify: database larger than the HBM budget: processing it in ranges (unique k-mer counts follow the -x rule)" << endl;
   if (getenv("KUQ_SPARSE_SLOTS")) cfg.sparse_set_slots = strtoull(getenv("KUQ_SPARSE_SLOTS"), NULL, 10);
   if (getenv("KUQ_DEVICE")) cfg.device = atoi(getenv("KUQ_DEVICE"));
   kuq_ctx *ctx = NULL;
   int rc = kuq_create(&cfg, &ctx);
   if (rc) die(EX_UNAVAILABLE, string("libkuq: ") + kuq_strerror(rc));
-  rc = kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, 0, 0);
-  if (rc) die(EX_DATAERR, kuq_last_error(ctx));
+  map<uint32_t, uint64_t> chunk_db_counts;
+  if (!chunk_budget) {
+    rc = kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, 0, 0);
+    if (rc) die(EX_DATAERR, kuq_last_error(ctx));
+  }
   if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;
 
   TaxDB tax;
@@ -608,7 +721,8 @@ int main(int argc, char **argv) {
 
   struct timeval tv1, tv2;
   gettimeofday(&tv1, NULL);
-  for (int i = optind; i < argc; i++) process_file(ctx, argv[i]);
+  if (chunk_budget) run_chunked(ctx, kdb, idx, chunk_budget, argc, argv, chunk_db_counts);
+  else for (int i = optind; i < argc; i++) process_file(ctx, argv[i]);
   gettimeofday(&tv2, NULL);
   {                                                                 // report_stats, classify.cpp:361-375
     double seconds = get_seconds(tv1, tv2);
@@ -634,13 +748,17 @@ int main(int argc, char **argv) {
     }
     if (!counts_ok) {                                               // classify.cpp:275-284 via kuq_db_taxids
       cerr << "Writing kmer counts to " << fname << "... [only once for this database, may take a while] " << endl;
-      uint32_t m = 0;
-      kuq_db_taxids(ctx, NULL, NULL, 0, &m);
-      vector<uint32_t> tt(m);
-      vector<uint64_t> cc(m);
-      if (m) kuq_db_taxids(ctx, tt.data(), cc.data(), m, &m);
       ofstream ofs(fname);
-      for (uint32_t i = 0; i < m; i++) ofs << tt[i] << '\t' << cc[i] << '\n';
+      if (chunk_budget) {
+        for (auto &kv : chunk_db_counts) ofs << kv.first << '\t' << kv.second << '\n';
+      } else {
+        uint32_t m = 0;
+        kuq_db_taxids(ctx, NULL, NULL, 0, &m);
+        vector<uint32_t> tt(m);
+        vector<uint64_t> cc(m);
+        if (m) kuq_db_taxids(ctx, tt.data(), cc.data(), m, &m);
+        for (uint32_t i = 0; i < m; i++) ofs << tt[i] << '\t' << cc[i] << '\n';
+      }
     }
     {
       cerr << "Reading genome sizes from " << fname << " ...";

@@ -40,7 +40,7 @@ struct Slot {
   uint32_t *u_inserts = nullptr, *u_distinct = nullptr, *u_set_count = nullptr, *u_ncand = nullptr;
   uint8_t *u_cand = nullptr, *u_taxon_cand = nullptr;
   uint64_t *d_canon = nullptr;                 // scratch between the stages
-  uint32_t *d_bins = nullptr, *d_dense = nullptr;
+  uint32_t *d_bins = nullptr, *d_dense = nullptr, *d_codes_in = nullptr;
   uint32_t *d_run_start = nullptr, *d_run_count = nullptr;
   uint2 *d_runs = nullptr;
   unsigned long long *d_scalars = nullptr;   // [0] run cursor, [1] n_classified, [2] chunk counter(u32) [3] error(u32)
@@ -137,7 +137,7 @@ cudaError_t hmalloc(T **p, uint64_t n) { return cudaMallocHost((void **)p, n * s
 void free_slot(Slot &s) {
   cudaFree(s.d_bases); cudaFree(s.d_clean); cudaFree(s.d_offsets); cudaFree(s.d_unit); cudaFree(s.d_call);
   cudaFree(s.d_nwin); cudaFree(s.d_codes); cudaFree(s.d_run_start); cudaFree(s.d_run_count); cudaFree(s.d_runs);
-  cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense);
+  cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense); cudaFree(s.d_codes_in);
   cudaFree(s.u_keys); cudaFree(s.u_last); cudaFree(s.u_set_keys); cudaFree(s.u_inserts); cudaFree(s.u_distinct);
   cudaFree(s.u_set_count); cudaFree(s.u_ncand); cudaFree(s.u_cand); cudaFree(s.u_taxon_cand);
   cudaFreeHost(s.h_call); cudaFreeHost(s.h_nwin); cudaFreeHost(s.h_run_start); cudaFreeHost(s.h_run_count);
@@ -760,6 +760,98 @@ int kuq_set_taxonomy(kuq_ctx *ctx, const uint32_t *taxid, const uint32_t *parent
 }
 
 // ---- classification -------------------------------------------------------------------------------------------
+namespace {
+// copy one batch of reads (host) into the slot; returns the total number of bases
+int upload_reads(kuq_ctx *ctx, Slot &s, const char *bases, const uint64_t *read_offsets, uint32_t n_reads, uint64_t *total_out) {
+  if (n_reads > ctx->cfg.max_reads_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%u reads > slot capacity %u", n_reads, ctx->cfg.max_reads_per_batch);
+  const uint64_t base0 = n_reads ? read_offsets[0] : 0;
+  const uint64_t total = n_reads ? read_offsets[n_reads] - base0 : 0;
+  if (total > ctx->cfg.max_bases_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%llu bases > slot capacity %llu", (unsigned long long)total, (unsigned long long)ctx->cfg.max_bases_per_batch);
+  if (total >= (1ull << 32)) return fail(ctx, KUQ_E_CAPACITY, "batches are limited to 4 Gbases");
+  *total_out = total;
+  if (!n_reads) return KUQ_OK;
+  CU(cudaMemcpyAsync(s.d_bases, bases + base0, total, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemsetAsync(s.d_bases + total, 'N', SLACK, s.stream));
+  if (base0 == 0) {
+    CU(cudaMemcpyAsync(s.d_offsets, read_offsets, (n_reads + 1ull) * 8, cudaMemcpyHostToDevice, s.stream));
+  } else {
+    std::vector<uint64_t> tmp(n_reads + 1);
+    for (uint32_t i = 0; i <= n_reads; i++) tmp[i] = read_offsets[i] - base0;
+    CU(cudaMemcpy(s.d_offsets, tmp.data(), (n_reads + 1ull) * 8, cudaMemcpyHostToDevice));
+  }
+  return KUQ_OK;
+}
+}  // namespace
+
+int kuq_lookup_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                     uint32_t *codes_out, uint32_t *n_windows_out) {
+  int rc = check_slot(ctx, 0);
+  if (rc) return rc;
+  if (n_reads && (!bases || !read_offsets || !codes_out)) return fail(ctx, KUQ_E_INVALID_ARG, "NULL batch buffers");
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[0];
+  if (s.busy) return fail(ctx, KUQ_E_STATE, "slot 0 still has an unread batch");
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  uint64_t total = 0;
+  rc = upload_reads(ctx, s, bases, read_offsets, n_reads, &total);
+  if (rc) return rc;
+  s.n_reads = n_reads; s.flags = 0; s.total_bases = total; s.external = false;
+  Params p;
+  fill_params(ctx, s, p, s.d_bases, s.d_offsets, nullptr, n_reads, 0);
+  // positions without a window are not written by the kernels: give the caller zeros there
+  CU(cudaMemsetAsync(s.d_dense, 0, total * 4, s.stream));
+  rc = launch_on_slot(ctx, s, MODE_LOOKUP, p);
+  if (rc) return rc;
+  if (n_reads) {
+    CU(cudaMemcpyAsync(codes_out, s.d_dense, total * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (n_windows_out) CU(cudaMemcpyAsync(n_windows_out, s.d_nwin, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+  }
+  CU(cudaStreamSynchronize(s.stream));
+  return KUQ_OK;
+}
+
+int kuq_resolve_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
+                      const uint32_t *codes_in, const uint32_t *unit_id, uint32_t flags, kuq_batch_result *out) {
+  int rc = check_slot(ctx, 0);
+  if (rc) return rc;
+  if (!out || (n_reads && (!bases || !read_offsets || !codes_in))) return fail(ctx, KUQ_E_INVALID_ARG, "NULL batch buffers");
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[0];
+  if (s.busy) return fail(ctx, KUQ_E_STATE, "slot 0 still has an unread batch");
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  uint64_t total = 0;
+  rc = upload_reads(ctx, s, bases, read_offsets, n_reads, &total);
+  if (rc) return rc;
+  if (!s.d_codes_in) CU(dmalloc(&s.d_codes_in, ctx->cfg.max_bases_per_batch + SLACK));
+  if (n_reads) CU(cudaMemcpyAsync(s.d_codes_in, codes_in, total * 4, cudaMemcpyHostToDevice, s.stream));
+  s.n_reads = n_reads; s.flags = flags; s.total_bases = total; s.external = false;
+  const uint32_t *d_unit = nullptr;
+  if (ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && n_reads) {
+    if (unit_id) memcpy(s.h_unit, unit_id, n_reads * 4ull);
+    else cut_units(ctx, read_offsets, n_reads, s.h_unit);
+    CU(cudaMemcpyAsync(s.d_unit, s.h_unit, n_reads * 4ull, cudaMemcpyHostToDevice, s.stream));
+    d_unit = s.d_unit;
+  }
+  Params p;
+  fill_params(ctx, s, p, s.d_bases, s.d_offsets, d_unit, n_reads, flags);
+  p.codes_in = s.d_codes_in;
+  rc = launch_on_slot(ctx, s, MODE_RESOLVE, p);
+  if (rc) return rc;
+  if (n_reads) {
+    CU(cudaMemcpyAsync(s.h_call, s.d_call, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(s.h_nwin, s.d_nwin, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    if (!(flags & KUQ_F_NO_RUNS)) {
+      CU(cudaMemcpyAsync(s.h_run_start, s.d_run_start, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+      CU(cudaMemcpyAsync(s.h_run_count, s.d_run_count, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    }
+  }
+  CU(cudaMemcpyAsync(s.h_scalars, s.d_scalars, 8 * 8, cudaMemcpyDeviceToHost, s.stream));
+  s.busy = true;
+  return kuq_wait_batch(ctx, 0, out);
+}
+
 int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint64_t *read_offsets, uint32_t n_reads,
                      const uint32_t *unit_id, uint32_t flags) {
   int rc = check_slot(ctx, slot);
@@ -770,24 +862,10 @@ int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint6
   if (s.busy) return fail(ctx, KUQ_E_STATE, "slot %u still has an unread batch: call kuq_wait_batch first", slot);
   rc = ensure_ready(ctx);
   if (rc) return rc;
-  if (n_reads > ctx->cfg.max_reads_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%u reads > slot capacity %u", n_reads, ctx->cfg.max_reads_per_batch);
-  const uint64_t base0 = n_reads ? read_offsets[0] : 0;
-  const uint64_t total = n_reads ? read_offsets[n_reads] - base0 : 0;
-  if (total > ctx->cfg.max_bases_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%llu bases > slot capacity %llu", (unsigned long long)total, (unsigned long long)ctx->cfg.max_bases_per_batch);
-  if (total >= (1ull << 32)) return fail(ctx, KUQ_E_CAPACITY, "batches are limited to 4 Gbases");
+  uint64_t total = 0;
+  rc = upload_reads(ctx, s, bases, read_offsets, n_reads, &total);
+  if (rc) return rc;
   s.n_reads = n_reads; s.flags = flags; s.total_bases = total; s.external = false;
-  // H2D: bases, offsets (rebased to 0 on the device by subtracting base0 in a tiny host loop only when needed)
-  if (n_reads) {
-    CU(cudaMemcpyAsync(s.d_bases, bases + base0, total, cudaMemcpyHostToDevice, s.stream));
-    CU(cudaMemsetAsync(s.d_bases + total, 'N', SLACK, s.stream));
-    if (base0 == 0) {
-      CU(cudaMemcpyAsync(s.d_offsets, read_offsets, (n_reads + 1ull) * 8, cudaMemcpyHostToDevice, s.stream));
-    } else {
-      std::vector<uint64_t> tmp(n_reads + 1);
-      for (uint32_t i = 0; i <= n_reads; i++) tmp[i] = read_offsets[i] - base0;
-      CU(cudaMemcpy(s.d_offsets, tmp.data(), (n_reads + 1ull) * 8, cudaMemcpyHostToDevice));
-    }
-  }
   const uint32_t *d_unit = nullptr;
   if (ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && n_reads) {
     if (unit_id) memcpy(s.h_unit, unit_id, n_reads * 4ull);

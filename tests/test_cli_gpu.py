@@ -12,12 +12,12 @@ pytestmark = pytest.mark.gpu
 G = util.GOLDEN
 
 
-def _run(tmp_path, tag, extra, reads):
+def _run(tmp_path, tag, extra, reads, env_extra=None):
     exe = build.build_classify()
     out, rep = tmp_path / f"{tag}.kraken", tmp_path / f"{tag}.report.tsv"
     cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
            os.path.join(G, "taxDB"), "-t", "1", "-r", str(rep), "-o", str(out)] + extra + [os.path.join(G, reads)]
-    env = dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22))
+    env = dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22), **(env_extra or {}))
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     return out, rep, r
@@ -82,3 +82,26 @@ def test_cli_flags(tmp_path):
     assert subprocess.run(base + ["-M"], capture_output=True, env=env).returncode == 0
     # unsupported modes fail loudly
     assert subprocess.run(base + ["-q", reads], capture_output=True, env=env).returncode != 0
+
+
+@pytest.mark.parametrize("size", ["40K", "16K", "100K"])
+def test_cli_database_ranges(tmp_path, size):
+    """-x with a database that must be split (process_file_with_db_chunk, classify.cpp:566-791): the database is
+    staged range by range, every range looks the whole input up, the merged taxa are resolved in a final pass.
+    Same Kraken output and report as the reference's `-x 40K` run, whatever the chunk size."""
+    import shutil
+    db = tmp_path / "db"
+    db.mkdir()
+    for f in ("database.kdb", "database.idx", "taxDB"):
+        shutil.copy(os.path.join(G, f), db / f)                       # no database.kdb.counts: must be regenerated
+    exe = build.build_classify()
+    out, rep = tmp_path / "o.kraken", tmp_path / "o.report.tsv"
+    cmd = [exe, "-d", str(db / "database.kdb"), "-i", str(db / "database.idx"), "-a", str(db / "taxDB"), "-t", "1",
+           "-r", str(rep), "-o", str(out), "-x", size, os.path.join(G, "reads.fa")]
+    env = dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22), KUQ_FORCE_CHUNKS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Database split into" in r.stderr and "split into 1 chunks" not in r.stderr
+    assert open(out).read() == open(os.path.join(G, "chunked.kraken")).read()
+    assert _report_lines(rep) == _report_lines(os.path.join(G, "chunked.report.tsv"))
+    assert open(db / "database.kdb.counts").read() == open(os.path.join(G, "database.kdb.counts")).read()
