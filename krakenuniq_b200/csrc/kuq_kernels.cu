@@ -160,6 +160,7 @@ struct Block64 {         // 32 bases: 2-bit codes, first base in bits 63:62; amb
   uint64_t codes;
   uint32_t amb;
   uint32_t mark;         // bit l = a window ENDS at base l (only for cleaned reads, see clean_read)
+  bool skip;             // the block holds a '\n' / '\r' (not set for cleaned reads)
 };
 
 // Convert 32 characters (lane = position) — krakenutil.cpp:253-273.  Positions >= len read as ambiguous.
@@ -178,6 +179,7 @@ __device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uin
   b.codes = ((uint64_t)hi << 32) | lo;
   b.amb = __ballot_sync(0xFFFFFFFFu, !ok);
   b.mark = marks ? __ballot_sync(0xFFFFFFFFu, mk != 0) : 0u;
+  b.skip = !marks && __any_sync(0xFFFFFFFFu, !ok && (c == '\n' || c == '\r'));
   return b;
 }
 
@@ -186,19 +188,26 @@ constexpr uint32_t BIN_AMBIG = 0xFFFFFFFEu;   // scratch marker: window with a n
 
 // Stage 1 for one read (one warp, one slot of 32 windows at a time): canonical k-mer and minimizer bin of every
 // window → scratch.  Pure ALU + shuffles, no dependent memory access.
-__device__ void scan_read(const Params &p, uint32_t r, const char *seq, uint32_t len, uint32_t raw_len,
+// FAST = the (k, m) = (31, 15) of every published KrakenUniq database, with the window arithmetic as constants.
+// Returns false (having possibly written a prefix of the read's windows, all of which the caller rewrites) when it
+// meets a skipped character: the read then goes through clean_read.
+template <bool FAST>
+__device__ bool scan_read(const Params &p, uint32_t r, const char *seq, uint32_t len, uint32_t raw_len,
                           uint64_t out_base, uint32_t lane, bool marks) {
   const DbView &db = p.db;
-  const uint32_t k = db.k, nt = db.nt;
+  const uint32_t k = FAST ? 31u : db.k, nt = FAST ? 15u : db.nt;
+  const uint32_t n_mini = FAST ? 17u : db.n_mini;
   // candidate windows; every one of them is a scanner window unless the read was cleaned (marks), in which case
   // only the marked ones are (the scanner drops a window per skipped character, see clean_read)
   const uint32_t nwin = len >= k ? len - k + 1 : 0;           // classify.cpp:913-914
   uint32_t n_out = 0;                                         // windows emitted so far
   if (nwin > 0) {
     Block64 A = load_block(seq, len, 0, lane, marks);
+    if (A.skip) return false;
     const uint32_t nslots = (nwin + 31) / 32;
     for (uint32_t s = 0; s < nslots; s++) {
       Block64 B = load_block(seq, len, s + 1, lane, marks);
+      if (B.skip) return false;
       const uint32_t i = s * 32 + lane;
       bool valid = i < nwin;
       if (marks) valid = valid && (((((uint64_t)B.mark << 32) | A.mark) >> (lane + k - 1)) & 1);
@@ -222,7 +231,9 @@ __device__ void scan_read(const Params &p, uint32_t r, const char *seq, uint32_t
       uint32_t m1 = db.xor_mask ^ (f1 < r1 ? f1 : r1);
       // sliding-window minimum of width n_mini by doubling: after the loop m0 holds min over [q, q+n_mini)
       uint32_t w = 1;
-      while (2 * w <= db.n_mini) {
+#pragma unroll
+      for (int step = 0; step < 5; step++) {                  // n_mini <= 31 → at most 4 doublings
+        if (2 * w > n_mini) break;
         uint32_t src = (lane + w) & 31;
         uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
         bool wrap = lane + w >= 32;
@@ -230,8 +241,8 @@ __device__ void scan_read(const Params &p, uint32_t r, const char *seq, uint32_t
         m1 = min(m1, wrap ? 0xFFFFFFFFu : x1);
         w *= 2;
       }
-      if (w < db.n_mini) {                                    // [q, q+n_mini) = [q, q+w) U [q+n_mini-w, q+n_mini)
-        uint32_t d = db.n_mini - w;
+      if (w < n_mini) {                                       // [q, q+n_mini) = [q, q+w) U [q+n_mini-w, q+n_mini)
+        uint32_t d = n_mini - w;
         uint32_t src = (lane + d) & 31;
         uint32_t x0 = __shfl_sync(0xFFFFFFFFu, m0, src), x1 = __shfl_sync(0xFFFFFFFFu, m1, src);
         m0 = min(m0, lane + d >= 32 ? x1 : x0);
@@ -246,6 +257,7 @@ __device__ void scan_read(const Params &p, uint32_t r, const char *seq, uint32_t
   // positions of the read's text that carry no window
   for (uint32_t q = n_out + lane; q < raw_len; q += 32) p.bins[out_base + q] = BIN_NONE;
   if (lane == 0) p.n_windows[r] = n_out;
+  return true;
 }
 
 // A read that contains '\n' / '\r' (CRLF input).  KmerScanner::next_kmer (krakenutil.cpp:239-278)
@@ -338,6 +350,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) k_scan(const __grid_constant__
   }
   __syncthreads();
   uint32_t phase[N_STAGES] = {0, 0};
+  const bool fast = p.db.k == 31 && p.db.nt == 15;
   for (uint32_t it = 0;; it++) {
     const uint32_t st = it & 1;
     const uint32_t c = ss->chunk[st];
@@ -359,19 +372,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) k_scan(const __grid_constant__
       uint32_t len = raw_len;
       const char *seq = staged ? reinterpret_cast<const char *>(stage_buf + st * STAGE_BYTES + (b0 - a0))
                                : p.bases + b0;
-      // pre-scan for skipped characters (rare: CRLF input)
-      bool skip = false;
-      for (uint32_t pos = lane; pos < len; pos += 32) {
-        char ch = seq[pos];
-        skip |= (ch == '\n') | (ch == '\r');
-      }
-      bool marks = false;
-      if (__any_sync(0xFFFFFFFFu, skip)) {
+      const bool done = fast ? scan_read<true>(p, r, seq, len, raw_len, b0, lane, false)
+                             : scan_read<false>(p, r, seq, len, raw_len, b0, lane, false);
+      if (!done) {   // the read holds '\n' / '\r' (rare: CRLF input): replay the scanner, then rescan the cleaned copy
         len = clean_read(seq, len, p.clean + b0, p.db.k, lane);
-        seq = p.clean + b0;
-        marks = true;
+        scan_read<false>(p, r, p.clean + b0, len, raw_len, b0, lane, true);
       }
-      scan_read(p, r, seq, len, raw_len, b0, lane, marks);
     }
     __syncthreads();
   }
