@@ -338,8 +338,15 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (kern_ms / 1e3) / 1e9
+    traffic = None
+    try:    # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+        if args.db_records == 666_000_000 and B == 1_000_000:
+            traffic = tj["k_lookup_dense_only_bytes" if args.hll_mode == 2 else "k_lookup_exact_hll_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_lookup<MODE_FUSED>", "kernel_ms": kern_ms,
+                "traffic": traffic, "kernel": "k_lookup<MODE_FUSED>", "kernel_ms": kern_ms,
                 "stage_ms": {"k_scan": float(st_ms[0]), "k_lookup": float(st_ms[1]), "k_resolve": float(st_ms[2])},
                 "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_read": algo_bytes / B,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, of measured)" if peaks else "fallback 6650 GB/s"}
