@@ -26,11 +26,16 @@ def main():
     dev = f"cuda:{local}"
     dist.init_process_group("nccl", device_id=torch.device(dev))
     rng = np.random.default_rng(17)
-    tax = synth.make_taxonomy(6)
-    genomes = synth.random_genomes(rng, 6, 3000, 0.2)
+    # 4 abundant species (their per-unit sketches convert to dense) + 40 rare ones (stay sparse everywhere)
+    tax = synth.make_taxonomy(44)
+    genomes = synth.random_genomes(rng, 44, 2000, 0.2)
     km, tx = synth.label_kmers(genomes, synth.species_ids(tax), tax, 31)
     kdb, idx = synth.build_db_images(km, tx, 31, 9, 2)
-    bases, offs = synth.sample_reads(rng, genomes, 6000, 150, 0.01, 0.1, 0.2)
+    b1, o1 = synth.sample_reads(rng, genomes[:4], 5000, 150, 0.01, 0.1, 0.2)
+    b2, o2 = synth.sample_reads(rng, genomes[4:], 1000, 150, 0.01, 0.1, 0.0)
+    perm = rng.permutation(6000)
+    allb = np.concatenate([b1, b2]).reshape(6000, 150)[perm].reshape(-1)
+    bases, offs = allb, np.arange(6001, dtype=np.uint64) * np.uint64(150)
     n = len(offs) - 1
     unit = 30000          # small work units so that some taxa convert to dense and others stay sparse
 
@@ -110,6 +115,7 @@ def main():
         run.finish()
         oc = run.counts()
         assert np.array_equal(calls, want_res["call"])
+        assert 5 < int(want["sparse"].sum()) < len(want["taxid"]) - 2, "the case must mix sparse and dense taxa"
         for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
             assert np.array_equal(oc[key], want[key]), ("oracle", key)
         print(f"multigpu_check OK on {world} GPUs: replicas and minimizer-range shards reproduce the single-GPU state "
