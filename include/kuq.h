@@ -48,7 +48,7 @@ extern "C" {
 #define KUQ_E_STATE (-6)          /* call order: DB and taxonomy must be set before classifying, ... */
 #define KUQ_E_CAPACITY (-7)       /* batch larger than the configured slot capacity */
 #define KUQ_E_NOMEM (-8)          /* host or device allocation failed */
-#define KUQ_E_TAXA_OVERFLOW (-9)  /* a read hit more distinct taxa than the on-chip hit list holds */
+#define KUQ_E_TAXA_OVERFLOW (-9)  /* pool for the hit tables of reads with > 32 distinct taxa exhausted */
 #define KUQ_E_TAXONOMY (-10)      /* cyclic parent chain in the taxonomy */
 
 /* per-window code for an ambiguous k-mer ("A:" in the Kraken hit list, classify.cpp:846-848) */

@@ -41,6 +41,8 @@ struct Slot {
   uint8_t *u_cand = nullptr, *u_taxon_cand = nullptr;
   uint64_t *d_canon = nullptr;                 // scratch between the stages
   uint32_t *d_bins = nullptr, *d_dense = nullptr, *d_codes_in = nullptr;
+  unsigned long long *d_ovf = nullptr;          // hit-table pool for reads with > 32 distinct taxa
+  uint64_t ovf_entries = 0;
   uint32_t *d_run_start = nullptr, *d_run_count = nullptr;
   uint2 *d_runs = nullptr;
   unsigned long long *d_scalars = nullptr;   // [0] run cursor, [1] n_classified, [2] chunk counter(u32) [3] error(u32)
@@ -137,7 +139,7 @@ cudaError_t hmalloc(T **p, uint64_t n) { return cudaMallocHost((void **)p, n * s
 void free_slot(Slot &s) {
   cudaFree(s.d_bases); cudaFree(s.d_clean); cudaFree(s.d_offsets); cudaFree(s.d_unit); cudaFree(s.d_call);
   cudaFree(s.d_nwin); cudaFree(s.d_codes); cudaFree(s.d_run_start); cudaFree(s.d_run_count); cudaFree(s.d_runs);
-  cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense); cudaFree(s.d_codes_in);
+  cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense); cudaFree(s.d_codes_in); cudaFree(s.d_ovf);
   cudaFree(s.u_keys); cudaFree(s.u_last); cudaFree(s.u_set_keys); cudaFree(s.u_inserts); cudaFree(s.u_distinct);
   cudaFree(s.u_set_count); cudaFree(s.u_ncand); cudaFree(s.u_cand); cudaFree(s.u_taxon_cand);
   cudaFreeHost(s.h_call); cudaFreeHost(s.h_nwin); cudaFreeHost(s.h_run_start); cudaFreeHost(s.h_run_count);
@@ -223,6 +225,10 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(dmalloc(&s.d_canon, mb + SLACK));
   CU(dmalloc(&s.d_bins, mb + SLACK));
   CU(dmalloc(&s.d_dense, mb + SLACK));
+  // worst case one table of < 4 * windows entries per read: 4 entries (64 B) per base always suffices, but reads that
+  // need it are rare: a pool of max(bases / 4, 1 Mi) entries + the largest single table
+  s.ovf_entries = std::max<uint64_t>(mb / 4, 1ull << 20);
+  CU(dmalloc(&s.d_ovf, 2 * s.ovf_entries));
   CU(dmalloc(&s.d_run_start, mr));
   CU(dmalloc(&s.d_run_count, mr));
   // every resolving warp may leave one partly used block of 256 run slots behind (k_resolve)
@@ -503,6 +509,9 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.chunk_counter = reinterpret_cast<uint32_t *>(s.d_scalars + 2);
   p.error_flag = reinterpret_cast<uint32_t *>(s.d_scalars + 3);
   p.stats = s.d_scalars + 4;
+  p.ovf_mem = s.d_ovf;
+  p.ovf_cursor = s.d_scalars + 6;
+  p.ovf_capacity = s.ovf_entries;
   p.regs = ctx->d_regs;
   p.n_kmers = ctx->d_n_kmers;
   p.n_reads_ctr = ctx->d_n_reads;
@@ -559,7 +568,7 @@ const char *kuq_strerror(int code) {
     case KUQ_E_STATE: return "call order / state error";
     case KUQ_E_CAPACITY: return "capacity exceeded";
     case KUQ_E_NOMEM: return "out of memory";
-    case KUQ_E_TAXA_OVERFLOW: return "a read hit more than 32 distinct taxa";
+    case KUQ_E_TAXA_OVERFLOW: return "hit-table pool exhausted (too many reads with more than 32 distinct taxa in one batch)";
     case KUQ_E_TAXONOMY: return "malformed taxonomy";
     default: return "unknown error";
   }
@@ -904,7 +913,7 @@ int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
   s.kernel_ms = ms;
   const uint32_t err = (uint32_t)(s.h_scalars[3] & 0xFFFFFFFFu);
-  if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
   int rc2 = check_sparse_fill(ctx);
@@ -991,7 +1000,7 @@ int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.kernel_ms = ms;
   uint32_t err = 0;
   CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
-  if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "a read of this batch hit more than 32 distinct taxa");
+  if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
   return check_sparse_fill(ctx);

@@ -475,6 +475,101 @@ __device__ __forceinline__ uint32_t umap_slot(const UnitMap &u, uint32_t unit, u
   return 0xFFFFFFFFu;
 }
 
+// Reads that hit more than 32 distinct taxa (long reads, contigs): the hit list moves to a hash table in HBM taken from
+// a per-batch pool ({taxon+1 << 32 | count, score} per entry).  Same arithmetic as the register path, just slower.
+struct OverflowPool {
+  unsigned long long *mem;        // 2 words per entry
+  unsigned long long *cursor;     // entries handed out
+  uint64_t capacity;              // entries
+};
+
+__device__ uint32_t resolve_overflow(const Params &p, const OverflowPool &pool, const uint32_t *codes_src, uint64_t out_base,
+                                     uint32_t nwin, uint32_t unit, bool counting, bool units, uint32_t lane) {
+  // capacity: next power of two >= 2 * windows (distinct taxa <= windows)
+  uint32_t cap = 64;
+  while (cap < 2 * nwin) cap <<= 1;
+  unsigned long long start = 0;
+  if (lane == 0) start = atomicAdd(pool.cursor, (unsigned long long)cap);
+  start = __shfl_sync(0xFFFFFFFFu, start, 0);
+  if (start + cap > pool.capacity) {
+    if (lane == 0) atomicExch(p.error_flag, 1u);
+    return 0;
+  }
+  unsigned long long *tab = pool.mem + 2 * start;
+  for (uint32_t i = lane; i < cap; i += 32) { tab[2 * i] = 0; tab[2 * i + 1] = 0; }
+  __syncwarp();
+  auto find = [&](uint32_t t) -> int {              // slot of taxon t or -1
+    uint32_t s = (uint32_t)mix64(t) & (cap - 1);
+    for (uint32_t probe = 0; probe < cap; probe++) {
+      const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(tab + 2 * s);
+      if (e == 0) return -1;
+      if ((uint32_t)(e >> 32) == t + 1) return (int)s;
+      s = (s + 1) & (cap - 1);
+    }
+    return -1;
+  };
+  // hit_counts[taxon]++ over all windows
+  for (uint32_t i = lane; i < nwin; i += 32) {
+    const uint32_t t = codes_src[out_base + i];
+    if (t == AMBIG || t == 0) continue;
+    uint32_t s = (uint32_t)mix64(t) & (cap - 1);
+    for (;;) {
+      unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(tab + 2 * s);
+      if (e == 0) {
+        e = atomicCAS(tab + 2 * s, 0ull, ((unsigned long long)(t + 1) << 32) | 1ull);
+        if (e == 0) break;
+      }
+      if ((uint32_t)(e >> 32) == t + 1) { atomicAdd(tab + 2 * s, 1ull); break; }
+      s = (s + 1) & (cap - 1);
+    }
+  }
+  __syncwarp();
+  // score(t) = sum of hit counts along t's root path (krakenutil.cpp:156-177)
+  uint32_t best = 0;
+  for (uint32_t s = lane; s < cap; s += 32) {
+    const unsigned long long e = tab[2 * s];
+    if (!e) continue;
+    const uint32_t t = (uint32_t)(e >> 32) - 1, c = (uint32_t)e;
+    if (counting) {
+      atomicAdd(p.n_kmers + t, (unsigned long long)c);
+      if (units) {
+        uint32_t sl = umap_slot(p.units, unit, t, true);
+        if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
+        else atomicAdd(p.units.inserts + sl, c);
+      }
+    }
+    uint32_t score = 0;
+    for (uint32_t node = t; node; node = __ldg(p.tax.parent + node)) {
+      int q = find(node);
+      if (q >= 0) score += (uint32_t)tab[2 * q];
+    }
+    tab[2 * s + 1] = score;
+    best = max(best, score);
+  }
+  best = __reduce_max_sync(0xFFFFFFFFu, best);
+  __syncwarp();
+  if (best == 0) return 0;
+  // ties → LCA of all tied taxa, folded in ascending taxid order (std::set iteration, krakenutil.cpp:190-196)
+  uint32_t acc = 0;
+  unsigned long long last = 0;          // raw taxid + 1 of the last folded taxon
+  for (;;) {
+    unsigned long long mn = ~0ull;      // smallest (raw+1) << 32 | dense among the tied entries above `last`
+    for (uint32_t s = lane; s < cap; s += 32) {
+      const unsigned long long e = tab[2 * s];
+      if (!e || (uint32_t)tab[2 * s + 1] != best) continue;
+      const uint32_t t = (uint32_t)(e >> 32) - 1;
+      const unsigned long long r1 = (unsigned long long)__ldg(p.tax.raw + t) + 1;
+      if (r1 > last) mn = min(mn, (r1 << 32) | t);
+    }
+    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+    if (mn == ~0ull) break;
+    const uint32_t t = (uint32_t)mn;
+    acc = acc ? lca_dense(p.tax, acc, t) : t;
+    last = mn >> 32;
+  }
+  return acc;
+}
+
 // Stage 3: one warp per read.  hit_counts (classify.cpp:941-942), resolve_tree / lca (krakenutil.cpp:90-118,
 // 149-200), the per-taxon counters (classify.cpp:939,968) and the run-length encoded hit list (:826-861).
 constexpr int RUN_BUF = 96;      // runs buffered per warp before they are flushed to global memory
@@ -558,7 +653,11 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
 
     // ---- resolve_tree (krakenutil.cpp:149-200) ------------------------------------------------------------
     uint32_t call = 0;
-    if (n_hits == 1) {
+    if (overflow) {
+      OverflowPool pool{p.ovf_mem, p.ovf_cursor, p.ovf_capacity};
+      call = resolve_overflow(p, pool, codes_src, out_base, nwin, units ? p.unit_id[r] : 0, counting, units, lane);
+      n_hits = 0;                                               // counters were booked from the table
+    } else if (n_hits == 1) {
       call = __shfl_sync(0xFFFFFFFFu, my_t, 0);                 // a single hit taxon is its own best path
     } else if (n_hits > 1) {
       // score(t) = sum of hit counts along t's root path (:156-177); lane j walks entry j
@@ -594,10 +693,7 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       }
     }
     const uint32_t call_raw = call ? __ldg(p.tax.raw + call) : 0;
-    if (lane == 0) {
-      p.call[r] = call_raw;
-      if (overflow) atomicExch(p.error_flag, 1u);
-    }
+    if (lane == 0) p.call[r] = call_raw;
     // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
     if (units) {
       // inserts per (work unit, taxon): the necessary condition for a per-unit sketch to convert

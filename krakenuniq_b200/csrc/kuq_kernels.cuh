@@ -120,6 +120,10 @@ struct Params {
   uint8_t *dense_flag;          // [n_sketch]
   SparseSet sparse;
   UnitMap units;
+  // pool for the hit tables of reads with more than 32 distinct taxa (2 u64 per entry)
+  unsigned long long *ovf_mem;
+  unsigned long long *ovf_cursor;
+  uint64_t ovf_capacity;
 };
 
 // returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup

@@ -239,3 +239,41 @@ def test_golden_report_kmers_column(tag, unit, mode):
     for taxid, row in rep.items():
         u, r, k = clf.clade(members[taxid])
         assert (row["reads"], row["kmers"]) == (r, u), (taxid, row, r, u, k)
+
+
+@pytest.mark.parametrize("hll_mode,unit", [(binding.HLL_DENSE_ONLY, 500000), (binding.HLL_PRELOAD, 5000)])
+def test_reads_with_more_than_32_taxa(oracle, hll_mode, unit):
+    """long reads / contigs: the hit list leaves the registers for a hash table in HBM"""
+    rng = np.random.default_rng(77)
+    n_sp = 90
+    tax = synth.make_taxonomy(n_sp, 12, 4)
+    sp = synth.species_ids(tax)
+    genomes = [rng.integers(0, 4, 400, dtype=np.uint8) for _ in range(n_sp)]
+    km, tx = synth.label_kmers(genomes, sp, tax, K)
+    kdb, idx = synth.build_db_images(km, tx, K, 7, 2)
+    g = [synth.decode(x).tobytes() for x in genomes]
+    seqs = []
+    for n_taxa in (33, 40, 64, 90):                 # pieces of 45 bases → 15 windows per species
+        order = rng.permutation(n_sp)[:n_taxa]
+        seqs.append(b"".join(g[i][50:95] for i in order))
+        seqs.append(b"".join(g[i][50:95 + (j % 3)] for j, i in enumerate(order)))      # unequal counts → no tie
+    seqs.append(b"".join(g[i][10:390] for i in range(n_sp)))                          # a 34 kb "contig"
+    seqs += [g[i][0:150] for i in range(10)]                                            # ordinary reads around them
+    bases, offs = synth.pack_reads(seqs)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=hll_mode, unit=unit)
+
+
+def test_paired_reads_merged_with_N(oracle):
+    """--paired input as read_merger.pl writes it: mate1 + 'N' + mate2 (scripts/read_merger.pl:187-191)"""
+    tax, genomes, kdb, idx, _, _ = _synthetic(55, 9, 2, n_genomes=6)
+    rng = np.random.default_rng(9)
+    g = [synth.decode(x).tobytes() for x in genomes]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    seqs = []
+    for _ in range(400):
+        i = int(rng.integers(0, 6)); s = int(rng.integers(0, 2000))
+        m1 = g[i][s:s + 150]
+        m2 = g[i][s + 250:s + 400].translate(comp)[::-1]
+        seqs.append(m1 + b"N" + m2)
+    bases, offs = synth.pack_reads(seqs)
+    _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_PRELOAD, unit=30000)
