@@ -56,7 +56,7 @@ def build_classify(force: bool = False) -> str:
     if not force and os.path.exists(CLASSIFY) and os.path.getmtime(CLASSIFY) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
         return CLASSIFY
     os.makedirs(os.path.dirname(CLASSIFY), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", src, "-o", CLASSIFY, "-L" + os.path.dirname(LIB), "-lkuq", "-lz",
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-fopenmp", src, "-o", CLASSIFY, "-L" + os.path.dirname(LIB), "-lkuq", "-lz",
            "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -20,6 +20,12 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <omp.h>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
 #include <algorithm>
 #include <cinttypes>
 #include <cstdio>
@@ -44,6 +50,7 @@ static bool Populate_memory = false, Only_classified_kraken_output = false, Prin
 static uint64_t Populate_memory_size = 0;
 static string Classified_output_file, Unclassified_output_file, Kraken_output_file, Report_output_file, TaxDB_file;
 static size_t Work_unit_size = 500000;      // DEF_WORK_UNIT_SIZE, classify.cpp:38
+static int Num_threads = 1;
 static int HLL_PRECISION = 14;              // readcounts.hpp:29 (only selects report columns, classify.cpp:289)
 static unsigned long long total_classified = 0, total_sequences = 0, total_bases = 0;
 
@@ -108,7 +115,8 @@ static void parse_command_line(int argc, char **argv) {
       case 't':
         sig = atoll(optarg);
         if (sig <= 0) die(EX_USAGE, "can't use nonpositive thread count");
-        break;                                   // host threads are not the engine here; accepted for compatibility
+        Num_threads = (int)sig;                  // host threads: parallel FASTA/FASTQ parsing and text formatting
+        break;
       case 'p': HLL_PRECISION = atoi(optarg); break;
       case 'q': Quick_mode = true; break;
       case 'm':
@@ -433,6 +441,9 @@ struct Mapped {
   }
 };
 
+static double now_s() { struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + t.tv_usec / 1e6; }
+static const bool Timing = getenv("KUQ_TIMING") != NULL;
+#define TICK(label) do { if (Timing) { double t__ = now_s(); fprintf(stderr, "\n[timing] %-28s %.3f s\n", label, t__ - T0__); T0__ = t__; } } while (0)
 static double get_seconds(struct timeval a, struct timeval b) {
   return (b.tv_sec - a.tv_sec) + (b.tv_usec - a.tv_usec) / 1e6;
 }
@@ -496,7 +507,372 @@ static void emit_results(const Batch &b, const kuq_batch_result &res) {
   if (Print_kraken) Kraken_out.write(out);
 }
 
+static inline void append_u32(string &o, uint32_t v) {       // decimal without snprintf
+  char buf[10];
+  int n = 0;
+  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) o += buf[--n];
+}
+
+// background writer: formatted text is handed over batch by batch and written in order while the next batch is
+// being gathered / classified / formatted
+struct OutJob { vector<string> kraken, classified, unclassified; };
+struct Writer {
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<OutJob> q;
+  std::deque<OutJob> spare;              // written jobs, recycled so that their string buffers stay mapped
+  bool done = false;
+  std::thread th;
+  void start() { th = std::thread([this] { run(); }); }
+  void push(OutJob &&j) { { std::lock_guard<std::mutex> l(m); q.push_back(std::move(j)); } cv.notify_one(); }
+  OutJob take(size_t parts) {
+    OutJob j;
+    { std::lock_guard<std::mutex> l(m); if (!spare.empty()) { j = std::move(spare.front()); spare.pop_front(); } }
+    j.kraken.resize(parts); j.classified.resize(parts); j.unclassified.resize(parts);
+    for (auto &x : j.kraken) x.clear();
+    for (auto &x : j.classified) x.clear();
+    for (auto &x : j.unclassified) x.clear();
+    return j;
+  }
+  void finish() { { std::lock_guard<std::mutex> l(m); done = true; } cv.notify_one(); if (th.joinable()) th.join(); }
+  void run();
+};
+
+void Writer::run() {
+  for (;;) {
+    OutJob j;
+    {
+      std::unique_lock<std::mutex> l(m);
+      cv.wait(l, [this] { return done || !q.empty(); });
+      if (q.empty()) return;
+      j = std::move(q.front());
+      q.pop_front();
+    }
+    for (auto &x : j.kraken) Kraken_out.write(x);
+    for (auto &x : j.classified) Classified_out.write(x);
+    for (auto &x : j.unclassified) Unclassified_out.write(x);
+    { std::lock_guard<std::mutex> l(m); if (spare.size() < 3) spare.push_back(std::move(j)); }
+  }
+}
+
+// ---- parallel ingest for plain (uncompressed) files --------------------------------------------------------------
+// The file is mmap'ed and cut into chunks at record boundaries; every chunk is parsed by its own thread into
+// zero-copy views (FASTQ) with exactly the record semantics of src/seqreader.cpp; a sequential pass over the read
+// lengths then cuts work units and batches like process_file (classify.cpp:506-521); sequence text is gathered into
+// pinned buffers and the Kraken lines are formatted by all threads.
+struct View {
+  const char *hdr; uint32_t hdr_len;      // header line without the leading '>' / '@'
+  const char *seq; uint32_t seq_len;      // FASTQ / single-line FASTA: points into the file
+  const char *qual; uint32_t qual_len;
+  int64_t owned;                          // >= 0: index into the chunk's arena (multi-line FASTA)
+};
+struct ChunkParse {
+  vector<View> reads;
+  vector<string> arena;
+  bool stopped = false;                   // parser hit the end-of-input condition of the reference reader
+  string warning;
+};
+
+static inline const char *line_end(const char *p, const char *end) {
+  const char *nl = (const char *)memchr(p, '\n', end - p);
+  return nl ? nl : end;
+}
+
+// FASTQ records [p, end): FastqReader::next_sequence, seqreader.cpp:93-129
+static void parse_fastq_chunk(const char *p, const char *end, const char *file_end, ChunkParse &out) {
+  while (p < end) {
+    const char *e0 = line_end(p, file_end);
+    if (e0 == p) { out.stopped = true; return; }                                  // empty line (:101-104)
+    if (*p != '@') {
+      if (*p != '\r') out.warning = "malformed fastq file - sequence header (" + string(p, e0 - p) + ")";
+      out.stopped = true;
+      return;
+    }
+    const char *s = e0 < file_end ? e0 + 1 : file_end;
+    const char *e1 = line_end(s, file_end);
+    const char *pl = e1 < file_end ? e1 + 1 : file_end;
+    const char *e2 = line_end(pl, file_end);
+    if (e2 == pl || *pl != '+') {
+      if (e2 == pl || *pl != '\r') out.warning = "malformed fastq file - quality header (" + string(pl, e2 - pl) + ")";
+      out.stopped = true;
+      return;
+    }
+    const char *q = e2 < file_end ? e2 + 1 : file_end;
+    const char *e3 = line_end(q, file_end);
+    View v;
+    v.hdr = p + 1; v.hdr_len = (uint32_t)(e0 - p - 1);
+    v.seq = s; v.seq_len = (uint32_t)(e1 - s);
+    v.qual = q; v.qual_len = (uint32_t)(e3 - q);
+    v.owned = -1;
+    out.reads.push_back(v);
+    p = e3 < file_end ? e3 + 1 : file_end;
+  }
+}
+
+// FASTA records [p, end): FastaReader::next_sequence, seqreader.cpp:34-79.  `p` is at a '>' line start.
+static void parse_fasta_chunk(const char *p, const char *end, const char *file_end, ChunkParse &out) {
+  while (p < end) {
+    const char *e0 = line_end(p, file_end);
+    if (*p != '>') { out.warning = "malformed fasta file - expected header char > not found"; out.stopped = true; return; }
+    // a last header line that is not newline-terminated sets eofbit while being read into the line buffer, and the
+    // reader then reports !good() before using it (seqreader.cpp:37-40,62-66): that record is never produced
+    if (e0 == file_end) { out.stopped = true; return; }
+    View v;
+    v.hdr = p + 1; v.hdr_len = (uint32_t)(e0 - p - 1);
+    v.qual = NULL; v.qual_len = 0; v.owned = -1;
+    const char *s = e0 < file_end ? e0 + 1 : file_end;
+    // sequence lines until the next line that starts with '>'
+    const char *first = s, *first_end = line_end(s, file_end);
+    const char *nxt = first_end < file_end ? first_end + 1 : file_end;
+    if (s >= file_end) { v.seq = s; v.seq_len = 0; out.reads.push_back(v); return; }
+    if (*s == '>') { v.seq = s; v.seq_len = 0; out.reads.push_back(v); p = s; continue; }
+    if (nxt >= file_end || *nxt == '>') {                                          // single-line sequence: zero copy
+      v.seq = first; v.seq_len = (uint32_t)(first_end - first);
+      out.reads.push_back(v);
+      p = nxt;
+      continue;
+    }
+    string acc(first, first_end - first);
+    const char *q = nxt;
+    while (q < file_end && *q != '>') {
+      const char *qe = line_end(q, file_end);
+      acc.append(q, qe - q);
+      q = qe < file_end ? qe + 1 : file_end;
+    }
+    v.owned = (int64_t)out.arena.size();
+    v.seq = NULL; v.seq_len = (uint32_t)acc.size();
+    out.arena.push_back(std::move(acc));
+    out.reads.push_back(v);
+    p = q;
+  }
+}
+
+// start of the first record at or after `p` (chunk boundary search)
+static const char *next_record_start(const char *p, const char *file_begin, const char *file_end, bool fastq) {
+  if (p <= file_begin) return file_begin;
+  // move to the start of the next line
+  const char *nl = (const char *)memchr(p - 1, '\n', file_end - (p - 1));
+  if (!nl) return file_end;
+  p = nl + 1;
+  while (p < file_end) {
+    const char *e0 = line_end(p, file_end);
+    if (!fastq) { if (*p == '>') return p; }
+    else if (*p == '@') {
+      // a header is followed two lines later by the '+' line; a quality line that starts with '@' is not
+      const char *l1 = e0 < file_end ? e0 + 1 : file_end;
+      const char *e1 = line_end(l1, file_end);
+      const char *l2 = e1 < file_end ? e1 + 1 : file_end;
+      if (l2 < file_end && *l2 == '+' && l1 < file_end && *l1 != '@') return p;
+    }
+    p = e0 < file_end ? e0 + 1 : file_end;
+  }
+  return file_end;
+}
+
+static bool process_file_parallel(kuq_ctx *ctx, const char *filename) {
+  int fd = ::open(filename, O_RDONLY);
+  if (fd < 0) return false;
+  struct stat sb;
+  if (fstat(fd, &sb) < 0 || !S_ISREG(sb.st_mode) || sb.st_size < 2) { ::close(fd); return false; }
+  const size_t size = sb.st_size;
+  const char *base = (const char *)mmap(0, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (base == MAP_FAILED) return false;
+  if ((unsigned char)base[0] == 0x1f && (unsigned char)base[1] == 0x8b) { munmap((void *)base, size); return false; }   // gzip
+  madvise((void *)base, size, MADV_WILLNEED);
+  const char *fend = base + size;
+  const bool fastq = Fastq_input = base[0] == '@';                                  // determine_input_file_type
+  const int T = std::max(1, Num_threads);
+  const int n_chunks = (int)std::min<size_t>((size_t)T * 4, std::max<size_t>(1, size / (1 << 20)));
+  vector<const char *> cut(n_chunks + 1);
+  cut[0] = base; cut[n_chunks] = fend;
+  for (int c = 1; c < n_chunks; c++) cut[c] = next_record_start(base + size * c / n_chunks, base, fend, fastq);
+  for (int c = 1; c <= n_chunks; c++) if (cut[c] < cut[c - 1]) cut[c] = cut[c - 1];
+  double T0__ = now_s();
+  vector<ChunkParse> parsed(n_chunks);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+  for (int c = 0; c < n_chunks; c++) {
+    if (cut[c] >= cut[c + 1]) continue;
+    if (fastq) parse_fastq_chunk(cut[c], cut[c + 1], fend, parsed[c]);
+    else parse_fasta_chunk(cut[c], cut[c + 1], fend, parsed[c]);
+  }
+  TICK("parse");
+  // the reference stops at the first record its reader rejects
+  size_t n_total = 0;
+  int last_chunk = n_chunks;
+  for (int c = 0; c < n_chunks; c++) {
+    n_total += parsed[c].reads.size();
+    if (parsed[c].stopped) {
+      if (!parsed[c].warning.empty()) fprintf(stderr, "classify: %s\n", parsed[c].warning.c_str());
+      last_chunk = c + 1;
+      break;
+    }
+  }
+  vector<size_t> first_of(last_chunk + 1, 0);
+  for (int c = 0; c < last_chunk; c++) first_of[c + 1] = first_of[c] + parsed[c].reads.size();
+  auto view = [&](size_t i, int &c) -> const View & {
+    while (first_of[c + 1] <= i) c++;
+    return parsed[c].reads[i - first_of[c]];
+  };
+  // work units and batches (classify.cpp:506-521): batches end at unit boundaries
+  struct Cut { size_t begin, end; uint64_t bases; };
+  vector<Cut> batches;
+  {
+    const uint64_t BATCH_NT = 96ull << 20;
+    uint64_t unit_nt = 0, batch_nt = 0;
+    size_t begin = 0, unit_first = 0;
+    int c = 0;
+    for (size_t i = 0; i < n_total; i++) {
+      const uint32_t len = view(i, c).seq_len;
+      unit_nt += len; batch_nt += len;
+      bool close_unit = unit_nt >= Work_unit_size;
+      if (close_unit) { unit_nt = 0; unit_first = i + 1; }
+      if ((close_unit && (batch_nt >= BATCH_NT || i + 1 - begin >= (1u << 20) - 4096)) ||
+          (!close_unit && (i + 1 - begin >= (1u << 20) - 1 || batch_nt >= (150ull << 20)))) {
+        batches.push_back({begin, i + 1, batch_nt});
+        begin = i + 1; batch_nt = 0;
+        if (!close_unit) unit_first = i + 1;
+      }
+    }
+    size_t end = n_total;
+    if (unit_nt == 0 && unit_first < n_total) end = unit_first;    // last unit with zero length is dropped (:523-524)
+    if (end > begin) {
+      uint64_t nt = 0;
+      int c2 = 0;
+      for (size_t i = begin; i < end; i++) nt += view(i, c2).seq_len;
+      batches.push_back({begin, end, nt});
+    }
+  }
+  TICK("units+batches");
+  double t_fill = 0, t_emit = 0, t_wait = 0, t_submit = 0;
+  // two host staging sets, filled / formatted by all threads while the GPU works on the other one
+  struct Stage { char *bases = NULL; uint64_t cap = 0; uint64_t *offs = NULL; size_t offs_cap = 0; size_t begin = 0, end = 0; };
+  Stage st[2];
+  auto fill = [&](Stage &s, const Cut &b) {
+    if (s.cap < b.bases + 64) {
+      if (s.bases) kuq_host_free(s.bases);
+      s.cap = std::max<uint64_t>(b.bases + 64, 160ull << 20);
+      s.bases = (char *)kuq_host_alloc(s.cap);
+      if (!s.bases) die(EX_OSERR, "pinned allocation failed");
+    }
+    s.begin = b.begin; s.end = b.end;
+    const size_t n = b.end - b.begin;
+    if (s.offs_cap < n + 2) {
+      if (s.offs) kuq_host_free(s.offs);
+      s.offs_cap = std::max<size_t>(n + 2, (1u << 20) + 8);
+      s.offs = (uint64_t *)kuq_host_alloc(s.offs_cap * 8);
+      if (!s.offs) die(EX_OSERR, "pinned allocation failed");
+    }
+    s.offs[0] = 0;
+    { int c = 0; for (size_t i = 0; i < n; i++) s.offs[i + 1] = s.offs[i] + view(b.begin + i, c).seq_len; }
+#pragma omp parallel num_threads(T)
+    {
+      int c = 0;
+#pragma omp for schedule(static)
+      for (size_t i = 0; i < n; i++) {
+        int cc = c;
+        const View &v = view(b.begin + i, cc);
+        c = cc;
+        const char *src = v.owned >= 0 ? parsed[cc].arena[v.owned].data() : v.seq;
+        memcpy(s.bases + s.offs[i], src, v.seq_len);
+      }
+    }
+  };
+  Writer writer;
+  writer.start();
+  auto emit = [&](Stage &s, const kuq_batch_result &res) {
+    const size_t n = s.end - s.begin;
+    const int parts = T;
+    OutJob job = writer.take(parts);
+    vector<string> &kr = job.kraken, &cl = job.classified, &un = job.unclassified;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int pi = 0; pi < parts; pi++) {
+      const size_t a = n * pi / parts, b = n * (pi + 1) / parts;
+      string &out = kr[pi];
+      out.reserve((b - a) * 64);
+      int c = 0;
+      for (size_t i = a; i < b; i++) {
+        const View &v = view(s.begin + i, c);
+        const uint32_t call = res.call[i];
+        const char *seq = s.bases + s.offs[i];
+        if ((Print_unclassified && !call) || (Print_classified && call)) {       // print_sequence, :794-805
+          string &o = call ? cl[pi] : un[pi];
+          o += fastq ? '@' : '>';
+          o.append(v.hdr, v.hdr_len); o += '\n';
+          o.append(seq, v.seq_len); o += '\n';
+          if (fastq) { o += "+\n"; o.append(v.qual, v.qual_len); o += '\n'; }
+        }
+        if (!Print_kraken) continue;
+        if (!call && Only_classified_kraken_output) continue;
+        out += call ? "C\t" : "U\t";
+        {   // id = first whitespace-delimited token of the header line
+          uint32_t x = 0;
+          while (x < v.hdr_len && isspace((unsigned char)v.hdr[x])) x++;
+          uint32_t y = x;
+          while (y < v.hdr_len && !isspace((unsigned char)v.hdr[y])) y++;
+          out.append(v.hdr + x, y - x);
+        }
+        out += '\t';
+        append_u32(out, call);
+        out += '\t';
+        append_u32(out, v.seq_len);
+        out += '\t';
+        if (res.run_count[i] == 0) out += "0:0";
+        for (uint32_t j = 0; j < res.run_count[i]; j++) {
+          const kuq_run &run = res.runs[res.run_start[i] + j];
+          if (j) out += ' ';
+          if (run.code == KUQ_CODE_AMBIG) out += 'A'; else append_u32(out, run.code);
+          out += ':';
+          append_u32(out, run.count);
+        }
+        if (Print_sequence) { out += '\t'; out.append(seq, v.seq_len); }
+        out += '\n';
+      }
+    }
+    writer.push(std::move(job));
+    total_classified += res.n_classified;
+    total_sequences += n;
+    total_bases += s.offs[n];
+    fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
+  };
+  int inflight = -1;
+  for (size_t bi = 0; bi < batches.size(); bi++) {
+    const int cur = (int)(bi & 1);
+    double a = now_s();
+    fill(st[cur], batches[bi]);
+    double b = now_s();
+    if (kuq_submit_batch(ctx, (uint32_t)cur, st[cur].bases, st[cur].offs, (uint32_t)(st[cur].end - st[cur].begin), NULL, 0))
+      die(EX_SOFTWARE, kuq_last_error(ctx));
+    double c = now_s();
+    t_fill += b - a; t_submit += c - b;
+    if (inflight >= 0) {
+      kuq_batch_result res;
+      if (kuq_wait_batch(ctx, (uint32_t)inflight, &res)) die(EX_SOFTWARE, kuq_last_error(ctx));
+      double d = now_s();
+      emit(st[inflight], res);
+      t_wait += d - c; t_emit += now_s() - d;
+    }
+    inflight = cur;
+  }
+  if (inflight >= 0) {
+    kuq_batch_result res;
+    double c = now_s();
+    if (kuq_wait_batch(ctx, (uint32_t)inflight, &res)) die(EX_SOFTWARE, kuq_last_error(ctx));
+    double d = now_s();
+    emit(st[inflight], res);
+    t_wait += d - c; t_emit += now_s() - d;
+  }
+  { double w0 = now_s(); writer.finish(); if (Timing) fprintf(stderr, "\n[timing] writer drain %.3f s\n", now_s() - w0); }
+  if (Timing) fprintf(stderr, "\n[timing] fill %.3f submit %.3f wait %.3f emit %.3f s over %zu batches\n", t_fill, t_submit, t_wait, t_emit, batches.size());
+  if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
+  for (auto &s : st) { if (s.bases) kuq_host_free(s.bases); if (s.offs) kuq_host_free(s.offs); }
+  munmap((void *)base, size);
+  return true;
+}
+
 static void process_file(kuq_ctx *ctx, const char *filename) {
+  if (!getenv("KUQ_SERIAL_INGEST") && process_file_parallel(ctx, filename)) return;   // plain files: parallel path
   SeqReader reader;
   if (!reader.in.open(filename)) die(EX_NOINPUT, string("can't open ") + filename);
   Fastq_input = reader.fastq = reader.in.peek() == '@';            // determine_input_file_type, :377-388
@@ -696,8 +1072,10 @@ int main(int argc, char **argv) {
   if (rc) die(EX_UNAVAILABLE, string("libkuq: ") + kuq_strerror(rc));
   map<uint32_t, uint64_t> chunk_db_counts;
   if (!chunk_budget) {
+    double T0__ = now_s();
     rc = kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, 0, 0);
     if (rc) die(EX_DATAERR, kuq_last_error(ctx));
+    TICK("stage_db");
   }
   if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;
 
@@ -775,7 +1153,9 @@ int main(int argc, char **argv) {
       cerr << " done" << endl;
     }
     ostringstream rep;
+    double T0__ = now_s();
     print_report(ctx, tax, rep);
+    TICK("print_report");
     OutStream ro;
     ro.open(Report_output_file, true);                              // appended to the wrapper's 2 header lines
     ro.write(rep.str());

@@ -63,8 +63,18 @@ struct Slot {
 
 }  // namespace
 
+struct CountsHost {
+  std::vector<unsigned long long> n_kmers, n_reads;
+  std::vector<uint32_t> hist;      // [n_sketch][64]
+  std::vector<uint8_t> dense_flag;
+  std::vector<uint32_t> distinct;
+  std::vector<uint32_t> sparse_hist;   // [n_sketch][64] rank histogram of the sparse tier
+};
+
 struct kuq_ctx {
   kuq_config cfg;
+  CountsHost snap;                 // host copy of the per-taxon state, valid until the next batch
+  bool snap_valid = false;
   int device = 0;
   int n_sm = 148;
   std::string err;
@@ -524,6 +534,7 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
 }
 
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
+  ctx->snap_valid = false;
   const bool units = mode != MODE_LOOKUP && ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && p.unit_id && !(p.flags & 4u);
   if (units) {
     int rc = prepare_unit_map(ctx, s);
@@ -1067,17 +1078,11 @@ int kuq_finish(kuq_ctx *ctx) {
 }
 
 namespace {
-struct CountsHost {
-  std::vector<unsigned long long> n_kmers, n_reads;
-  std::vector<uint32_t> hist;      // [n_sketch][64]
-  std::vector<uint8_t> dense_flag;
-  std::vector<uint32_t> distinct;
-  std::vector<uint32_t> sparse_hist;   // [n_sketch][64] rank histogram of the sparse tier
-};
 int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
   if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  ctx->snap_valid = false;
   h.n_kmers.resize(ctx->n_sketch);
   h.n_reads.resize(ctx->n_taxa);
   h.hist.resize((size_t)ctx->n_sketch * 64);
@@ -1109,14 +1114,15 @@ int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
     CU(cudaStreamSynchronize(ctx->aux));
     cudaFree(d_sh);
   }
+  if (&h == &ctx->snap) ctx->snap_valid = true;
   return KUQ_OK;
 }
 }  // namespace
 
 int kuq_counts_size(kuq_ctx *ctx, uint32_t *n) {
   if (!ctx || !n) return KUQ_E_INVALID_ARG;
-  CountsHost h;
-  int rc = fetch_counts(ctx, h);
+  CountsHost &h = ctx->snap;
+  int rc = ctx->snap_valid ? KUQ_OK : fetch_counts(ctx, h);
   if (rc) return rc;
   uint32_t c = 0;
   for (uint32_t d = 0; d < ctx->n_taxa; d++)
@@ -1128,8 +1134,8 @@ int kuq_counts_size(kuq_ctx *ctx, uint32_t *n) {
 int kuq_read_counts(kuq_ctx *ctx, uint32_t *taxid, uint64_t *n_reads, uint64_t *n_kmers, uint64_t *unique,
                     uint8_t *is_sparse, uint32_t cap) {
   if (!ctx) return KUQ_E_INVALID_ARG;
-  CountsHost h;
-  int rc = fetch_counts(ctx, h);
+  CountsHost &h = ctx->snap;
+  int rc = ctx->snap_valid ? KUQ_OK : fetch_counts(ctx, h);
   if (rc) return rc;
   std::vector<std::pair<uint32_t, uint32_t>> rows;   // (taxid, dense)
   for (uint32_t d = 0; d < ctx->n_taxa; d++)
@@ -1161,37 +1167,35 @@ int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t 
   if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  if (!ctx->snap_valid) {
+    int rc = fetch_counts(ctx, ctx->snap);
+    if (rc) return rc;
+  }
+  const CountsHost &h = ctx->snap;
   std::vector<uint32_t> members;
   uint64_t reads = 0, kmers = 0;
   for (uint32_t i = 0; i < n; i++) {
     auto it = ctx->dense_of_raw.find(taxids[i]);
     if (it == ctx->dense_of_raw.end()) continue;
-    uint32_t d = it->second;
-    unsigned long long r = 0, km = 0;
-    CU(cudaMemcpy(&r, ctx->d_n_reads + d, 8, cudaMemcpyDeviceToHost));
-    if (d < ctx->n_sketch) {
-      CU(cudaMemcpy(&km, ctx->d_n_kmers + d, 8, cudaMemcpyDeviceToHost));
-      if (km) members.push_back(d);
-    }
-    reads += r; kmers += km;
+    const uint32_t d = it->second;
+    reads += h.n_reads[d];
+    if (d < ctx->n_sketch && h.n_kmers[d]) { kmers += h.n_kmers[d]; members.push_back(d); }
   }
   uint64_t u = 0;
   // clade sketch = merge of the members' sketches: dense as soon as one member is dense
   // (hyperloglogplus.cpp:604-621), else the union of the sparse sets (:600-603)
   bool any_dense = ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY;
   uint64_t sum_distinct = 0;
-  if (!any_dense && !members.empty()) {
-    if (ctx->cfg.hll_mode == KUQ_HLL_CHUNKED) {
-      launch_flag_dense_global(ctx->d_sparse_distinct, ctx->d_dense_flag, ctx->n_sketch, ctx->aux);
-      CU(cudaStreamSynchronize(ctx->aux));
-    }
-    for (uint32_t d : members) {
-      uint8_t f = 0; uint32_t dc = 0;
-      CU(cudaMemcpy(&f, ctx->d_dense_flag + d, 1, cudaMemcpyDeviceToHost));
-      CU(cudaMemcpy(&dc, ctx->d_sparse_distinct + d, 4, cudaMemcpyDeviceToHost));
-      any_dense |= f != 0;
-      sum_distinct += dc;
-    }
+  for (uint32_t d : members) { any_dense |= h.dense_flag[d] != 0; sum_distinct += h.distinct[d]; }
+  if (members.size() == 1) {
+    // a clade with a single contributing taxon has that taxon's sketch
+    const uint32_t d = members[0];
+    u = any_dense ? ertl_dense_hist(&h.hist[(size_t)d * 64], kmers)
+                  : ertl_sparse_hist(&h.sparse_hist[(size_t)d * 64], h.distinct[d], kmers);
+    if (n_reads) *n_reads = reads;
+    if (n_kmers) *n_kmers = kmers;
+    if (unique) *unique = u;
+    return KUQ_OK;
   }
   if (!members.empty() && !any_dense) {
     std::vector<uint8_t> member(ctx->n_sketch, 0);
@@ -1290,6 +1294,7 @@ int kuq_sparse_import(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
   int rc = ensure_ready(ctx);
   if (rc) return rc;
   if (!ctx->d_sparse_slots || !n) return KUQ_OK;
+  ctx->snap_valid = false;
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
   SparseSet ss;
@@ -1321,6 +1326,7 @@ int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint3
 
 int kuq_reset_counts(kuq_ctx *ctx) {
   if (!ctx) return KUQ_E_INVALID_ARG;
+  ctx->snap_valid = false;
   if (!ctx->finalized) return KUQ_OK;
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));

@@ -52,6 +52,37 @@ def test_cli_matches_reference_outputs(tmp_path, tag, extra, reads):
     assert want_err[1].strip() in r.stderr and want_err[2].strip() in r.stderr
 
 
+@pytest.mark.parametrize("threads,serial", [("8", False), ("3", False), ("1", True)])
+@pytest.mark.parametrize("tag,extra,reads", [("preload_u20000", ["-M", "-u", "20000"], "reads.fa"),
+                                              ("fastq", ["-M"], "reads_300.fq"), ("crlf", ["-M"], "reads_crlf_60.fa")])
+def test_cli_ingest_paths(tmp_path, threads, serial, tag, extra, reads):
+    """parallel mmap ingest (any -t) and the serial zlib reader give the reference's bytes"""
+    exe = build.build_classify()
+    out, rep = tmp_path / "o.kraken", tmp_path / "o.report.tsv"
+    cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
+           os.path.join(G, "taxDB"), "-t", threads, "-r", str(rep), "-o", str(out)] + extra + [os.path.join(G, reads)]
+    env = dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22), **({"KUQ_SERIAL_INGEST": "1"} if serial else {}))
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == open(os.path.join(G, f"{tag}.kraken")).read()
+    assert _report_lines(rep) == _report_lines(os.path.join(G, f"{tag}.report.tsv"))
+
+
+def test_cli_gz_input(tmp_path):
+    import gzip
+    import shutil
+    gz = tmp_path / "reads.fq.gz"
+    with open(os.path.join(G, "reads_300.fq"), "rb") as fi, gzip.open(gz, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    exe = build.build_classify()
+    out = tmp_path / "o.kraken"
+    cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
+           os.path.join(G, "taxDB"), "-M", "-o", str(out), str(gz)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22)))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == open(os.path.join(G, "fastq.kraken")).read()
+
+
 def test_cli_flags(tmp_path):
     exe = build.build_classify()
     base = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
