@@ -196,6 +196,21 @@ int kuq_lookup_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const ui
 int kuq_resolve_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
                        uint32_t n_reads, uint64_t total_bases, const uint32_t *d_codes_in,
                        const uint32_t *d_unit_id, uint32_t flags);
+/* Fused lookup + scatter for a database sharded by minimizer range over the GPUs of one node: text positions
+ * [base_bounds[j], base_bounds[j+1]) belong to the reads GPU j resolves; every hit of the staged range is stored
+ * straight into d_codes_peers[j] (that GPU's zero-initialised buffer, mapped with kuq_ipc_open) over NVLink, so no
+ * reduction is needed afterwards.  Synchronise the ranks (e.g. a barrier) before the owners call
+ * kuq_resolve_device on their buffer. */
+int kuq_lookup_device_peers(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                            uint32_t n_reads, uint64_t total_bases, uint32_t *const *d_codes_peers,
+                            const uint64_t *base_bounds, uint32_t n_peers);
+/* Device memory that other ranks can map (cudaMalloc + CUDA IPC); handles are 64 opaque bytes. */
+void *kuq_device_alloc(kuq_ctx *ctx, uint64_t bytes);
+void kuq_device_free(kuq_ctx *ctx, void *p);
+int kuq_device_memset(kuq_ctx *ctx, uint32_t slot, void *p, int value, uint64_t bytes);   /* async on the slot's stream */
+int kuq_ipc_export(kuq_ctx *ctx, void *d_ptr, uint8_t handle64[64]);
+int kuq_ipc_open(kuq_ctx *ctx, const uint8_t handle64[64], void **d_ptr_out);
+int kuq_ipc_close(kuq_ctx *ctx, void *d_ptr);
 int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot);
 int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out);
 /* With KUQ_F_STATS: number of non-ambiguous windows looked up by the slot's last batch and the sum over them of

@@ -98,6 +98,14 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_classify_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32]),
         "kuq_lookup_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_uint32]),
         "kuq_resolve_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, vp, C.c_uint32]),
+        "kuq_lookup_device_peers": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, C.POINTER(vp), u64p,
+                                             C.c_uint32]),
+        "kuq_device_alloc": (vp, [vp, C.c_uint64]),
+        "kuq_device_free": (None, [vp, vp]),
+        "kuq_device_memset": (C.c_int, [vp, C.c_uint32, vp, C.c_int, C.c_uint64]),
+        "kuq_ipc_export": (C.c_int, [vp, vp, u8p]),
+        "kuq_ipc_open": (C.c_int, [vp, u8p, C.POINTER(vp)]),
+        "kuq_ipc_close": (C.c_int, [vp, vp]),
         "kuq_sync_slot": (C.c_int, [vp, C.c_uint32]),
         "kuq_slot_device_result": (C.c_int, [vp, C.c_uint32, C.POINTER(DeviceResult)]),
         "kuq_slot_stream": (vp, [vp, C.c_uint32]),
@@ -277,6 +285,40 @@ class Classifier:
     def resolve_device(self, slot, d_bases, d_offsets, n_reads, total_bases, d_codes_in, d_unit=None, flags=0):
         self._ck(self.L.kuq_resolve_device(self.h, slot, d_bases, d_offsets, n_reads, total_bases, d_codes_in, d_unit,
                                            flags))
+
+    def lookup_device_peers(self, slot, d_bases, d_offsets, n_reads, total_bases, peer_ptrs, base_bounds):
+        n = len(peer_ptrs)
+        arr = (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in peer_ptrs])
+        bounds = np.ascontiguousarray(base_bounds, np.uint64)
+        assert len(bounds) == n + 1
+        self._ck(self.L.kuq_lookup_device_peers(self.h, slot, d_bases, d_offsets, n_reads, total_bases, arr,
+                                                _p(bounds, u64p), n))
+
+    def device_alloc(self, nbytes):
+        p = self.L.kuq_device_alloc(self.h, nbytes)
+        if not p:
+            raise KuqError(-8, "device allocation failed")
+        return p
+
+    def device_free(self, p):
+        self.L.kuq_device_free(self.h, p)
+
+    def device_memset(self, slot, p, value, nbytes):
+        self._ck(self.L.kuq_device_memset(self.h, slot, p, value, nbytes))
+
+    def ipc_export(self, p) -> bytes:
+        h = np.zeros(64, np.uint8)
+        self._ck(self.L.kuq_ipc_export(self.h, p, _p(h, u8p)))
+        return h.tobytes()
+
+    def ipc_open(self, handle: bytes):
+        h = np.frombuffer(handle, np.uint8).copy()
+        out = C.c_void_p()
+        self._ck(self.L.kuq_ipc_open(self.h, _p(h, u8p), C.byref(out)))
+        return out.value
+
+    def ipc_close(self, p):
+        self._ck(self.L.kuq_ipc_close(self.h, p))
 
     def sync(self, slot):
         self._ck(self.L.kuq_sync_slot(self.h, slot))

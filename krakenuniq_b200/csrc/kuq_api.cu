@@ -54,6 +54,7 @@ struct Slot {
   unsigned long long *h_scalars = nullptr;
   // in-flight batch
   bool busy = false;
+  bool timed = false;      // the timing events of this slot have been recorded at least once
   uint32_t n_reads = 0, flags = 0;
   uint64_t total_bases = 0;
   double kernel_ms = 0;
@@ -549,6 +550,7 @@ int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   CU(cudaEventRecord(s.ev_stage[1], s.stream));
   if (p.n_reads) ctx->launches += launch_classify(mode, p, ctx->n_sm, s.stream, s.ev_stage);
   CU(cudaEventRecord(s.ev_k1, s.stream));
+  s.timed = true;
   // HLL mode rule: which taxa have a sketch that converted to dense
   if (p.n_reads && mode != MODE_LOOKUP && !(p.flags & 4u)) {
     if (units) ctx->launches += launch_unit_accounting(p, ctx->n_sm, s.stream);
@@ -921,7 +923,8 @@ int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
   CU(cudaStreamSynchronize(s.stream));
   s.busy = false;
   float ms = 0;
-  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  if (s.timed) cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  (void)cudaGetLastError();
   s.kernel_ms = ms;
   const uint32_t err = (uint32_t)(s.h_scalars[3] & 0xFFFFFFFFu);
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
@@ -1002,13 +1005,81 @@ int kuq_resolve_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const u
   return device_call(ctx, slot, MODE_RESOLVE, d_bases, d_read_offsets, n_reads, total_bases, d_unit_id, flags, nullptr, d_codes_in, 0);
 }
 
+int kuq_lookup_device_peers(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
+                            uint32_t n_reads, uint64_t total_bases, uint32_t *const *d_codes_peers,
+                            const uint64_t *base_bounds, uint32_t n_peers) {
+  if (!d_codes_peers || !base_bounds || n_peers == 0 || n_peers > 8) return KUQ_E_INVALID_ARG;
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (n_reads && (!d_bases || !d_read_offsets)) return fail(ctx, KUQ_E_INVALID_ARG, "NULL device buffers");
+  if ((uintptr_t)d_bases & 15) return fail(ctx, KUQ_E_INVALID_ARG, "d_bases must be 16-byte aligned");
+  CU(cudaSetDevice(ctx->device));
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  Slot &s = ctx->slots[slot];
+  if (n_reads > ctx->cfg.max_reads_per_batch || total_bases > ctx->cfg.max_bases_per_batch)
+    return fail(ctx, KUQ_E_CAPACITY, "batch exceeds the slot capacity");
+  s.n_reads = n_reads; s.flags = 0; s.total_bases = total_bases; s.external = true;
+  Params p;
+  fill_params(ctx, s, p, d_bases, d_read_offsets, nullptr, n_reads, 0);
+  p.only_hits = 1;
+  p.n_peers = n_peers;
+  for (uint32_t j = 0; j < n_peers; j++) { p.peer_codes[j] = d_codes_peers[j]; p.peer_bounds[j] = base_bounds[j]; }
+  p.peer_bounds[n_peers] = base_bounds[n_peers];
+  return launch_on_slot(ctx, s, MODE_LOOKUP, p);
+}
+
+// ---- device memory that can be shared with the other ranks of a node (CUDA IPC) --------------------------------
+void *kuq_device_alloc(kuq_ctx *ctx, uint64_t bytes) {
+  if (!ctx) return nullptr;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+  void *p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void kuq_device_free(kuq_ctx *ctx, void *p) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (p) cudaFree(p);
+}
+int kuq_device_memset(kuq_ctx *ctx, uint32_t slot, void *p, int value, uint64_t bytes) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(p, value, bytes, ctx->slots[slot].stream));
+  return KUQ_OK;
+}
+int kuq_ipc_export(kuq_ctx *ctx, void *d_ptr, uint8_t handle64[64]) {
+  if (!ctx || !d_ptr || !handle64) return KUQ_E_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle64, &h, 64);
+  return KUQ_OK;
+}
+int kuq_ipc_open(kuq_ctx *ctx, const uint8_t handle64[64], void **d_ptr_out) {
+  if (!ctx || !handle64 || !d_ptr_out) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return KUQ_OK;
+}
+int kuq_ipc_close(kuq_ctx *ctx, void *d_ptr) {
+  if (!ctx || !d_ptr) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return KUQ_OK;
+}
+
 int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   int rc = check_slot(ctx, slot);
   if (rc) return rc;
   Slot &s = ctx->slots[slot];
   CU(cudaStreamSynchronize(s.stream));
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.kernel_ms = ms;
+  if (s.timed && cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.kernel_ms = ms;
+  (void)cudaGetLastError();      // never leave a stale error code behind for the next CUDA user of this process
   uint32_t err = 0;
   CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
@@ -1060,9 +1131,12 @@ int kuq_last_stage_ms(kuq_ctx *ctx, uint32_t slot, double *ms3) {
   Slot &s = ctx->slots[slot];
   CU(cudaStreamSynchronize(s.stream));
   float a = 0, b = 0, c = 0;
-  cudaEventElapsedTime(&a, s.ev_k0, s.ev_stage[0]);
-  cudaEventElapsedTime(&b, s.ev_stage[0], s.ev_stage[1]);
-  cudaEventElapsedTime(&c, s.ev_stage[1], s.ev_k1);
+  if (s.timed) {
+    cudaEventElapsedTime(&a, s.ev_k0, s.ev_stage[0]);
+    cudaEventElapsedTime(&b, s.ev_stage[0], s.ev_stage[1]);
+    cudaEventElapsedTime(&c, s.ev_stage[1], s.ev_k1);
+  }
+  (void)cudaGetLastError();
   ms3[0] = a; ms3[1] = b; ms3[2] = c;
   return KUQ_OK;
 }

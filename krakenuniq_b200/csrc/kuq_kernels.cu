@@ -393,12 +393,14 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
   const DbView &db = p.db;
   const uint32_t hi_mask = (uint32_t)(db.key_mask >> 32);
   const bool counting = (MODE == MODE_FUSED) && !(p.flags & 4u);
-  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.total_bases;
+  // only the text of this call's reads (the scratch beyond it may hold windows of an earlier call on the slot)
+  const uint64_t g_begin = p.offsets[0], g_end = p.offsets[p.n_reads];
+  for (uint64_t g = g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g_end;
        g += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t bin = __ldg(p.bins + g);
     if (bin == BIN_NONE) continue;
     if (bin == BIN_AMBIG) {
-      if (!p.only_hits) p.codes_dense[g] = AMBIG;
+      if (!p.only_hits && !(MODE == MODE_LOOKUP && p.n_peers)) p.codes_dense[g] = AMBIG;
       continue;
     }
     const uint64_t canon = __ldg(p.canon + g);
@@ -445,7 +447,16 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
     }
     // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
     // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
-    if (MODE == MODE_RESOLVE || !p.only_hits || taxon != 0) p.codes_dense[g] = taxon;
+    if (MODE == MODE_LOOKUP && p.n_peers) {
+      // fused lookup + scatter: the hit goes to the GPU that resolves this read, as a peer store over NVLink
+      if (taxon != 0) {
+        uint32_t j = 0;
+        while (j + 1 < p.n_peers && g >= p.peer_bounds[j + 1]) j++;
+        p.peer_codes[j][g] = taxon;
+      }
+    } else if (MODE == MODE_RESOLVE || !p.only_hits || taxon != 0) {
+      p.codes_dense[g] = taxon;
+    }
     if (counting || (MODE == MODE_RESOLVE && !(p.flags & 4u))) {
       const uint64_t h = fmix64(canon);
       hll_update(p.regs, taxon, h);

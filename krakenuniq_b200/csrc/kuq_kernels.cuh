@@ -112,6 +112,11 @@ struct Params {
   uint32_t *chunk_counter;      // dynamic chunk scheduler
   uint32_t *error_flag;
   uint32_t only_hits;           // MODE_LOOKUP: write hits only (peer-memory merge)
+  // MODE_LOOKUP over NVLink: text positions [peer_bounds[j], peer_bounds[j+1]) belong to the reads GPU j resolves;
+  // their hits are stored straight into that GPU's buffer (peer memory mapped through CUDA IPC)
+  uint32_t n_peers;
+  uint32_t *peer_codes[8];
+  uint64_t peer_bounds[9];
   unsigned long long *stats;    // flag 8: [0] += looked-up windows, [1] += sum of ceil(log2(bin size + 1))
   // per-taxon state
   uint8_t *regs;                // [n_sketch][4096]

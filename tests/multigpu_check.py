@@ -106,6 +106,53 @@ def main():
     for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
         assert np.array_equal(got[key], want[key]), (rank, "shards", key, got[key], want[key])
 
+    # ---- shards with the fused lookup + NVLink peer scatter (no reduction of ids) -------------------------------
+    def share(r):
+        a, b = kdist.partition(n, world, r)
+        while a > 0 and a < n and units[a] == units[a - 1]:
+            a += 1
+        while b < n and b > 0 and units[b] == units[b - 1]:
+            b += 1
+        return a, b
+    shares = [share(r) for r in range(world)]
+    assert shares[rank] == (lo, hi)
+    sp = fresh()
+    sp.set_db_taxid_universe(all_t)
+    sp.stage_db(kdb, idx, cuts[rank], cuts[rank + 1])
+    nbytes = (int(offs[-1]) + 64) * 4
+    my_buf = sp.device_alloc(nbytes)
+    sp.device_memset(0, my_buf, 0, nbytes)
+    sp.sync(0)
+    handles = [None] * world
+    dist.all_gather_object(handles, sp.ipc_export(my_buf))
+    peers = [my_buf if r == rank else sp.ipc_open(handles[r]) for r in range(world)]
+    bounds = np.array([int(offs[shares[r][0]]) for r in range(world)] + [int(offs[-1])], np.uint64)
+    bounds[0] = 0
+    dist.barrier()                                         # every buffer is zeroed
+    sp.lookup_device_peers(0, d_bases.data_ptr(), d_offs.data_ptr(), n, int(offs[-1]), peers, bounds)
+    sp.sync(0)
+    torch.cuda.synchronize()
+    dist.barrier()                                         # every rank's hits have landed
+    if hi > lo:
+        sub_offs = d_offs[lo:hi + 2].contiguous()
+        sp.resolve_device(0, d_bases.data_ptr(), sub_offs.data_ptr(), hi - lo, int(offs[-1]), my_buf,
+                          d_units[lo:hi].contiguous().data_ptr())
+        sp.sync(0)
+    sp.finish()
+    kdist.merge_classifier_state(sp, dev)
+    got = sp.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        if not np.array_equal(got[key], want[key]):
+            bad = np.nonzero(got[key] != want[key])[0]
+            raise AssertionError((rank, "peer shards", key, bad[:8].tolist(), got["taxid"][bad[:8]].tolist(),
+                                  got[key][bad[:8]].tolist(), want[key][bad[:8]].tolist(), got["sparse"][bad[:8]].tolist()))
+    dist.barrier()
+    for r in range(world):
+        if r != rank:
+            sp.ipc_close(peers[r])
+    dist.barrier()
+    sp.device_free(my_buf)
+
     # and against the oracle (rank 0)
     if rank == 0:
         from oracle.oracle_py import Oracle
@@ -118,7 +165,7 @@ def main():
         assert 5 < int(want["sparse"].sum()) < len(want["taxid"]) - 2, "the case must mix sparse and dense taxa"
         for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
             assert np.array_equal(oc[key], want[key]), ("oracle", key)
-        print(f"multigpu_check OK on {world} GPUs: replicas and minimizer-range shards reproduce the single-GPU state "
+        print(f"multigpu_check OK on {world} GPUs: replicas, minimizer-range shards (NCCL id merge) and shards with NVLink peer scatter reproduce the single-GPU state "
               f"({len(want['taxid'])} taxa, {int(want['sparse'].sum())} sparse)")
     dist.barrier()
     dist.destroy_process_group()
