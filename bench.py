@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--db-records", type=int, default=666_000_000, help="records of the synthetic database")
+    ap.add_argument("--db-passes", type=int, default=1, help="build the synthetic DB in this many minimizer ranges")
     ap.add_argument("--genomes", type=int, default=2000)
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads in the pool")
     ap.add_argument("--batch-reads", type=int, default=1_000_000, help="reads per step")
@@ -57,6 +58,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hll-mode", type=int, default=0, help="0 preload rule (reference default), 1 chunked, 2 dense only")
     ap.add_argument("--cache-dir", default=os.environ.get("KUQ_BENCH_CACHE", "/dev/shm"))
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "shards"],
+                    help="multi-GPU layout: replicas (DB on every GPU, reads partitioned) or minimizer-range shards")
+    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
+                    help="shards: hits stored into the owner's buffer over NVLink (p2p) or ids all-reduced (nccl)")
     return ap.parse_args()
 
 
@@ -192,13 +197,14 @@ def main():
 
     from krakenuniq_b200 import synth_gpu
     t_gen = time.time()
-    db = synth_gpu.GpuDatabase(args.db_records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev)
+    db = synth_gpu.GpuDatabase(args.db_records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev,
+                               passes=args.db_passes)
     n_pool = max(args.reads, args.batch_reads)
     # every rank draws its own reads (seed + rank): reads are partitioned across GPUs
     pool_bases, _ = db.sample_reads(n_pool, READ_LEN, seed=3 + 1000 * rank)
     torch.cuda.synchronize()
     gen_s = time.time() - t_gen
-    workload = (f"configs[1]: {db.key_ct * 12 / 1e9:.1f} GB synthetic KrakenDB (k={K}, m={NT}, {db.key_ct} records) "
+    workload = (f"{'configs[1]' if args.db_records == 666_000_000 else 'scaled configs[1]'}: {db.key_ct * 12 / 1e9:.1f} GB synthetic KrakenDB (k={K}, m={NT}, {db.key_ct} records) "
                 f"+ {8 * ((1 << (2 * NT)) + 1) / 1e9:.1f} GB index in HBM, {n_pool} x {READ_LEN} bp reads, "
                 f"{args.batch_reads} reads per step")
     n_batches = n_pool // args.batch_reads
@@ -245,6 +251,8 @@ def main():
             cpu_baseline = {"value": None, "unit": "Mreads/s", "cores": host_threads(), "kind": "reference",
                             "sample": f"failed: {e}"[:300]}
 
+    if args.mode == "shards":
+        return run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workload, gen_s)
     clf = binding.Classifier(device=local_rank, n_slots=3, max_reads=B, max_bases=B * READ_LEN + 4096,
                              hll_mode=args.hll_mode, sparse_set_slots=1 << 30)
     clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2)
@@ -428,6 +436,123 @@ def main():
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
+    return 0
+
+
+def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workload, gen_s):
+    """the database is split into `world` minimizer ranges (balanced by records, like
+    prepare_chunking); every GPU scans the SAME batch and looks up the k-mers whose minimizer it owns; read r is
+    resolved by one owner GPU.  Merge of the per-window ids: `p2p` = each hit is stored by the lookup kernel straight
+    into the owner's buffer over NVLink (fused lookup + scatter, CUDA IPC mapped peer memory); `nccl` = every rank
+    writes its own buffer and the buffers are max-all-reduced.  value = reads of the job / time."""
+    import torch
+    from krakenuniq_b200 import binding
+    from krakenuniq_b200 import dist as kdist
+    B = args.batch_reads
+    n_pool = max(args.reads, B)
+    n_batches = n_pool // B
+    n_bins = 1 << (2 * NT)
+    # range cuts balanced by record count
+    targets = torch.tensor([db.key_ct * r // world for r in range(world + 1)], device=dev)
+    cuts = torch.searchsorted(db.offsets, targets, right=False).tolist()
+    cuts[0], cuts[-1] = 0, n_bins
+    lo_bin, hi_bin = cuts[rank], cuts[rank + 1]
+    rec_lo = int(db.offsets[lo_bin].item()); rec_hi = int(db.offsets[hi_bin].item())
+    clf = binding.Classifier(device=local_rank, n_slots=2, max_reads=B, max_bases=B * READ_LEN + 4096,
+                             hll_mode=args.hll_mode, sparse_set_slots=1 << 30)
+    clf.set_db_taxid_universe(np.array(db.species, np.uint32))
+    clf.attach_db_device(db.records.data_ptr() + rec_lo * 12, rec_hi - rec_lo, db.offsets.data_ptr() + lo_bin * 8,
+                         K, NT, 2, lo_bin, hi_bin)
+    clf.set_taxonomy(*db.parent_map())
+    per_unit = -(-500000 // READ_LEN)
+    # owner shares: whole work units, contiguous
+    n_units = -(-B // per_unit)
+    share_units = [kdist.partition(n_units, world, r) for r in range(world)]
+    shares = [(min(a * per_unit, B), min(b * per_unit, B)) for a, b in share_units]
+    lo, hi = shares[rank]
+    d_offsets = (torch.arange(B + 2, dtype=torch.int64, device=dev) * READ_LEN)
+    unit_local = (torch.arange(B, dtype=torch.int64, device=dev) // per_unit).to(torch.int32)
+    total = B * READ_LEN
+    nbytes = (total + 64) * 4
+    my_buf = clf.device_alloc(nbytes)
+    bounds = np.array([s[0] * READ_LEN for s in shares] + [total], np.uint64)
+    bounds[0] = 0
+    peers = None
+    if args.merge == "p2p":
+        handles = [None] * world
+        dist.all_gather_object(handles, clf.ipc_export(my_buf))
+        peers = [my_buf if r == rank else clf.ipc_open(handles[r]) for r in range(world)]
+    my_t = kdist.device_view(my_buf, nbytes, torch.int32, dev)
+    stream = torch.cuda.ExternalStream(clf.slot_stream(0), device=dev)
+    keep = {}
+
+    def step(i):
+        bptr = pool_bases.data_ptr() + (i % n_batches) * B * READ_LEN
+        clf.device_memset(0, my_buf, 0, nbytes)
+        clf.sync(0)
+        dist.barrier()                                       # all buffers zeroed
+        if args.merge == "p2p":
+            clf.lookup_device_peers(0, bptr, d_offsets.data_ptr(), B, total, peers, bounds)
+            clf.sync(0)
+            dist.barrier()                                   # all hits landed
+        else:
+            clf.lookup_device(0, bptr, d_offsets.data_ptr(), B, total, my_buf, only_hits=1)
+            clf.sync(0)
+            dist.all_reduce(my_t, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+        if hi > lo:
+            u = unit_local[lo:hi] + i * n_units
+            keep[i % 3] = u
+            clf.resolve_device(0, bptr, d_offsets.data_ptr() + lo * 8, hi - lo, total, my_buf,
+                               u.data_ptr() if args.hll_mode == 0 else None)
+
+    assert lo % 2 == 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    s = 0
+    for _ in range(args.warmup):
+        step(s); s += 1
+    clf.sync(0); torch.cuda.synchronize(); dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    launches0 = clf.launch_count()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+    for _ in range(args.steps):
+        step(s); s += 1
+    with torch.cuda.stream(stream):
+        ev1.record(stream)
+    clf.sync(0); torch.cuda.synchronize(); dist.barrier()
+    sampler.mark(t0, time.time())
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(ms.item())
+    launches = clf.launch_count() - launches0
+    st = clf.last_stage_ms(0)
+    tm0 = torch.cuda.Event(enable_timing=True); tm1 = torch.cuda.Event(enable_timing=True)
+    tm0.record(); kdist.merge_classifier_state(clf, dev); tm1.record(); torch.cuda.synchronize()
+    merge_ms = tm0.elapsed_time(tm1)
+    clocks = sampler.stop()
+    if rank == 0:
+        value = B * args.steps / (dev_ms / 1e3) / 1e6
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload, "parallelism": f"database sharded by minimizer range over {world} GPUs "
+                       f"({(rec_hi - rec_lo) * 12 / 1e9:.1f} GB of records on rank 0), every GPU scans every batch, "
+                       f"id merge = {args.merge}", "hll_mode": ["preload rule", "chunked rule", "dense only"][args.hll_mode],
+                       "timing": "CUDA events on the slot stream around the K steps (host barriers between the phases "
+                                 "included), max over ranks", "end_of_run_merge_ms": merge_ms, "workload_gen_s": gen_s,
+                       "owner_stage_ms_last_step": {"k_scan": st[0], "k_lookup(hll from merged ids)": st[1], "k_resolve": st[2]}},
+            "gpu_launches": int(launches), "clocks": clocks}))
+    dist.barrier()
+    if peers:
+        for r in range(world):
+            if r != rank:
+                clf.ipc_close(peers[r])
+    dist.barrier()
+    dist.destroy_process_group()
     return 0
 
 

@@ -74,54 +74,92 @@ class GpuDatabase:
     """A synthetic database resident in HBM in the on-disk layout."""
 
     def __init__(self, n_records: int, n_genomes: int = 2000, k: int = 31, nt: int = 15, idx_type: int = 2,
-                 seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26):
+                 seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26, passes: int = 1):
+        """`passes` > 1 builds the database one minimizer range at a time (temporaries of one range only), for
+        databases whose sort would not fit next to the result (tens of GB and more, > 2^32 records)."""
         self.k, self.nt, self.idx_type = k, nt, idx_type
         dev = torch.device(device)
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed)
         n_pos = n_records                       # one window per position (duplicates are removed below)
-        self.genome = torch.randint(0, 4, (n_pos + k - 1,), dtype=torch.uint8, device=dev, generator=gen)
+        self.genome = torch.empty(n_pos + k - 1, dtype=torch.uint8, device=dev)
+        for a in range(0, n_pos + k - 1, 1 << 30):      # randint in pieces: no multi-GB int64 temporaries
+            c = min(1 << 30, n_pos + k - 1 - a)
+            self.genome[a:a + c] = torch.randint(0, 4, (c,), dtype=torch.uint8, device=dev, generator=gen)
         self.rows, self.species = make_taxonomy_rows(n_genomes)
         self.genome_len = (n_pos + n_genomes - 1) // n_genomes
         sp = torch.tensor(self.species, dtype=torch.int32, device=dev)
-        keys = torch.empty(n_pos, dtype=torch.int64, device=dev)
-        bins = torch.empty(n_pos, dtype=torch.int32, device=dev)
-        for a in range(0, n_pos, chunk):
-            c = min(chunk, n_pos - a)
-            km = canonical(forward_kmers(self.genome, a, c, k), k)
-            keys[a:a + c] = km
-            bins[a:a + c] = bin_key(km, k, nt, idx_type).to(torch.int32)
-            del km
-        # sort by (bin, key): key sort, then a stable bin sort
-        keys, order = torch.sort(keys)
-        bins = bins[order]
-        taxa = sp[(order // self.genome_len).to(torch.int64)]
-        del order
-        # drop duplicate keys (same k-mer at two positions / palindromes): keep the first owner
-        keep = torch.ones(n_pos, dtype=torch.bool, device=dev)
-        keep[1:] = keys[1:] != keys[:-1]
-        if not bool(keep.all()):
-            keys, bins, taxa = keys[keep], bins[keep], taxa[keep]
-        del keep
-        bins, order = torch.sort(bins, stable=True)
-        keys = keys[order]
-        taxa = taxa[order]
-        del order
-        n = keys.numel()
-        self.key_ct = n
-        rec = torch.empty((n, 3), dtype=torch.int32, device=dev)
-        rec[:, 0] = (keys & 0xFFFFFFFF).to(torch.int32)          # wraps to the same 32 bits
-        rec[:, 1] = (keys >> 32).to(torch.int32)
-        rec[:, 2] = taxa
-        self.records = rec                                       # (n, 3) int32 == packed 12-byte records
-        del keys, taxa
-        counts = torch.bincount(bins.to(torch.int64), minlength=1 << (2 * nt))
-        del bins
-        off = torch.zeros((1 << (2 * nt)) + 1, dtype=torch.int64, device=dev)
+        n_bins = 1 << (2 * nt)
+        # minimizer-range cut points for the passes, from the bins of a sample (bins are heavily skewed)
+        if passes > 1:
+            m = min(n_pos, 1 << 24)
+            sb = bin_key(canonical(forward_kmers(self.genome, 0, m, k), k), k, nt, idx_type)
+            q = torch.quantile(sb.to(torch.float64)[:: max(1, m >> 20)], torch.linspace(0, 1, passes + 1, device=dev,
+                                                                                  dtype=torch.float64))
+            cuts = [0] + [int(x) for x in q[1:-1].tolist()] + [n_bins]
+            del sb
+        else:
+            cuts = [0, n_bins]
+        rec = torch.empty((n_pos, 3), dtype=torch.int32, device=dev)      # (n, 3) int32 == packed 12-byte records
+        counts = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+        out = 0
+        for pi in range(len(cuts) - 1):
+            lo, hi = cuts[pi], cuts[pi + 1]
+            if hi <= lo:
+                continue
+            keys_l, bins_l, pos_l = [], [], []
+            for a in range(0, n_pos, chunk):
+                c = min(chunk, n_pos - a)
+                km = canonical(forward_kmers(self.genome, a, c, k), k)
+                bn = bin_key(km, k, nt, idx_type)
+                if passes > 1:
+                    sel = (bn >= lo) & (bn < hi)
+                    keys_l.append(km[sel])
+                    bins_l.append(bn[sel].to(torch.int32))
+                    pos_l.append(torch.nonzero(sel).squeeze(1) + a)
+                    del sel
+                else:
+                    keys_l.append(km)
+                    bins_l.append(bn.to(torch.int32))
+                del km, bn
+            keys = torch.cat(keys_l); del keys_l
+            bins = torch.cat(bins_l); del bins_l
+            if passes > 1:
+                pos = torch.cat(pos_l); del pos_l
+            # sort by (bin, key): key sort, then a stable bin sort
+            keys, order = torch.sort(keys)
+            bins = bins[order]
+            owner = (pos[order] if passes > 1 else order) // self.genome_len
+            taxa = sp[owner.to(torch.int64)]
+            del order, owner
+            if passes > 1:
+                del pos
+            # drop duplicate keys (same k-mer at two positions / palindromes): keep the first owner
+            keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+            keep[1:] = keys[1:] != keys[:-1]
+            if not bool(keep.all()):
+                keys, bins, taxa = keys[keep], bins[keep], taxa[keep]
+            del keep
+            bins, order = torch.sort(bins, stable=True)
+            keys = keys[order]
+            taxa = taxa[order]
+            del order
+            n = keys.numel()
+            rec[out:out + n, 0] = (keys & 0xFFFFFFFF).to(torch.int32)      # wraps to the same 32 bits
+            rec[out:out + n, 1] = (keys >> 32).to(torch.int32)
+            rec[out:out + n, 2] = taxa
+            out += n
+            counts += torch.bincount(bins.to(torch.int64), minlength=n_bins)
+            del keys, taxa, bins
+            torch.cuda.empty_cache() if dev.type == "cuda" else None
+        self.key_ct = out
+        self.records = rec[:out]
+        off = torch.zeros(n_bins + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts, 0, out=off[1:])
         del counts
         self.offsets = off
-        torch.cuda.empty_cache()
+        if dev.type == "cuda":
+            torch.cuda.empty_cache()
 
     # ---- host images (for the reference binary / the oracle) --------------------------------------------------
     def kdb_header(self) -> np.ndarray:

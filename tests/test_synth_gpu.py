@@ -65,3 +65,11 @@ def test_reads_shape_and_content():
         km, ok = synth.forward_kmers(synth.encode(b[i * 150:(i + 1) * 150]), 31)
         hits += any(int(c) in keyset for c in synth.canonical(km, 31).tolist())
     assert hits > 60
+
+
+def test_multi_pass_generation_equals_single_pass():
+    a = synth_gpu.GpuDatabase(30000, n_genomes=7, k=31, nt=7, seed=11, device="cpu", chunk=9000)
+    b = synth_gpu.GpuDatabase(30000, n_genomes=7, k=31, nt=7, seed=11, device="cpu", chunk=9000, passes=3)
+    assert a.key_ct == b.key_ct
+    assert np.array_equal(a.records.numpy(), b.records.numpy())
+    assert np.array_equal(a.offsets.numpy(), b.offsets.numpy())
