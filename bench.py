@@ -369,6 +369,7 @@ def main():
         host_bufs.append((p, hb))
     n_slots = 3
     d2h_bytes = [0]
+    sanity = {"reads": 0, "classified": 0}
     e2e_step = [step]
 
     def run_e2e(n_steps):
@@ -378,11 +379,13 @@ def main():
             if len(inflight) == n_slots:
                 res = clf.wait(inflight.pop(0))
                 d2h_bytes[0] = 4 * B * 4 + 8 * res["n_runs"] + 64
+                sanity["reads"] += B; sanity["classified"] += res["n_classified"]
             clf.submit(slot, host_bufs[s % n_host][0], host_offsets, h_units(e2e_step[0])); e2e_step[0] += 1
             inflight.append(slot)
         for slot in inflight:
             res = clf.wait(slot)
             d2h_bytes[0] = 4 * B * 4 + 8 * res["n_runs"] + 64
+            sanity["reads"] += B; sanity["classified"] += res["n_classified"]
 
     run_e2e(max(args.warmup, 3))
     barrier()
@@ -432,6 +435,8 @@ def main():
                         "how": "kuq_submit_batch/kuq_wait_batch over 3 slots, pinned host reads, results = calls + "
                                "window counts + RLE hit lists"},
                 "gpu_launches": int(launches),
+                "sanity": {"classified_fraction": sanity["classified"] / max(sanity["reads"], 1),
+                           "expected": "about 0.80: 80 % of the reads are sampled from the database genomes (1 % substitutions)"},
                 "clocks": clocks}
         print(json.dumps(line))
     if dist:
