@@ -197,14 +197,21 @@ def main():
 
     from krakenuniq_b200 import synth_gpu
     t_gen = time.time()
+    sharded = args.mode == "shards" and world > 1
     db = synth_gpu.GpuDatabase(args.db_records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev,
-                               passes=args.db_passes)
+                               passes=args.db_passes, shard=(rank, world) if sharded else None)
     n_pool = max(args.reads, args.batch_reads)
-    # every rank draws its own reads (seed + rank): reads are partitioned across GPUs
-    pool_bases, _ = db.sample_reads(n_pool, READ_LEN, seed=3 + 1000 * rank)
+    # replicas: every rank draws its own reads (seed + rank), reads are partitioned across GPUs;
+    # shards: every GPU scans the same reads
+    pool_bases, _ = db.sample_reads(n_pool, READ_LEN, seed=3 + (0 if sharded else 1000 * rank))
     torch.cuda.synchronize()
     gen_s = time.time() - t_gen
-    workload = (f"{'configs[1]' if args.db_records == 666_000_000 else 'scaled configs[1]'}: {db.key_ct * 12 / 1e9:.1f} GB synthetic KrakenDB (k={K}, m={NT}, {db.key_ct} records) "
+    total_records = db.key_ct
+    if sharded:
+        t = torch.tensor([db.key_ct], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        total_records = int(t.item())
+    workload = (f"{'configs[1]' if args.db_records == 666_000_000 else 'scaled configs[1]'}: {total_records * 12 / 1e9:.1f} GB synthetic KrakenDB (k={K}, m={NT}, {total_records} records) "
                 f"+ {8 * ((1 << (2 * NT)) + 1) / 1e9:.1f} GB index in HBM, {n_pool} x {READ_LEN} bp reads, "
                 f"{args.batch_reads} reads per step")
     n_batches = n_pool // args.batch_reads
@@ -457,17 +464,13 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     n_pool = max(args.reads, B)
     n_batches = n_pool // B
     n_bins = 1 << (2 * NT)
-    # range cuts balanced by record count
-    targets = torch.tensor([db.key_ct * r // world for r in range(world + 1)], device=dev)
-    cuts = torch.searchsorted(db.offsets, targets, right=False).tolist()
-    cuts[0], cuts[-1] = 0, n_bins
-    lo_bin, hi_bin = cuts[rank], cuts[rank + 1]
-    rec_lo = int(db.offsets[lo_bin].item()); rec_hi = int(db.offsets[hi_bin].item())
+    # every rank generated only its own minimizer range (GpuDatabase(shard=...)): ranges hold about equal records
+    lo_bin, hi_bin = db.bin_lo, db.bin_hi
+    rec_lo, rec_hi = 0, db.key_ct
     clf = binding.Classifier(device=local_rank, n_slots=2, max_reads=B, max_bases=B * READ_LEN + 4096,
                              hll_mode=args.hll_mode, sparse_set_slots=1 << 30)
     clf.set_db_taxid_universe(np.array(db.species, np.uint32))
-    clf.attach_db_device(db.records.data_ptr() + rec_lo * 12, rec_hi - rec_lo, db.offsets.data_ptr() + lo_bin * 8,
-                         K, NT, 2, lo_bin, hi_bin)
+    clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2, lo_bin, hi_bin)
     clf.set_taxonomy(*db.parent_map())
     per_unit = -(-500000 // READ_LEN)
     # owner shares: whole work units, contiguous
@@ -538,6 +541,9 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     tm0.record(); kdist.merge_classifier_state(clf, dev); tm1.record(); torch.cuda.synchronize()
     merge_ms = tm0.elapsed_time(tm1)
     clocks = sampler.stop()
+    cnt = clf.counts()
+    tot_reads = int(cnt["n_reads"].sum())
+    unclassified = int(cnt["n_reads"][cnt["taxid"] == 0].sum())
     if rank == 0:
         value = B * args.steps / (dev_ms / 1e3) / 1e6
         print(json.dumps({
@@ -550,6 +556,8 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
                        "timing": "CUDA events on the slot stream around the K steps (host barriers between the phases "
                                  "included), max over ranks", "end_of_run_merge_ms": merge_ms, "workload_gen_s": gen_s,
                        "owner_stage_ms_last_step": {"k_scan": st[0], "k_lookup(hll from merged ids)": st[1], "k_resolve": st[2]}},
+            "sanity": {"reads_counted": tot_reads, "classified_fraction": 1.0 - unclassified / max(tot_reads, 1),
+                       "expected": "about 0.80 (80 % of the reads come from the database genomes)"},
             "gpu_launches": int(launches), "clocks": clocks}))
     dist.barrier()
     if peers:

@@ -74,9 +74,13 @@ class GpuDatabase:
     """A synthetic database resident in HBM in the on-disk layout."""
 
     def __init__(self, n_records: int, n_genomes: int = 2000, k: int = 31, nt: int = 15, idx_type: int = 2,
-                 seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26, passes: int = 1):
+                 seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26, passes: int = 1,
+                 shard: tuple[int, int] | None = None):
         """`passes` > 1 builds the database one minimizer range at a time (temporaries of one range only), for
-        databases whose sort would not fit next to the result (tens of GB and more, > 2^32 records)."""
+        databases whose sort would not fit next to the result (tens of GB and more, > 2^32 records).
+        `shard` = (rank, world): keep only this rank's minimizer range of a database cut into `world` ranges with
+        about equal record counts (every rank derives the same cut points from the same sample); `offsets` is then
+        the local slice for bins [bin_lo, bin_hi] starting at 0."""
         self.k, self.nt, self.idx_type = k, nt, idx_type
         dev = torch.device(device)
         gen = torch.Generator(device=dev)
@@ -90,18 +94,25 @@ class GpuDatabase:
         self.genome_len = (n_pos + n_genomes - 1) // n_genomes
         sp = torch.tensor(self.species, dtype=torch.int32, device=dev)
         n_bins = 1 << (2 * nt)
-        # minimizer-range cut points for the passes, from the bins of a sample (bins are heavily skewed)
-        if passes > 1:
+        # minimizer-range cut points for the shards / passes, from the bins of a sample (bins are heavily skewed)
+        self.bin_lo, self.bin_hi = 0, n_bins
+        n_parts = (shard[1] if shard else 1) * passes
+        if n_parts > 1:
             m = min(n_pos, 1 << 24)
             sb = bin_key(canonical(forward_kmers(self.genome, 0, m, k), k), k, nt, idx_type)
-            q = torch.quantile(sb.to(torch.float64)[:: max(1, m >> 20)], torch.linspace(0, 1, passes + 1, device=dev,
+            q = torch.quantile(sb.to(torch.float64)[:: max(1, m >> 20)], torch.linspace(0, 1, n_parts + 1, device=dev,
                                                                                   dtype=torch.float64))
             cuts = [0] + [int(x) for x in q[1:-1].tolist()] + [n_bins]
             del sb
+            if shard:
+                cuts = cuts[shard[0] * passes:(shard[0] + 1) * passes + 1]
+                self.bin_lo, self.bin_hi = cuts[0], cuts[-1]
         else:
             cuts = [0, n_bins]
-        rec = torch.empty((n_pos, 3), dtype=torch.int32, device=dev)      # (n, 3) int32 == packed 12-byte records
-        counts = torch.zeros(n_bins, dtype=torch.int64, device=dev)
+        selective = n_parts > 1
+        n_rows = n_pos if not shard else int(n_pos / shard[1] * 1.25) + (1 << 20)
+        rec = torch.empty((n_rows, 3), dtype=torch.int32, device=dev)     # (n, 3) int32 == packed 12-byte records
+        counts = torch.zeros(self.bin_hi - self.bin_lo, dtype=torch.int64, device=dev)
         out = 0
         for pi in range(len(cuts) - 1):
             lo, hi = cuts[pi], cuts[pi + 1]
@@ -112,7 +123,7 @@ class GpuDatabase:
                 c = min(chunk, n_pos - a)
                 km = canonical(forward_kmers(self.genome, a, c, k), k)
                 bn = bin_key(km, k, nt, idx_type)
-                if passes > 1:
+                if selective:
                     sel = (bn >= lo) & (bn < hi)
                     keys_l.append(km[sel])
                     bins_l.append(bn[sel].to(torch.int32))
@@ -124,15 +135,15 @@ class GpuDatabase:
                 del km, bn
             keys = torch.cat(keys_l); del keys_l
             bins = torch.cat(bins_l); del bins_l
-            if passes > 1:
+            if selective:
                 pos = torch.cat(pos_l); del pos_l
             # sort by (bin, key): key sort, then a stable bin sort
             keys, order = torch.sort(keys)
             bins = bins[order]
-            owner = (pos[order] if passes > 1 else order) // self.genome_len
+            owner = (pos[order] if selective else order) // self.genome_len
             taxa = sp[owner.to(torch.int64)]
             del order, owner
-            if passes > 1:
+            if selective:
                 del pos
             # drop duplicate keys (same k-mer at two positions / palindromes): keep the first owner
             keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
@@ -145,16 +156,17 @@ class GpuDatabase:
             taxa = taxa[order]
             del order
             n = keys.numel()
+            assert out + n <= n_rows, "shard larger than planned: raise the row reserve"
             rec[out:out + n, 0] = (keys & 0xFFFFFFFF).to(torch.int32)      # wraps to the same 32 bits
             rec[out:out + n, 1] = (keys >> 32).to(torch.int32)
             rec[out:out + n, 2] = taxa
             out += n
-            counts += torch.bincount(bins.to(torch.int64), minlength=n_bins)
+            counts += torch.bincount(bins.to(torch.int64) - self.bin_lo, minlength=self.bin_hi - self.bin_lo)
             del keys, taxa, bins
             torch.cuda.empty_cache() if dev.type == "cuda" else None
         self.key_ct = out
         self.records = rec[:out]
-        off = torch.zeros(n_bins + 1, dtype=torch.int64, device=dev)
+        off = torch.zeros(self.bin_hi - self.bin_lo + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts, 0, out=off[1:])
         del counts
         self.offsets = off

@@ -73,3 +73,18 @@ def test_multi_pass_generation_equals_single_pass():
     assert a.key_ct == b.key_ct
     assert np.array_equal(a.records.numpy(), b.records.numpy())
     assert np.array_equal(a.offsets.numpy(), b.offsets.numpy())
+
+
+def test_sharded_generation_partitions_the_database():
+    full = synth_gpu.GpuDatabase(30000, n_genomes=7, k=31, nt=7, seed=11, device="cpu", chunk=9000)
+    recs, n = [], 0
+    for r in range(3):
+        sh = synth_gpu.GpuDatabase(30000, n_genomes=7, k=31, nt=7, seed=11, device="cpu", chunk=9000, passes=2,
+                                   shard=(r, 3))
+        lo, hi = sh.bin_lo, sh.bin_hi
+        want_off = full.offsets[lo:hi + 1] - full.offsets[lo]
+        assert np.array_equal(sh.offsets.numpy(), want_off.numpy())
+        a, b = int(full.offsets[lo]), int(full.offsets[hi])
+        assert np.array_equal(sh.records.numpy(), full.records[a:b].numpy())
+        n += sh.key_ct
+    assert n == full.key_ct
