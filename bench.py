@@ -13,7 +13,10 @@ over one batch of 1 M reads (150 MB of read text, > L2; the lookups touch the 16
 `value`  : device-resident inputs, CUDA events on the launching stream (the slot's stream), max over ranks.
 `e2e`    : the same metric through the C ABI with HOST buffers: pinned reads → H2D → kernel → D2H of calls and
            run-length hit lists every step, pipelined over the context's batch slots.
-Multi-GPU: the database fits one card, so ranks are replicas; reads are partitioned across
+`--mode shards` (BASELINE configs[3]): the database is cut into one minimizer range per GPU
+(each rank builds only its range), every GPU scans every batch, hits go to the owner GPU over NVLink
+(`--merge p2p`, fused lookup + peer scatter) or through an NCCL all-reduce (`--merge nccl`).
+Multi-GPU default: the database fits one card, so ranks are replicas; reads are partitioned across
 ranks (weak scaling: 1 M reads per rank per step); the only collective is the once-per-run merge of the per-taxon
 state (allreduce MAX over HLL registers, SUM over counters, all-gather of the sparse-tier keys); it is not part of a
 step and is reported separately as config.end_of_run_merge_ms.
