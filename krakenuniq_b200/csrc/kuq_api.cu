@@ -256,12 +256,6 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   return KUQ_OK;
 }
 
-// the (taxon, code) set behind the sparse tier must stay well below its capacity (open addressing)
-int check_sparse_fill(kuq_ctx *ctx) {
-  (void)ctx;   // saturation is reported by the kernels through the slot's error flag (code 4)
-  return KUQ_OK;
-}
-
 int check_slot(kuq_ctx *ctx, uint32_t slot) {
   if (!ctx) return KUQ_E_INVALID_ARG;
   if (slot >= ctx->slots.size()) return fail(ctx, KUQ_E_INVALID_ARG, "slot %u out of range (%zu slots)", slot, ctx->slots.size());
@@ -930,8 +924,6 @@ int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
-  int rc2 = check_sparse_fill(ctx);
-  if (rc2) return rc2;
   const uint64_t n_runs = (s.flags & KUQ_F_NO_RUNS) ? 0 : s.h_scalars[0];
   if (n_runs) {
     if (n_runs > s.h_runs_cap) {
@@ -1085,7 +1077,7 @@ int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
-  return check_sparse_fill(ctx);
+  return KUQ_OK;
 }
 
 int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out) {

@@ -277,3 +277,48 @@ def test_paired_reads_merged_with_N(oracle):
         seqs.append(m1 + b"N" + m2)
     bases, offs = synth.pack_reads(seqs)
     _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_PRELOAD, unit=30000)
+
+
+@pytest.mark.parametrize("n_ranges", [2, 5])
+def test_database_ranges_through_the_halves(oracle, n_ranges):
+    """chunked database (classify.cpp:566-791) through the C ABI halves: stage one minimizer range at a time,
+    kuq_lookup_batch for every range, element-wise max merge, kuq_resolve_batch — same calls, hit lists and
+    (chunked-rule) counters as the oracle's one-pass run."""
+    tax, genomes, kdb, idx, bases, offs = _synthetic(91, 9, 2, n_genomes=5, n_reads=700)
+    db = oracle.open_db(kdb, idx)
+    pm = oracle.parent_map(*tax.parent_map())
+    run = oracle.run(db, pm, 500000, 1)
+    calls, codes, code_off = run.classify(bases, offs)
+    run.finish()
+    want = run.counts(want_regs=True)
+
+    n_bins = 1 << 18
+    idx_off = np.frombuffer(idx[8:].tobytes(), np.uint64)
+    cuts = [int(np.searchsorted(idx_off, idx_off[-1] * r // n_ranges)) for r in range(n_ranges + 1)]
+    cuts[0], cuts[-1] = 0, n_bins
+    clf = _classifier(hll_mode=binding.HLL_CHUNKED)
+    clf.set_taxonomy(*tax.parent_map())
+    universe = set()
+    for r in range(n_ranges):                       # pass 0: the taxids of every range
+        if cuts[r + 1] > cuts[r]:
+            clf.stage_db(kdb, idx, cuts[r], cuts[r + 1])
+            universe |= set(clf.db_taxids()[0].tolist())
+    clf.set_db_taxid_universe(np.array(sorted(universe), np.uint32))
+    merged = np.zeros(int(offs[-1]), np.uint32)
+    for r in range(n_ranges):
+        if cuts[r + 1] <= cuts[r]:
+            continue
+        clf.stage_db(kdb, idx, cuts[r], cuts[r + 1])
+        part, nwin = clf.lookup(bases, offs)
+        amb = part == binding.AMBIG
+        merged = np.where(amb, merged, np.maximum(merged, part))
+    res = clf.resolve(bases, offs, merged, flags=binding.F_WANT_CODES)
+    clf.finish()
+    assert np.array_equal(res["call"], calls)
+    assert np.array_equal(res["n_windows"], np.diff(code_off).astype(np.uint32))
+    for i in range(len(offs) - 1):
+        w = codes[int(code_off[i]):int(code_off[i + 1])]
+        assert np.array_equal(_runs_to_codes(res, i), w), f"runs of read {i}"
+    got = clf.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        assert np.array_equal(got[key], want[key]), key
