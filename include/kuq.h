@@ -181,8 +181,8 @@ void kuq_host_free(void *p);
 /* ---- classification, device buffers (inputs already in HBM) ---------------------------------------------- */
 /* d_bases must be 16-byte aligned with 32 readable bytes of slack after the last base (TMA bulk loads fetch
  * whole 16-byte blocks); d_read_offsets (16-byte aligned, n_reads + 2 entries readable) are relative to d_bases.  Asynchronous on the slot's stream;
- * kuq_sync_slot() waits.  d_unit_id may be NULL (units cut on the host need the offsets: pass h_read_offsets,
- * or NULL when hll_mode == KUQ_HLL_DENSE_ONLY / KUQ_HLL_CHUNKED). */
+ * kuq_sync_slot() waits.  d_unit_id: work-unit id of every read (device array) — required with KUQ_HLL_PRELOAD
+ * (the per-unit sketches of classify.cpp:525 are what the mode rule is about), NULL otherwise. */
 int kuq_classify_device(kuq_ctx *ctx, uint32_t slot, const char *d_bases, const uint64_t *d_read_offsets,
                         uint32_t n_reads, uint64_t total_bases, const uint32_t *d_unit_id, uint32_t flags);
 /* Stage 1 only (classify_sequence_with_db_chunk): per-window DENSE taxon ids of the staged DB range into

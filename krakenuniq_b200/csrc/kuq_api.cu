@@ -970,6 +970,9 @@ static int device_call(kuq_ctx *ctx, uint32_t slot, int mode, const char *d_base
   CU(cudaSetDevice(ctx->device));
   rc = ensure_ready(ctx);
   if (rc) return rc;
+  if (mode != MODE_LOOKUP && ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && !d_unit && !(flags & KUQ_F_NO_COUNTS) && n_reads)
+    return fail(ctx, KUQ_E_INVALID_ARG, "KUQ_HLL_PRELOAD needs the work-unit id of every read (d_unit_id) to "
+                "reproduce the per-unit sketches; pass it, or create the context with KUQ_HLL_CHUNKED / KUQ_HLL_DENSE_ONLY");
   Slot &s = ctx->slots[slot];
   if (n_reads > ctx->cfg.max_reads_per_batch || total_bases > ctx->cfg.max_bases_per_batch)
     return fail(ctx, KUQ_E_CAPACITY, "batch exceeds the slot capacity");

@@ -978,11 +978,8 @@ int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedSt
 //      MODE_RESOLVE: scan → HLL from merged codes → resolve    (owner of the reads after the merge)
 int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cudaEvent_t *stage_events) {
   const int smem = classify_smem_bytes();
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
+  // per device (function attributes belong to the current context): cheap enough to set on every call
+  cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int launches = 0;
   if (p.n_reads == 0) return 0;
   int grid = n_sm * 4;
