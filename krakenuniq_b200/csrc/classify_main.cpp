@@ -723,8 +723,14 @@ static bool process_file_parallel(kuq_ctx *ctx, const char *filename) {
     uint64_t unit_nt = 0, batch_nt = 0;
     size_t begin = 0, unit_first = 0;
     int c = 0;
+    const uint64_t SLOT_NT = 280ull << 20;            // below the slot capacity (288 MiB)
     for (size_t i = 0; i < n_total; i++) {
       const uint32_t len = view(i, c).seq_len;
+      if (len > SLOT_NT) die(EX_DATAERR, "a single sequence is longer than 280 Mbp: not supported");
+      if (batch_nt + len > SLOT_NT && i > begin) {    // a very long sequence is coming: close the batch before it
+        batches.push_back({begin, i, batch_nt});
+        begin = i; batch_nt = 0;
+      }
       unit_nt += len; batch_nt += len;
       bool close_unit = unit_nt >= Work_unit_size;
       if (close_unit) { unit_nt = 0; unit_first = i + 1; }
@@ -904,6 +910,25 @@ static void process_file(kuq_ctx *ctx, const char *filename) {
   while (reader.valid) {
     Batch &b = batches[cur];
     if (!reader.next(r, b.bases)) break;
+    if (r.seq_len > (280ull << 20)) die(EX_DATAERR, "a single sequence is longer than 280 Mbp: not supported");
+    if (b.bases.size() > (280ull << 20) && !b.reads.empty()) {
+      // the sequence just read does not fit next to the batch: move it to the next batch
+      Batch &nb = batches[cur ^ 1];
+      string seq = b.bases.substr(r.seq_off);
+      b.bases.resize(r.seq_off);
+      submit(cur);
+      cur ^= 1;
+      unit_first_read = 0;
+      Batch &b2 = batches[cur];
+      (void)nb;
+      r.seq_off = b2.bases.size();
+      b2.bases += seq;
+      b2.reads.push_back(r);
+      b2.offs.push_back(b2.bases.size());
+      unit_nt += r.seq_len;
+      if (unit_nt >= Work_unit_size) { unit_nt = 0; unit_first_read = b2.reads.size(); }
+      continue;
+    }
     b.reads.push_back(r);
     b.offs.push_back(b.bases.size());
     unit_nt += r.seq_len;
@@ -1060,6 +1085,7 @@ int main(int argc, char **argv) {
   kuq_config cfg;
   kuq_config_default(&cfg);
   cfg.n_slots = 2;
+  cfg.max_bases_per_batch = 288ull << 20;      // one read may be a whole chromosome (the largest human one is 248 Mbp)
   cfg.work_unit_size = Work_unit_size;
   // -x (or a database that has to be split) → one global sketch per taxon (classify.cpp:719); else per work unit
   cfg.hll_mode = (Populate_memory_size > 0 || chunk_budget) ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;

@@ -496,9 +496,11 @@ struct OverflowPool {
 
 __device__ uint32_t resolve_overflow(const Params &p, const OverflowPool &pool, const uint32_t *codes_src, uint64_t out_base,
                                      uint32_t nwin, uint32_t unit, bool counting, bool units, uint32_t lane) {
-  // capacity: next power of two >= 2 * windows (distinct taxa <= windows)
+  // capacity: next power of two >= 2 * (upper bound of distinct taxa); distinct taxa <= windows
+  // (and <= taxa that own a sketch: only database values can be hits)
+  const uint32_t most = min(nwin, p.tax.n_sketch);
   uint32_t cap = 64;
-  while (cap < 2 * nwin) cap <<= 1;
+  while (cap < 2 * most) cap <<= 1;
   unsigned long long start = 0;
   if (lane == 0) start = atomicAdd(pool.cursor, (unsigned long long)cap);
   start = __shfl_sync(0xFFFFFFFFu, start, 0);

@@ -136,3 +136,36 @@ def test_cli_database_ranges(tmp_path, size):
     assert open(out).read() == open(os.path.join(G, "chunked.kraken")).read()
     assert _report_lines(rep) == _report_lines(os.path.join(G, "chunked.report.tsv"))
     assert open(db / "database.kdb.counts").read() == open(os.path.join(G, "database.kdb.counts")).read()
+
+
+def test_cli_long_contigs_match_oracle(tmp_path, oracle):
+    """multi-line FASTA contigs (hundreds of kb, > 32 distinct taxa): Kraken lines equal to the oracle's"""
+    import numpy as np
+    from krakenuniq_b200 import synth
+    rng = np.random.default_rng(3)
+    kdb = np.fromfile(os.path.join(G, "database.kdb"), np.uint8)
+    idx = np.fromfile(os.path.join(G, "database.idx"), np.uint8)
+    tax = synth.Taxonomy.read(os.path.join(G, "taxDB"))
+    _, seqs = util.read_fasta(os.path.join(G, "reads.fa"))
+    pool = [s for s in seqs if len(s) == 150 and b"N" not in s]
+    contigs = [b"".join(pool[int(j)] for j in rng.integers(0, len(pool), n)) for n in (5, 400, 2500)]
+    fa = tmp_path / "contigs.fa"
+    with open(fa, "wb") as f:
+        for i, c in enumerate(contigs):
+            f.write(b">contig%d some description\n" % i)
+            for a in range(0, len(c), 80):
+                f.write(c[a:a + 80] + b"\n")
+    db = oracle.open_db(kdb, idx)
+    pm = oracle.parent_map(*tax.parent_map())
+    run = oracle.run(db, pm, 500000, 0)
+    bases, offs = synth.pack_reads(contigs)
+    calls, codes, code_off = run.classify(bases, offs)
+    want = util.kraken_lines([f"contig{i}" for i in range(3)], contigs, calls, codes, code_off)
+    exe = build.build_classify()
+    for threads in ("1", "6"):
+        out = tmp_path / f"o{threads}.kraken"
+        cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
+               os.path.join(G, "taxDB"), "-M", "-t", threads, "-o", str(out), str(fa)]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22)))
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert open(out).read() == want
