@@ -515,8 +515,16 @@ static readcounts *cm_get(countmap *m, uint32_t taxid) {               /* operat
 
 /* classify_sequence(), classify.cpp:897-1012 (Quick_mode off, one database, Map_UIDs off).  `counts` receives
  * add_kmer (:939) for every non-ambiguous window — taxon 0 for misses — and incrementReadCount (:968). */
+static uint32_t classify_read_multi(const kuqo_db *const *dbs, uint32_t n_db, const kuqo_parent_map *pm, const char *seq,
+                                    size_t len, uint32_t *codes, uint32_t *n_windows, countmap *counts);
 static uint32_t classify_read_into(const kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len,
                                    uint32_t *codes, uint32_t *n_windows, countmap *counts) {
+  return classify_read_multi(&db, 1, pm, seq, len, codes, n_windows, counts);
+}
+/* several databases: the first one that holds the key decides, even if it stores taxon 0 (classify.cpp:928-936) */
+static uint32_t classify_read_multi(const kuqo_db *const *dbs, uint32_t n_db, const kuqo_parent_map *pm, const char *seq,
+                                    size_t len, uint32_t *codes, uint32_t *n_windows, countmap *counts) {
+  const kuqo_db *db = dbs[0];
   uint32_t n = 0;
   uint32_t *hit_taxa = NULL, *hit_cnt = NULL, n_hits = 0;
   if (len >= db->k) {
@@ -534,7 +542,8 @@ static uint32_t classify_read_into(const kuqo_db *db, const kuqo_parent_map *pm,
       }
       uint64_t canon = kuqo_canonical(kmers[i], db->k);                     /* :925 */
       uint32_t v;
-      if (kuqo_kmer_query(db, canon, &v)) taxon = v;                        /* :928-936 */
+      for (uint32_t d = 0; d < n_db; d++)                                   /* :928-936 */
+        if (kuqo_kmer_query(dbs[d], canon, &v)) { taxon = v; break; }
       if (counts) {
         readcounts *rc = cm_get(counts, taxon);                             /* :939 */
         ++rc->n_kmers;
@@ -588,6 +597,8 @@ size_t kuqo_hitlist_string(const uint32_t *codes, uint32_t n, char *buf, size_t 
 /* whole run                                                                                               */
 /* ======================================================================================================= */
 struct kuqo_run {
+  const kuqo_db *dbs[16];
+  uint32_t n_db;
   const kuqo_db *db;
   const kuqo_parent_map *pm;
   uint64_t unit_size;
@@ -599,7 +610,7 @@ struct kuqo_run {
 
 kuqo_run *kuqo_run_new(const kuqo_db *db, const kuqo_parent_map *pm, uint64_t work_unit_size, int mode) {
   kuqo_run *r = (kuqo_run *)calloc(1, sizeof(*r));
-  r->db = db; r->pm = pm; r->unit_size = work_unit_size ? work_unit_size : 500000; r->mode = mode;
+  r->db = db; r->dbs[0] = db; r->n_db = 1; r->pm = pm; r->unit_size = work_unit_size ? work_unit_size : 500000; r->mode = mode;
   cm_init(&r->global); cm_init(&r->local);
   return r;
 }
@@ -633,7 +644,7 @@ int kuqo_run_classify(kuqo_run *r, const char *bases, const uint64_t *offsets, u
     uint32_t nw = 0;
     /* preload: work unit's private map (:525,530-535); chunked: the global map directly (:719,747) */
     countmap *target = r->mode == 0 ? &r->local : &r->global;
-    uint32_t call = classify_read_into(r->db, r->pm, seq, len, scratch, &nw, target);
+    uint32_t call = classify_read_multi(r->dbs, r->n_db, r->pm, seq, len, scratch, &nw, target);
     calls_out[i] = call;
     if (code_offsets_out) code_offsets_out[i] = code_pos;
     if (codes_out) memcpy(codes_out + code_pos, scratch, 4 * (size_t)nw);
@@ -690,4 +701,11 @@ uint64_t kuqo_run_clade(const kuqo_run *r, const uint32_t *taxa, uint32_t n, uin
   if (n_reads) *n_reads = reads;
   if (n_kmers) *n_kmers = kmers;
   return u;
+}
+
+/* classify -d db1 -d db2 ...: databases are tried in command-line order for every k-mer (classify.cpp:928-936) */
+int kuqo_run_add_db(kuqo_run *r, const kuqo_db *db) {
+  if (r->n_db >= 16 || db->k != r->dbs[0]->k) return -1;      /* all databases must share k (:203-210) */
+  r->dbs[r->n_db++] = db;
+  return 0;
 }

@@ -96,6 +96,8 @@ uint32_t kuqo_run_n_taxa(const kuqo_run *r);
 void kuqo_run_counts(const kuqo_run *r, uint32_t *taxid, uint64_t *n_reads, uint64_t *n_kmers,
                      uint64_t *unique_est, uint8_t *is_sparse, uint8_t *regs);
 
+/* further databases, tried in order after the first one for every k-mer (classify.cpp:928-936); same k required */
+int kuqo_run_add_db(kuqo_run *r, const kuqo_db *db);
 /* clade roll-up (TaxReport ctor, taxdb.hpp:956-973): sums the listed taxa's ReadCounts; returns unique estimate */
 uint64_t kuqo_run_clade(const kuqo_run *r, const uint32_t *taxa, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers);
 

@@ -112,6 +112,8 @@ class Oracle:
         L.kuqo_run_n_taxa.restype = C.c_uint32
         L.kuqo_run_n_taxa.argtypes = [C.c_void_p]
         L.kuqo_run_counts.argtypes = [C.c_void_p, u32p, u64p, u64p, u64p, u8p, u8p]
+        L.kuqo_run_add_db.restype = C.c_int
+        L.kuqo_run_add_db.argtypes = [C.c_void_p, C.POINTER(_DB)]
         L.kuqo_run_clade.restype = C.c_uint64
         L.kuqo_run_clade.argtypes = [C.c_void_p, u32p, C.c_uint32, u64p, u64p]
 
@@ -258,6 +260,12 @@ class OracleRun:
             self.o.L.kuqo_run_free(self.h)
         except Exception:
             pass
+
+    def add_db(self, db: "OracleDB"):
+        """a further database, tried after the earlier ones for every k-mer (classify -d a -d b)"""
+        self._more = getattr(self, "_more", []) + [db]
+        if self.o.L.kuqo_run_add_db(self.h, C.byref(db.s)) != 0:
+            raise ValueError("databases must share k")
 
     def classify(self, bases: np.ndarray, offsets: np.ndarray, want_codes=True):
         bases = np.ascontiguousarray(bases, np.uint8)
