@@ -150,6 +150,13 @@ int kuq_db_taxids(kuq_ctx *ctx, uint32_t *taxid, uint64_t *count, uint32_t cap, 
 /* Optional: the taxids of ALL database records when only a range is staged (other chunks / other GPUs), so that
  * every participant numbers taxa identically.  Must precede the first classify/lookup call. */
 int kuq_set_db_taxid_universe(kuq_ctx *ctx, const uint32_t *taxid, uint32_t n);
+/* Several databases (`classify -d a -d b`): every k-mer takes the value of the FIRST database that holds the key,
+ * even when that value is taxon 0 (classify.cpp:928-936).  With on != 0 the lookup calls report such a stored zero
+ * as KUQ_CODE_FOUND_ZERO instead of 0, so that the caller's merge over databases can stop at it; the resolve calls
+ * read KUQ_CODE_FOUND_ZERO as 0 in any case.  The caller stages the databases one after the other, runs
+ * kuq_lookup_* against each, keeps the first non-zero code per position and hands the result to kuq_resolve_*. */
+#define KUQ_CODE_FOUND_ZERO 0xFFFFFFFDu
+int kuq_mark_zero_hits(kuq_ctx *ctx, int on);
 
 /* ---- taxonomy: Parent_map (taxdb.hpp:383-398): taxid → parent taxid, 0 for the root / unknown parent --------- */
 int kuq_set_taxonomy(kuq_ctx *ctx, const uint32_t *taxid, const uint32_t *parent_taxid, uint32_t n);

@@ -87,6 +87,7 @@ def load_library(rebuild_if_stale: bool = False):
                                            C.c_uint64]),
         "kuq_db_taxids": (C.c_int, [vp, u32p, u64p, C.c_uint32, u32p]),
         "kuq_set_db_taxid_universe": (C.c_int, [vp, u32p, C.c_uint32]),
+        "kuq_mark_zero_hits": (C.c_int, [vp, C.c_int]),
         "kuq_set_taxonomy": (C.c_int, [vp, u32p, u32p, C.c_uint32]),
         "kuq_classify_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, C.c_uint32, C.POINTER(BatchResult)]),
         "kuq_submit_batch": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint32, u32p, C.c_uint32]),
@@ -199,6 +200,10 @@ class Classifier:
         if n.value:
             self._ck(self.L.kuq_db_taxids(self.h, _p(t, u32p), _p(c, u64p), n.value, C.byref(n)))
         return t, c
+
+    def mark_zero_hits(self, on=True):
+        """several databases: lookups report a stored taxon 0 as CODE_FOUND_ZERO (kuq_mark_zero_hits)"""
+        self._ck(self.L.kuq_mark_zero_hits(self.h, 1 if on else 0))
 
     def set_db_taxid_universe(self, taxids):
         t = np.ascontiguousarray(taxids, np.uint32)

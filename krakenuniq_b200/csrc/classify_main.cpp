@@ -35,6 +35,7 @@
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <set>
 #include <sstream>
 #include <string>
 #include <unordered_map>
@@ -455,6 +456,7 @@ struct Batch {
   vector<Read> reads;
   vector<uint32_t> codes;             // chunked mode: per-window dense ids merged over the database ranges
   bool fastq = false;
+  int file = 0;                       // index of the input file (work units do not span files)
   void clear() { bases.clear(); offs.assign(1, 0); reads.clear(); codes.clear(); }
 };
 
@@ -1058,16 +1060,90 @@ static void run_chunked(kuq_ctx *ctx, const Mapped &kdb, const Mapped &idx, uint
   if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
 }
 
+// ---- several databases: `-d a -d b` (classify.cpp:928-936) ----------------------------------------------------
+// For every k-mer the reference asks the databases in command-line order and keeps the value of the first one
+// that holds the key — a stored taxon 0 included.  One database is resident in HBM at a time: the reads are
+// looked up against each in turn (kuq_lookup_batch reports a stored zero as KUQ_CODE_FOUND_ZERO), the first
+// non-zero code per window survives, and a final pass classifies from the merged codes with the per-work-unit
+// sketch rule of the preloaded path.  The databases may differ in minimizer length and index type, not in k.
+static void run_multi_db(kuq_ctx *ctx, const vector<Mapped> &kdbs, const vector<Mapped> &idxs, int argc, char **argv,
+                         vector<map<uint32_t, uint64_t>> &db_counts) {
+  const size_t n_db = kdbs.size();
+  db_counts.assign(n_db, {});
+  set<uint32_t> all;
+  for (size_t d = 0; d < n_db; d++) {                      // pass 0: one numbering of the taxa for all databases
+    if (kuq_stage_db(ctx, kdbs[d].p, kdbs[d].size, idxs[d].p, idxs[d].size, 0, 0)) die(EX_DATAERR, kuq_last_error(ctx));
+    uint32_t m = 0;
+    kuq_db_taxids(ctx, NULL, NULL, 0, &m);
+    vector<uint32_t> tt(m);
+    vector<uint64_t> cc(m);
+    if (m) kuq_db_taxids(ctx, tt.data(), cc.data(), m, &m);
+    for (uint32_t i = 0; i < m; i++) { db_counts[d][tt[i]] += cc[i]; all.insert(tt[i]); }
+  }
+  {
+    vector<uint32_t> u(all.begin(), all.end());
+    if (kuq_set_db_taxid_universe(ctx, u.data(), (uint32_t)u.size())) die(EX_SOFTWARE, kuq_last_error(ctx));
+  }
+  if (kuq_mark_zero_hits(ctx, 1)) die(EX_SOFTWARE, "kuq_mark_zero_hits");
+  vector<Batch> batches;
+  for (int i = optind; i < argc; i++) {
+    size_t first = batches.size();
+    load_file_batches(argv[i], batches);
+    for (size_t j = first; j < batches.size(); j++) batches[j].file = i;
+  }
+  for (auto &b : batches) b.codes.assign(b.bases.size() + 1, 0);
+  vector<uint32_t> tmp;
+  for (size_t d = 0; d < n_db; d++) {
+    if (kuq_stage_db(ctx, kdbs[d].p, kdbs[d].size, idxs[d].p, idxs[d].size, 0, 0)) die(EX_DATAERR, kuq_last_error(ctx));
+    uint64_t seqs = 0;
+    for (auto &b : batches) {
+      tmp.assign(b.bases.size() + 1, 0);
+      if (kuq_lookup_batch(ctx, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), tmp.data(), NULL))
+        die(EX_SOFTWARE, kuq_last_error(ctx));
+      for (size_t j = 0; j < b.bases.size(); j++) if (b.codes[j] == 0) b.codes[j] = tmp[j];   // first hit wins
+      seqs += b.reads.size();
+      fprintf(stderr, "\r Processed %llu sequences (database %zu of %zu)", (unsigned long long)seqs, d + 1, n_db);
+    }
+    fprintf(stderr, "\r Processed %llu sequences\n", (unsigned long long)seqs);
+  }
+  for (size_t bi = 0; bi < batches.size(); bi++) {
+    Batch &b = batches[bi];
+    kuq_batch_result res;
+    if (kuq_resolve_batch(ctx, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), b.codes.data(), NULL, 0, &res))
+      die(EX_SOFTWARE, kuq_last_error(ctx));
+    Fastq_input = b.fastq;
+    emit_results(b, res);
+    total_classified += res.n_classified;
+    total_sequences += b.reads.size();
+    total_bases += b.bases.size();
+    fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
+    if (bi + 1 == batches.size() || batches[bi + 1].file != b.file)
+      if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));      // work units do not span input files
+  }
+}
+
 int main(int argc, char **argv) {
   parse_command_line(argc, argv);
   if (Map_UIDs) die(EX_USAGE, "-I (UID mapping) is not supported by the GPU classify");
   if (Quick_mode) die(EX_USAGE, "-q (quick mode) is not supported by the GPU classify");
-  if (DB_filenames.size() > 1) die(EX_USAGE, "only one database (-d) is supported by the GPU classify");
+  if (DB_filenames.size() != Index_filenames.size()) die(EX_USAGE, "Must specify a index file for each database file");
+  const size_t n_db = DB_filenames.size();
+  if (n_db > 1 && Populate_memory_size > 0) die(EX_USAGE, "-x with several databases is not supported by the GPU classify");
   if (Populate_memory && Populate_memory_size == 0) cerr << "Loading database(s)... " << endl;
-  cerr << " Database " << DB_filenames[0] << endl;
-  Mapped kdb, idx;
-  kdb.open(DB_filenames[0]);
-  idx.open(Index_filenames[0]);
+  vector<Mapped> kdbs(n_db), idxs(n_db);
+  for (size_t i = 0; i < n_db; i++) {
+    cerr << " Database " << DB_filenames[i] << endl;
+    kdbs[i].open(DB_filenames[i]);
+    idxs[i].open(Index_filenames[i]);
+  }
+  Mapped &kdb = kdbs[0], &idx = idxs[0];
+  for (size_t i = 1; i < n_db; i++) {                               // classify.cpp:203-210
+    auto k_of = [](const Mapped &m) { return m.size >= 16 ? (int)(((const uint64_t *)m.p)[1] / 2) : 0; };
+    if (k_of(kdbs[i]) != k_of(kdb)) {
+      fprintf(stderr, "Different k-mer sizes in databases 1 and %zu: %i vs %i!\n", i + 1, k_of(kdb), k_of(kdbs[i]));
+      exit(1);
+    }
+  }
   if (optind == argc) {                                            // `-M` without inputs: page-cache warm-up idiom
     if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;
     return 0;
@@ -1081,6 +1157,11 @@ int main(int argc, char **argv) {
   if (getenv("KUQ_HBM_BUDGET")) hbm_budget = strtoull(getenv("KUQ_HBM_BUDGET"), NULL, 10);
   uint64_t chunk_budget = 0;
   if (kdb.size + idx.size > hbm_budget) chunk_budget = hbm_budget;
+  if (n_db > 1) {
+    for (size_t i = 0; i < n_db; i++)
+      if (kdbs[i].size + idxs[i].size > hbm_budget) die(EX_USAGE, "with several databases each one has to fit the HBM budget");
+    chunk_budget = 0;
+  }
   if (Populate_memory_size > 0 && getenv("KUQ_FORCE_CHUNKS")) chunk_budget = Populate_memory_size;
   kuq_config cfg;
   kuq_config_default(&cfg);
@@ -1097,7 +1178,8 @@ int main(int argc, char **argv) {
   int rc = kuq_create(&cfg, &ctx);
   if (rc) die(EX_UNAVAILABLE, string("libkuq: ") + kuq_strerror(rc));
   map<uint32_t, uint64_t> chunk_db_counts;
-  if (!chunk_budget) {
+  vector<map<uint32_t, uint64_t>> multi_db_counts;
+  if (!chunk_budget && n_db == 1) {
     double T0__ = now_s();
     rc = kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, 0, 0);
     if (rc) die(EX_DATAERR, kuq_last_error(ctx));
@@ -1125,7 +1207,8 @@ int main(int argc, char **argv) {
 
   struct timeval tv1, tv2;
   gettimeofday(&tv1, NULL);
-  if (chunk_budget) run_chunked(ctx, kdb, idx, chunk_budget, argc, argv, chunk_db_counts);
+  if (n_db > 1) run_multi_db(ctx, kdbs, idxs, argc, argv, multi_db_counts);
+  else if (chunk_budget) run_chunked(ctx, kdb, idx, chunk_budget, argc, argv, chunk_db_counts);
   else for (int i = optind; i < argc; i++) process_file(ctx, argv[i]);
   gettimeofday(&tv2, NULL);
   {                                                                 // report_stats, classify.cpp:361-375
@@ -1141,7 +1224,8 @@ int main(int argc, char **argv) {
   if (!Report_output_file.empty() && Report_output_file != "off") {
     gettimeofday(&tv1, NULL);
     cerr << "Writing report file to " << Report_output_file << "  ..\n";
-    const string fname = DB_filenames[0] + ".counts";
+    for (size_t d = 0; d < n_db; d++) {                             // classify.cpp:262-285, once per database
+    const string fname = DB_filenames[d] + ".counts";
     bool counts_ok = false;
     {
       ifstream ifs(fname);
@@ -1153,7 +1237,9 @@ int main(int argc, char **argv) {
     if (!counts_ok) {                                               // classify.cpp:275-284 via kuq_db_taxids
       cerr << "Writing kmer counts to " << fname << "... [only once for this database, may take a while] " << endl;
       ofstream ofs(fname);
-      if (chunk_budget) {
+      if (n_db > 1) {
+        for (auto &kv : multi_db_counts[d]) ofs << kv.first << '\t' << kv.second << '\n';
+      } else if (chunk_budget) {
         for (auto &kv : chunk_db_counts) ofs << kv.first << '\t' << kv.second << '\n';
       } else {
         uint32_t m = 0;
@@ -1177,6 +1263,7 @@ int main(int argc, char **argv) {
         tax.set_genome_size(taxid, size);
       }
       cerr << " done" << endl;
+    }
     }
     ostringstream rep;
     double T0__ = now_s();

@@ -102,6 +102,7 @@ struct kuq_ctx {
 
   // taxonomy
   bool tax_set = false, finalized = false;
+  bool mark_zero_hits = false;            // kuq_mark_zero_hits: lookups report stored taxon 0 as KUQ_CODE_FOUND_ZERO
   std::vector<uint32_t> tax_ids, tax_parents;
   std::vector<uint32_t> raw_of_dense;
   std::unordered_map<uint32_t, uint32_t> dense_of_raw;
@@ -530,6 +531,7 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
 
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   ctx->snap_valid = false;
+  if (mode == MODE_LOOKUP && ctx->mark_zero_hits) p.flags |= 16u;
   const bool units = mode != MODE_LOOKUP && ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && p.unit_id && !(p.flags & 4u);
   if (units) {
     int rc = prepare_unit_map(ctx, s);
@@ -760,6 +762,12 @@ int kuq_set_db_taxid_universe(kuq_ctx *ctx, const uint32_t *taxid, uint32_t n) {
   if (!ctx || (!taxid && n)) return KUQ_E_INVALID_ARG;
   if (ctx->finalized) return fail(ctx, KUQ_E_STATE, "taxid universe must be declared before the first classification");
   ctx->universe.assign(taxid, taxid + n);
+  return KUQ_OK;
+}
+
+int kuq_mark_zero_hits(kuq_ctx *ctx, int on) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  ctx->mark_zero_hits = on != 0;
   return KUQ_OK;
 }
 

@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
     uint32_t taxon = 0;
     if (MODE == MODE_RESOLVE) {
       taxon = p.codes_in[g];                                 // merged dense ids of all database ranges
+      if (taxon == FOUND_ZERO) taxon = 0;                    // a stored taxon 0 counts like a miss from here on
     } else if (bin >= db.bin_lo && bin < db.bin_hi) {
       const uint64_t *o = db.offsets + (bin - db.bin_lo);
       const uint64_t o0 = __ldg(o), o1 = __ldg(o + 1);
@@ -439,7 +440,11 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
         while (m) {
           const int t = __ffs(m) - 1;
           m &= m - 1;
-          if ((__ldg(b + 3 * t + 1) & hi_mask) == chi) { taxon = __ldg(b + 3 * t + 2); m = 0; }   // value = dense id
+          if ((__ldg(b + 3 * t + 1) & hi_mask) == chi) {
+            taxon = __ldg(b + 3 * t + 2);                        // value = dense id
+            if (MODE == MODE_LOOKUP && taxon == 0 && (p.flags & 16u)) taxon = FOUND_ZERO;
+            m = 0;
+          }
         }
       }
     } else if (p.flags & 8u) {

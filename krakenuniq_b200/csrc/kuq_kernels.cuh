@@ -28,6 +28,9 @@
 namespace kuq {
 
 constexpr uint32_t AMBIG = 0xFFFFFFFFu;
+// MODE_LOOKUP with flag 16: the key IS in the database but stores taxon 0 (an un-LCA'd record).  With several
+// databases that still ends the search (classify.cpp:928-936), so the lookup has to tell it from a miss.
+constexpr uint32_t FOUND_ZERO = 0xFFFFFFFDu;
 constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 constexpr int CHUNK_READS = 64;            // reads per CTA work item

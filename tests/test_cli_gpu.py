@@ -169,3 +169,20 @@ def test_cli_long_contigs_match_oracle(tmp_path, oracle):
         r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22)))
         assert r.returncode == 0, r.stderr[-2000:]
         assert open(out).read() == want
+
+
+@pytest.mark.parametrize("tag", ["ab", "ba"])
+def test_cli_two_databases_first_hit(tmp_path, tag):
+    """classify -d A -d B (both orders): the first database holding a k-mer decides, a stored taxon 0 included
+    (classify.cpp:928-936); the report adds up the genome sizes of both .counts files (classify.cpp:262-285)."""
+    M = os.path.join(util.ROOT, "tests", "golden", "multidb")
+    a = ["-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx")]
+    b = ["-d", os.path.join(M, "db2.kdb"), "-i", os.path.join(M, "db2.idx")]
+    exe = build.build_classify()
+    out, rep = tmp_path / f"{tag}.kraken", tmp_path / f"{tag}.report.tsv"
+    cmd = [exe] + (a + b if tag == "ab" else b + a) + ["-a", os.path.join(G, "taxDB"), "-t", "1", "-M", "-u", "20000",
+                                                      "-r", str(rep), "-o", str(out), os.path.join(G, "reads.fa")]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22)))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == open(os.path.join(M, f"{tag}.kraken")).read()
+    assert _report_lines(rep) == _report_lines(os.path.join(M, f"{tag}.report.tsv"))
