@@ -516,16 +516,21 @@ static readcounts *cm_get(countmap *m, uint32_t taxid) {               /* operat
 /* classify_sequence(), classify.cpp:897-1012 (Quick_mode off, one database, Map_UIDs off).  `counts` receives
  * add_kmer (:939) for every non-ambiguous window — taxon 0 for misses — and incrementReadCount (:968). */
 static uint32_t classify_read_multi(const kuqo_db *const *dbs, uint32_t n_db, const kuqo_parent_map *pm, const char *seq,
-                                    size_t len, uint32_t *codes, uint32_t *n_windows, countmap *counts);
+                                    size_t len, uint32_t *codes, uint32_t *n_windows, countmap *counts,
+                                    uint32_t quick_min, int quick_stop);
 static uint32_t classify_read_into(const kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len,
                                    uint32_t *codes, uint32_t *n_windows, countmap *counts) {
-  return classify_read_multi(&db, 1, pm, seq, len, codes, n_windows, counts);
+  return classify_read_multi(&db, 1, pm, seq, len, codes, n_windows, counts, 0, 0);
 }
-/* several databases: the first one that holds the key decides, even if it stores taxon 0 (classify.cpp:928-936) */
+/* several databases: the first one that holds the key decides, even if it stores taxon 0 (classify.cpp:928-936).
+ * Quick mode (-q, -m quick_min): the preloaded path leaves the k-mer loop at the quick_min-th hit (:943-944,
+ * quick_stop = 1) and calls that hit's taxon (:963-964); the -x path looks at every k-mer, stops COUNTING hits at
+ * quick_min (:701-702) and calls the taxon of the read's last non-ambiguous k-mer (:705-721,737-738). */
 static uint32_t classify_read_multi(const kuqo_db *const *dbs, uint32_t n_db, const kuqo_parent_map *pm, const char *seq,
-                                    size_t len, uint32_t *codes, uint32_t *n_windows, countmap *counts) {
+                                    size_t len, uint32_t *codes, uint32_t *n_windows, countmap *counts,
+                                    uint32_t quick_min, int quick_stop) {
   const kuqo_db *db = dbs[0];
-  uint32_t n = 0;
+  uint32_t n = 0, quick_hits = 0, last_taxon = 0;
   uint32_t *hit_taxa = NULL, *hit_cnt = NULL, n_hits = 0;
   if (len >= db->k) {
     size_t cap = len - db->k + 2;
@@ -549,17 +554,25 @@ static uint32_t classify_read_multi(const kuqo_db *const *dbs, uint32_t n_db, co
         ++rc->n_kmers;
         kuqo_hll_insert(rc->hll, canon);
       }
+      last_taxon = taxon;
       if (taxon) {                                                          /* :941-942 */
         uint32_t j = 0;
         for (; j < n_hits; j++) if (hit_taxa[j] == taxon) break;
         if (j == n_hits) { hit_taxa[n_hits] = taxon; hit_cnt[n_hits] = 0; n_hits++; }
         hit_cnt[j]++;
+        if (quick_min && quick_hits < quick_min) quick_hits++;
+        if (quick_min && quick_stop && quick_hits >= quick_min) {           /* :943-944: leaves before :947 */
+          codes[i] = taxon;
+          n = i + 1;
+          break;
+        }
       }
       codes[i] = taxon;                                                     /* :947 */
     }
     free(kmers); free(amb);
   }
-  uint32_t call = kuqo_resolve_tree(pm, hit_taxa, hit_cnt, n_hits);         /* :965 */
+  uint32_t call = quick_min ? (quick_hits >= quick_min ? last_taxon : 0)    /* :963-964 */
+                            : kuqo_resolve_tree(pm, hit_taxa, hit_cnt, n_hits);   /* :965 */
   free(hit_taxa); free(hit_cnt);
   if (counts) cm_get(counts, call)->n_reads++;                              /* :968 */
   *n_windows = n;
@@ -606,6 +619,7 @@ struct kuqo_run {
   countmap global;      /* taxon_counts, classify.cpp:78 */
   countmap local;       /* my_taxon_counts of the open work unit, :525 */
   uint64_t unit_nt;     /* total_nt of the open work unit, :508,519 */
+  uint32_t quick_min;   /* -q: Minimum_hit_count (-m, default 1); 0 = quick mode off */
 };
 
 kuqo_run *kuqo_run_new(const kuqo_db *db, const kuqo_parent_map *pm, uint64_t work_unit_size, int mode) {
@@ -644,7 +658,7 @@ int kuqo_run_classify(kuqo_run *r, const char *bases, const uint64_t *offsets, u
     uint32_t nw = 0;
     /* preload: work unit's private map (:525,530-535); chunked: the global map directly (:719,747) */
     countmap *target = r->mode == 0 ? &r->local : &r->global;
-    uint32_t call = classify_read_multi(r->dbs, r->n_db, r->pm, seq, len, scratch, &nw, target);
+    uint32_t call = classify_read_multi(r->dbs, r->n_db, r->pm, seq, len, scratch, &nw, target, r->quick_min, r->mode == 0);
     calls_out[i] = call;
     if (code_offsets_out) code_offsets_out[i] = code_pos;
     if (codes_out) memcpy(codes_out + code_pos, scratch, 4 * (size_t)nw);
@@ -709,3 +723,6 @@ int kuqo_run_add_db(kuqo_run *r, const kuqo_db *db) {
   r->dbs[r->n_db++] = db;
   return 0;
 }
+
+/* classify -q [-m min_hits]; min_hits = 0 switches quick mode off */
+void kuqo_run_set_quick(kuqo_run *r, uint32_t min_hits) { r->quick_min = min_hits; }

@@ -98,6 +98,9 @@ void kuqo_run_counts(const kuqo_run *r, uint32_t *taxid, uint64_t *n_reads, uint
 
 /* further databases, tried in order after the first one for every k-mer (classify.cpp:928-936); same k required */
 int kuqo_run_add_db(kuqo_run *r, const kuqo_db *db);
+/* quick mode (-q -m min_hits; classify.cpp:943-944,963-964 preloaded, :701-702,737-738 with -x); the codes of a read
+ * then cover the windows actually visited; "Q:hits" = min(hits among them, min_hits).  0 = off. */
+void kuqo_run_set_quick(kuqo_run *r, uint32_t min_hits);
 /* clade roll-up (TaxReport ctor, taxdb.hpp:956-973): sums the listed taxa's ReadCounts; returns unique estimate */
 uint64_t kuqo_run_clade(const kuqo_run *r, const uint32_t *taxa, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers);
 

@@ -267,6 +267,12 @@ class OracleRun:
         if self.o.L.kuqo_run_add_db(self.h, C.byref(db.s)) != 0:
             raise ValueError("databases must share k")
 
+    def set_quick(self, min_hits: int):
+        """classify -q -m min_hits (0 = off)"""
+        self.o.L.kuqo_run_set_quick.argtypes = [C.c_void_p, C.c_uint32]
+        self.o.L.kuqo_run_set_quick.restype = None
+        self.o.L.kuqo_run_set_quick(self.h, min_hits)
+
     def classify(self, bases: np.ndarray, offsets: np.ndarray, want_codes=True):
         bases = np.ascontiguousarray(bases, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.uint64)
