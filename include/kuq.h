@@ -157,6 +157,15 @@ int kuq_set_db_taxid_universe(kuq_ctx *ctx, const uint32_t *taxid, uint32_t n);
  * kuq_lookup_* against each, keeps the first non-zero code per position and hands the result to kuq_resolve_*. */
 #define KUQ_CODE_FOUND_ZERO 0xFFFFFFFDu
 int kuq_mark_zero_hits(kuq_ctx *ctx, int on);
+/* Quick mode, `classify -q [-m min_hits]` (Quick_mode / Minimum_hit_count, classify.cpp:44-45; min_hits = 0 turns it
+ * off).  Classification and resolve calls then skip resolve_tree: a read is called as soon as it has min_hits hits.
+ *   stop_at_last_hit != 0 — the preloaded path (:943-944,963-964): the read ends at its min_hits-th hit; later
+ *     k-mers are neither looked at nor counted; the call is that hit's taxon.  n_windows = windows visited.
+ *   stop_at_last_hit == 0 — the -x path (:701-702,705-721,737-738): every k-mer is counted, hits stop counting at
+ *     min_hits and the call is the taxon of the read's last unambiguous k-mer (0 if that one missed).
+ * Either way run_count[r] (d_run_count) carries the "Q:<hits>" value of the Kraken line (:989-990), no runs are
+ * produced (as with KUQ_F_NO_RUNS) and a read with fewer than min_hits hits stays unclassified. */
+int kuq_set_quick_mode(kuq_ctx *ctx, uint32_t min_hits, int stop_at_last_hit);
 
 /* ---- taxonomy: Parent_map (taxdb.hpp:383-398): taxid → parent taxid, 0 for the root / unknown parent --------- */
 int kuq_set_taxonomy(kuq_ctx *ctx, const uint32_t *taxid, const uint32_t *parent_taxid, uint32_t n);

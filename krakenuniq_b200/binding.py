@@ -88,6 +88,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_db_taxids": (C.c_int, [vp, u32p, u64p, C.c_uint32, u32p]),
         "kuq_set_db_taxid_universe": (C.c_int, [vp, u32p, C.c_uint32]),
         "kuq_mark_zero_hits": (C.c_int, [vp, C.c_int]),
+        "kuq_set_quick_mode": (C.c_int, [vp, C.c_uint32, C.c_int]),
         "kuq_set_taxonomy": (C.c_int, [vp, u32p, u32p, C.c_uint32]),
         "kuq_classify_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, C.c_uint32, C.POINTER(BatchResult)]),
         "kuq_submit_batch": (C.c_int, [vp, C.c_uint32, vp, u64p, C.c_uint32, u32p, C.c_uint32]),
@@ -200,6 +201,10 @@ class Classifier:
         if n.value:
             self._ck(self.L.kuq_db_taxids(self.h, _p(t, u32p), _p(c, u64p), n.value, C.byref(n)))
         return t, c
+
+    def set_quick_mode(self, min_hits, stop_at_last_hit=True):
+        """classify -q -m min_hits (0 = off); stop_at_last_hit=False gives the -x path's rule (kuq_set_quick_mode)"""
+        self._ck(self.L.kuq_set_quick_mode(self.h, int(min_hits), 1 if stop_at_last_hit else 0))
 
     def mark_zero_hits(self, on=True):
         """several databases: lookups report a stored taxon 0 as CODE_FOUND_ZERO (kuq_mark_zero_hits)"""

@@ -9,8 +9,7 @@
 //   stats / progress lines         src/classify.cpp:361-375, 555-558
 //   taxDB reader, genome sizes     src/taxdb.hpp:563-605, 850-885
 //   report (clades, sorting, cols) src/taxdb.hpp:928-1123, src/classify.cpp:286-328
-// Not supported (exit with a message): -q/-m quick mode, -I uid mapping, several -d databases, databases larger
-// than HBM with -x (the range driver is next-round work; -x with a database that fits runs the chunked HLL rule).
+// Not supported (exit with a message): -I uid mapping, -q or -x together with several -d databases.
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -46,6 +45,7 @@
 using namespace std;
 
 static vector<string> DB_filenames, Index_filenames;
+static uint32_t Minimum_hit_count = 1;        // -m (classify.cpp:45)
 static bool Quick_mode = false, Print_classified = false, Print_unclassified = false, Print_kraken = true;
 static bool Populate_memory = false, Only_classified_kraken_output = false, Print_sequence = false, Map_UIDs = false;
 static uint64_t Populate_memory_size = 0;
@@ -123,6 +123,7 @@ static void parse_command_line(int argc, char **argv) {
       case 'm':
         sig = atoll(optarg);
         if (sig <= 0) die(EX_USAGE, "can't use nonpositive minimum hit count");
+        Minimum_hit_count = (uint32_t)sig;
         break;
       case 'c': Only_classified_kraken_output = true; break;
       case 'C': Print_classified = true; Classified_output_file = optarg; break;
@@ -495,8 +496,9 @@ static void emit_results(const Batch &b, const kuq_batch_result &res) {
     out += '\t';
     snprintf(num, sizeof num, "%" PRIu64, r.seq_len); out += num;
     out += '\t';
-    if (res.run_count[i] == 0) out += "0:0";                         // :994-995
-    for (uint32_t j = 0; j < res.run_count[i]; j++) {               // hitlist_string, :826-861
+    if (Quick_mode) { snprintf(num, sizeof num, "Q:%u", res.run_count[i]); out += num; }   // :989-990
+    else if (res.run_count[i] == 0) out += "0:0";                    // :994-995
+    for (uint32_t j = 0; !Quick_mode && j < res.run_count[i]; j++) {   // hitlist_string, :826-861
       const kuq_run &run = res.runs[res.run_start[i] + j];
       if (j) out += ' ';
       if (run.code == KUQ_CODE_AMBIG) snprintf(num, sizeof num, "A:%u", run.count);
@@ -826,8 +828,9 @@ static bool process_file_parallel(kuq_ctx *ctx, const char *filename) {
         out += '\t';
         append_u32(out, v.seq_len);
         out += '\t';
-        if (res.run_count[i] == 0) out += "0:0";
-        for (uint32_t j = 0; j < res.run_count[i]; j++) {
+        if (Quick_mode) { out += "Q:"; append_u32(out, res.run_count[i]); }
+        else if (res.run_count[i] == 0) out += "0:0";
+        for (uint32_t j = 0; !Quick_mode && j < res.run_count[i]; j++) {
           const kuq_run &run = res.runs[res.run_start[i] + j];
           if (j) out += ' ';
           if (run.code == KUQ_CODE_AMBIG) out += 'A'; else append_u32(out, run.code);
@@ -1125,7 +1128,7 @@ static void run_multi_db(kuq_ctx *ctx, const vector<Mapped> &kdbs, const vector<
 int main(int argc, char **argv) {
   parse_command_line(argc, argv);
   if (Map_UIDs) die(EX_USAGE, "-I (UID mapping) is not supported by the GPU classify");
-  if (Quick_mode) die(EX_USAGE, "-q (quick mode) is not supported by the GPU classify");
+  if (Quick_mode && DB_filenames.size() > 1) die(EX_USAGE, "-q with several databases is not supported by the GPU classify");
   if (DB_filenames.size() != Index_filenames.size()) die(EX_USAGE, "Must specify a index file for each database file");
   const size_t n_db = DB_filenames.size();
   if (n_db > 1 && Populate_memory_size > 0) die(EX_USAGE, "-x with several databases is not supported by the GPU classify");
@@ -1177,6 +1180,8 @@ int main(int argc, char **argv) {
   kuq_ctx *ctx = NULL;
   int rc = kuq_create(&cfg, &ctx);
   if (rc) die(EX_UNAVAILABLE, string("libkuq: ") + kuq_strerror(rc));
+  // -q: the preloaded path leaves a read at its -m'th hit; with -x every k-mer is counted (classify.cpp:943-944 / :701-738)
+  if (Quick_mode && kuq_set_quick_mode(ctx, Minimum_hit_count, Populate_memory_size == 0)) die(EX_SOFTWARE, kuq_last_error(ctx));
   map<uint32_t, uint64_t> chunk_db_counts;
   vector<map<uint32_t, uint64_t>> multi_db_counts;
   if (!chunk_budget && n_db == 1) {

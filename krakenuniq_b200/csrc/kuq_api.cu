@@ -102,6 +102,8 @@ struct kuq_ctx {
 
   // taxonomy
   bool tax_set = false, finalized = false;
+  uint32_t quick_min = 0;                 // kuq_set_quick_mode: classify -q -m quick_min (0 = off)
+  bool quick_stop = false;                // reads end at their quick_min-th hit (preloaded path) or not (-x path)
   bool mark_zero_hits = false;            // kuq_mark_zero_hits: lookups report stored taxon 0 as KUQ_CODE_FOUND_ZERO
   std::vector<uint32_t> tax_ids, tax_parents;
   std::vector<uint32_t> raw_of_dense;
@@ -532,6 +534,12 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   ctx->snap_valid = false;
   if (mode == MODE_LOOKUP && ctx->mark_zero_hits) p.flags |= 16u;
+  if (mode != MODE_LOOKUP && ctx->quick_min) {           // "Q:hits" replaces the hit list (classify.cpp:989-990)
+    p.quick_min = ctx->quick_min;
+    p.quick_stop = ctx->quick_stop;
+    p.flags |= KUQ_F_NO_RUNS;
+    s.flags |= KUQ_F_NO_RUNS;
+  }
   const bool units = mode != MODE_LOOKUP && ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && p.unit_id && !(p.flags & 4u);
   if (units) {
     int rc = prepare_unit_map(ctx, s);
@@ -765,6 +773,15 @@ int kuq_set_db_taxid_universe(kuq_ctx *ctx, const uint32_t *taxid, uint32_t n) {
   return KUQ_OK;
 }
 
+int kuq_set_quick_mode(kuq_ctx *ctx, uint32_t min_hits, int stop_at_last_hit) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  for (auto &s : ctx->slots)
+    if (s.busy) return fail(ctx, KUQ_E_STATE, "quick mode cannot change while a batch is in flight");
+  ctx->quick_min = min_hits;
+  ctx->quick_stop = min_hits && stop_at_last_hit;
+  return KUQ_OK;
+}
+
 int kuq_mark_zero_hits(kuq_ctx *ctx, int on) {
   if (!ctx) return KUQ_E_INVALID_ARG;
   ctx->mark_zero_hits = on != 0;
@@ -866,7 +883,7 @@ int kuq_resolve_batch(kuq_ctx *ctx, const char *bases, const uint64_t *read_offs
   if (n_reads) {
     CU(cudaMemcpyAsync(s.h_call, s.d_call, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaMemcpyAsync(s.h_nwin, s.d_nwin, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
-    if (!(flags & KUQ_F_NO_RUNS)) {
+    if (!(flags & KUQ_F_NO_RUNS) || ctx->quick_min) {
       CU(cudaMemcpyAsync(s.h_run_start, s.d_run_start, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
       CU(cudaMemcpyAsync(s.h_run_count, s.d_run_count, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
     }
@@ -905,7 +922,7 @@ int kuq_submit_batch(kuq_ctx *ctx, uint32_t slot, const char *bases, const uint6
   if (n_reads) {
     CU(cudaMemcpyAsync(s.h_call, s.d_call, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
     CU(cudaMemcpyAsync(s.h_nwin, s.d_nwin, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
-    if (!(flags & KUQ_F_NO_RUNS)) {
+    if (!(flags & KUQ_F_NO_RUNS) || ctx->quick_min) {
       CU(cudaMemcpyAsync(s.h_run_start, s.d_run_start, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
       CU(cudaMemcpyAsync(s.h_run_count, s.d_run_count, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
     }

@@ -593,6 +593,10 @@ __device__ uint32_t resolve_overflow(const Params &p, const OverflowPool &pool, 
 constexpr int RUN_BUF = 96;      // runs buffered per warp before they are flushed to global memory
 constexpr uint32_t RUN_BLOCK = 256;   // run slots a warp takes from the global cursor at a time
 
+// QUICK (classify -q): no resolve_tree; hits = min(#hits, quick_min) goes to run_count[] ("Q:hits", :989-990) and the
+// call is the taxon of the last unambiguous window once quick_min hits were seen (:963-964 after k_quick_cut ended
+// the read at that hit; :705-721,737-738 on the -x path, where the last window of the whole read decides).
+template <bool QUICK>
 __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Params p) {
   __shared__ uint2 s_runs[CTA_WARPS][RUN_BUF];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -626,6 +630,7 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
     uint32_t n_hits = 0, n_miss = 0, n_runs = 0;
     uint32_t carry_code = 0;
     bool overflow = false;
+    uint32_t q_hits = 0, q_last = 0;                            // QUICK: hits seen, taxon of the last unambiguous window
     const uint32_t nslots = (nwin + 31) / 32;
     for (uint32_t s = 0; s < nslots; s++) {
       const uint32_t i = s * 32 + lane;
@@ -651,6 +656,11 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       // hit_counts[taxon]++, aggregated per distinct taxon of the slot
       n_miss += __popc(__ballot_sync(0xFFFFFFFFu, look && taxon == 0));
       uint32_t rem = __ballot_sync(0xFFFFFFFFu, look && taxon != 0);
+      if (QUICK) {
+        q_hits += __popc(rem);
+        const uint32_t lm = __ballot_sync(0xFFFFFFFFu, look);
+        if (lm) q_last = __shfl_sync(0xFFFFFFFFu, taxon, 31 - __clz(lm));
+      }
       while (rem) {
         const int ldr = __ffs(rem) - 1;
         const uint32_t t = __shfl_sync(0xFFFFFFFFu, taxon, ldr);
@@ -675,9 +685,9 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       OverflowPool pool{p.ovf_mem, p.ovf_cursor, p.ovf_capacity};
       call = resolve_overflow(p, pool, codes_src, out_base, nwin, units ? p.unit_id[r] : 0, counting, units, lane);
       n_hits = 0;                                               // counters were booked from the table
-    } else if (n_hits == 1) {
+    } else if (!QUICK && n_hits == 1) {
       call = __shfl_sync(0xFFFFFFFFu, my_t, 0);                 // a single hit taxon is its own best path
-    } else if (n_hits > 1) {
+    } else if (!QUICK && n_hits > 1) {
       // score(t) = sum of hit counts along t's root path (:156-177); lane j walks entry j
       uint32_t node = lane < n_hits ? my_t : 0;
       uint32_t score = 0;
@@ -709,6 +719,11 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
         }
         call = acc;
       }
+    }
+    if (QUICK) {
+      const uint32_t hits = min(q_hits, p.quick_min);
+      call = hits >= p.quick_min ? q_last : 0;
+      if (lane == 0) p.run_count[r] = hits;
     }
     const uint32_t call_raw = call ? __ldg(p.tax.raw + call) : 0;
     if (lane == 0) p.call[r] = call_raw;
@@ -978,6 +993,37 @@ void launch_sparse_import(const unsigned long long *keys, uint64_t n, const Spar
   if (n) k_sparse_import<<<(int)min((uint64_t)148 * 16, (n + 255) / 256), 256, 0, stream>>>(keys, n, s, dense_flag, error_flag);
 }
 
+// Quick mode, preloaded path: the k-mer loop of classify_sequence leaves at the quick_min-th hit (classify.cpp:943-944),
+// so the windows behind it are never looked at — no add_kmer, no hit.  One warp per read finds that window in the
+// looked-up codes, shortens the read to it and wipes the later windows from the scan scratch; the counting pass
+// (k_lookup<MODE_RESOLVE>), the per-unit accounting and k_resolve<true> then see the read the reference saw.
+__global__ void __launch_bounds__(256) k_quick_cut(const __grid_constant__ Params p, const uint32_t *codes) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + warp; r < p.n_reads; r += warps_total) {
+    const uint64_t base = p.offsets[r];
+    const uint32_t nwin = p.n_windows[r];
+    uint32_t seen = 0, cutoff = nwin;
+    for (uint32_t s = 0; s * 32 < nwin; s++) {
+      const uint32_t i = s * 32 + lane;
+      const uint32_t c = i < nwin ? codes[base + i] : 0;
+      const uint32_t bm = __ballot_sync(0xFFFFFFFFu, c != 0 && c != AMBIG && c != FOUND_ZERO);
+      const uint32_t cnt = __popc(bm);
+      if (seen + cnt >= p.quick_min) {
+        uint32_t m = bm;
+        for (uint32_t j = seen + 1; j < p.quick_min; j++) m &= m - 1;   // drop the hits before the quick_min-th
+        cutoff = s * 32 + (uint32_t)__ffs(m) - 1;
+        break;
+      }
+      seen += cnt;
+    }
+    if (cutoff < nwin) {
+      for (uint32_t i = cutoff + 1 + lane; i < nwin; i += 32) p.bins[base + i] = BIN_NONE;
+      if (lane == 0) p.n_windows[r] = cutoff + 1;
+    }
+  }
+}
+
 int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedState); }
 
 // mode MODE_FUSED : scan → lookup (+HLL) → resolve            (whole database on this GPU)
@@ -995,14 +1041,30 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
   launches++;
   if (stage_events) cudaEventRecord(stage_events[0], stream);
   const int lgrid = (int)min((uint64_t)n_sm * 8 * 8, (p.total_bases + 255) / 256);
-  if (mode == MODE_FUSED) k_lookup<MODE_FUSED><<<lgrid, 256, 0, stream>>>(p);
+  const bool quick = p.quick_min != 0 && mode != MODE_LOOKUP;
+  if (quick && p.quick_stop) {
+    // lookup first, end every read at its quick_min-th hit, then count what is left
+    Params q = p;
+    if (mode == MODE_FUSED) {
+      q.only_hits = 0; q.n_peers = 0; q.flags &= ~16u;
+      k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(q);
+      launches++;
+      q.codes_in = p.codes_dense;
+    }
+    const int cgrid = (int)min((uint32_t)n_sm * 8, (p.n_reads + 7) / 8);
+    k_quick_cut<<<cgrid, 256, 0, stream>>>(p, q.codes_in);
+    q.flags = p.flags;
+    k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(q);
+    launches += 2;
+  } else if (mode == MODE_FUSED) k_lookup<MODE_FUSED><<<lgrid, 256, 0, stream>>>(p);
   else if (mode == MODE_LOOKUP) k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(p);
   else k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(p);
-  launches++;
+  if (!(quick && p.quick_stop)) launches++;
   if (stage_events) cudaEventRecord(stage_events[1], stream);
   if (mode != MODE_LOOKUP) {
     const int rgrid = (int)min((uint32_t)n_sm * 4 * 2, (p.n_reads + CTA_WARPS - 1) / CTA_WARPS);
-    k_resolve<<<rgrid, 256, 0, stream>>>(p);
+    if (quick) k_resolve<true><<<rgrid, 256, 0, stream>>>(p);
+    else k_resolve<false><<<rgrid, 256, 0, stream>>>(p);
     launches++;
   }
   return launches;

@@ -132,6 +132,10 @@ struct Params {
   unsigned long long *ovf_mem;
   unsigned long long *ovf_cursor;
   uint64_t ovf_capacity;
+  // quick mode (classify -q -m quick_min; 0 = off).  quick_stop: the read ends at its quick_min-th hit
+  // (classify.cpp:943-944); otherwise every k-mer counts and only the call rule changes (the -x path, :701-738)
+  uint32_t quick_min;
+  uint32_t quick_stop;
 };
 
 // returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup

@@ -186,3 +186,25 @@ def test_cli_two_databases_first_hit(tmp_path, tag):
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(out).read() == open(os.path.join(M, f"{tag}.kraken")).read()
     assert _report_lines(rep) == _report_lines(os.path.join(M, f"{tag}.report.tsv"))
+
+
+@pytest.mark.parametrize("tag,extra,reads,env", [
+    ("q1", ["-M", "-q"], "reads.fa", None),
+    ("q3_u20000", ["-M", "-q", "-m", "3", "-u", "20000"], "reads.fa", None),
+    ("q40", ["-M", "-q", "-m", "40"], "reads.fa", None),
+    ("q2_crlf", ["-M", "-q", "-m", "2"], "reads_crlf_60.fa", None),
+    ("q2_chunked", ["-x", "40K", "-q", "-m", "2"], "reads.fa", None),
+    ("q2_chunked", ["-x", "40K", "-q", "-m", "2"], "reads.fa", {"KUQ_FORCE_CHUNKS": "1"}),
+    # a database that has to be cut into ranges WITHOUT -x keeps the preloaded path's rule (reads end at the hit);
+    # the sketches are global then, so only the Kraken lines are compared
+    ("q3_u20000", ["-M", "-q", "-m", "3", "-u", "20000"], "reads.fa", {"KUQ_HBM_BUDGET": "40000"}),
+])
+def test_cli_quick_mode(tmp_path, tag, extra, reads, env):
+    """classify -q [-m N] against the unmodified reference (tests/golden/quick, make_golden_quick.py):
+    "Q:hits" lines, calls, and every report column — preloaded rule (classify.cpp:943-944,963-964) and -x rule
+    (:701-702,705-721,737-738)."""
+    Q = os.path.join(util.ROOT, "tests", "golden", "quick")
+    out, rep, r = _run(tmp_path, tag, extra, reads, env)
+    assert open(out).read() == open(os.path.join(Q, f"{tag}.kraken")).read()
+    if not (env and "KUQ_HBM_BUDGET" in env):
+        assert _report_lines(rep) == _report_lines(os.path.join(Q, f"{tag}.report.tsv"))
