@@ -470,18 +470,56 @@ typedef struct {
   uint64_t n_reads, n_kmers;
   kuqo_hll *hll;
 } readcounts;
+/* classifyExact (EXACT_COUNTING, classify.cpp:46-49): the container of ReadCounts is a set of canonical k-mers
+ * (khset64_t) instead of a sketch; add_kmer inserts (readcounts.hpp:71-74), += is the set union (:76-81), the unique
+ * count is the set size (:127-130).  All per-taxon sets of a run live in one set of (taxon, k-mer) pairs. */
+typedef struct {
+  uint32_t *taxon;
+  uint64_t *kmer;
+  uint8_t *used;
+  uint64_t n, cap;
+} pairset;
 typedef struct {
   readcounts *e;
   uint32_t n, cap_e;
   uint32_t *slot;      /* open addressing: index+1 into e, 0 = empty */
   uint32_t cap_s;
+  pairset *exact;      /* not NULL: exact counting; shared by the work units' maps and the global one */
 } countmap;
+
+static uint64_t pair_hash(uint32_t taxon, uint64_t kmer) { return kuqo_fmix64(kmer ^ ((uint64_t)taxon << 32) ^ taxon); }
+static int ps_insert(pairset *p, uint32_t taxon, uint64_t kmer) {          /* 1 = new */
+  if (p->cap == 0 || 2 * (p->n + 1) > p->cap) {
+    uint64_t ncap = p->cap ? p->cap * 2 : 1024;
+    uint32_t *nt = (uint32_t *)malloc(4 * ncap);
+    uint64_t *nk = (uint64_t *)malloc(8 * ncap);
+    uint8_t *nu = (uint8_t *)calloc(ncap, 1);
+    for (uint64_t i = 0; i < p->cap; i++) {
+      if (!p->used[i]) continue;
+      uint64_t s = pair_hash(p->taxon[i], p->kmer[i]) & (ncap - 1);
+      while (nu[s]) s = (s + 1) & (ncap - 1);
+      nu[s] = 1; nt[s] = p->taxon[i]; nk[s] = p->kmer[i];
+    }
+    free(p->taxon); free(p->kmer); free(p->used);
+    p->taxon = nt; p->kmer = nk; p->used = nu; p->cap = ncap;
+  }
+  uint64_t s = pair_hash(taxon, kmer) & (p->cap - 1);
+  while (p->used[s]) {
+    if (p->taxon[s] == taxon && p->kmer[s] == kmer) return 0;
+    s = (s + 1) & (p->cap - 1);
+  }
+  p->used[s] = 1; p->taxon[s] = taxon; p->kmer[s] = kmer; p->n++;
+  return 1;
+}
+static void ps_free(pairset *p) { if (p) { free(p->taxon); free(p->kmer); free(p->used); free(p); } }
 
 static void cm_init(countmap *m) { memset(m, 0, sizeof(*m)); }
 static void cm_clear(countmap *m) {
+  pairset *keep = m->exact;
   for (uint32_t i = 0; i < m->n; i++) kuqo_hll_free(m->e[i].hll);
   free(m->e); free(m->slot);
   memset(m, 0, sizeof(*m));
+  m->exact = keep;
 }
 static readcounts *cm_get(countmap *m, uint32_t taxid) {               /* operator[] */
   if (m->cap_s == 0 || 2 * (m->n + 1) > m->cap_s) {
@@ -552,7 +590,8 @@ static uint32_t classify_read_multi(const kuqo_db *const *dbs, uint32_t n_db, co
       if (counts) {
         readcounts *rc = cm_get(counts, taxon);                             /* :939 */
         ++rc->n_kmers;
-        kuqo_hll_insert(rc->hll, canon);
+        if (counts->exact) ps_insert(counts->exact, taxon, canon);
+        else kuqo_hll_insert(rc->hll, canon);
       }
       last_taxon = taxon;
       if (taxon) {                                                          /* :941-942 */
@@ -630,6 +669,7 @@ kuqo_run *kuqo_run_new(const kuqo_db *db, const kuqo_parent_map *pm, uint64_t wo
 }
 void kuqo_run_free(kuqo_run *r) {
   if (!r) return;
+  ps_free(r->global.exact);
   cm_clear(&r->global); cm_clear(&r->local); free(r);
 }
 /* critical(write_output) merge, classify.cpp:542-544: taxon_counts[t] += move(local[t])
@@ -644,6 +684,7 @@ static void flush_unit(kuqo_run *r) {
   }
   cm_clear(&r->local);
   cm_init(&r->local);
+  r->local.exact = r->global.exact;
   r->unit_nt = 0;
 }
 int kuqo_run_classify(kuqo_run *r, const char *bases, const uint64_t *offsets, uint32_t n_reads,
@@ -690,6 +731,12 @@ void kuqo_run_counts(const kuqo_run *r, uint32_t *taxid, uint64_t *n_reads, uint
     n_reads[i] = tmp[i].n_reads;
     n_kmers[i] = tmp[i].n_kmers;
     unique_est[i] = kuqo_hll_cardinality(tmp[i].hll);      /* uniqueKmerCount, readcounts.hpp:121-124 */
+    if (r->global.exact) {                                 /* set size, readcounts.hpp:127-130 */
+      const pairset *ps = r->global.exact;
+      uint64_t c = 0;
+      for (uint64_t s = 0; s < ps->cap; s++) c += ps->used[s] && ps->taxon[s] == tmp[i].taxid;
+      unique_est[i] = c;
+    }
     is_sparse[i] = (uint8_t)tmp[i].hll->sparse;
     if (regs) kuqo_hll_registers(tmp[i].hll, regs + (size_t)HLL_M * i);
   }
@@ -712,6 +759,17 @@ uint64_t kuqo_run_clade(const kuqo_run *r, const uint32_t *taxa, uint32_t n, uin
   }
   uint64_t u = kuqo_hll_cardinality(acc);
   kuqo_hll_free(acc);
+  if (r->global.exact) {                                   /* union of the members' k-mer sets */
+    const pairset *ps = r->global.exact;
+    pairset *un = (pairset *)calloc(1, sizeof(*un));
+    for (uint64_t s = 0; s < ps->cap; s++) {
+      if (!ps->used[s]) continue;
+      for (uint32_t i = 0; i < n; i++)
+        if (taxa[i] == ps->taxon[s]) { ps_insert(un, 0, ps->kmer[s]); break; }
+    }
+    u = un->n;
+    ps_free(un);
+  }
   if (n_reads) *n_reads = reads;
   if (n_kmers) *n_kmers = kmers;
   return u;
@@ -726,3 +784,10 @@ int kuqo_run_add_db(kuqo_run *r, const kuqo_db *db) {
 
 /* classify -q [-m min_hits]; min_hits = 0 switches quick mode off */
 void kuqo_run_set_quick(kuqo_run *r, uint32_t min_hits) { r->quick_min = min_hits; }
+
+/* classifyExact: exact distinct k-mer counts per taxon / clade instead of the HLL estimate (classify.cpp:46-49) */
+void kuqo_run_set_exact(kuqo_run *r, int on) {
+  if (on && !r->global.exact) r->global.exact = (pairset *)calloc(1, sizeof(pairset));
+  if (!on) { ps_free(r->global.exact); r->global.exact = NULL; }
+  r->local.exact = r->global.exact;
+}

@@ -98,6 +98,9 @@ void kuqo_run_counts(const kuqo_run *r, uint32_t *taxid, uint64_t *n_reads, uint
 
 /* further databases, tried in order after the first one for every k-mer (classify.cpp:928-936); same k required */
 int kuqo_run_add_db(kuqo_run *r, const kuqo_db *db);
+/* classifyExact (EXACT_COUNTING, classify.cpp:46-49; readcounts.hpp:71-81,127-130): unique counts become exact set
+ * sizes (per taxon) / union sizes (per clade).  Call before the first kuqo_run_classify. */
+void kuqo_run_set_exact(kuqo_run *r, int on);
 /* quick mode (-q -m min_hits; classify.cpp:943-944,963-964 preloaded, :701-702,737-738 with -x); the codes of a read
  * then cover the windows actually visited; "Q:hits" = min(hits among them, min_hits).  0 = off. */
 void kuqo_run_set_quick(kuqo_run *r, uint32_t min_hits);

@@ -267,6 +267,12 @@ class OracleRun:
         if self.o.L.kuqo_run_add_db(self.h, C.byref(db.s)) != 0:
             raise ValueError("databases must share k")
 
+    def set_exact(self, on=True):
+        """classifyExact: exact distinct counts instead of HLL estimates"""
+        self.o.L.kuqo_run_set_exact.argtypes = [C.c_void_p, C.c_int]
+        self.o.L.kuqo_run_set_exact.restype = None
+        self.o.L.kuqo_run_set_exact(self.h, 1 if on else 0)
+
     def set_quick(self, min_hits: int):
         """classify -q -m min_hits (0 = off)"""
         self.o.L.kuqo_run_set_quick.argtypes = [C.c_void_p, C.c_uint32]
