@@ -58,6 +58,10 @@ extern "C" {
 #define KUQ_HLL_PRELOAD 0   /* per-work-unit sketches merged into the global map (classify.cpp:525,542-544) */
 #define KUQ_HLL_CHUNKED 1   /* one global sketch per taxon (classify.cpp:719) — the `-x` path */
 #define KUQ_HLL_DENSE_ONLY 2 /* p=12 registers only, no sparse-tier emulation (fastest; estimates = dense Ertl) */
+#define KUQ_HLL_EXACT 3     /* classifyExact (EXACT_COUNTING, classify.cpp:46-49): sets of k-mers instead of sketches;
+                               `unique` of kuq_read_counts / kuq_clade_counts is the exact set / union size.  The
+                               (taxon, k-mer) table takes kuq_config.sparse_set_slots entries of 16 bytes.
+                               ROUND 1: written after the GPU budget was spent — compiles, not yet run on hardware */
 
 /* flags of the classify calls */
 #define KUQ_F_WANT_CODES 1u     /* also return the per-window codes (4 B per base position) */

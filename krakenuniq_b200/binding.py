@@ -16,7 +16,7 @@ import numpy as np
 from . import build as _build
 
 AMBIG = 0xFFFFFFFF
-HLL_PRELOAD, HLL_CHUNKED, HLL_DENSE_ONLY = 0, 1, 2
+HLL_PRELOAD, HLL_CHUNKED, HLL_DENSE_ONLY, HLL_EXACT = 0, 1, 2, 3
 F_WANT_CODES, F_NO_RUNS, F_NO_COUNTS, F_STATS = 1, 2, 4, 8
 
 u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)

@@ -50,18 +50,22 @@ CLASSIFY = os.path.join(PKG, "bin", "classify")
 
 
 def build_classify(force: bool = False) -> str:
-    """The drop-in `classify` executable (host C++ over libkuq.so)."""
+    """The drop-in `classify` executable (host C++ over libkuq.so) and, from the same source with -DEXACT_COUNTING
+    like the reference's Makefile, `classifyExact` (what `krakenuniq --exact` runs)."""
     src = os.path.join(CSRC, "classify_main.cpp")
     build(force=force)
-    if not force and os.path.exists(CLASSIFY) and os.path.getmtime(CLASSIFY) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+    exact = CLASSIFY + "Exact"
+    newest = max(os.path.getmtime(src), os.path.getmtime(LIB))
+    if not force and all(os.path.exists(x) and os.path.getmtime(x) >= newest for x in (CLASSIFY, exact)):
         return CLASSIFY
     os.makedirs(os.path.dirname(CLASSIFY), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-fopenmp", src, "-o", CLASSIFY, "-L" + os.path.dirname(LIB), "-lkuq", "-lz",
-           "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("g++ failed building classify")
+    for out, defs in ((CLASSIFY, []), (exact, ["-DEXACT_COUNTING"])):
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-fopenmp"] + defs + [src, "-o", out, "-L" + os.path.dirname(LIB),
+               "-lkuq", "-lz", "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building " + os.path.basename(out))
     return CLASSIFY
 
 

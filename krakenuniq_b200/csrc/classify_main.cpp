@@ -1173,6 +1173,11 @@ int main(int argc, char **argv) {
   cfg.work_unit_size = Work_unit_size;
   // -x (or a database that has to be split) → one global sketch per taxon (classify.cpp:719); else per work unit
   cfg.hll_mode = (Populate_memory_size > 0 || chunk_budget) ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;
+#ifdef EXACT_COUNTING
+  // classifyExact (classify.cpp:46-49): sets of k-mers instead of sketches; work units and chunks make no difference
+  cfg.hll_mode = KUQ_HLL_EXACT;
+  if (Quick_mode) die(EX_USAGE, "-q is not supported by the GPU classifyExact");
+#endif
   if (chunk_budget && !Populate_memory_size)
     cerr << "classify: database larger than the HBM budget: processing it in ranges (unique k-mer counts follow the -x rule)" << endl;
   if (getenv("KUQ_SPARSE_SLOTS")) cfg.sparse_set_slots = strtoull(getenv("KUQ_SPARSE_SLOTS"), NULL, 10);

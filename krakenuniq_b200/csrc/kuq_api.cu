@@ -70,6 +70,7 @@ struct CountsHost {
   std::vector<uint8_t> dense_flag;
   std::vector<uint32_t> distinct;
   std::vector<uint32_t> sparse_hist;   // [n_sketch][64] rank histogram of the sparse tier
+  std::vector<unsigned long long> exact;   // KUQ_HLL_EXACT: [n_sketch] distinct k-mers per taxon
 };
 
 struct kuq_ctx {
@@ -118,6 +119,9 @@ struct kuq_ctx {
   unsigned long long *d_sparse_slots = nullptr, *d_sparse_used = nullptr;
   uint32_t *d_sparse_distinct = nullptr;
   uint64_t sparse_cap = 0;
+  ExactPair *d_exact = nullptr;           // KUQ_HLL_EXACT: the (taxon, k-mer) table and the per-taxon set sizes
+  unsigned long long *d_exact_count = nullptr;
+  uint64_t exact_cap = 0;
 
   // work-unit cutting across batches (classify.cpp:506-521)
   uint64_t unit_nt = 0;
@@ -178,6 +182,8 @@ void free_tax_state(kuq_ctx *ctx) {
   cudaFree(ctx->d_parent); cudaFree(ctx->d_raw); cudaFree(ctx->d_depth);
   cudaFree(ctx->d_regs); cudaFree(ctx->d_dense_flag); cudaFree(ctx->d_n_kmers); cudaFree(ctx->d_n_reads);
   cudaFree(ctx->d_sparse_slots); cudaFree(ctx->d_sparse_used); cudaFree(ctx->d_sparse_distinct);
+  cudaFree(ctx->d_exact); cudaFree(ctx->d_exact_count);
+  ctx->d_exact = nullptr; ctx->d_exact_count = nullptr;
   ctx->d_parent = ctx->d_raw = nullptr; ctx->d_depth = nullptr; ctx->d_regs = ctx->d_dense_flag = nullptr;
   ctx->d_n_kmers = ctx->d_n_reads = nullptr; ctx->d_sparse_slots = ctx->d_sparse_used = nullptr;
   ctx->d_sparse_distinct = nullptr;
@@ -381,7 +387,13 @@ int finalize(kuq_ctx *ctx) {
   CU(cudaMemset(ctx->d_dense_flag, 0, ctx->n_sketch));
   CU(cudaMemset(ctx->d_n_kmers, 0, ctx->n_sketch * 8ull));
   CU(cudaMemset(ctx->d_n_reads, 0, ctx->n_taxa * 8ull));
-  if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
+  if (ctx->cfg.hll_mode == KUQ_HLL_EXACT) {
+    ctx->exact_cap = ctx->cfg.sparse_set_slots;            // entries of 16 B
+    CU(dmalloc(&ctx->d_exact, ctx->exact_cap));
+    CU(dmalloc(&ctx->d_exact_count, ctx->n_sketch));
+    CU(cudaMemset(ctx->d_exact, 0, ctx->exact_cap * 16ull));
+    CU(cudaMemset(ctx->d_exact_count, 0, ctx->n_sketch * 8ull));
+  } else if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
     ctx->sparse_cap = ctx->cfg.sparse_set_slots;
     CU(dmalloc(&ctx->d_sparse_slots, ctx->sparse_cap));
     CU(dmalloc(&ctx->d_sparse_used, 1));
@@ -528,6 +540,9 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.sparse.mask = ctx->sparse_cap ? ctx->sparse_cap - 1 : 0;
   p.sparse.n_used = ctx->d_sparse_used;
   p.sparse.distinct = ctx->d_sparse_distinct;
+  p.exact.slots = ctx->d_exact;
+  p.exact.mask = ctx->exact_cap ? ctx->exact_cap - 1 : 0;
+  p.exact.count = ctx->d_exact_count;
   set_unit_ptrs(p, s);
 }
 
@@ -620,7 +635,7 @@ int kuq_create(const kuq_config *cfg_in, kuq_ctx **out) {
     if (!cfg.work_unit_size) cfg.work_unit_size = d.work_unit_size;
     if (!cfg.sparse_set_slots) cfg.sparse_set_slots = d.sparse_set_slots;
   }
-  if (cfg.hll_mode > KUQ_HLL_DENSE_ONLY || cfg.n_slots > 16) return KUQ_E_INVALID_ARG;
+  if (cfg.hll_mode > KUQ_HLL_EXACT || cfg.n_slots > 16) return KUQ_E_INVALID_ARG;
   // round the sparse set to a power of two
   uint64_t sc = 1024;
   while (sc < cfg.sparse_set_slots) sc <<= 1;
@@ -777,6 +792,7 @@ int kuq_set_quick_mode(kuq_ctx *ctx, uint32_t min_hits, int stop_at_last_hit) {
   if (!ctx) return KUQ_E_INVALID_ARG;
   for (auto &s : ctx->slots)
     if (s.busy) return fail(ctx, KUQ_E_STATE, "quick mode cannot change while a batch is in flight");
+  if (min_hits && ctx->cfg.hll_mode == KUQ_HLL_EXACT) return fail(ctx, KUQ_E_INVALID_ARG, "quick mode is not available with KUQ_HLL_EXACT");
   ctx->quick_min = min_hits;
   ctx->quick_stop = min_hits && stop_at_last_hit;
   return KUQ_OK;
@@ -1191,7 +1207,10 @@ int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
   CU(cudaMemcpyAsync(h.hist.data(), d_hist, (uint64_t)ctx->n_sketch * 64 * 4, cudaMemcpyDeviceToHost, ctx->aux));
   CU(cudaStreamSynchronize(ctx->aux));
   cudaFree(d_hist);
-  if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
+  if (ctx->cfg.hll_mode == KUQ_HLL_EXACT) {
+    h.exact.resize(ctx->n_sketch);
+    CU(cudaMemcpy(h.exact.data(), ctx->d_exact_count, ctx->n_sketch * 8ull, cudaMemcpyDeviceToHost));
+  } else if (ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY) {
     if (ctx->cfg.hll_mode == KUQ_HLL_CHUNKED) {
       launch_flag_dense_global(ctx->d_sparse_distinct, ctx->d_dense_flag, ctx->n_sketch, ctx->aux);
       ctx->launches++;
@@ -1244,9 +1263,11 @@ int kuq_read_counts(kuq_ctx *ctx, uint32_t *taxid, uint64_t *n_reads, uint64_t *
     if (n_kmers) n_kmers[i] = nk;
     // the sketch the reference would hold: dense registers if some per-unit (or the global) sketch converted,
     // else the union of the encoded hashes (sparse tier)
-    const bool sparse = d < ctx->n_sketch && ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY && !h.dense_flag[d];
+    const bool exact = ctx->cfg.hll_mode == KUQ_HLL_EXACT;
+    const bool sparse = d < ctx->n_sketch && !exact && ctx->cfg.hll_mode != KUQ_HLL_DENSE_ONLY && !h.dense_flag[d];
     uint64_t u = 0;
-    if (d < ctx->n_sketch && nk)
+    if (exact) u = d < ctx->n_sketch ? h.exact[d] : 0;     // khset size, readcounts.hpp:127-130
+    else if (d < ctx->n_sketch && nk)
       u = sparse ? ertl_sparse_hist(&h.sparse_hist[(size_t)d * 64], h.distinct[d], nk)
                  : ertl_dense_hist(&h.hist[(size_t)d * 64], nk);
     if (unique) unique[i] = u;
@@ -1276,6 +1297,39 @@ int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t 
     if (d < ctx->n_sketch && h.n_kmers[d]) { kmers += h.n_kmers[d]; members.push_back(d); }
   }
   uint64_t u = 0;
+  if (ctx->cfg.hll_mode == KUQ_HLL_EXACT) {
+    // the clade's container is the union of the members' k-mer sets (readcounts.hpp:76-81)
+    uint64_t sum = 0;
+    for (uint32_t d : members) sum += h.exact[d];
+    if (members.size() == 1) {
+      u = sum;
+    } else if (!members.empty()) {
+      std::vector<uint8_t> member(ctx->n_sketch, 0);
+      for (uint32_t d : members) member[d] = 1;
+      uint64_t cap = 1024;
+      while (cap < 2 * sum + 16) cap <<= 1;
+      uint8_t *d_member; unsigned long long *d_set; unsigned long long *d_cnt;
+      CU(dmalloc(&d_member, ctx->n_sketch));
+      CU(dmalloc(&d_set, cap));
+      CU(dmalloc(&d_cnt, 2));
+      CU(cudaMemcpyAsync(d_member, member.data(), ctx->n_sketch, cudaMemcpyHostToDevice, ctx->aux));
+      CU(cudaMemsetAsync(d_set, 0, cap * 8, ctx->aux));
+      CU(cudaMemsetAsync(d_cnt, 0, 16, ctx->aux));
+      ExactSet es{ctx->d_exact, ctx->exact_cap - 1, ctx->d_exact_count};
+      launch_exact_union(es, d_member, d_set, cap - 1, d_cnt, reinterpret_cast<uint32_t *>(d_cnt + 1), ctx->aux);
+      ctx->launches++;
+      unsigned long long out[2];
+      CU(cudaMemcpyAsync(out, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->aux));
+      CU(cudaStreamSynchronize(ctx->aux));
+      cudaFree(d_member); cudaFree(d_set); cudaFree(d_cnt);
+      if (out[1]) return fail(ctx, KUQ_E_CAPACITY, "internal: clade union scratch overflow");
+      u = out[0];
+    }
+    if (n_reads) *n_reads = reads;
+    if (n_kmers) *n_kmers = kmers;
+    if (unique) *unique = u;
+    return KUQ_OK;
+  }
   // clade sketch = merge of the members' sketches: dense as soon as one member is dense
   // (hyperloglogplus.cpp:604-621), else the union of the sparse sets (:600-603)
   bool any_dense = ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY;
@@ -1432,6 +1486,10 @@ int kuq_reset_counts(kuq_ctx *ctx) {
     CU(cudaMemset(ctx->d_sparse_slots, 0, ctx->sparse_cap * 8ull));
     CU(cudaMemset(ctx->d_sparse_used, 0, 8));
     CU(cudaMemset(ctx->d_sparse_distinct, 0, ctx->n_sketch * 4ull));
+  }
+  if (ctx->d_exact) {
+    CU(cudaMemset(ctx->d_exact, 0, ctx->exact_cap * 16ull));
+    CU(cudaMemset(ctx->d_exact_count, 0, ctx->n_sketch * 8ull));
   }
   ctx->unit_nt = 0;
   ctx->unit_next = 0;

@@ -993,6 +993,65 @@ void launch_sparse_import(const unsigned long long *keys, uint64_t n, const Spar
   if (n) k_sparse_import<<<(int)min((uint64_t)148 * 16, (n + 255) / 256), 256, 0, stream>>>(keys, n, s, dense_flag, error_flag);
 }
 
+// ---- exact counting (classifyExact) ---------------------------------------------------------------------------
+// 1 = new pair, 0 = already there, -1 = table full.  Entries go 0 → final in one 128-bit CAS and never change again.
+__device__ __forceinline__ int exact_insert(const ExactSet &e, uint32_t taxon, uint64_t canon) {
+  const ExactPair want{canon + 1ull, (unsigned long long)taxon + 1ull};
+  const ExactPair empty{0ull, 0ull};
+  uint64_t s = mix64(canon * 0x9E3779B97F4A7C15ull + taxon) & e.mask;
+  for (uint64_t probe = 0; probe <= e.mask; probe++) {
+    const ulonglong2 seen = __ldcg(reinterpret_cast<const ulonglong2 *>(e.slots + s));    // one 16-byte load
+    ExactPair cur{seen.x, seen.y};
+    if (cur.kmer1 == 0 || cur.taxon1 == 0) {                // empty (or a load that raced with the writer): ask atomically
+      cur = atomicCAS(e.slots + s, empty, want);
+      if (cur.kmer1 == 0 && cur.taxon1 == 0) return 1;
+    }
+    if (cur.kmer1 == want.kmer1 && cur.taxon1 == want.taxon1) return 0;
+    s = (s + 1) & e.mask;
+  }
+  return -1;
+}
+
+// add_kmer of the exact container (readcounts.hpp:71-74 with khset64_t): thread per text position, after the lookup
+// wrote the window's dense taxon (0 for a miss) to codes_dense
+__global__ void __launch_bounds__(256) k_exact_insert(const __grid_constant__ Params p) {
+  const uint64_t g_begin = p.offsets[0], g_end = p.offsets[p.n_reads];
+  for (uint64_t g = g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g_end;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t bin = __ldg(p.bins + g);
+    if (bin == BIN_NONE || bin == BIN_AMBIG) continue;
+    const uint32_t taxon = p.codes_dense[g];
+    const int ins = exact_insert(p.exact, taxon, __ldg(p.canon + g));
+    if (ins > 0) atomicAdd(p.exact.count + taxon, 1ull);
+    else if (ins < 0) atomicExch(p.error_flag, 4u);
+  }
+}
+
+// distinct k-mers among the pairs whose taxon is a clade member
+__global__ void k_exact_union(ExactSet e, const uint8_t *member, unsigned long long *scratch, uint64_t smask,
+                              unsigned long long *n_distinct, uint32_t *overflow) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= e.mask; i += (uint64_t)gridDim.x * blockDim.x) {
+    const ExactPair pr = e.slots[i];
+    if (!pr.kmer1 || !member[pr.taxon1 - 1]) continue;
+    uint64_t q = mix64(pr.kmer1) & smask;
+    for (uint64_t probe = 0; probe <= smask; probe++) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(scratch + q);
+      if (cur == pr.kmer1) break;
+      if (cur == 0) {
+        cur = atomicCAS(scratch + q, 0ull, pr.kmer1);
+        if (cur == 0) { atomicAdd(n_distinct, 1ull); break; }
+        if (cur == pr.kmer1) break;
+      }
+      q = (q + 1) & smask;
+      if (probe == smask) atomicExch(overflow, 1u);
+    }
+  }
+}
+void launch_exact_union(const ExactSet &e, const uint8_t *member, unsigned long long *scratch_set, uint64_t scratch_mask,
+                        unsigned long long *n_distinct, uint32_t *overflow, cudaStream_t stream) {
+  if (e.slots) k_exact_union<<<148 * 16, 256, 0, stream>>>(e, member, scratch_set, scratch_mask, n_distinct, overflow);
+}
+
 // Quick mode, preloaded path: the k-mer loop of classify_sequence leaves at the quick_min-th hit (classify.cpp:943-944),
 // so the windows behind it are never looked at — no add_kmer, no hit.  One warp per read finds that window in the
 // looked-up codes, shortens the read to it and wipes the later windows from the scan scratch; the counting pass
@@ -1042,7 +1101,19 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
   if (stage_events) cudaEventRecord(stage_events[0], stream);
   const int lgrid = (int)min((uint64_t)n_sm * 8 * 8, (p.total_bases + 255) / 256);
   const bool quick = p.quick_min != 0 && mode != MODE_LOOKUP;
-  if (quick && p.quick_stop) {
+  const bool exact = p.hll_mode == 3u && mode != MODE_LOOKUP;
+  if (exact) {
+    // classifyExact: plain lookup (no sketch work), then the k-mer sets, then the usual resolve
+    Params q = p;
+    if (mode == MODE_FUSED) {
+      q.only_hits = 0; q.n_peers = 0; q.flags &= ~16u;
+      k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(q);
+    } else {
+      q.flags |= 4u;                                         // merged codes → codes_dense, no sketches
+      k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(q);
+    }
+    if (!(p.flags & 4u)) { k_exact_insert<<<lgrid, 256, 0, stream>>>(p); launches++; }
+  } else if (quick && p.quick_stop) {
     // lookup first, end every read at its quick_min-th hit, then count what is left
     Params q = p;
     if (mode == MODE_FUSED) {
@@ -1059,7 +1130,7 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
   } else if (mode == MODE_FUSED) k_lookup<MODE_FUSED><<<lgrid, 256, 0, stream>>>(p);
   else if (mode == MODE_LOOKUP) k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(p);
   else k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(p);
-  if (!(quick && p.quick_stop)) launches++;
+  if (exact || !(quick && p.quick_stop)) launches++;
   if (stage_events) cudaEventRecord(stage_events[1], stream);
   if (mode != MODE_LOOKUP) {
     const int rgrid = (int)min((uint32_t)n_sm * 4 * 2, (p.n_reads + CTA_WARPS - 1) / CTA_WARPS);

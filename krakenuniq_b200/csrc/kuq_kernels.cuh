@@ -85,6 +85,18 @@ struct UnitMap {
   uint32_t set_mask;
 };
 
+// classifyExact (EXACT_COUNTING, classify.cpp:46-49): the per-taxon container is a set of canonical k-mers.  All
+// sets of a run share one open-addressing table of 16-byte entries, filled with 128-bit compare-and-swap.
+struct alignas(16) ExactPair {
+  unsigned long long kmer1;    // canonical k-mer + 1 (0 = empty slot)
+  unsigned long long taxon1;   // dense taxon id + 1
+};
+struct ExactSet {
+  ExactPair *slots;
+  uint64_t mask;               // capacity - 1 (power of two)
+  unsigned long long *count;   // [n_sketch] distinct k-mers per taxon == khset size (readcounts.hpp:127-130)
+};
+
 struct Params {
   DbView db;
   TaxView tax;
@@ -136,6 +148,7 @@ struct Params {
   // (classify.cpp:943-944); otherwise every k-mer counts and only the call rule changes (the -x path, :701-738)
   uint32_t quick_min;
   uint32_t quick_stop;
+  ExactSet exact;               // hll_mode 3 (KUQ_HLL_EXACT)
 };
 
 // returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup
@@ -160,6 +173,9 @@ void launch_flag_dense_global(const uint32_t *distinct, uint8_t *dense_flag, uin
 void launch_sparse_histograms(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag,
                               uint32_t *hist, cudaStream_t stream);
 // distinct codes of the union of the member taxa (member[t] != 0): rank histogram hist64 via a scratch set
+// exact mode: distinct k-mers over the member taxa (set union of ReadCounts::operator+=, readcounts.hpp:76-81)
+void launch_exact_union(const ExactSet &e, const uint8_t *member, unsigned long long *scratch_set, uint64_t scratch_mask,
+                        unsigned long long *n_distinct, uint32_t *overflow, cudaStream_t stream);
 void launch_sparse_union(const unsigned long long *slots, uint64_t cap, const uint8_t *member,
                          unsigned long long *scratch_set, uint64_t scratch_mask, uint32_t *hist64, uint32_t *overflow,
                          cudaStream_t stream);
