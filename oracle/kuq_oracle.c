@@ -791,3 +791,100 @@ void kuqo_run_set_exact(kuqo_run *r, int on) {
   if (!on) { ps_free(r->global.exact); r->global.exact = NULL; }
   r->local.exact = r->global.exact;
 }
+
+/* ======================================================================================================= */
+/* database build: db_sort and set_lcas                                                  */
+/* ======================================================================================================= */
+
+/* db_sort.cpp:41-78 (main) with make_index (krakendb.cpp:118-148) and bin_and_sort_data (db_sort.cpp:80-116):
+ * records go to the bin of bin_key(key, nt) — the key as stored, no canonicalisation — in input order, then every
+ * bin is sorted by key; the header is copied; the index is always written as KRAKIX2.  Keys are distinct in a
+ * Jellyfish dump, so qsort's instability cannot show.  kdb_out: jdb_bytes, idx_out: 8 + 8 * (4^nt + 1) bytes. */
+typedef struct { uint64_t key; uint32_t pos; } sort_item;
+static int cmp_item(const void *a, const void *b) {
+  uint64_t x = ((const sort_item *)a)->key, y = ((const sort_item *)b)->key;
+  return x < y ? -1 : x > y;
+}
+int kuqo_db_sort(const void *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, void *kdb_out, void *idx_out) {
+  const uint8_t *p = (const uint8_t *)jdb_image;
+  if (!p || jdb_bytes < 56 || memcmp(p, "JFLISTDN", 8) != 0 || nt < 1 || nt > 15) return -1;
+  uint64_t key_bits, val_len, key_ct;
+  memcpy(&key_bits, p + 8, 8); memcpy(&val_len, p + 16, 8); memcpy(&key_ct, p + 48, 8);
+  if (val_len != 4) return -2;
+  const unsigned k = (unsigned)(key_bits / 2), key_len = (unsigned)(key_bits / 8 + !!(key_bits % 8));
+  const uint64_t pair_sz = key_len + 4, header = 72 + 2 * (4 + 8 * key_bits);
+  if (jdb_bytes < header + key_ct * pair_sz) return -3;
+  const uint8_t *src = p + header;
+  const uint64_t entries = 1ull << (2 * nt);
+  uint64_t *offsets = (uint64_t *)calloc(entries + 1, 8);
+  uint64_t *bins = (uint64_t *)malloc(8 * (key_ct ? key_ct : 1));
+  for (uint64_t i = 0; i < key_ct; i++) {                                      /* make_index, :126-134 */
+    uint64_t kmer = 0;
+    memcpy(&kmer, src + i * pair_sz, key_len);
+    bins[i] = kuqo_bin_key(kmer, k, nt, 2);
+    offsets[bins[i] + 1]++;
+  }
+  for (uint64_t i = 1; i <= entries; i++) offsets[i] += offsets[i - 1];        /* :136-139 */
+  uint8_t *idx = (uint8_t *)idx_out;
+  memcpy(idx, "KRAKIX2", 7);                                                   /* :144-147 */
+  idx[7] = (uint8_t)nt;
+  memcpy(idx + 8, offsets, 8 * (entries + 1));
+  uint8_t *out = (uint8_t *)kdb_out;
+  memcpy(out, p, header);                                                      /* db_sort.cpp:56-58,71 */
+  uint8_t *data = out + header;
+  uint64_t *pos = (uint64_t *)malloc(8 * entries);
+  memcpy(pos, offsets, 8 * entries);
+  for (uint64_t i = 0; i < key_ct; i++) {                                      /* :96-107 */
+    uint8_t *dst = data + pair_sz * pos[bins[i]]++;
+    memcpy(dst, src + i * pair_sz, pair_sz);
+    if (zero_vals) memset(dst + key_len, 0, 4);
+  }
+  sort_item *tmp = NULL;
+  uint64_t tmp_cap = 0;
+  uint8_t *buf = NULL;
+  for (uint64_t b = 0; b < entries; b++) {                                     /* :110-115, pair_cmp :118-128 */
+    const uint64_t n = offsets[b + 1] - offsets[b];
+    if (n < 2) continue;
+    if (n > tmp_cap) { tmp_cap = n; tmp = (sort_item *)realloc(tmp, sizeof(sort_item) * n); buf = (uint8_t *)realloc(buf, pair_sz * n); }
+    uint8_t *base = data + offsets[b] * pair_sz;
+    for (uint64_t i = 0; i < n; i++) { tmp[i].key = 0; memcpy(&tmp[i].key, base + i * pair_sz, key_len); tmp[i].pos = (uint32_t)i; }
+    qsort(tmp, n, sizeof(sort_item), cmp_item);
+    for (uint64_t i = 0; i < n; i++) memcpy(buf + i * pair_sz, base + (uint64_t)tmp[i].pos * pair_sz, pair_sz);
+    memcpy(base, buf, n * pair_sz);
+  }
+  free(tmp); free(buf); free(pos); free(bins); free(offsets);
+  return 0;
+}
+
+/* set_lcas() for one library sequence, set_lcas.cpp:429-476 (taxid mode, no forced contaminants): every
+ * unambiguous k-mer found in the database gets value = lca(taxid, value).  process_single_file cuts the sequence
+ * into pieces of SKIP_LEN that overlap by k-1 (:363-364), which visits every k-mer exactly once, like one scan.
+ * `db` must have been opened on a writable image.  Returns the number of k-mers that were not in the database
+ * (the reference stops at the first one unless -x, :441-443). */
+uint64_t kuqo_set_lcas_sequence(kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len, uint32_t taxid) {
+  uint64_t missing = 0;
+  if (len < db->k) return 0;
+  size_t cap = len - db->k + 2;
+  uint64_t *kmers = (uint64_t *)malloc(8 * cap);
+  uint8_t *amb = (uint8_t *)malloc(cap);
+  uint32_t n = kuqo_scan(seq, len, db->k, kmers, amb);
+  for (uint32_t i = 0; i < n; i++) {
+    if (amb[i]) continue;                                                       /* :434-435 */
+    const uint64_t kmer = kuqo_canonical(kmers[i], db->k);
+    const uint64_t b = kuqo_bin_key(kmer, db->k, db->nt, db->idx_type);
+    int64_t lo = (int64_t)db->offsets[b], hi = (int64_t)db->offsets[b + 1] - 1, at = -1;
+    while (lo <= hi) {
+      int64_t mid = lo + (hi - lo) / 2;
+      uint64_t c = db_key_at(db, (uint64_t)mid);
+      if (kmer > c) lo = mid + 1; else if (kmer < c) hi = mid - 1; else { at = mid; break; }
+    }
+    if (at < 0) { missing++; continue; }                                        /* :439-447 */
+    uint8_t *val = (uint8_t *)(uintptr_t)(db->pairs + db->pair_sz * (uint64_t)at + db->key_len);
+    uint32_t v;
+    memcpy(&v, val, 4);
+    v = kuqo_lca(pm, taxid, v);                                                 /* :461 */
+    memcpy(val, &v, 4);
+  }
+  free(kmers); free(amb);
+  return missing;
+}

@@ -107,6 +107,14 @@ void kuqo_run_set_quick(kuqo_run *r, uint32_t min_hits);
 /* clade roll-up (TaxReport ctor, taxdb.hpp:956-973): sums the listed taxa's ReadCounts; returns unique estimate */
 uint64_t kuqo_run_clade(const kuqo_run *r, const uint32_t *taxa, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers);
 
+/* ---- database build ------------------------------------------------------------------ */
+/* db_sort (db_sort.cpp:41-116, make_index krakendb.cpp:118-148): unsorted Jellyfish-style image → database.kdb
+ * image (jdb_bytes bytes) + KRAKIX2 index image (8 + 8 * (4^nt + 1) bytes).  zero_vals = db_sort -z. */
+int kuqo_db_sort(const void *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, void *kdb_out, void *idx_out);
+/* set_lcas for one library sequence (set_lcas.cpp:429-476): value = lca(taxid, value) for every k-mer of the
+ * sequence that the database holds; `db` must be open on a WRITABLE image.  Returns #k-mers not in the database. */
+uint64_t kuqo_set_lcas_sequence(kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len, uint32_t taxid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,24 @@ class Oracle:
         call = self.L.kuqo_classify_read(C.byref(db.s), pm.h, seq, len(seq), _p(codes, u32p), C.byref(nw))
         return call, codes[:nw.value].copy()
 
+    def db_sort(self, jdb: np.ndarray, nt: int, zero_vals=False):
+        """db_sort [-z] -n nt: unsorted Jellyfish-style image → (database.kdb image, KRAKIX2 index image)"""
+        jdb = np.ascontiguousarray(jdb, np.uint8)
+        kdb = np.zeros(jdb.size, np.uint8)
+        idx = np.zeros(8 + 8 * (4 ** nt + 1), np.uint8)
+        self.L.kuqo_db_sort.restype = C.c_int
+        self.L.kuqo_db_sort.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        rc = self.L.kuqo_db_sort(jdb.ctypes.data, jdb.size, nt, 1 if zero_vals else 0, kdb.ctypes.data, idx.ctypes.data)
+        if rc != 0:
+            raise ValueError(f"kuqo_db_sort failed: {rc}")
+        return kdb, idx
+
+    def set_lcas_sequence(self, db: "OracleDB", pm, seq: bytes, taxid: int) -> int:
+        """set_lcas for one library sequence; updates db.kdb (the image the OracleDB was opened on) in place"""
+        self.L.kuqo_set_lcas_sequence.restype = C.c_uint64
+        self.L.kuqo_set_lcas_sequence.argtypes = [C.POINTER(_DB), C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32]
+        return self.L.kuqo_set_lcas_sequence(C.byref(db.s), pm.h, seq, len(seq), taxid)
+
     def run(self, db, pm, work_unit_size=500000, mode=0):
         return OracleRun(self, db, pm, work_unit_size, mode)
 
