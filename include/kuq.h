@@ -275,6 +275,24 @@ int kuq_reset_counts(kuq_ctx *ctx);
  * 730-752) — exported so bindings and tests can call the exact code the report path uses. */
 uint64_t kuq_ertl_dense(const uint8_t *regs4096, uint64_t n_observed);
 
+/* ---- database build.  ROUND 1: compiled for sm_100a, not yet run on hardware ------------- */
+/* db_sort [-z] -n nt (db_sort.cpp:41-116 + KrakenDB::make_index, krakendb.cpp:118-148): unsorted Jellyfish-style
+ * image → database.kdb image (kdb_out: header + key_ct * (key_len + 4) bytes) and KRAKIX2 index image (idx_out:
+ * 8 + 8 * (4^nt + 1) bytes).  Needs no context.  err (optional) receives a message on failure. */
+int kuq_db_sort(int device, const void *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, void *kdb_out,
+                void *idx_out, char *err, uint64_t err_cap);
+/* set_lcas (set_lcas.cpp:429-476): for every k-mer of the library pieces that the staged database holds,
+ * value = lca(taxid of the piece, value).  A piece is a stretch of one library sequence; consecutive pieces of a
+ * sequence overlap by k-1 bases (the reference's SKIP_LEN pieces, :363-364).  The context needs the database
+ * (kuq_stage_db, whole) and the taxonomy (kuq_set_taxonomy); every taxid must be in the taxonomy — the reference
+ * skips other sequences (:336-341) and so must the caller.  *n_missing += k-mers the database lacks (set_lcas
+ * without -x stops there, :441-443).  After the first call the context cannot classify any more. */
+int kuq_set_lcas_batch(kuq_ctx *ctx, const char *bases, const uint64_t *piece_offsets, uint32_t n_pieces,
+                       const uint32_t *taxid, uint64_t *n_missing);
+/* Copy the record values of the staged database (as taxids) into the value fields of a host database.kdb image
+ * with the same records — what set_lcas leaves in the memory-mapped file. */
+int kuq_export_db_values(kuq_ctx *ctx, void *kdb_image, uint64_t kdb_bytes);
+
 #ifdef __cplusplus
 }
 #endif

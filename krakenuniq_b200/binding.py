@@ -88,6 +88,9 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_db_taxids": (C.c_int, [vp, u32p, u64p, C.c_uint32, u32p]),
         "kuq_set_db_taxid_universe": (C.c_int, [vp, u32p, C.c_uint32]),
         "kuq_mark_zero_hits": (C.c_int, [vp, C.c_int]),
+        "kuq_db_sort": (C.c_int, [C.c_int, vp, C.c_uint64, C.c_uint32, C.c_int, vp, vp, C.c_char_p, C.c_uint64]),
+        "kuq_set_lcas_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, u64p]),
+        "kuq_export_db_values": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_set_quick_mode": (C.c_int, [vp, C.c_uint32, C.c_int]),
         "kuq_set_taxonomy": (C.c_int, [vp, u32p, u32p, C.c_uint32]),
         "kuq_classify_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, C.c_uint32, C.POINTER(BatchResult)]),
@@ -205,6 +208,21 @@ class Classifier:
     def set_quick_mode(self, min_hits, stop_at_last_hit=True):
         """classify -q -m min_hits (0 = off); stop_at_last_hit=False gives the -x path's rule (kuq_set_quick_mode)"""
         self._ck(self.L.kuq_set_quick_mode(self.h, int(min_hits), 1 if stop_at_last_hit else 0))
+
+    def set_lcas(self, bases: np.ndarray, piece_offsets: np.ndarray, taxids) -> int:
+        """kuq_set_lcas_batch: fold the pieces' taxids into the staged database's values; returns #k-mers not found"""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offs = np.ascontiguousarray(piece_offsets, np.uint64)
+        t = np.ascontiguousarray(taxids, np.uint32)
+        missing = C.c_uint64(0)
+        buf = bases if bases.size else np.zeros(1, np.uint8)
+        self._ck(self.L.kuq_set_lcas_batch(self.h, buf.ctypes.data, _p(offs, u64p), len(offs) - 1, _p(t, u32p), C.byref(missing)))
+        return missing.value
+
+    def export_db_values(self, kdb: np.ndarray):
+        """kuq_export_db_values: write the device record values (taxids) into the host image `kdb` in place"""
+        assert kdb.dtype == np.uint8 and kdb.flags["C_CONTIGUOUS"]
+        self._ck(self.L.kuq_export_db_values(self.h, kdb.ctypes.data, kdb.size))
 
     def mark_zero_hits(self, on=True):
         """several databases: lookups report a stored taxon 0 as CODE_FOUND_ZERO (kuq_mark_zero_hits)"""
@@ -417,3 +435,19 @@ def decode_runs(res, i):
     """hit list of read i as [(code, count), ...] from a classify() result"""
     s, c = int(res["run_start"][i]), int(res["run_count"][i])
     return [(int(a), int(b)) for a, b in res["runs"][s:s + c]]
+
+
+def db_sort(jdb: np.ndarray, nt: int, zero_vals=False, device=0):
+    """kuq_db_sort: unsorted Jellyfish-style image → (database.kdb image, KRAKIX2 index image), on the GPU"""
+    L = load_library()
+    jdb = np.ascontiguousarray(jdb, np.uint8)
+    key_bits = int(np.frombuffer(jdb[8:16].tobytes(), np.uint64)[0])
+    key_ct = int(np.frombuffer(jdb[48:56].tobytes(), np.uint64)[0])
+    size = 72 + 2 * (4 + 8 * key_bits) + key_ct * ((key_bits + 7) // 8 + 4)
+    kdb = np.zeros(size, np.uint8)
+    idx = np.zeros(8 + 8 * (4 ** nt + 1), np.uint8)
+    err = C.create_string_buffer(512)
+    rc = L.kuq_db_sort(device, jdb.ctypes.data, jdb.size, nt, 1 if zero_vals else 0, kdb.ctypes.data, idx.ctypes.data, err, 512)
+    if rc != 0:
+        raise KuqError(rc, err.value.decode() or L.kuq_strerror(rc).decode())
+    return kdb, idx

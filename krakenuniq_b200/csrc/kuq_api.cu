@@ -123,6 +123,7 @@ struct kuq_ctx {
   unsigned long long *d_exact_count = nullptr;
   uint64_t exact_cap = 0;
 
+  bool lca_mode = false;                  // kuq_set_lcas_batch ran: record values are LCA results, not classifiable
   // work-unit cutting across batches (classify.cpp:506-521)
   uint64_t unit_nt = 0;
   uint32_t unit_next = 0;
@@ -547,6 +548,7 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
 }
 
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
+  if (ctx->lca_mode) return fail(ctx, KUQ_E_STATE, "this context built a database (kuq_set_lcas_batch): stage it anew to classify");
   ctx->snap_valid = false;
   if (mode == MODE_LOOKUP && ctx->mark_zero_hits) p.flags |= 16u;
   if (mode != MODE_LOOKUP && ctx->quick_min) {           // "Q:hits" replaces the hit list (classify.cpp:989-990)
@@ -1501,6 +1503,80 @@ uint64_t kuq_ertl_dense(const uint8_t *regs, uint64_t n_observed) {
   memset(C, 0, sizeof C);
   for (uint32_t i = 0; i < HLL_M; i++) C[regs[i] > 65 ? 65 : regs[i]]++;
   return ertl_from_hist(C, 64 - HLL_P, HLL_M, n_observed);
+}
+
+// ---- database build (ROUND 1: compiled, not yet run on hardware) ---------------------------------
+int kuq_db_sort(int device, const void *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, void *kdb_out,
+                void *idx_out, char *err, uint64_t err_cap) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    if (err && err_cap) snprintf(err, err_cap, "db_sort: no CUDA device (there is no CPU path)");
+    (void)cudaGetLastError();
+    return KUQ_E_NO_DEVICE;
+  }
+  if (device < 0 || device >= n_dev || cudaSetDevice(device) != cudaSuccess) return KUQ_E_INVALID_ARG;
+  int rc = dbsort_device((const uint8_t *)jdb_image, jdb_bytes, nt, zero_vals, (uint8_t *)kdb_out, (uint8_t *)idx_out, err, err_cap);
+  return rc ? KUQ_E_DB_FORMAT : KUQ_OK;
+}
+
+int kuq_set_lcas_batch(kuq_ctx *ctx, const char *bases, const uint64_t *piece_offsets, uint32_t n_pieces,
+                       const uint32_t *taxid, uint64_t *n_missing) {
+  int rc = check_slot(ctx, 0);
+  if (rc) return rc;
+  if (n_pieces && (!bases || !piece_offsets || !taxid)) return fail(ctx, KUQ_E_INVALID_ARG, "NULL batch buffers");
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[0];
+  if (s.busy) return fail(ctx, KUQ_E_STATE, "slot 0 still has an unread batch");
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  if (n_pieces > ctx->cfg.max_reads_per_batch) return fail(ctx, KUQ_E_CAPACITY, "%u pieces > slot capacity %u", n_pieces, ctx->cfg.max_reads_per_batch);
+  if (ctx->bin_lo != 0 || ctx->rec_base != 0) return fail(ctx, KUQ_E_STATE, "set_lcas needs the whole database staged");
+  for (uint32_t i = 0; i < n_pieces; i++) {
+    // the reference skips sequences whose taxid the taxonomy does not hold (set_lcas.cpp:336-341): the caller's job
+    auto it = ctx->dense_of_raw.find(taxid[i]);
+    if (taxid[i] == 0 || it == ctx->dense_of_raw.end())
+      return fail(ctx, KUQ_E_INVALID_ARG, "piece %u: taxid %u is not in the taxonomy", i, taxid[i]);
+    s.h_unit[i] = it->second;
+  }
+  uint64_t total = 0;
+  rc = upload_reads(ctx, s, bases, piece_offsets, n_pieces, &total);
+  if (rc) return rc;
+  s.n_reads = n_pieces; s.flags = 0; s.total_bases = total; s.external = false;
+  if (n_pieces) CU(cudaMemcpyAsync(s.d_unit, s.h_unit, n_pieces * 4ull, cudaMemcpyHostToDevice, s.stream));
+  Params p;
+  fill_params(ctx, s, p, s.d_bases, s.d_offsets, s.d_unit, n_pieces, 0);
+  CU(cudaMemsetAsync(s.d_scalars, 0, 8 * 8, s.stream));
+  ctx->lca_mode = true;
+  ctx->snap_valid = false;
+  ctx->launches += launch_set_lcas(p, ctx->n_sm, s.stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(s.h_scalars, s.d_scalars, 8 * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  if (n_missing) *n_missing = s.h_scalars[4];
+  return KUQ_OK;
+}
+
+int kuq_export_db_values(kuq_ctx *ctx, void *kdb_image, uint64_t kdb_bytes) {
+  if (!ctx || !kdb_image) return KUQ_E_INVALID_ARG;
+  if (!ctx->db_staged || !ctx->db_owned) return fail(ctx, KUQ_E_STATE, "no database staged from a host image");
+  if (ctx->bin_lo != 0 || ctx->rec_base != 0) return fail(ctx, KUQ_E_STATE, "only a fully staged database can be exported");
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  const uint64_t key_bits = 2ull * ctx->k, header = 72 + 2 * (4 + 8 * key_bits);
+  if (kdb_bytes < header + ctx->key_ct * 12) return fail(ctx, KUQ_E_INVALID_ARG, "image too small for %llu records", (unsigned long long)ctx->key_ct);
+  std::vector<uint8_t> rec(ctx->key_ct * 12);
+  CU(cudaMemcpy(rec.data(), ctx->d_pairs, rec.size(), cudaMemcpyDeviceToHost));
+  uint8_t *out = (uint8_t *)kdb_image + header;
+  for (uint64_t i = 0; i < ctx->key_ct; i++) {
+    uint32_t v;
+    memcpy(&v, rec.data() + i * 12 + 8, 4);
+    if (ctx->db_remapped) {                                 // dense id → taxid
+      if (v >= ctx->n_taxa) return fail(ctx, KUQ_E_STATE, "record %llu holds an unknown dense id %u", (unsigned long long)i, v);
+      v = ctx->raw_of_dense[v];
+    }
+    memcpy(out + i * 12 + 8, &v, 4);
+  }
+  return KUQ_OK;
 }
 
 }  // extern "C"

@@ -1142,6 +1142,64 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
 }
 
 // ------------------------------------------------------------------------------------------------------
+// set_lcas (set_lcas.cpp:429-476), SURVEY.md §8 f4.  ROUND 1: compiled, not yet run on hardware.
+// Library sequences arrive cut into pieces (the reference's SKIP_LEN pieces, :363-364); unit_id[r] carries the dense
+// taxid of piece r.  One warp per piece, lane = window: find the record of the canonical k-mer and fold the
+// sequence's taxid into its value with lca() through a CAS loop.  lca over taxa of one tree is associative,
+// commutative and idempotent (default ancestor 1), so the order in which pieces and sequences land does not matter.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_set_lcas(const __grid_constant__ Params p) {
+  const DbView &db = p.db;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  uint8_t *pairs = const_cast<uint8_t *>(db.pairs);
+  for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + warp; r < p.n_reads; r += warps_total) {
+    const uint64_t base = p.offsets[r];
+    const uint32_t nwin = p.n_windows[r];
+    const uint32_t t = p.unit_id[r];
+    for (uint32_t i = lane; i < nwin; i += 32) {
+      const uint32_t bin = __ldg(p.bins + base + i);
+      if (bin == BIN_NONE || bin == BIN_AMBIG) continue;                  // :434-435
+      if (bin < db.bin_lo || bin >= db.bin_hi) continue;                  // another range of the database
+      const uint64_t canon = __ldg(p.canon + base + i);
+      const uint64_t *o = db.offsets + (bin - db.bin_lo);
+      uint64_t lo = __ldg(o) - db.rec_base, hi = __ldg(o + 1) - db.rec_base;
+      bool found = false;
+      while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t key = load_key(db.pairs, mid, db.key_mask);
+        if (key < canon) lo = mid + 1;
+        else if (key > canon) hi = mid;
+        else { lo = mid; found = true; break; }
+      }
+      if (!found) { atomicAdd(p.stats, 1ull); continue; }                 // "kmer found in sequence that is not in database"
+      uint32_t *val = reinterpret_cast<uint32_t *>(pairs + lo * 12) + 2;
+      uint32_t old = *reinterpret_cast<volatile uint32_t *>(val);
+      for (;;) {
+        const uint32_t nw = lca_dense(p.tax, t, old);                     // :461
+        if (nw == old) break;
+        const uint32_t prev = atomicCAS(val, old, nw);
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+  }
+}
+
+// scan the pieces, then fold their taxids into the record values; returns #kernels launched
+int launch_set_lcas(const Params &p, int n_sm, cudaStream_t stream) {
+  if (p.n_reads == 0) return 0;
+  const int smem = classify_smem_bytes();
+  cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int grid = n_sm * 4;
+  if ((uint32_t)grid > p.n_chunks) grid = (int)p.n_chunks;
+  k_scan<<<grid, CTA_THREADS, smem, stream>>>(p);
+  const int rgrid = (int)min((uint32_t)n_sm * 8, (p.n_reads + 7) / 8);
+  k_set_lcas<<<rgrid, 256, 0, stream>>>(p);
+  return 2;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // database staging: distinct taxids + record counts (KrakenDB::count_taxons, krakendb.cpp:90-113) and the
 // in-place rewrite taxid → dense id
 // ------------------------------------------------------------------------------------------------------

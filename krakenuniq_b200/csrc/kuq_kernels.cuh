@@ -154,6 +154,11 @@ struct Params {
 // returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup
 int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cudaEvent_t *stage_events);
 int classify_smem_bytes();
+// set_lcas: k_scan + k_set_lcas over library pieces (p.unit_id = dense taxid per piece, p.stats[0] += k-mers not found)
+int launch_set_lcas(const Params &p, int n_sm, cudaStream_t stream);
+// db_sort on the device (kuq_dbbuild.cu)
+int dbsort_device(const uint8_t *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, uint8_t *kdb_out,
+                  uint8_t *idx_out, char *err, size_t err_cap);
 
 // database staging helpers
 void launch_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t *keys, unsigned long long *counts,

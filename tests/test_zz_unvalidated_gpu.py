@@ -75,3 +75,57 @@ def test_exact_mode_matches_oracle_sets(oracle):
     members = util.clade_members(tax.rows, want["taxid"])
     for taxid, mem in members.items():
         assert clf.clade(mem) == run.clade(mem), taxid
+
+
+@pytest.mark.parametrize("nt,zero", [(5, True), (7, False), (11, True)])
+def test_gpu_db_sort_matches_oracle(oracle, nt, zero):
+    """kuq_db_sort (CUB radix sorts + our minimizer / gather kernels) == the oracle's db_sort, which is pinned
+    against the reference executable (tests/test_oracle_db_build.py)"""
+    from krakenuniq_b200 import binding, synth
+    rng = np.random.default_rng(nt)
+    keys = np.unique(rng.integers(0, 1 << 62, 50000, dtype=np.uint64))
+    rng.shuffle(keys)
+    rec = np.zeros(len(keys), synth._REC)
+    rec["key"], rec["taxon"] = keys, rng.integers(0, 1 << 20, len(keys))
+    jdb = np.concatenate([synth.kdb_header(31, len(keys)), rec.view(np.uint8)])
+    want_kdb, want_idx = oracle.db_sort(jdb, nt, zero)
+    kdb, idx = binding.db_sort(jdb, nt, zero)
+    assert np.array_equal(idx, want_idx)
+    assert np.array_equal(kdb, want_kdb[:kdb.size])
+
+
+def test_gpu_set_lcas_matches_oracle(oracle):
+    """kuq_set_lcas_batch over SKIP_LEN-style pieces == the oracle's set_lcas (pinned against the reference tool)"""
+    from krakenuniq_b200 import binding, synth
+    rng = np.random.default_rng(5)
+    tax = synth.make_taxonomy(8, 4, 2, first_id=100)
+    sp = synth.species_ids(tax)
+    genomes = synth.random_genomes(rng, 8, 2500, shared_frac=0.35)
+    ks = []
+    for g in genomes:
+        km, ok = synth.forward_kmers(g, 31)
+        ks.append(synth.canonical(km[ok], 31))
+    allk = np.unique(np.concatenate(ks))
+    drop = rng.random(len(allk)) < 0.05                      # some library k-mers are not in the database (-x)
+    kdb0, idx = synth.build_db_images(allk[~drop], np.zeros(int((~drop).sum()), np.uint32), 31, 6, 2)
+    seqs = [synth.decode(g).tobytes() for g in genomes]
+    seqs[2] = seqs[2][:900] + b"N" + seqs[2][901:]
+    ids, parents = tax.parent_map()
+    pm = oracle.parent_map(ids, parents)
+    odb = oracle.open_db(kdb0.copy(), idx)
+    missing = sum(oracle.set_lcas_sequence(odb, pm, s, t) for s, t in zip(seqs, sp))
+    # pieces of 400 bases overlapping by k-1, as process_single_file cuts them (set_lcas.cpp:363-364)
+    pieces, taxids = [], []
+    for s, t in zip(seqs, sp):
+        for i in range(0, len(s), 400):
+            pieces.append(s[i:i + 400 + 30])
+            taxids.append(t)
+    bases, offs = synth.pack_reads(pieces)
+    clf = binding.Classifier(max_reads=1 << 16, max_bases=16 << 20)
+    clf.stage_db(kdb0, idx)
+    clf.set_taxonomy(ids, parents)
+    got_missing = clf.set_lcas(bases, offs, taxids)
+    out = kdb0.copy()
+    clf.export_db_values(out)
+    assert np.array_equal(out, odb.kdb)
+    assert got_missing == missing
