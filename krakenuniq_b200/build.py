@@ -69,6 +69,26 @@ def build_classify(force: bool = False) -> str:
     return CLASSIFY
 
 
+def build_dbtools(force: bool = False):
+    """The drop-in `db_sort` and `set_lcas` executables (host C++ over libkuq.so)."""
+    src = os.path.join(CSRC, "dbbuild_main.cpp")
+    build(force=force)
+    outs = [(os.path.join(PKG, "bin", "db_sort"), []), (os.path.join(PKG, "bin", "set_lcas"), ["-DTOOL_SET_LCAS"])]
+    newest = max(os.path.getmtime(src), os.path.getmtime(LIB))
+    if not force and all(os.path.exists(o) and os.path.getmtime(o) >= newest for o, _ in outs):
+        return [o for o, _ in outs]
+    os.makedirs(os.path.join(PKG, "bin"), exist_ok=True)
+    for out, defs in outs:
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall"] + defs + [src, "-o", out, "-L" + os.path.dirname(LIB), "-lkuq",
+               "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed building " + os.path.basename(out))
+    return [o for o, _ in outs]
+
+
 if __name__ == "__main__":
+    build_dbtools(force="--force" in sys.argv)
     build_classify(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

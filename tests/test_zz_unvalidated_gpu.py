@@ -129,3 +129,56 @@ def test_gpu_set_lcas_matches_oracle(oracle):
     clf.export_db_values(out)
     assert np.array_equal(out, odb.kdb)
     assert got_missing == missing
+
+
+def test_cli_db_sort_and_set_lcas_rebuild_the_golden_database(tmp_path, oracle):
+    """The drop-in db_sort + set_lcas executables on a seeded library: same database.kdb / .idx bytes as the oracle's
+    (pinned) CPU statements of the two tools, same .counts file as count_taxons would write."""
+    from krakenuniq_b200 import synth
+    db_sort, set_lcas = build.build_dbtools()
+    rng = np.random.default_rng(21)
+    tax = synth.make_taxonomy(6, 3, 2, first_id=100)
+    sp = synth.species_ids(tax)
+    genomes = synth.random_genomes(rng, 6, 1500, shared_frac=0.3)
+    ks = []
+    for g in genomes:
+        km, ok = synth.forward_kmers(g, 31)
+        ks.append(synth.canonical(km[ok], 31))
+    allk = np.unique(np.concatenate(ks))
+    rng.shuffle(allk)
+    jdb = synth.unsorted_jdb_image(allk, 31)
+    jdb.tofile(tmp_path / "database.jdb")
+    names = [f"seq{i}" for i in range(6)] + ["unknown_tax", "novel.2"]
+    extra = rng.integers(0, 4, 700, dtype=np.uint8)
+    seqs = [synth.decode(g).tobytes() for g in genomes] + [synth.decode(genomes[0][:400]).tobytes(),
+                                                           synth.decode(genomes[1][:300]).tobytes() + b"N" + synth.decode(extra).tobytes()]
+    taxids = list(sp) + [4242, sp[3]]
+    with open(tmp_path / "lib.fa", "wb") as f:
+        for n, s in zip(names, seqs):
+            f.write(b">" + n.encode() + b" some description\n")
+            for i in range(0, len(s), 61):
+                f.write(s[i:i + 61] + b"\n")
+    with open(tmp_path / "seqid2taxid.map", "w") as f:
+        for n, t in zip(names, taxids):
+            f.write(f"{n[:-2] if n.endswith('.2') else n}\t{t}\n")
+    tax.write(str(tmp_path / "taxDB"))
+    r = subprocess.run([db_sort, "-z", "-n", "6", "-d", "database.jdb", "-o", "database0.kdb", "-i", "database.idx"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want_kdb0, want_idx = oracle.db_sort(jdb, 6, True)
+    assert np.array_equal(np.fromfile(tmp_path / "database.idx", np.uint8), want_idx)
+    assert np.array_equal(np.fromfile(tmp_path / "database0.kdb", np.uint8), want_kdb0)
+    r = subprocess.run([set_lcas, "-x", "-d", "database0.kdb", "-i", "database.idx", "-b", "taxDB", "-m", "seqid2taxid.map",
+                        "-F", "lib.fa", "-c", "database.kdb.counts"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ids, parents = tax.parent_map()
+    pm = oracle.parent_map(ids, parents)
+    odb = oracle.open_db(want_kdb0.copy(), want_idx)
+    known = set(int(t) for t in ids)
+    for s, t in zip(seqs, taxids):
+        if t in known:
+            oracle.set_lcas_sequence(odb, pm, s, t)
+    assert np.array_equal(np.fromfile(tmp_path / "database0.kdb", np.uint8), odb.kdb)
+    _, _, vals = synth.parse_kdb(odb.kdb)
+    t, c = np.unique(vals, return_counts=True)
+    assert open(tmp_path / "database.kdb.counts").read() == "".join(f"{a}\t{b}\n" for a, b in zip(t.tolist(), c.tolist()))
