@@ -9,6 +9,7 @@
 // minimizer of every stored key, bin histogram, record gather — are ours.  Records never move during the sorts:
 // only (key, index) and (bin, index) pairs do, and one gather at the end writes the 12-byte records.
 #include "kuq_kernels.cuh"
+#include "kuq_minimizer.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -19,29 +20,6 @@
 
 namespace kuq {
 namespace {
-
-__device__ __forceinline__ uint64_t revcomp_n(uint64_t x, uint32_t n) {       // krakendb.cpp:218-225
-  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
-  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
-  x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
-  x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
-  x = (x >> 32) | (x << 32);
-  return (~x) >> (64 - 2 * n);
-}
-
-// KrakenDB::bin_key(kmer, nt), krakendb.cpp:200-215, on the key AS STORED (db_sort does not canonicalise, :101)
-__device__ __forceinline__ uint32_t bin_key_of(uint64_t kmer, uint32_t k, uint32_t nt) {
-  const uint64_t mask = (1ull << (2 * nt)) - 1;
-  const uint64_t xor_mask = 0xe37e28c4271b5a2dull & mask;                     // INDEX2_XOR_MASK, :45
-  uint64_t best = ~0ull;
-  for (uint32_t i = 0; i + nt <= k; i++) {
-    const uint64_t m = kmer & mask, rc = revcomp_n(m, nt);
-    const uint64_t t = xor_mask ^ (m < rc ? m : rc);
-    best = t < best ? t : best;
-    kmer >>= 2;
-  }
-  return (uint32_t)best;
-}
 
 // one thread per record: key, its bin, its position; the bin histogram on the way (make_index :126-134)
 __global__ void k_dbs_keys(const uint8_t *pairs, uint64_t n, uint32_t key_len, uint32_t k, uint32_t nt,

@@ -1,6 +1,7 @@
 """CPU-side checks of the C-ABI library: it builds, loads, exports every symbol include/kuq.h declares, refuses to
 run without a GPU (no CPU fallback), and its host-only estimator equals the oracle's."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -42,3 +43,24 @@ def test_host_estimator_matches_oracle(lib, oracle):
         assert binding.ertl_dense(regs, n) == oracle.ertl_dense(regs, n)
     regs = np.full(4096, 53, np.uint8)
     assert binding.ertl_dense(regs, 1 << 60) == oracle.ertl_dense(regs, 1 << 60)
+
+
+def test_scalar_minimizer_matches_oracle(tmp_path, oracle):
+    """kuq_minimizer.cuh (the per-key bin_key the GPU db_sort uses) compiled for the host == the oracle's bin_key"""
+    import ctypes
+    import subprocess
+    src = tmp_path / "m.cpp"
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "krakenuniq_b200", "csrc", "kuq_minimizer.cuh")
+    src.write_text(f'#include "{hdr}"\nextern "C" void bins(const uint64_t *k, uint64_t n, uint32_t kk, uint32_t nt, '
+                   'uint32_t *out) { for (uint64_t i = 0; i < n; i++) out[i] = kuq::bin_key_of(k[i], kk, nt); }\n')
+    so = tmp_path / "m.so"
+    subprocess.run(["/usr/bin/g++", "-O2", "-shared", "-fPIC", "-x", "c++", str(src), "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(0)
+    for k, nt in [(31, 15), (31, 7), (31, 1), (25, 12), (16, 8)]:
+        keys = rng.integers(0, 1 << (2 * k), 4000, dtype=np.uint64)
+        keys[:4] = [0, (1 << (2 * k)) - 1, 0x5555555555555555 & ((1 << (2 * k)) - 1), 1]
+        out = np.zeros(len(keys), np.uint32)
+        lib.bins(keys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(keys)), k, nt, out.ctypes.data_as(ctypes.c_void_p))
+        want = np.array([oracle.bin_key(int(x), k, nt, 2) for x in keys.tolist()], np.uint64)
+        assert np.array_equal(out.astype(np.uint64), want), (k, nt)
