@@ -987,7 +987,10 @@ static vector<pair<uint64_t, uint64_t>> plan_ranges(const uint64_t *offsets, uin
   return ranges;
 }
 
-static void load_file_batches(const char *filename, vector<Batch> &out) {
+// unit_aligned: batches end where a work unit of process_file ends (classify.cpp:506-521) and a last unit of total
+// length 0 is dropped like there (:523-524) — what the per-work-unit sketch rule of the preloaded path needs.  The -x
+// path of the reference reads sequence by sequence without work units (:566-791): unit_aligned = false.
+static void load_file_batches(const char *filename, vector<Batch> &out, bool unit_aligned = false) {
   SeqReader reader;
   if (!reader.in.open(filename)) die(EX_NOINPUT, string("can't open ") + filename);
   bool fq = reader.fastq = reader.in.peek() == '@';
@@ -995,12 +998,30 @@ static void load_file_batches(const char *filename, vector<Batch> &out) {
   out.emplace_back();
   out.back().fastq = fq;
   Read r;
+  uint64_t unit_nt = 0;
+  size_t unit_first_read = 0;        // first read of the open work unit inside the current batch
   while (reader.valid) {
     Batch &b = out.back();
     if (!reader.next(r, b.bases)) break;
     b.reads.push_back(r);
     b.offs.push_back(b.bases.size());
-    if (b.bases.size() >= BATCH_NT || b.reads.size() >= (1u << 20) - 1) { out.emplace_back(); out.back().fastq = fq; }
+    bool cut;
+    if (!unit_aligned) {
+      cut = b.bases.size() >= BATCH_NT || b.reads.size() >= (1u << 20) - 1;
+    } else {
+      unit_nt += r.seq_len;
+      const bool close_unit = unit_nt >= Work_unit_size;
+      if (close_unit) { unit_nt = 0; unit_first_read = b.reads.size(); }
+      cut = close_unit ? (b.bases.size() >= BATCH_NT || b.reads.size() >= (1u << 20) - 4096)
+                       : (b.reads.size() >= (1u << 20) - 1 || b.bases.size() >= (150ull << 20));   // one huge unit: counted as two
+    }
+    if (cut) { out.emplace_back(); out.back().fastq = fq; unit_first_read = 0; }
+  }
+  if (unit_aligned && unit_nt == 0 && unit_first_read < out.back().reads.size()) {
+    Batch &b = out.back();
+    b.bases.resize(b.offs[unit_first_read]);
+    b.reads.resize(unit_first_read);
+    b.offs.resize(unit_first_read + 1);
   }
   if (out.back().reads.empty()) out.pop_back();
   reader.in.close();
@@ -1091,7 +1112,7 @@ static void run_multi_db(kuq_ctx *ctx, const vector<Mapped> &kdbs, const vector<
   vector<Batch> batches;
   for (int i = optind; i < argc; i++) {
     size_t first = batches.size();
-    load_file_batches(argv[i], batches);
+    load_file_batches(argv[i], batches, true);
     for (size_t j = first; j < batches.size(); j++) batches[j].file = i;
   }
   for (auto &b : batches) b.codes.assign(b.bases.size() + 1, 0);

@@ -64,3 +64,31 @@ def test_scalar_minimizer_matches_oracle(tmp_path, oracle):
         lib.bins(keys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(keys)), k, nt, out.ctypes.data_as(ctypes.c_void_p))
         want = np.array([oracle.bin_key(int(x), k, nt, 2) for x in keys.tolist()], np.uint64)
         assert np.array_equal(out.astype(np.uint64), want), (k, nt)
+
+
+def test_executables_fail_loudly_without_a_gpu(tmp_path):
+    """No CPU path anywhere: on a box without an sm_100 device every drop-in executable stops with EX_UNAVAILABLE"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from krakenuniq_b200 import synth
+    from tests import util
+    build.build_classify()
+    db_sort, set_lcas = build.build_dbtools()
+    G = util.GOLDEN
+    db = ["-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx")]
+    exe = os.path.dirname(build.CLASSIFY)
+    keys = np.unique(np.random.default_rng(0).integers(0, 1 << 62, 500, dtype=np.uint64))
+    synth.unsorted_jdb_image(keys, 31).tofile(tmp_path / "t.jdb")
+    (tmp_path / "map").write_text("r0\t100\n")
+    cmds = [[os.path.join(exe, "classify")] + db + ["-a", os.path.join(G, "taxDB"), "-M", os.path.join(G, "reads.fa")],
+            [os.path.join(exe, "classifyExact")] + db + ["-a", os.path.join(G, "taxDB"), "-M", os.path.join(G, "reads.fa")],
+            [db_sort, "-n", "5", "-d", str(tmp_path / "t.jdb"), "-o", str(tmp_path / "t.kdb"), "-i", str(tmp_path / "t.idx")],
+            [set_lcas] + db + ["-b", os.path.join(G, "taxDB"), "-m", str(tmp_path / "map"), "-F", os.path.join(G, "reads.fa"), "-p"]]
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 69, (cmd[0], r.returncode, r.stderr[-300:])
+        assert "no CPU path" in r.stderr
+        assert r.stdout == ""
+    assert not os.path.exists(tmp_path / "t.kdb")
