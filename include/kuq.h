@@ -285,10 +285,16 @@ int kuq_db_sort(int device, const void *jdb_image, uint64_t jdb_bytes, uint32_t 
  * value = lca(taxid of the piece, value).  A piece is a stretch of one library sequence; consecutive pieces of a
  * sequence overlap by k-1 bases (the reference's SKIP_LEN pieces, :363-364).  The context needs the database
  * (kuq_stage_db, whole) and the taxonomy (kuq_set_taxonomy); every taxid must be in the taxonomy — the reference
- * skips other sequences (:336-341) and so must the caller.  *n_missing += k-mers the database lacks (set_lcas
- * without -x stops there, :441-443).  After the first call the context cannot classify any more. */
+ * skips other sequences (:336-341) and so must the caller.  *n_missing = k-mers of this batch the database lacks (set_lcas
+ * without -x stops there, :441-443).  After the first call the context cannot classify any more.
+ * flags: KUQ_LCA_FORCE_CONTAMINANT = set_lcas -T (what build_db.sh always passes: a value of 32630 'synthetic
+ * construct' / 81077 'artificial sequences' sticks and a piece with such a taxid overwrites instead of taking the LCA,
+ * :462-474; between those two taxids the first to arrive wins, so one batch may hold pieces of only one of them),
+ * KUQ_LCA_RESET = -R (the value becomes 0, :458-459). */
+#define KUQ_LCA_FORCE_CONTAMINANT 1u
+#define KUQ_LCA_RESET 2u
 int kuq_set_lcas_batch(kuq_ctx *ctx, const char *bases, const uint64_t *piece_offsets, uint32_t n_pieces,
-                       const uint32_t *taxid, uint64_t *n_missing);
+                       const uint32_t *taxid, uint32_t flags, uint64_t *n_missing);
 /* Copy the record values of the staged database (as taxids) into the value fields of a host database.kdb image
  * with the same records — what set_lcas leaves in the memory-mapped file. */
 int kuq_export_db_values(kuq_ctx *ctx, void *kdb_image, uint64_t kdb_bytes);

@@ -89,7 +89,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_set_db_taxid_universe": (C.c_int, [vp, u32p, C.c_uint32]),
         "kuq_mark_zero_hits": (C.c_int, [vp, C.c_int]),
         "kuq_db_sort": (C.c_int, [C.c_int, vp, C.c_uint64, C.c_uint32, C.c_int, vp, vp, C.c_char_p, C.c_uint64]),
-        "kuq_set_lcas_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, u64p]),
+        "kuq_set_lcas_batch": (C.c_int, [vp, vp, u64p, C.c_uint32, u32p, C.c_uint32, u64p]),
         "kuq_export_db_values": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_set_quick_mode": (C.c_int, [vp, C.c_uint32, C.c_int]),
         "kuq_set_taxonomy": (C.c_int, [vp, u32p, u32p, C.c_uint32]),
@@ -209,14 +209,15 @@ class Classifier:
         """classify -q -m min_hits (0 = off); stop_at_last_hit=False gives the -x path's rule (kuq_set_quick_mode)"""
         self._ck(self.L.kuq_set_quick_mode(self.h, int(min_hits), 1 if stop_at_last_hit else 0))
 
-    def set_lcas(self, bases: np.ndarray, piece_offsets: np.ndarray, taxids) -> int:
-        """kuq_set_lcas_batch: fold the pieces' taxids into the staged database's values; returns #k-mers not found"""
+    def set_lcas(self, bases: np.ndarray, piece_offsets: np.ndarray, taxids, flags=0) -> int:
+        """kuq_set_lcas_batch: fold the pieces' taxids into the staged database's values; returns #k-mers not found.
+        flags: 1 = set_lcas -T, 2 = -R"""
         bases = np.ascontiguousarray(bases, np.uint8)
         offs = np.ascontiguousarray(piece_offsets, np.uint64)
         t = np.ascontiguousarray(taxids, np.uint32)
         missing = C.c_uint64(0)
         buf = bases if bases.size else np.zeros(1, np.uint8)
-        self._ck(self.L.kuq_set_lcas_batch(self.h, buf.ctypes.data, _p(offs, u64p), len(offs) - 1, _p(t, u32p), C.byref(missing)))
+        self._ck(self.L.kuq_set_lcas_batch(self.h, buf.ctypes.data, _p(offs, u64p), len(offs) - 1, _p(t, u32p), flags, C.byref(missing)))
         return missing.value
 
     def export_db_values(self, kdb: np.ndarray):

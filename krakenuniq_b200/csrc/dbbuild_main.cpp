@@ -5,8 +5,7 @@
 // hardware.  The oracle's CPU statements of both tools are pinned against the reference executables
 // (tests/test_oracle_db_build.py).
 //
-// set_lcas options NOT supported (exit with a message): -I (UIDs), -a / -A (new taxonomy ids), -T (forced
-// contaminant taxids), -R (reset).
+// set_lcas options NOT supported (exit with a message): -I (UIDs), -a / -A (new taxonomy ids).
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -123,6 +122,7 @@ static const char *TOOL = "set_lcas";
 static const size_t SKIP_LEN = 50000;                    // set_lcas.cpp:31
 static bool Allow_extra_kmers = false, verbose = false, Operate_in_RAM = false, Pretend = false;
 static uint32_t Minimum_sequence_size = 0;
+static uint32_t Lca_flags = 0;                           // -T → KUQ_LCA_FORCE_CONTAMINANT, -R → KUQ_LCA_RESET
 static string DB_filename, Index_filename, TaxDB_filename, File_to_taxon_map_filename, ID_to_taxon_map_filename,
     Multi_fasta_filename, Output_DB_filename, Kmer_count_filename;
 
@@ -139,13 +139,15 @@ static void usage(int exit_code = EX_USAGE) {
        << "  -f filename      File to taxon map" << endl
        << "  -F filename      Multi-FASTA file with sequence data" << endl
        << "  -m filename      Sequence ID to taxon map" << endl
+       << "  -T               When a k-mer appears in a 'synthetic construct' sequence, force the taxID to be the 'synthetic construct' taxID, instead of the LCA." << endl
+       << "  -R               Reset the taxIDs of the k-mers of the sequences to 0" << endl
        << "  -E #             Exclude sequences that are shorter than the threshold." << endl
        << "  -c filename      Write k-mer counts per taxon to filename" << endl
        << "  -p               Pretend - do not write database back to disk" << endl
        << "  -v               Verbose output" << endl
        << "  -h               Print this message" << endl << endl
        << "-F and -m must be specified together.  If -f is given, -F/-m are ignored." << endl
-       << "(GPU build: -I, -a, -A, -T and -R are not supported)" << endl;
+       << "(GPU build: -I, -a and -A are not supported)" << endl;
   exit(exit_code);
 }
 
@@ -186,6 +188,7 @@ struct Batch {
   string bases;
   vector<uint64_t> offs{0};
   vector<uint32_t> taxids;
+  uint32_t contaminant = 0;        // the one contaminant taxid (32630 / 81077) this batch holds, 0 = none yet
 };
 static kuq_ctx *Ctx = NULL;
 static uint32_t K = 0;
@@ -195,15 +198,20 @@ static const uint64_t BATCH_NT = 64ull << 20;
 static void flush(Batch &b) {
   if (b.taxids.empty()) return;
   uint64_t missing = 0;
-  if (kuq_set_lcas_batch(Ctx, b.bases.data(), b.offs.data(), (uint32_t)b.taxids.size(), b.taxids.data(), &missing))
+  if (kuq_set_lcas_batch(Ctx, b.bases.data(), b.offs.data(), (uint32_t)b.taxids.size(), b.taxids.data(), Lca_flags, &missing))
     die(EX_SOFTWARE, kuq_last_error(Ctx), TOOL);
   if (missing && !Allow_extra_kmers) die(EX_DATAERR, "kmer found in sequence that is not in database", TOOL);   // :441-443
   Missing_total += missing;
-  b.bases.clear(); b.offs.assign(1, 0); b.taxids.clear();
+  b.bases.clear(); b.offs.assign(1, 0); b.taxids.clear(); b.contaminant = 0;
 }
 
 // the reference's pieces: [i, i + SKIP_LEN + k - 1) for i = 0, SKIP_LEN, ... (set_lcas.cpp:363-364, 399-400)
 static void add_sequence(Batch &b, const string &seq, uint32_t taxid) {
+  if (taxid == 32630u || taxid == 81077u) {              // TID_CONTAMINANT1/2, set_lcas.cpp:88-89
+    // under -T the first contaminant taxid to reach a k-mer stays: keep file order between the two kinds
+    if (b.contaminant && b.contaminant != taxid) flush(b);
+    b.contaminant = taxid;
+  }
   for (size_t i = 0; i < seq.size(); i += SKIP_LEN) {
     const size_t len = min(seq.size() - i, SKIP_LEN + K - 1);
     if (b.bases.size() + len > BATCH_NT || b.taxids.size() >= (1u << 19)) flush(b);
@@ -235,7 +243,9 @@ int main(int argc, char **argv) {
       case 'E': Minimum_sequence_size = (uint32_t)atoi(optarg); break;
       case 'p': Pretend = true; break;
       case 'n': case 'S': break;
-      case 'I': case 'a': case 'A': case 'T': case 'R':
+      case 'T': Lca_flags |= KUQ_LCA_FORCE_CONTAMINANT; break;
+      case 'R': Lca_flags |= KUQ_LCA_RESET; break;
+      case 'I': case 'a': case 'A':
         die(EX_USAGE, string("option -") + (char)opt + " is not supported by the GPU set_lcas", TOOL);
       default: usage();
     }

@@ -1520,7 +1520,7 @@ int kuq_db_sort(int device, const void *jdb_image, uint64_t jdb_bytes, uint32_t 
 }
 
 int kuq_set_lcas_batch(kuq_ctx *ctx, const char *bases, const uint64_t *piece_offsets, uint32_t n_pieces,
-                       const uint32_t *taxid, uint64_t *n_missing) {
+                       const uint32_t *taxid, uint32_t flags, uint64_t *n_missing) {
   int rc = check_slot(ctx, 0);
   if (rc) return rc;
   if (n_pieces && (!bases || !piece_offsets || !taxid)) return fail(ctx, KUQ_E_INVALID_ARG, "NULL batch buffers");
@@ -1538,6 +1538,12 @@ int kuq_set_lcas_batch(kuq_ctx *ctx, const char *bases, const uint64_t *piece_of
       return fail(ctx, KUQ_E_INVALID_ARG, "piece %u: taxid %u is not in the taxonomy", i, taxid[i]);
     s.h_unit[i] = it->second;
   }
+  if (flags & KUQ_LCA_FORCE_CONTAMINANT) {
+    // first-come-first-kept between the two contaminant taxids is the one order dependence of -T: one kind per batch
+    bool c1 = false, c2 = false;
+    for (uint32_t i = 0; i < n_pieces; i++) { c1 |= taxid[i] == 32630u; c2 |= taxid[i] == 81077u; }
+    if (c1 && c2) return fail(ctx, KUQ_E_INVALID_ARG, "with KUQ_LCA_FORCE_CONTAMINANT a batch may hold pieces of taxid 32630 or of 81077, not both");
+  }
   uint64_t total = 0;
   rc = upload_reads(ctx, s, bases, piece_offsets, n_pieces, &total);
   if (rc) return rc;
@@ -1545,6 +1551,12 @@ int kuq_set_lcas_batch(kuq_ctx *ctx, const char *bases, const uint64_t *piece_of
   if (n_pieces) CU(cudaMemcpyAsync(s.d_unit, s.h_unit, n_pieces * 4ull, cudaMemcpyHostToDevice, s.stream));
   Params p;
   fill_params(ctx, s, p, s.d_bases, s.d_offsets, s.d_unit, n_pieces, 0);
+  p.lca_flags = flags & 3u;
+  {
+    auto c1 = ctx->dense_of_raw.find(32630u), c2 = ctx->dense_of_raw.find(81077u);   // set_lcas.cpp:88-89
+    p.lca_keep[0] = c1 == ctx->dense_of_raw.end() ? 0 : c1->second;
+    p.lca_keep[1] = c2 == ctx->dense_of_raw.end() ? 0 : c2->second;
+  }
   CU(cudaMemsetAsync(s.d_scalars, 0, 8 * 8, s.stream));
   ctx->lca_mode = true;
   ctx->snap_valid = false;

@@ -1147,6 +1147,8 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
 // taxid of piece r.  One warp per piece, lane = window: find the record of the canonical k-mer and fold the
 // sequence's taxid into its value with lca() through a CAS loop.  lca over taxa of one tree is associative,
 // commutative and idempotent (default ancestor 1), so the order in which pieces and sequences land does not matter.
+// Under -T a contaminant taxid beats everything and sticks; with at most ONE of the two contaminant taxids per batch
+// (the host side sees to that) the outcome is again independent of the order inside the batch.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_set_lcas(const __grid_constant__ Params p) {
   const DbView &db = p.db;
@@ -1176,7 +1178,12 @@ __global__ void __launch_bounds__(256) k_set_lcas(const __grid_constant__ Params
       uint32_t *val = reinterpret_cast<uint32_t *>(pairs + lo * 12) + 2;
       uint32_t old = *reinterpret_cast<volatile uint32_t *>(val);
       for (;;) {
-        const uint32_t nw = lca_dense(p.tax, t, old);                     // :461
+        uint32_t nw;
+        if (p.lca_flags & 2u) nw = 0;                                     // -R, :458-459
+        else if (!(p.lca_flags & 1u)) nw = lca_dense(p.tax, t, old);      // :461
+        else if (old != 0 && (old == p.lca_keep[0] || old == p.lca_keep[1])) nw = old;   // -T: contaminants stick, :465-466
+        else if (t == p.lca_keep[0] || t == p.lca_keep[1]) nw = t;        // :467-470
+        else nw = lca_dense(p.tax, t, old);                               // :472
         if (nw == old) break;
         const uint32_t prev = atomicCAS(val, old, nw);
         if (prev == old) break;

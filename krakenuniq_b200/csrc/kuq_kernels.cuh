@@ -149,6 +149,9 @@ struct Params {
   uint32_t quick_min;
   uint32_t quick_stop;
   ExactSet exact;               // hll_mode 3 (KUQ_HLL_EXACT)
+  // set_lcas: 1 = -T (values lca_keep[] stick, pieces with such a taxid overwrite), 2 = -R (values become 0)
+  uint32_t lca_flags;
+  uint32_t lca_keep[2];         // dense ids of taxids 32630 / 81077 (0 = not in the taxonomy)
 };
 
 // returns #kernels launched; stage_events[0] / [1] (optional) are recorded after k_scan / k_lookup

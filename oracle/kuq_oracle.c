@@ -862,6 +862,13 @@ int kuqo_db_sort(const void *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zer
  * `db` must have been opened on a writable image.  Returns the number of k-mers that were not in the database
  * (the reference stops at the first one unless -x, :441-443). */
 uint64_t kuqo_set_lcas_sequence(kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len, uint32_t taxid) {
+  return kuqo_set_lcas_sequence_flags(db, pm, seq, len, taxid, 0);
+}
+/* flags: 1 = -T (Force_contaminant_taxid, :462-474: values 32630 / 81077 stick, a sequence with one of these taxids
+ * overwrites instead of taking the LCA), 2 = -R (Reset_taxid, :458-459: the value becomes 0) */
+uint64_t kuqo_set_lcas_sequence_flags(kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len, uint32_t taxid,
+                                      uint32_t flags) {
+  const uint32_t C1 = 32630, C2 = 81077;                                        /* set_lcas.cpp:88-89 */
   uint64_t missing = 0;
   if (len < db->k) return 0;
   size_t cap = len - db->k + 2;
@@ -882,7 +889,11 @@ uint64_t kuqo_set_lcas_sequence(kuqo_db *db, const kuqo_parent_map *pm, const ch
     uint8_t *val = (uint8_t *)(uintptr_t)(db->pairs + db->pair_sz * (uint64_t)at + db->key_len);
     uint32_t v;
     memcpy(&v, val, 4);
-    v = kuqo_lca(pm, taxid, v);                                                 /* :461 */
+    if (flags & 2u) v = 0;                                                      /* :458-459 */
+    else if (!(flags & 1u)) v = kuqo_lca(pm, taxid, v);                         /* :461 */
+    else if (v == C1 || v == C2) { /* keep, :465-466 */ }
+    else if (taxid == C1 || taxid == C2) v = taxid;                             /* :467-470 */
+    else v = kuqo_lca(pm, taxid, v);                                            /* :472 */
     memcpy(val, &v, 4);
   }
   free(kmers); free(amb);

@@ -114,6 +114,10 @@ int kuqo_db_sort(const void *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zer
 /* set_lcas for one library sequence (set_lcas.cpp:429-476): value = lca(taxid, value) for every k-mer of the
  * sequence that the database holds; `db` must be open on a WRITABLE image.  Returns #k-mers not in the database. */
 uint64_t kuqo_set_lcas_sequence(kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len, uint32_t taxid);
+/* flags: 1 = set_lcas -T (values 32630 'synthetic construct' / 81077 'artificial sequences' stick; a sequence with
+ * such a taxid overwrites instead of taking the LCA, :462-474), 2 = -R (the value is reset to 0, :458-459) */
+uint64_t kuqo_set_lcas_sequence_flags(kuqo_db *db, const kuqo_parent_map *pm, const char *seq, size_t len, uint32_t taxid,
+                                      uint32_t flags);
 
 #ifdef __cplusplus
 }

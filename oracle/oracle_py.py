@@ -180,11 +180,13 @@ class Oracle:
             raise ValueError(f"kuqo_db_sort failed: {rc}")
         return kdb, idx
 
-    def set_lcas_sequence(self, db: "OracleDB", pm, seq: bytes, taxid: int) -> int:
-        """set_lcas for one library sequence; updates db.kdb (the image the OracleDB was opened on) in place"""
-        self.L.kuqo_set_lcas_sequence.restype = C.c_uint64
-        self.L.kuqo_set_lcas_sequence.argtypes = [C.POINTER(_DB), C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32]
-        return self.L.kuqo_set_lcas_sequence(C.byref(db.s), pm.h, seq, len(seq), taxid)
+    def set_lcas_sequence(self, db: "OracleDB", pm, seq: bytes, taxid: int, flags: int = 0) -> int:
+        """set_lcas for one library sequence; updates db.kdb (the image the OracleDB was opened on) in place.
+        flags: 1 = -T, 2 = -R"""
+        f = self.L.kuqo_set_lcas_sequence_flags
+        f.restype = C.c_uint64
+        f.argtypes = [C.POINTER(_DB), C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32]
+        return f(C.byref(db.s), pm.h, seq, len(seq), taxid, flags)
 
     def run(self, db, pm, work_unit_size=500000, mode=0):
         return OracleRun(self, db, pm, work_unit_size, mode)

@@ -100,3 +100,69 @@ def test_set_lcas_matches_reference(oracle, tmp_path):
     got = dict(zip(keys.tolist(), vals.tolist()))
     for kk, t in zip(km.tolist(), tx.tolist()):
         assert got[kk] == t
+
+
+def test_set_lcas_contaminant_and_reset_flags_match_reference(oracle, tmp_path):
+    """set_lcas -T (what build_db.sh always passes: 'synthetic construct' 32630 / 'artificial sequences' 81077 stick,
+    set_lcas.cpp:462-474) and -TR (values of the library's k-mers reset to 0, :458-459)"""
+    _need_ref()
+    rng, tax, sp, genomes, allk = _library(33)
+    tax = synth.Taxonomy(tax.rows + [(32630, 1, "synthetic construct", "species"), (81077, 1, "artificial sequences", "species")])
+    g = [synth.decode(x).tobytes() for x in genomes]
+    novel1 = synth.decode(rng.integers(0, 4, 300, dtype=np.uint8)).tobytes()
+    vec1 = g[2][200:500] + novel1 + g[0][900:1100]           # contaminant 1: parts of genomes 2 and 0
+    vec2 = g[2][350:650] + g[4][100:400]                     # contaminant 2: overlaps vec1 on genome 2, plus genome 4
+    names = ["seq0", "seq1", "seq2", "vec1", "seq3", "vec2", "seq4", "seq5"]
+    seqs = [g[0], g[1], g[2], vec1, g[3], vec2, g[4], g[5]]
+    taxids = [sp[0], sp[1], sp[2], 32630, sp[3], 81077, sp[4], sp[5]]
+    ks = [allk]
+    for s in (vec1,):
+        km, ok = synth.forward_kmers(synth.encode(s), K)
+        ks.append(synth.canonical(km[ok], K))
+    allk2 = np.unique(np.concatenate(ks))
+    rng.shuffle(allk2)
+    with open(tmp_path / "lib.fa", "wb") as f:
+        for n, s in zip(names, seqs):
+            f.write(b">" + n.encode() + b"\n" + s + b"\n")
+    with open(tmp_path / "seqid2taxid.map", "w") as f:
+        for n, t in zip(names, taxids):
+            f.write(f"{n}\t{t}\n")
+    tax.write(str(tmp_path / "taxDB"))
+    synth.unsorted_jdb_image(allk2, K).tofile(tmp_path / "database.jdb")
+    r = oracle_py.run_ref_tool("db_sort", ["-z", "-n", 6, "-d", "database.jdb", "-o", "database0.kdb", "-i", "database.idx"], cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    kdb0 = np.fromfile(tmp_path / "database0.kdb", np.uint8)
+    idx = np.fromfile(tmp_path / "database.idx", np.uint8)
+    ids, parents = tax.parent_map()
+    pm = oracle.parent_map(ids, parents)
+
+    def ref(flags_arg, fa="lib.fa"):
+        r = oracle_py.run_ref_tool("set_lcas", ["-x", "-d", "database0.kdb", "-i", "database.idx", "-b", "taxDB", "-m",
+                                                "seqid2taxid.map", "-F", fa, flags_arg], cwd=tmp_path)
+        assert r.returncode == 0, r.stderr
+        return np.fromfile(tmp_path / "database0.kdb", np.uint8)
+
+    want = ref("-T")
+    db = oracle.open_db(kdb0.copy(), idx)
+    for s, t in zip(seqs, taxids):
+        oracle.set_lcas_sequence(db, pm, s, t, flags=1)
+    assert np.array_equal(db.kdb, want)
+    _, keys, vals = synth.parse_kdb(db.kdb)
+    got = dict(zip(keys.tolist(), vals.tolist()))
+    km, ok = synth.forward_kmers(synth.encode(g[2][350:500]), K)      # shared by both contaminants: the first one wins
+    assert {got[int(c)] for c in synth.canonical(km[ok], K).tolist()} == {32630}
+    km, ok = synth.forward_kmers(synth.encode(g[4][100:400]), K)      # contaminant 2 before its genome in the file
+    assert {got[int(c)] for c in synth.canonical(km[ok], K).tolist()} == {81077}
+
+    # the hierarchical re-labelling of build_db.sh:286-296: -TR on a sub-library, then -T on it
+    with open(tmp_path / "sub.fa", "wb") as f:
+        for n, s in list(zip(names, seqs))[2:5]:
+            f.write(b">" + n.encode() + b"\n" + s + b"\n")
+    want = ref("-TR", "sub.fa")
+    for s, t in list(zip(seqs, taxids))[2:5]:
+        oracle.set_lcas_sequence(db, pm, s, t, flags=3)
+    assert np.array_equal(db.kdb, want)
+    want = ref("-T", "sub.fa")
+    for s, t in list(zip(seqs, taxids))[2:5]:
+        oracle.set_lcas_sequence(db, pm, s, t, flags=1)
+    assert np.array_equal(db.kdb, want)

@@ -179,6 +179,17 @@ def test_cli_db_sort_and_set_lcas_rebuild_the_golden_database(tmp_path, oracle):
         if t in known:
             oracle.set_lcas_sequence(odb, pm, s, t)
     assert np.array_equal(np.fromfile(tmp_path / "database0.kdb", np.uint8), odb.kdb)
+    # -TR then -T on a sub-library, as build_db.sh:286-296 re-labels hierarchically
+    with open(tmp_path / "sub.fa", "wb") as f:
+        for n, s in list(zip(names, seqs))[1:3]:
+            f.write(b">" + n.encode() + b"\n" + s + b"\n")
+    for fl, code in (("-TR", 3), ("-T", 1)):
+        r = subprocess.run([set_lcas, "-x", "-d", "database0.kdb", "-i", "database.idx", "-b", "taxDB", "-m", "seqid2taxid.map",
+                            "-F", "sub.fa", fl, "-c", "database.kdb.counts"], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for s, t in list(zip(seqs, taxids))[1:3]:
+            oracle.set_lcas_sequence(odb, pm, s, t, flags=code)
+        assert np.array_equal(np.fromfile(tmp_path / "database0.kdb", np.uint8), odb.kdb), fl
     _, _, vals = synth.parse_kdb(odb.kdb)
     t, c = np.unique(vals, return_counts=True)
     assert open(tmp_path / "database.kdb.counts").read() == "".join(f"{a}\t{b}\n" for a, b in zip(t.tolist(), c.tolist()))
