@@ -1063,7 +1063,13 @@ static void run_chunked(kuq_ctx *ctx, const Mapped &kdb, const Mapped &idx, uint
       tmp.assign(b.bases.size() + 1, 0);
       if (kuq_lookup_batch(ctx, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), tmp.data(), NULL))
         die(EX_SOFTWARE, kuq_last_error(ctx));
-      for (size_t j = 0; j < b.bases.size(); j++) if (tmp[j] > b.codes[j]) b.codes[j] = tmp[j];   // merge, :390-485
+      {
+        uint32_t *dst = b.codes.data();
+        const uint32_t *src = tmp.data();
+        const long long n = (long long)b.bases.size();
+#pragma omp parallel for schedule(static) num_threads(Num_threads)
+        for (long long j = 0; j < n; j++) if (src[j] > dst[j]) dst[j] = src[j];                     // merge, :390-485
+      }
       seqs += b.reads.size();
       fprintf(stderr, "\r Processed %llu sequences (database chunk %zu of %zu)", (unsigned long long)seqs, c + 1, ranges.size());
     }
@@ -1124,7 +1130,13 @@ static void run_multi_db(kuq_ctx *ctx, const vector<Mapped> &kdbs, const vector<
       tmp.assign(b.bases.size() + 1, 0);
       if (kuq_lookup_batch(ctx, b.bases.data(), b.offs.data(), (uint32_t)b.reads.size(), tmp.data(), NULL))
         die(EX_SOFTWARE, kuq_last_error(ctx));
-      for (size_t j = 0; j < b.bases.size(); j++) if (b.codes[j] == 0) b.codes[j] = tmp[j];   // first hit wins
+      {
+        uint32_t *dst = b.codes.data();
+        const uint32_t *src = tmp.data();
+        const long long n = (long long)b.bases.size();
+#pragma omp parallel for schedule(static) num_threads(Num_threads)
+        for (long long j = 0; j < n; j++) if (dst[j] == 0) dst[j] = src[j];                         // first hit wins
+      }
       seqs += b.reads.size();
       fprintf(stderr, "\r Processed %llu sequences (database %zu of %zu)", (unsigned long long)seqs, d + 1, n_db);
     }
