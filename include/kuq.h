@@ -60,8 +60,7 @@ extern "C" {
 #define KUQ_HLL_DENSE_ONLY 2 /* p=12 registers only, no sparse-tier emulation (fastest; estimates = dense Ertl) */
 #define KUQ_HLL_EXACT 3     /* classifyExact (EXACT_COUNTING, classify.cpp:46-49): sets of k-mers instead of sketches;
                                `unique` of kuq_read_counts / kuq_clade_counts is the exact set / union size.  The
-                               (taxon, k-mer) table takes kuq_config.sparse_set_slots entries of 16 bytes.
-                               ROUND 1: written after the GPU budget was spent — compiles, not yet run on hardware */
+                               (taxon, k-mer) table takes kuq_config.sparse_set_slots entries of 16 bytes. */
 
 /* flags of the classify calls */
 #define KUQ_F_WANT_CODES 1u     /* also return the per-window codes (4 B per base position) */
@@ -275,7 +274,16 @@ int kuq_reset_counts(kuq_ctx *ctx);
  * 730-752) — exported so bindings and tests can call the exact code the report path uses. */
 uint64_t kuq_ertl_dense(const uint8_t *regs4096, uint64_t n_observed);
 
-/* ---- database build.  ROUND 1: compiled for sm_100a, not yet run on hardware ------------- */
+/* ---- measurement aid: the random-access roofline of SURVEY.md §8(d) ------------------------------------------- */
+/* Random 32-byte-sector gather ceiling of the device's HBM: a kernel with k_lookup's launch shape (256 threads,
+ * 8 CTAs per SM) issues independent loads at hashed sector addresses of a freshly allocated buffer of buffer_bytes
+ * (use several GB: far beyond L2) until n_sectors_to_read sectors were touched; bytes_per_access = 32 (whole
+ * sector) or 8 (one word of it — the sector is still what HBM moves).  Best of three timed launches after one
+ * warm-up, CUDA events.  Returns sectors/s (in 1e9) and the same as GB/s of 32-byte sectors.  Needs no context. */
+int kuq_random_gather_peak(int device, uint64_t buffer_bytes, uint64_t n_sectors_to_read, uint32_t bytes_per_access,
+                           double *gsectors_per_s, double *gbytes_per_s, double *kernel_ms);
+
+/* ---- database build ---------------------------------------------------------------------- */
 /* db_sort [-z] -n nt (db_sort.cpp:41-116 + KrakenDB::make_index, krakendb.cpp:118-148): unsorted Jellyfish-style
  * image → database.kdb image (kdb_out: header + key_ct * (key_len + 4) bytes) and KRAKIX2 index image (idx_out:
  * 8 + 8 * (4^nt + 1) bytes).  Needs no context.  err (optional) receives a message on failure. */

@@ -129,6 +129,8 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_sparse_import": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_reset_counts": (C.c_int, [vp]),
         "kuq_ertl_dense": (C.c_uint64, [u8p, C.c_uint64]),
+        "kuq_random_gather_peak": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)            # AttributeError here = the library does not export what kuq.h declares
@@ -430,6 +432,16 @@ def ertl_dense(regs: np.ndarray, n_observed: int) -> int:
     L = load_library()
     regs = np.ascontiguousarray(regs, np.uint8)
     return int(L.kuq_ertl_dense(_p(regs, u8p), n_observed))
+
+
+def random_gather_peak(device=0, buffer_bytes=16 << 30, n_sectors=1 << 30, bytes_per_access=32):
+    """kuq_random_gather_peak: (G sectors/s, GB/s of 32-byte sectors, kernel ms) — SURVEY.md §8(d)'s second roofline"""
+    L = load_library()
+    gs, gb, ms = C.c_double(), C.c_double(), C.c_double()
+    rc = L.kuq_random_gather_peak(device, buffer_bytes, n_sectors, bytes_per_access, C.byref(gs), C.byref(gb), C.byref(ms))
+    if rc != 0:
+        raise KuqError(rc, L.kuq_strerror(rc).decode())
+    return gs.value, gb.value, ms.value
 
 
 def decode_runs(res, i):

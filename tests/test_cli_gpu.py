@@ -111,8 +111,9 @@ def test_cli_flags(tmp_path):
     assert gzip.open(gz, "rt").read() == open(os.path.join(G, "fastq.kraken")).read()
     # -M without input files is the page-cache warm-up idiom: a no-op that succeeds
     assert subprocess.run(base + ["-M"], capture_output=True, env=env).returncode == 0
-    # unsupported modes fail loudly
-    assert subprocess.run(base + ["-q", reads], capture_output=True, env=env).returncode != 0
+    # unsupported modes fail loudly: -I (UID mapping) is outside the hot path
+    r = subprocess.run(base + ["-M", "-I", str(tmp_path / "uid.map"), reads], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "not supported" in r.stderr
 
 
 @pytest.mark.parametrize("size", ["40K", "16K", "100K"])

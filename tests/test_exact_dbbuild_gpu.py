@@ -1,7 +1,6 @@
-"""GPU tests of code written in round 1 AFTER the round's GPU budget was spent: it compiles for sm_100a, its oracle
-side is pinned against the reference on CPU, but it has not run on a B200 yet.  Skipped unless KUQ_RUN_UNVALIDATED=1
-so that the suite states the truth: these paths are unvalidated.  First job of round 2: run them, fix, move them into
-test_cli_gpu.py / test_gpu_parity.py."""
+"""GPU tests of SURVEY.md §8 rows f3 (classifyExact / KUQ_HLL_EXACT) and f4 (GPU db_sort / set_lcas): the drop-in
+executables and the C-ABI entry points against the oracle, whose CPU statements of these tools are pinned against the
+reference executables (tests/test_oracle_db_build.py, tests/test_golden.py::test_oracle_exact_counting)."""
 import os
 import subprocess
 
@@ -11,10 +10,7 @@ import pytest
 from krakenuniq_b200 import build
 from tests import util
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("KUQ_RUN_UNVALIDATED") != "1",
-                                 reason="written after round 1's GPU budget ran out; not yet run on hardware "
-                                        "(set KUQ_RUN_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 G = util.GOLDEN
 
 
