@@ -203,7 +203,10 @@ def main():
     sharded = args.mode == "shards" and world > 1
     db = synth_gpu.GpuDatabase(args.db_records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev,
                                passes=args.db_passes, shard=(rank, world) if sharded else None)
-    n_pool = max(args.reads, args.batch_reads)
+    # every step classifies reads no earlier step has seen (a re-classified read finds its records already flagged /
+    # its sparse-tier keys already stored and would be cheaper): the pool covers all steps of the run
+    steps_total = (args.warmup + args.steps) + 4 + (max(args.warmup, 3) + args.steps)
+    n_pool = max(args.reads, args.batch_reads * steps_total) if args.impl == "ours" and args.mode != "shards" else max(args.reads, args.batch_reads)
     # replicas: every rank draws its own reads (seed + rank), reads are partitioned across GPUs;
     # shards: every GPU scans the same reads
     pool_bases, _ = db.sample_reads(n_pool, READ_LEN, seed=3 + (0 if sharded else 1000 * rank))
@@ -247,16 +250,19 @@ def main():
     # ---------------- our arm ----------------------------------------------------------------------------------
     from krakenuniq_b200 import binding
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "classify")):
+    if rank == 0 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "classify")):
         try:
             threads = host_threads(args)
             sample = pool_bases[:args.cpu_sample_reads * READ_LEN].cpu().numpy()
             d, fq = ensure_files(args, db, sample)                 # must precede attach (values still raw taxids)
-            run_reference_classify(d, [fq], threads)               # warm-up
-            n_seq, secs = run_reference_classify(d, [fq], threads)
+            run_reference_classify(d, [fq], threads)               # warm-up (page cache, run-fq.sh:19)
+            n_files = 4                                            # same protocol as the reference arm: several files per run
+            n_seq, secs = run_reference_classify(d, [fq] * n_files, threads)
             cpu_baseline = {"value": n_seq / secs / 1e6, "unit": "Mreads/s", "cores": threads, "kind": "reference",
-                            "sample": f"oracle/_ref/classify -M -t {threads} -o /dev/null on {n_seq} reads of the same "
-                                      "workload; time from its own stats line (DB load excluded)"}
+                            "sample": f"oracle/_ref/classify -M -t {threads} -o /dev/null on {n_files} x {args.cpu_sample_reads} "
+                                      "reads of the same workload (FASTQ in tmpfs), after one warm-up run; time from its own "
+                                      "stats line (DB load excluded, FASTQ parsing + Kraken formatting included) — the "
+                                      "reference arm's protocol"}
         except Exception as e:  # noqa: BLE001
             cpu_baseline = {"value": None, "unit": "Mreads/s", "cores": host_threads(), "kind": "reference",
                             "sample": f"failed: {e}"[:300]}
@@ -313,6 +319,7 @@ def main():
     for _ in range(args.warmup):
         clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
     clf.sync(0)
+    clf.finish()                                  # the warm-up's flagged records are harvested outside the timed region
     barrier()
     launches0 = clf.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -322,10 +329,14 @@ def main():
         ev0.record(stream)
     for _ in range(args.steps):
         clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
+    # end of the run: the records flagged by the K steps become sparse-tier keys (kuq_finish) — part of the job, so
+    # inside the timed region
+    clf.finish()
     with torch.cuda.stream(stream):
         ev1.record(stream)
     clf.sync(0)
     barrier()
+    harvest_ms_value = clf.sparse_tier_info()["last_harvest_ms"]
     sampler.mark(t0, time.time())
     launches = clf.launch_count() - launches0
     dev_ms = ev0.elapsed_time(ev1)
@@ -356,31 +367,53 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (kern_ms / 1e3) / 1e9
-    traffic = None
-    try:    # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+    traffic, traffic_src = None, None
+    try:    # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture of THIS build
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
         if args.db_records == 666_000_000 and B == 1_000_000:
-            traffic = tj["k_lookup_dense_only_bytes" if args.hll_mode == 2 else "k_lookup_exact_hll_bytes"]
+            e = tj["k_lookup_dense_only" if args.hll_mode == 2 else "k_lookup_exact_hll"]
+            traffic = e["dram_bytes"]
+            traffic_src = {"capture": e["capture"], "kernel_ms_in_capture": e["kernel_ms"], "build": tj.get("build")}
     except Exception:
         pass
+    # second roofline: random 32-byte-sector gathers, measured here with k_lookup's launch shape
+    gather = None
+    try:
+        gs, gb, gms = binding.random_gather_peak(local_rank, 16 << 30, 1 << 29, 32)
+        sectors = n_lookups + sum_probes                       # 32*(1+P) bytes per looked-up k-mer
+        gather = {"random_gather_peak": gb, "unit": "GB/s of 32 B sectors", "gsectors_per_s": gs,
+                  "algorithmic_sectors_per_launch": int(sectors),
+                  "frac_random": 32.0 * sectors / (kern_ms / 1e3) / 1e9 / gb,
+                  "how": "kuq_random_gather_peak: independent loads at hashed sector addresses of a 16 GB buffer, 256 threads x "
+                         "8 CTAs/SM, best of 3; frac_random = 32*(1+P)*lookups / kernel time / this peak.  It exceeds 1 when "
+                         "consecutive windows share a minimizer bin (their sectors come from L1/L2, not DRAM)"}
+    except Exception as e:  # noqa: BLE001
+        gather = {"random_gather_peak": None, "error": str(e)[:200]}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_lookup<MODE_FUSED>", "kernel_ms": kern_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_lookup<MODE_FUSED>", "kernel_ms": kern_ms,
                 "stage_ms": {"k_scan": float(st_ms[0]), "k_lookup": float(st_ms[1]), "k_resolve": float(st_ms[2])},
                 "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_read": algo_bytes / B,
+                "random": gather,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, of measured)" if peaks else "fallback 6650 GB/s"}
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------------------
-    n_host = min(n_batches, 4)
+    # pinned host copies of the batches the e2e steps will classify (each batch once: no step re-sees reads)
+    n_e2e = max(args.warmup, 3) + args.steps
+    first = step % n_batches
+    n_host = min(n_batches, n_e2e)
     host_bufs = []
     for i in range(n_host):
         p = clf.L.kuq_host_alloc(B * READ_LEN + 64)
         hb = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(B * READ_LEN + 64,))
-        hb[:B * READ_LEN] = pool_bases[i * B * READ_LEN:(i + 1) * B * READ_LEN].cpu().numpy()
+        b = (first + i) % n_batches
+        hb[:B * READ_LEN] = pool_bases[b * B * READ_LEN:(b + 1) * B * READ_LEN].cpu().numpy()
         host_bufs.append((p, hb))
     n_slots = 3
     d2h_bytes = [0]
     sanity = {"reads": 0, "classified": 0}
     e2e_step = [step]
+
+    e2e_buf = [0]
 
     def run_e2e(n_steps):
         inflight = []
@@ -390,7 +423,8 @@ def main():
                 res = clf.wait(inflight.pop(0))
                 d2h_bytes[0] = 4 * B * 4 + 8 * res["n_runs"] + 64
                 sanity["reads"] += B; sanity["classified"] += res["n_classified"]
-            clf.submit(slot, host_bufs[s % n_host][0], host_offsets, h_units(e2e_step[0])); e2e_step[0] += 1
+            clf.submit(slot, host_bufs[e2e_buf[0] % n_host][0], host_offsets, h_units(e2e_step[0])); e2e_step[0] += 1
+            e2e_buf[0] += 1
             inflight.append(slot)
         for slot in inflight:
             res = clf.wait(slot)
@@ -398,11 +432,13 @@ def main():
             sanity["reads"] += B; sanity["classified"] += res["n_classified"]
 
     run_e2e(max(args.warmup, 3))
+    clf.finish()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
     run_e2e(args.steps)
+    clf.finish()                                  # harvest of the run's flagged records: part of the job
     torch.cuda.synchronize()
     e1.record()
     torch.cuda.synchronize()
@@ -434,9 +470,12 @@ def main():
                 "config": {"workload": workload, "parallelism": f"replicas x{world} (reads partitioned, DB replicated)",
                            "l2": "inputs larger than L2: 150 MB of reads per step, 16.6 GB database probed at random",
                            "hll_mode": ["preload rule", "chunked rule", "dense only"][args.hll_mode],
-                           "timing": "CUDA events on the slot stream, max over ranks; the once-per-run NCCL merge of the per-taxon "
-                                     "state (allreduce MAX/SUM + sparse-tier key all-gather) is timed separately",
+                           "timing": "CUDA events on the slot stream around K steps + the end-of-run harvest (kuq_finish), max over "
+                                     "ranks; the once-per-run NCCL merge of the per-taxon state across ranks is timed separately",
                            "end_of_run_merge_ms": merge_ms,
+                           "harvest_ms_in_timed_region": harvest_ms_value,
+                           "read_pool": f"{n_pool} reads: every step of the run classifies reads no earlier step saw",
+                           "sparse_tier": clf.sparse_tier_info(),
                            "workload_gen_s": gen_s},
                 "roofline": roofline,
                 "cpu_baseline": cpu_baseline,

@@ -265,6 +265,11 @@ int kuq_state_ptrs_get(kuq_ctx *ctx, kuq_state_ptrs *out);
  * peers' keys; together with allreduce(MAX) on d_dense_flag / d_regs and SUM on the counters this is the merge
  * `taxon_counts[t] += ...` of classify.cpp:542-544 across processes. */
 int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t *n);
+/* The sparse tier's device set: capacity in slots, keys held, how often a harvest re-allocated it, and the device time
+ * of the last harvest.  Hits reach the set lazily: the fused lookup only flags the database records it counted (the
+ * free top bit of the key word) and kuq_finish / kuq_read_counts / kuq_sparse_export / a re-stage turn the flagged
+ * records into (taxon, encoded hash) keys, growing the set first when it would pass a load factor of 0.7. */
+int kuq_sparse_tier_info(kuq_ctx *ctx, uint64_t *slots, uint64_t *keys, uint64_t *times_grown, double *last_harvest_ms);
 int kuq_sparse_import(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n);
 /* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);

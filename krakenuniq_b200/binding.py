@@ -128,6 +128,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_sparse_export": (C.c_int, [vp, vp, C.c_uint64, u64p]),
         "kuq_sparse_import": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_reset_counts": (C.c_int, [vp]),
+        "kuq_sparse_tier_info": (C.c_int, [vp, u64p, u64p, u64p, C.POINTER(C.c_double)]),
         "kuq_ertl_dense": (C.c_uint64, [u8p, C.c_uint64]),
         "kuq_random_gather_peak": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_double),
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -423,6 +424,11 @@ class Classifier:
 
     def sparse_import(self, d_keys, n):
         self._ck(self.L.kuq_sparse_import(self.h, d_keys, n))
+
+    def sparse_tier_info(self):
+        a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
+        self._ck(self.L.kuq_sparse_tier_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"slots": a.value, "keys": b.value, "times_grown": c.value, "last_harvest_ms": d.value}
 
     def reset_counts(self):
         self._ck(self.L.kuq_reset_counts(self.h))

@@ -45,6 +45,7 @@ struct Slot {
   uint64_t ovf_entries = 0;
   uint32_t *d_run_start = nullptr, *d_run_count = nullptr;
   uint2 *d_runs = nullptr;
+  uint64_t runs_cap = 0;
   unsigned long long *d_scalars = nullptr;   // [0] run cursor, [1] n_classified, [2] chunk counter(u32) [3] error(u32)
   // pinned host
   uint32_t *h_call = nullptr, *h_nwin = nullptr, *h_run_start = nullptr, *h_run_count = nullptr, *h_codes = nullptr;
@@ -123,6 +124,9 @@ struct kuq_ctx {
   unsigned long long *d_exact_count = nullptr;
   uint64_t exact_cap = 0;
 
+  bool seen_dirty = false;                // counted hits flagged records since the last harvest (SEEN_BIT)
+  uint64_t sparse_grown = 0;              // times the sparse-tier set was re-allocated at a harvest
+  double harvest_ms = 0;                  // device time of the last harvest
   bool lca_mode = false;                  // kuq_set_lcas_batch ran: record values are LCA results, not classifiable
   // work-unit cutting across batches (classify.cpp:506-521)
   uint64_t unit_nt = 0;
@@ -253,7 +257,9 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(dmalloc(&s.d_run_start, mr));
   CU(dmalloc(&s.d_run_count, mr));
   // every resolving warp may leave one partly used block of 256 run slots behind (k_resolve)
-  CU(dmalloc(&s.d_runs, mb + SLACK + 256ull * (uint64_t)ctx->n_sm * 64));
+  s.runs_cap = mb + SLACK + 256ull * (uint64_t)ctx->n_sm * 64;
+  if (s.runs_cap > 0xFFFFFF00ull) s.runs_cap = 0xFFFFFF00ull;   // run indices are 32-bit
+  CU(dmalloc(&s.d_runs, s.runs_cap));
   CU(dmalloc(&s.d_scalars, 8));
   CU(hmalloc(&s.h_call, mr));
   CU(hmalloc(&s.h_nwin, mr));
@@ -423,7 +429,8 @@ int remap_db(kuq_ctx *ctx) {
   uint32_t *d_missing;
   CU(dmalloc(&d_missing, 1));
   CU(cudaMemset(d_missing, 0, 4));
-  launch_remap_values(ctx->d_pairs, ctx->key_ct, ctx->d_tx_keys, ctx->d_tx_dense, ctx->tx_cap - 1, d_missing, ctx->aux);
+  launch_remap_values(ctx->d_pairs, ctx->key_ct, ctx->d_tx_keys, ctx->d_tx_dense, ctx->tx_cap - 1, d_missing,
+                      ctx->k >= 32 ? ~0ull : ((1ull << (2 * ctx->k)) - 1), ctx->aux);
   ctx->launches++;
   uint32_t missing = 0;
   CU(cudaMemcpyAsync(&missing, d_missing, 4, cudaMemcpyDeviceToHost, ctx->aux));
@@ -434,12 +441,84 @@ int remap_db(kuq_ctx *ctx) {
   return KUQ_OK;
 }
 
+// Sparse HLL tier of the hits: the fused lookup only flags the records it counted (SEEN_BIT); here the flagged
+// records of the staged range become (taxon, encoded hash) keys of the device set — the union the reference builds
+// with `taxon_counts[t] += ...` over sparse sketches (hyperloglogplus.cpp:600-603) — and the flags are cleared.
+// The number of keys is known before they are inserted, so the set grows here instead of failing mid-batch.
+int harvest_seen(kuq_ctx *ctx, bool discard) {
+  if (!ctx->seen_dirty) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  ctx->seen_dirty = false;
+  if (!ctx->d_pairs || !ctx->key_ct) return KUQ_OK;
+  const uint64_t key_mask = ctx->k >= 32 ? ~0ull : ((1ull << (2 * ctx->k)) - 1);
+  SparseSet ss;
+  ss.slots = ctx->d_sparse_slots; ss.mask = ctx->sparse_cap ? ctx->sparse_cap - 1 : 0; ss.n_used = ctx->d_sparse_used;
+  ss.distinct = ctx->d_sparse_distinct;
+  unsigned long long *d_stat;
+  CU(dmalloc(&d_stat, 2));
+  CU(cudaMemsetAsync(d_stat, 0, 16, ctx->aux));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->aux));
+  if (discard || !ctx->d_sparse_slots) {
+    launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 2, ctx->aux);
+    ctx->launches++;
+  } else {
+    launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 0, ctx->aux);
+    ctx->launches++;
+    unsigned long long n_new = 0;
+    CU(cudaMemcpyAsync(&n_new, d_stat, 8, cudaMemcpyDeviceToHost, ctx->aux));
+    std::vector<uint32_t> distinct(ctx->n_sketch);
+    CU(cudaMemcpyAsync(distinct.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaStreamSynchronize(ctx->aux));
+    uint64_t used = 0;
+    for (uint32_t v : distinct) used += v;
+    if ((used + n_new) * 10 > ctx->sparse_cap * 7) {             // keep the load factor below 0.7
+      uint64_t cap = ctx->sparse_cap;
+      while ((used + n_new) * 2 > cap) cap <<= 1;
+      unsigned long long *bigger = nullptr;
+      if (dmalloc(&bigger, cap) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(d_stat);
+        return fail(ctx, KUQ_E_NOMEM, "sparse-tier set: no room to grow from %llu to %llu slots", (unsigned long long)ctx->sparse_cap, (unsigned long long)cap);
+      }
+      CU(cudaMemsetAsync(bigger, 0, cap * 8ull, ctx->aux));
+      SparseSet nb = ss;
+      nb.slots = bigger; nb.mask = cap - 1;
+      launch_sparse_rehash(ctx->d_sparse_slots, ctx->sparse_cap, nb, reinterpret_cast<uint32_t *>(d_stat + 1), ctx->aux);
+      ctx->launches++;
+      CU(cudaStreamSynchronize(ctx->aux));
+      cudaFree(ctx->d_sparse_slots);
+      ctx->d_sparse_slots = bigger;
+      ctx->sparse_cap = cap;
+      ctx->sparse_grown++;
+      ss = nb;
+    }
+    launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 1, ctx->aux);
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(e1, ctx->aux));
+  unsigned long long st[2] = {0, 0};
+  CU(cudaMemcpyAsync(st, d_stat, 16, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx->harvest_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_stat);
+  ctx->snap_valid = false;
+  if ((uint32_t)st[1]) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated during the harvest (%llu slots)", (unsigned long long)ctx->sparse_cap);
+  return KUQ_OK;
+}
+
 int ensure_ready(kuq_ctx *ctx) {
   int rc = finalize(ctx);
   if (rc) return rc;
   return remap_db(ctx);
 }
 
+void set_unit_ptrs(Params &p, Slot &s);
 int prepare_unit_map(kuq_ctx *ctx, Slot &s) {
   if (ctx->cfg.hll_mode != KUQ_HLL_PRELOAD) return KUQ_OK;
   if (!s.u_keys) {
@@ -453,15 +532,10 @@ int prepare_unit_map(kuq_ctx *ctx, Slot &s) {
     CU(dmalloc(&s.u_set_keys, USET_CAP));
     CU(dmalloc(&s.u_set_count, USET_CAP));
   }
-  CU(cudaMemsetAsync(s.u_keys, 0, UMAP_CAP * 8ull, s.stream));
-  CU(cudaMemsetAsync(s.u_last, 0, UMAP_CAP * 8ull, s.stream));
-  CU(cudaMemsetAsync(s.u_inserts, 0, UMAP_CAP * 4ull, s.stream));
-  CU(cudaMemsetAsync(s.u_distinct, 0, UMAP_CAP * 4ull, s.stream));
-  CU(cudaMemsetAsync(s.u_cand, 0, UMAP_CAP, s.stream));
-  CU(cudaMemsetAsync(s.u_taxon_cand, 0, ctx->n_sketch, s.stream));
-  CU(cudaMemsetAsync(s.u_ncand, 0, 4, s.stream));
-  CU(cudaMemsetAsync(s.u_set_keys, 0, USET_CAP * 8ull, s.stream));
-  CU(cudaMemsetAsync(s.u_set_count, 0, USET_CAP * 4ull, s.stream));
+  Params tmp;
+  set_unit_ptrs(tmp, s);
+  launch_unit_clear(tmp.units, ctx->n_sketch, ctx->n_sm, s.stream);
+  ctx->launches++;
   return KUQ_OK;
 }
 
@@ -526,6 +600,7 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
   p.run_count = s.d_run_count;
   p.runs = s.d_runs;
   p.run_cursor = s.d_scalars;
+  p.runs_capacity = s.runs_cap;
   p.n_classified = s.d_scalars + 1;
   p.chunk_counter = reinterpret_cast<uint32_t *>(s.d_scalars + 2);
   p.error_flag = reinterpret_cast<uint32_t *>(s.d_scalars + 3);
@@ -570,6 +645,10 @@ int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   CU(cudaEventRecord(s.ev_stage[0], s.stream));
   CU(cudaEventRecord(s.ev_stage[1], s.stream));
   if (p.n_reads) ctx->launches += launch_classify(mode, p, ctx->n_sm, s.stream, s.ev_stage);
+  // the fused path flags the records of its counted hits (k_lookup); quick / exact runs go through the other halves
+  if (p.n_reads && mode == MODE_FUSED && !(p.flags & 4u) && ctx->cfg.hll_mode <= KUQ_HLL_CHUNKED &&
+      !(ctx->quick_min && ctx->quick_stop))
+    ctx->seen_dirty = true;
   CU(cudaEventRecord(s.ev_k1, s.stream));
   s.timed = true;
   // HLL mode rule: which taxa have a sketch that converted to dense
@@ -720,6 +799,7 @@ int kuq_stage_db(kuq_ctx *ctx, const void *kdb_image, uint64_t kdb_bytes, const 
   uint64_t rec_lo = offsets[bin_lo], rec_hi = offsets[bin_hi];
   if (rec_hi < rec_lo || rec_hi > key_ct) return fail(ctx, KUQ_E_DB_FORMAT, "index offsets inconsistent with key count");
   // taxonomy numbering survives a re-stage (chunked mode) as long as the new range only holds numbered taxids
+  { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
   free_db(ctx);
   ctx->k = k; ctx->nt = nt; ctx->idx_type = idx_type;
   ctx->bin_lo = bin_lo; ctx->bin_hi = bin_hi;
@@ -753,6 +833,7 @@ int kuq_attach_db_device(kuq_ctx *ctx, void *d_pairs, uint64_t key_ct, const uin
   uint64_t n_bins = 1ull << (2 * nt);
   if (bin_hi == 0 || bin_hi > n_bins) bin_hi = n_bins;
   if (bin_lo >= bin_hi) return fail(ctx, KUQ_E_INVALID_ARG, "empty minimizer range");
+  { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
   free_db(ctx);
   ctx->k = k; ctx->nt = nt; ctx->idx_type = idx_type;
   ctx->bin_lo = bin_lo; ctx->bin_hi = bin_hi;
@@ -966,6 +1047,7 @@ int kuq_wait_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
   const uint32_t err = (uint32_t)(s.h_scalars[3] & 0xFFFFFFFFu);
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
+  if (err == 5) return fail(ctx, KUQ_E_CAPACITY, "the hit lists of the batch need more run slots than the slot holds (%llu): use smaller batches", (unsigned long long)s.runs_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
   const uint64_t n_runs = (s.flags & KUQ_F_NO_RUNS) ? 0 : s.h_scalars[0];
   if (n_runs) {
@@ -1122,6 +1204,7 @@ int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
+  if (err == 5) return fail(ctx, KUQ_E_CAPACITY, "the hit lists of the batch need more run slots than the slot holds (%llu): use smaller batches", (unsigned long long)s.runs_cap);
   if (err) return fail(ctx, KUQ_E_CAPACITY, "per-batch work-unit bookkeeping overflowed (code %u): use smaller batches", err);
   return KUQ_OK;
 }
@@ -1186,7 +1269,7 @@ int kuq_finish(kuq_ctx *ctx) {
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
   ctx->unit_nt = 0;
   ctx->unit_next++;
-  return KUQ_OK;
+  return harvest_seen(ctx, false);
 }
 
 namespace {
@@ -1194,6 +1277,7 @@ int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
   if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
   ctx->snap_valid = false;
   h.n_kmers.resize(ctx->n_sketch);
   h.n_reads.resize(ctx->n_taxa);
@@ -1424,6 +1508,8 @@ int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t
   if (!ctx->d_sparse_slots) return KUQ_OK;                    // KUQ_HLL_DENSE_ONLY: no sparse tier
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  rc = harvest_seen(ctx, false);
+  if (rc) return rc;
   unsigned long long *d_n;
   CU(dmalloc(&d_n, 1));
   CU(cudaMemsetAsync(d_n, 0, 8, ctx->aux));
@@ -1436,6 +1522,26 @@ int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t
   cudaFree(d_n);
   *n = cnt;
   if (d_keys_out && cnt > cap) return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", cnt);
+  return KUQ_OK;
+}
+
+int kuq_sparse_tier_info(kuq_ctx *ctx, uint64_t *slots, uint64_t *keys, uint64_t *times_grown, double *last_harvest_ms) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  if (slots) *slots = ctx->sparse_cap;
+  if (times_grown) *times_grown = ctx->sparse_grown;
+  if (last_harvest_ms) *last_harvest_ms = ctx->harvest_ms;
+  if (keys) {
+    *keys = 0;
+    if (ctx->d_sparse_distinct) {
+      CU(cudaSetDevice(ctx->device));
+      for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+      std::vector<uint32_t> d(ctx->n_sketch);
+      CU(cudaMemcpy(d.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost));
+      for (uint32_t v : d) *keys += v;
+    }
+  }
   return KUQ_OK;
 }
 
@@ -1480,6 +1586,7 @@ int kuq_reset_counts(kuq_ctx *ctx) {
   if (!ctx->finalized) return KUQ_OK;
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  { int hrc = harvest_seen(ctx, true); if (hrc) return hrc; }
   CU(cudaMemset(ctx->d_regs, 0, (uint64_t)ctx->n_sketch * HLL_M));
   CU(cudaMemset(ctx->d_dense_flag, 0, ctx->n_sketch));
   CU(cudaMemset(ctx->d_n_kmers, 0, ctx->n_sketch * 8ull));

@@ -393,6 +393,9 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
   const DbView &db = p.db;
   const uint32_t hi_mask = (uint32_t)(db.key_mask >> 32);
   const bool counting = (MODE == MODE_FUSED) && !(p.flags & 4u);
+  // hits of the fused path reach the sparse tier through the record flag (see below); dense-only / exact runs have
+  // no sparse tier
+  const bool mark_seen = counting && p.hll_mode <= 1u;
   // only the text of this call's reads (the scratch beyond it may hold windows of an earlier call on the slot)
   const uint64_t g_begin = p.offsets[0], g_end = p.offsets[p.n_reads];
   for (uint64_t g = g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g_end;
@@ -440,9 +443,18 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
         while (m) {
           const int t = __ffs(m) - 1;
           m &= m - 1;
-          if ((__ldg(b + 3 * t + 1) & hi_mask) == chi) {
+          const uint32_t hiw = __ldg(b + 3 * t + 1);
+          if ((hiw & hi_mask) == chi) {
             taxon = __ldg(b + 3 * t + 2);                        // value = dense id
             if (MODE == MODE_LOOKUP && taxon == 0 && (p.flags & 16u)) taxon = FOUND_ZERO;
+            // Sparse HLL tier of a hit (hyperloglogplus.cpp:499-512): the (taxon, encoded hash) pair is a function
+            // of the RECORD, so instead of probing a hash set per window the record itself is flagged in the free
+            // top bit of its key word — the sector is in L1/L2 already, the flag costs no DRAM read, and only the
+            // first sighting of a record issues the atomic.  k_harvest_seen turns flagged records into set keys
+            // once per run.  A stale (non-coherent) load can only miss a flag another thread just set: the
+            // atomicOr is then redundant, never wrong.
+            if (mark_seen && taxon != 0 && !(hiw & SEEN_BIT))
+              atomicOr(const_cast<uint32_t *>(b + 3 * t + 1), SEEN_BIT);
             m = 0;
           }
         }
@@ -465,7 +477,8 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
     if (counting || (MODE == MODE_RESOLVE && !(p.flags & 4u))) {
       const uint64_t h = fmix64(canon);
       hll_update(p.regs, taxon, h);
-      if (p.hll_mode != 2u && !p.dense_flag[taxon]) {
+      // direct set insert: misses (taxon 0 has no record to flag) and the resolve half, which only sees merged ids
+      if (p.hll_mode != 2u && !(mark_seen && taxon != 0) && !p.dense_flag[taxon]) {
         const int ins = sparse_insert(p.sparse, taxon, encode_hash32(h));
         if (ins > 0) atomicAdd(p.sparse.distinct + taxon, 1u);
         else if (ins < 0) atomicExch(p.error_flag, 4u);       // set saturated
@@ -623,25 +636,59 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
   const uint32_t per_warp = (p.n_reads + warps_total - 1) / warps_total;
   const uint32_t r_begin = (blockIdx.x * CTA_WARPS + warp) * per_warp;
   const uint32_t r_end = min(r_begin + per_warp, p.n_reads);
+  // A warp works through its reads one after the other and every read is a chain of dependent loads (offset →
+  // codes → taxonomy → counters), so the kernel is latency bound (round 1: 36 % warps active, 6 % DRAM).  The loads
+  // that do not depend on the read's outcome are therefore issued one read ahead: while read r is resolved, the
+  // codes of read r+1 (first PRE_SLOTS x 32 windows) and the offset / window count / unit of read r+2 are in flight.
+  constexpr int PRE_SLOTS = 4;
+  const bool want_codes = (p.flags & 1u) != 0;
+  uint64_t base_a = 0, base_b = 0;                              // read r, read r+1
+  uint32_t nwin_a = 0, nwin_b = 0, unit_a = 0, unit_b = 0;
+  uint32_t pre[PRE_SLOTS];
+#pragma unroll
+  for (int j = 0; j < PRE_SLOTS; j++) pre[j] = 0;
+  if (r_begin < r_end) {
+    base_a = p.offsets[r_begin]; nwin_a = p.n_windows[r_begin];
+    if (units) unit_a = p.unit_id[r_begin];
+#pragma unroll
+    for (int j = 0; j < PRE_SLOTS; j++) { const uint32_t i = j * 32 + lane; pre[j] = i < nwin_a ? codes_src[base_a + i] : 0u; }
+  }
+  if (r_begin + 1 < r_end) {
+    base_b = p.offsets[r_begin + 1]; nwin_b = p.n_windows[r_begin + 1];
+    if (units) unit_b = p.unit_id[r_begin + 1];
+  }
   for (uint32_t r = r_begin; r < r_end; r++) {
-    const uint64_t out_base = p.offsets[r];
-    const uint32_t nwin = p.n_windows[r];
+    const uint64_t out_base = base_a;
+    const uint32_t nwin = nwin_a;
+    const uint32_t unit = unit_a;
+    uint32_t cur[PRE_SLOTS];
+#pragma unroll
+    for (int j = 0; j < PRE_SLOTS; j++) cur[j] = pre[j];
+    base_a = base_b; nwin_a = nwin_b; unit_a = unit_b;
+    if (r + 1 < r_end) {
+#pragma unroll
+      for (int j = 0; j < PRE_SLOTS; j++) { const uint32_t i = j * 32 + lane; pre[j] = i < nwin_a ? codes_src[base_a + i] : 0u; }
+    }
+    if (r + 2 < r_end) {
+      base_b = p.offsets[r + 2]; nwin_b = p.n_windows[r + 2];
+      if (units) unit_b = p.unit_id[r + 2];
+    }
     uint32_t my_t = 0, my_c = 0;                                // hit list: lane j holds entry j (dense id, count)
     uint32_t n_hits = 0, n_miss = 0, n_runs = 0;
     uint32_t carry_code = 0;
     bool overflow = false;
     uint32_t q_hits = 0, q_last = 0;                            // QUICK: hits seen, taxon of the last unambiguous window
     const uint32_t nslots = (nwin + 31) / 32;
-    for (uint32_t s = 0; s < nslots; s++) {
+    // one slot of 32 windows; c = dense id of the lane's window, 0 = miss, AMBIG.  Runs of the hit list break where
+    // the DENSE code changes (dense id <-> taxid is one to one); taxids are looked up per run when the list is flushed
+    auto do_slot = [&](uint32_t s, uint32_t c) {
       const uint32_t i = s * 32 + lane;
       const bool valid = i < nwin;
-      const uint32_t c = valid ? codes_src[out_base + i] : 0;
       const bool amb = valid && c == AMBIG;
       const bool look = valid && !amb;
       const uint32_t taxon = look ? c : 0;
-      const uint32_t raw = taxon ? __ldg(p.tax.raw + taxon) : 0;
-      const uint32_t out_code = amb ? AMBIG : raw;
-      if (valid && (p.flags & 1u)) p.codes[out_base + i] = out_code;
+      const uint32_t out_code = amb ? AMBIG : taxon;
+      if (want_codes && valid) p.codes[out_base + i] = amb ? AMBIG : (taxon ? __ldg(p.tax.raw + taxon) : 0u);
       // runs of the hit list
       uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, out_code, 1);
       if (lane == 0) prev = carry_code;
@@ -649,7 +696,7 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       const uint32_t bm = __ballot_sync(0xFFFFFFFFu, brk);
       if (want_runs && brk) {
         const uint32_t idx = n_runs + __popc(bm & ((1u << lane) - 1));
-        if (idx < RUN_BUF) s_runs[warp][idx] = make_uint2(out_code, i);   // (code, start); lengths at flush
+        if (idx < RUN_BUF) s_runs[warp][idx] = make_uint2(out_code, i);   // (dense code, start); lengths at flush
       }
       n_runs += __popc(bm);
       carry_code = __shfl_sync(0xFFFFFFFFu, out_code, 31);
@@ -677,13 +724,20 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
           overflow = true;
         }
       }
+    };
+#pragma unroll
+    for (int j = 0; j < PRE_SLOTS; j++)
+      if ((uint32_t)j < nslots) do_slot((uint32_t)j, cur[j]);
+    for (uint32_t s = PRE_SLOTS; s < nslots; s++) {
+      const uint32_t i = s * 32 + lane;
+      do_slot(s, i < nwin ? codes_src[out_base + i] : 0u);
     }
 
     // ---- resolve_tree (krakenutil.cpp:149-200) ------------------------------------------------------------
     uint32_t call = 0;
     if (overflow) {
       OverflowPool pool{p.ovf_mem, p.ovf_cursor, p.ovf_capacity};
-      call = resolve_overflow(p, pool, codes_src, out_base, nwin, units ? p.unit_id[r] : 0, counting, units, lane);
+      call = resolve_overflow(p, pool, codes_src, out_base, nwin, unit, counting, units, lane);
       n_hits = 0;                                               // counters were booked from the table
     } else if (!QUICK && n_hits == 1) {
       call = __shfl_sync(0xFFFFFFFFu, my_t, 0);                 // a single hit taxon is its own best path
@@ -730,7 +784,6 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
     // ---- counters: n_kmers per hit taxon (+ misses on taxon 0), n_reads of the call (classify.cpp:939,968) ---
     if (units) {
       // inserts per (work unit, taxon): the necessary condition for a per-unit sketch to convert
-      const uint32_t unit = p.unit_id[r];
       if (unit != unit_cur) { flush_unit(); unit_cur = unit; }
       unit_miss += n_miss;
       if (lane < n_hits) {
@@ -755,21 +808,30 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       if (lane == 0) {
         if (n_runs > blk_end - blk_next) {                      // take a fresh block (the old tail stays a hole)
           const uint32_t take = n_runs > RUN_BLOCK ? n_runs : RUN_BLOCK;
-          blk_next = (uint32_t)atomicAdd(p.run_cursor, (unsigned long long)take);
-          blk_end = blk_next + take;
+          const unsigned long long got = atomicAdd(p.run_cursor, (unsigned long long)take);
+          if (got + take > p.runs_capacity) {                   // run buffer exhausted: report, write nothing more
+            atomicExch(p.error_flag, 5u);
+            blk_next = blk_end = 0xFFFFFFFFu;
+          } else {
+            blk_next = (uint32_t)got;
+            blk_end = blk_next + take;
+          }
         }
         start = blk_next;
-        blk_next += n_runs;
+        if (blk_next != 0xFFFFFFFFu) blk_next += n_runs;
         p.run_start[r] = start;
         p.run_count[r] = n_runs;
       }
       start = __shfl_sync(0xFFFFFFFFu, start, 0);
       __syncwarp();
-      if (n_runs <= RUN_BUF) {
+      if (start == 0xFFFFFFFFu) {
+        // no room (KUQ_E_CAPACITY on the host side)
+      } else if (n_runs <= RUN_BUF) {
         for (uint32_t j = lane; j < n_runs; j += 32) {
           const uint2 a = s_runs[warp][j];
           const uint32_t end = j + 1 < n_runs ? s_runs[warp][j + 1].y : nwin;
-          p.runs[start + j] = make_uint2(a.x, end - a.y);
+          const uint32_t code = (a.x == AMBIG || a.x == 0) ? a.x : __ldg(p.tax.raw + a.x);
+          p.runs[start + j] = make_uint2(code, end - a.y);
         }
       } else {
         // long hit list (long read): recompute from the codes, walking the slots backwards so that each run
@@ -882,6 +944,29 @@ __global__ void k_unit_apply(const __grid_constant__ Params p) {
     }
     if (conv) p.dense_flag[taxon] = 1;
   }
+}
+
+// one launch instead of nine memsets: empty the per-batch (unit, taxon) map and its distinct-code set
+__global__ void __launch_bounds__(256) k_unit_clear(UnitMap u, uint32_t n_sketch) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  const uint64_t cap = (uint64_t)u.mask + 1, scap = (uint64_t)u.set_mask + 1;     // powers of two >= 1024
+  for (uint64_t i = tid; i < cap / 2; i += nth) {
+    reinterpret_cast<uint4 *>(u.keys)[i] = z;
+    reinterpret_cast<uint4 *>(u.last)[i] = z;
+  }
+  for (uint64_t i = tid; i < cap / 4; i += nth) {
+    reinterpret_cast<uint4 *>(u.inserts)[i] = z;
+    reinterpret_cast<uint4 *>(u.distinct)[i] = z;
+  }
+  for (uint64_t i = tid; i < cap / 16; i += nth) reinterpret_cast<uint4 *>(u.cand)[i] = z;
+  for (uint64_t i = tid; i < scap / 2; i += nth) reinterpret_cast<uint4 *>(u.set_keys)[i] = z;
+  for (uint64_t i = tid; i < scap / 4; i += nth) reinterpret_cast<uint4 *>(u.set_count)[i] = z;
+  for (uint64_t i = tid; i < n_sketch; i += nth) u.taxon_cand[i] = 0;
+  if (tid == 0) *u.n_cand = 0;
+}
+void launch_unit_clear(const UnitMap &u, uint32_t n_sketch, int n_sm, cudaStream_t stream) {
+  k_unit_clear<<<n_sm * 8, 256, 0, stream>>>(u, n_sketch);
 }
 
 int launch_unit_accounting(const Params &p, int n_sm, cudaStream_t stream) {
@@ -1242,7 +1327,7 @@ __global__ void k_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t 
 }
 
 __global__ void k_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, const uint32_t *dense,
-                               uint32_t cap_mask, uint32_t *missing) {
+                               uint32_t cap_mask, uint32_t *missing, uint32_t hi_mask) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t *vp = reinterpret_cast<uint32_t *>(pairs + i * 12) + 2;
     uint32_t v = *vp;
@@ -1255,7 +1340,54 @@ __global__ void k_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *k
     }
     if (d == 0xFFFFFFFFu) { atomicExch(missing, 1u); d = 0; }
     *vp = d;
+    // bits of the key word above 2k are ignored by the reference (krakendb.cpp:283-284) and serve as record flags
+    // here (SEEN_BIT): start from zero
+    if ((vp[-1] & ~hi_mask) != 0) vp[-1] &= hi_mask;
   }
+}
+
+// Flagged records → sparse-tier keys (once per run / before a range leaves HBM): for every record a counted hit
+// flagged, insert (taxon, encodeHashIn32Bit(hash(k-mer))) into the set unless the taxon went dense, and clear the
+// flag.  mode 0 = count the flagged records of taxa that are not dense (stats[0]), 1 = insert + clear, 2 = clear only.
+__global__ void __launch_bounds__(256) k_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint32_t hi_mask, const uint8_t *dense_flag,
+                                                      SparseSet set, unsigned long long *stats, uint32_t *error_flag, int mode) {
+  unsigned long long n_local = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(pairs + i * 12);
+    const uint32_t hiw = w[1];
+    if (!(hiw & SEEN_BIT)) continue;
+    const uint32_t taxon = w[2];
+    if (mode == 0) { n_local += dense_flag[taxon] ? 0 : 1; continue; }
+    w[1] = hiw & ~SEEN_BIT;
+    if (mode == 2 || dense_flag[taxon]) continue;
+    const uint64_t key = ((uint64_t)(hiw & hi_mask) << 32) | w[0];
+    const int ins = sparse_insert(set, taxon, encode_hash32(fmix64(key)));
+    if (ins > 0) atomicAdd(set.distinct + taxon, 1u);
+    else if (ins < 0) atomicExch(error_flag, 4u);
+  }
+  if (mode == 0) {
+    for (int o = 16; o; o >>= 1) n_local += __shfl_xor_sync(0xFFFFFFFFu, n_local, o);
+    if ((threadIdx.x & 31) == 0 && n_local) atomicAdd(stats, n_local);
+  }
+}
+void launch_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
+                         unsigned long long *stats, uint32_t *error_flag, int mode, cudaStream_t stream) {
+  if (!n_rec) return;
+  const int grid = (int)min((uint64_t)148 * 16, (n_rec + 255) / 256);
+  k_harvest_seen<<<grid, 256, 0, stream>>>(pairs, n_rec, (uint32_t)(key_mask >> 32), dense_flag, set, stats, error_flag, mode);
+}
+
+// re-insert the keys of an outgrown table into its successor (no per-taxon counting: the keys were counted before)
+__global__ void k_sparse_rehash(const unsigned long long *old_slots, uint64_t old_cap, SparseSet s, uint32_t *error_flag) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = old_slots[i];
+    if (!key) continue;
+    if (sparse_insert(s, (uint32_t)(key >> 32) - 1, (uint32_t)key) < 0) atomicExch(error_flag, 4u);
+  }
+}
+void launch_sparse_rehash(const unsigned long long *old_slots, uint64_t old_cap, const SparseSet &s, uint32_t *error_flag,
+                          cudaStream_t stream) {
+  if (old_cap) k_sparse_rehash<<<148 * 16, 256, 0, stream>>>(old_slots, old_cap, s, error_flag);
 }
 
 // C[taxon][v] = number of registers of the taxon holding v (registerHistogram, hyperloglogplus.cpp:337-354);
@@ -1303,10 +1435,10 @@ void launch_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t *keys,
   k_collect_taxids<<<grid, 256, 0, stream>>>(pairs, n_rec, keys, counts, cap_mask, overflow);
 }
 void launch_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, const uint32_t *dense,
-                         uint32_t cap_mask, uint32_t *missing, cudaStream_t stream) {
+                         uint32_t cap_mask, uint32_t *missing, uint64_t key_mask, cudaStream_t stream) {
   if (!n_rec) return;
   int grid = (int)min((uint64_t)148 * 8, (n_rec + 255) / 256);
-  k_remap_values<<<grid, 256, 0, stream>>>(pairs, n_rec, keys, dense, cap_mask, missing);
+  k_remap_values<<<grid, 256, 0, stream>>>(pairs, n_rec, keys, dense, cap_mask, missing, (uint32_t)(key_mask >> 32));
 }
 void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist, cudaStream_t stream) {
   if (!n_sketch) return;

@@ -38,6 +38,9 @@ constexpr int STAGE_BYTES = 24 * 1024;     // bytes of read text per shared-memo
 constexpr int N_STAGES = 2;
 constexpr uint32_t HLL_P = 12;
 constexpr uint32_t HLL_M = 4096;
+// Record flag in the key word's free top bit (keys hold 2k <= 62 bits; the reference masks the rest away,
+// krakendb.cpp:283-284): "a counted hit has seen this record since the last harvest" — the sparse HLL tier of hits.
+constexpr uint32_t SEEN_BIT = 0x80000000u;
 constexpr int SEARCH_WINDOW = 8;           // records scanned linearly once the bisection window is this small
 
 enum Mode { MODE_FUSED = 0, MODE_LOOKUP = 1, MODE_RESOLVE = 2 };
@@ -123,6 +126,7 @@ struct Params {
   uint32_t *run_count;
   uint2 *runs;
   unsigned long long *run_cursor;
+  uint64_t runs_capacity;       // entries of runs[]
   unsigned long long *n_classified;
   uint32_t *chunk_counter;      // dynamic chunk scheduler
   uint32_t *error_flag;
@@ -167,7 +171,12 @@ int dbsort_device(const uint8_t *jdb_image, uint64_t jdb_bytes, uint32_t nt, int
 void launch_collect_taxids(const uint8_t *pairs, uint64_t n_rec, uint32_t *keys, unsigned long long *counts,
                            uint32_t cap_mask, uint32_t *overflow, cudaStream_t stream);
 void launch_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, const uint32_t *dense,
-                         uint32_t cap_mask, uint32_t *missing, cudaStream_t stream);
+                         uint32_t cap_mask, uint32_t *missing, uint64_t key_mask, cudaStream_t stream);
+// flagged records → sparse-tier keys: mode 0 count (stats[0]), 1 insert + clear, 2 clear only
+void launch_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
+                         unsigned long long *stats, uint32_t *error_flag, int mode, cudaStream_t stream);
+void launch_sparse_rehash(const unsigned long long *old_slots, uint64_t old_cap, const SparseSet &s, uint32_t *error_flag,
+                          cudaStream_t stream);
 void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist /*[n_sketch][64]*/,
                                 cudaStream_t stream);
 void launch_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_members, uint8_t *out4096,
@@ -175,6 +184,7 @@ void launch_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_m
 void launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream);
 // HLL mode rule, per batch: mark candidate (unit, taxon) pairs, count their distinct codes, flag dense taxa
 int launch_unit_accounting(const Params &p, int n_sm, cudaStream_t stream);
+void launch_unit_clear(const UnitMap &u, uint32_t n_sketch, int n_sm, cudaStream_t stream);
 // chunked rule: one global sketch per taxon converts once it holds >= 1025 distinct codes
 void launch_flag_dense_global(const uint32_t *distinct, uint8_t *dense_flag, uint32_t n_sketch, cudaStream_t stream);
 // histogram of encoded ranks over the sparse set, per taxon: hist[t][64] (+ hist[t][63] unused)

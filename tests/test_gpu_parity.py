@@ -218,6 +218,45 @@ def test_hll_threshold_corner(oracle):
     _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_PRELOAD, unit=10 ** 9)
 
 
+def test_sparse_tier_grows_at_the_harvest_and_survives_several_readouts(oracle):
+    """The fused path only flags the records of its hits; kuq_finish / kuq_read_counts harvest the flags into the
+    (taxon, code) set.  Start with a set far too small (1024 slots): the harvest must grow it, and reading the
+    counts between batches (harvest, more batches, harvest again) must not change the final state."""
+    tax, genomes, kdb, idx, bases, offs = _synthetic(21, 8, 2, n_genomes=6, glen=3000, n_reads=900)
+    db = oracle.open_db(kdb, idx)
+    pm = oracle.parent_map(*tax.parent_map())
+    run = oracle.run(db, pm, 500000, 0)
+    run.classify(bases, offs, want_codes=False)
+    run.finish()
+    want = run.counts()
+    clf = _classifier(hll_mode=binding.HLL_PRELOAD, sparse_set_slots=1024)
+    clf.stage_db(kdb, idx)
+    clf.set_taxonomy(*tax.parent_map())
+    n = len(offs) - 1
+    cuts = [0, n // 3, n // 3, 2 * n // 3, n]                       # includes an empty batch
+    unit = np.zeros(n, np.uint32)                                   # one work unit, as the oracle saw it
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        clf.classify(bases, offs[a:b + 1], unit_id=unit[a:b])
+        clf.counts()                                                # readout in the middle of the run = a harvest
+    clf.finish()
+    got = clf.counts()
+    info = clf.sparse_tier_info()
+    assert info["times_grown"] >= 1 and info["slots"] > 1024 and info["keys"] <= info["slots"] * 0.7 + 1
+    assert np.array_equal(got["taxid"], want["taxid"])
+    assert np.array_equal(got["n_kmers"], want["n_kmers"]) and np.array_equal(got["n_reads"], want["n_reads"])
+    assert np.array_equal(got["sparse"], want["sparse"])
+    assert np.array_equal(got["unique"], want["unique"])
+    members = util.clade_members(tax.rows, want["taxid"])
+    for taxid, mem in members.items():
+        assert clf.clade(mem) == run.clade(mem), taxid
+    # reset wipes the record flags too: a second identical run gives the same state, not a union with stale flags
+    clf.reset_counts()
+    clf.classify(bases, offs, unit_id=unit)
+    clf.finish()
+    again = clf.counts()
+    assert np.array_equal(again["unique"], want["unique"]) and np.array_equal(again["n_kmers"], want["n_kmers"])
+
+
 @pytest.mark.parametrize("tag,unit,mode", [("preload", 500000, binding.HLL_PRELOAD),
                                            ("preload_u20000", 20000, binding.HLL_PRELOAD),
                                            ("chunked", 500000, binding.HLL_CHUNKED)])
