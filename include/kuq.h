@@ -271,6 +271,46 @@ int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t
  * records into (taxon, encoded hash) keys, growing the set first when it would pass a load factor of 0.7. */
 int kuq_sparse_tier_info(kuq_ctx *ctx, uint64_t *slots, uint64_t *keys, uint64_t *times_grown, double *last_harvest_ms);
 int kuq_sparse_import(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n);
+/* ---- database sharded by minimizer range over the GPUs of a node ------------------------------
+ * Who counts: with kuq_set_shard_counting(on) the GPU that FINDS a hit does that hit's sketch work inside the lookup
+ * half (kuq_lookup_device / kuq_lookup_device_peers): HLL register update and the record flag behind the sparse tier;
+ * the resolve half on the GPU that owns the read then only adds the misses (taxon 0), the counters and the per-unit
+ * bookkeeping.  Only valid when every looked-up window is counted exactly once (one database, no quick mode). */
+int kuq_set_shard_counting(kuq_ctx *ctx, int on);
+/* Step flags instead of host barriers.  A flag array is device memory of 8-byte counters that every peer has mapped
+ * (kuq_device_alloc + kuq_ipc_export/open).  kuq_signal_peers: in stream order on the slot — i.e. after everything
+ * queued before it, peer stores included, is complete — store `value` into d_flag_peers[j][my_index] for every
+ * peer j (system-scope fence first).  kuq_wait_flags: in stream order, spin until d_flags[0..n) >= value; after
+ * timeout_ms (0 → 20 s) it gives up and the next kuq_sync_slot returns KUQ_E_STATE instead of hanging the GPU. */
+int kuq_signal_peers(kuq_ctx *ctx, uint32_t slot, uint64_t *const *d_flag_peers, uint32_t n_peers, uint32_t my_index,
+                     uint64_t value);
+int kuq_wait_flags(kuq_ctx *ctx, uint32_t slot, const uint64_t *d_flags, uint32_t n, uint64_t value, uint32_t timeout_ms);
+/* End-of-run merge of the sparse tier across GPUs in O(keys / GPUs) per GPU (replicas or shards): the keys of the
+ * still-sparse taxa are grouped by the GPU that owns their CODE (hash(code) % n_parts; counts[j] keys for part j,
+ * parts stored back to back in d_keys_out; pass d_keys_out = NULL to get the counts only), exchanged with one
+ * all-to-all, and kuq_sparse_replace makes the received keys this GPU's set (duplicates collapse there).  Every key
+ * that can duplicate another — the same (taxon, code) from two GPUs, the same code under two taxa of a clade — lands
+ * on one GPU, so global per-taxon numbers are SUMS: kuq_sparse_summary writes this GPU's rank histograms
+ * ([n_sketch][64] uint32) and distinct counts ([n_sketch] uint32) to device buffers for an all-reduce(SUM), and
+ * kuq_set_sparse_summary installs the sums, which kuq_read_counts then reports (until the next batch).  Clade
+ * unions of several sparse taxa: sum kuq_clade_partial's hist64 over the GPUs and evaluate kuq_ertl_sparse /
+ * kuq_ertl_dense_hist (is_dense is the same on every GPU once dense flags and registers were all-reduced). */
+int kuq_sparse_export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_keys_out, uint64_t cap, uint64_t *counts);
+int kuq_sparse_replace(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n);
+int kuq_sparse_summary(kuq_ctx *ctx, uint32_t *d_hist_out, uint32_t *d_distinct_out);
+int kuq_set_sparse_summary(kuq_ctx *ctx, const uint32_t *d_hist, const uint32_t *d_distinct);
+int kuq_clade_partial(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers, int *is_dense,
+                      uint32_t *hist64);
+uint64_t kuq_ertl_sparse(const uint32_t *hist64, uint64_t n_observed);
+uint64_t kuq_ertl_dense_hist(const uint32_t *hist64, uint64_t n_observed);
+/* Stage 1 alone (KmerScanner + canonical_representation + bin_key, krakenutil.cpp:239-282, krakendb.cpp:200-246) on
+ * device buffers: canonical k-mer and minimizer bin of every window, indexed like the bases (window i of read r at
+ * d_read_offsets[r] + i; bins: 0xFFFFFFFE = ambiguous window, 0xFFFFFFFF = no window at this position).  Needs no
+ * staged database; used by the database-build tools and the synthetic-workload generator. */
+int kuq_scan_device(kuq_ctx *ctx, uint32_t slot, uint32_t k, uint32_t nt, uint32_t idx_type, const char *d_bases,
+                    const uint64_t *d_read_offsets, uint32_t n_reads, uint64_t total_bases, uint64_t *d_canon_out,
+                    uint32_t *d_bins_out);
+
 /* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);
 int kuq_reset_counts(kuq_ctx *ctx);

@@ -129,6 +129,17 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_sparse_import": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_reset_counts": (C.c_int, [vp]),
         "kuq_sparse_tier_info": (C.c_int, [vp, u64p, u64p, u64p, C.POINTER(C.c_double)]),
+        "kuq_set_shard_counting": (C.c_int, [vp, C.c_int]),
+        "kuq_signal_peers": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint64]),
+        "kuq_wait_flags": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint64, C.c_uint32]),
+        "kuq_sparse_export_partitioned": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, u64p]),
+        "kuq_sparse_replace": (C.c_int, [vp, vp, C.c_uint64]),
+        "kuq_sparse_summary": (C.c_int, [vp, vp, vp]),
+        "kuq_set_sparse_summary": (C.c_int, [vp, vp, vp]),
+        "kuq_clade_partial": (C.c_int, [vp, u32p, C.c_uint32, u64p, u64p, C.POINTER(C.c_int), u32p]),
+        "kuq_ertl_sparse": (C.c_uint64, [u32p, C.c_uint64]),
+        "kuq_ertl_dense_hist": (C.c_uint64, [u32p, C.c_uint64]),
+        "kuq_scan_device": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, vp]),
         "kuq_ertl_dense": (C.c_uint64, [u8p, C.c_uint64]),
         "kuq_random_gather_peak": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_double),
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -425,6 +436,41 @@ class Classifier:
     def sparse_import(self, d_keys, n):
         self._ck(self.L.kuq_sparse_import(self.h, d_keys, n))
 
+    def set_shard_counting(self, on=True):
+        self._ck(self.L.kuq_set_shard_counting(self.h, 1 if on else 0))
+
+    def signal_peers(self, slot, flag_ptrs, my_index, value):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self._ck(self.L.kuq_signal_peers(self.h, slot, arr, len(flag_ptrs), my_index, value))
+
+    def wait_flags(self, slot, d_flags, n, value, timeout_ms=0):
+        self._ck(self.L.kuq_wait_flags(self.h, slot, d_flags, n, value, timeout_ms))
+
+    def sparse_export_partitioned(self, n_parts, d_out=None, cap=0):
+        counts = np.zeros(n_parts, np.uint64)
+        self._ck(self.L.kuq_sparse_export_partitioned(self.h, n_parts, d_out, cap, _p(counts, u64p)))
+        return counts
+
+    def sparse_replace(self, d_keys, n):
+        self._ck(self.L.kuq_sparse_replace(self.h, d_keys, n))
+
+    def sparse_summary(self, d_hist, d_distinct):
+        self._ck(self.L.kuq_sparse_summary(self.h, d_hist, d_distinct))
+
+    def set_sparse_summary(self, d_hist, d_distinct):
+        self._ck(self.L.kuq_set_sparse_summary(self.h, d_hist, d_distinct))
+
+    def clade_partial(self, taxids):
+        """(reads, kmers, is_dense, hist64) of the listed taxa's merged sketch on THIS GPU (see kuq.h)"""
+        t = np.ascontiguousarray(taxids, np.uint32)
+        r, k, dflag = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        hist = np.zeros(64, np.uint32)
+        self._ck(self.L.kuq_clade_partial(self.h, _p(t, u32p), len(t), C.byref(r), C.byref(k), C.byref(dflag), _p(hist, u32p)))
+        return r.value, k.value, bool(dflag.value), hist
+
+    def scan_device(self, slot, k, nt, idx_type, d_bases, d_offsets, n_reads, total_bases, d_canon, d_bins):
+        self._ck(self.L.kuq_scan_device(self.h, slot, k, nt, idx_type, d_bases, d_offsets, n_reads, total_bases, d_canon, d_bins))
+
     def sparse_tier_info(self):
         a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
         self._ck(self.L.kuq_sparse_tier_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
@@ -438,6 +484,18 @@ def ertl_dense(regs: np.ndarray, n_observed: int) -> int:
     L = load_library()
     regs = np.ascontiguousarray(regs, np.uint8)
     return int(L.kuq_ertl_dense(_p(regs, u8p), n_observed))
+
+
+def ertl_sparse(hist64: np.ndarray, n_observed: int) -> int:
+    L = load_library()
+    h = np.ascontiguousarray(hist64, np.uint32)
+    return int(L.kuq_ertl_sparse(_p(h, u32p), n_observed))
+
+
+def ertl_dense_hist(hist64: np.ndarray, n_observed: int) -> int:
+    L = load_library()
+    h = np.ascontiguousarray(hist64, np.uint32)
+    return int(L.kuq_ertl_dense_hist(_p(h, u32p), n_observed))
 
 
 def random_gather_peak(device=0, buffer_bytes=16 << 30, n_sectors=1 << 30, bytes_per_access=32):

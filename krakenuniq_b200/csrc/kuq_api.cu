@@ -124,6 +124,10 @@ struct kuq_ctx {
   unsigned long long *d_exact_count = nullptr;
   uint64_t exact_cap = 0;
 
+  bool shard_counting = false;            // kuq_set_shard_counting: hits are counted by the GPU that finds them
+  uint32_t *d_sync_err = nullptr;         // set by a kuq_wait_flags that timed out
+  bool merged_summary = false;            // kuq_set_sparse_summary: snap.sparse_hist / distinct hold cross-GPU sums
+  std::vector<uint32_t> merged_hist, merged_distinct;
   bool seen_dirty = false;                // counted hits flagged records since the last harvest (SEEN_BIT)
   uint64_t sparse_grown = 0;              // times the sparse-tier set was re-allocated at a harvest
   double harvest_ms = 0;                  // device time of the last harvest
@@ -626,6 +630,12 @@ int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   if (ctx->lca_mode) return fail(ctx, KUQ_E_STATE, "this context built a database (kuq_set_lcas_batch): stage it anew to classify");
   ctx->snap_valid = false;
   if (mode == MODE_LOOKUP && ctx->mark_zero_hits) p.flags |= 16u;
+  if (ctx->shard_counting && mode != MODE_FUSED && !ctx->mark_zero_hits && !ctx->quick_min &&
+      ctx->cfg.hll_mode != KUQ_HLL_EXACT) {
+    p.flags |= 32u;
+    if (mode == MODE_LOOKUP && p.n_reads && ctx->cfg.hll_mode <= KUQ_HLL_CHUNKED) ctx->seen_dirty = true;
+  }
+  ctx->merged_summary = false;
   if (mode != MODE_LOOKUP && ctx->quick_min) {           // "Q:hits" replaces the hit list (classify.cpp:989-990)
     p.quick_min = ctx->quick_min;
     p.quick_stop = ctx->quick_stop;
@@ -752,6 +762,7 @@ void kuq_destroy(kuq_ctx *ctx) {
   for (auto &s : ctx->slots) free_slot(s);
   free_db(ctx);
   free_tax_state(ctx);
+  cudaFree(ctx->d_sync_err);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
   delete ctx;
 }
@@ -1201,6 +1212,10 @@ int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   if (s.timed && cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.kernel_ms = ms;
   (void)cudaGetLastError();      // never leave a stale error code behind for the next CUDA user of this process
   uint32_t err = 0;
+  if (ctx->d_sync_err) {
+    CU(cudaMemcpy(&err, ctx->d_sync_err, 4, cudaMemcpyDeviceToHost));
+    if (err) return fail(ctx, KUQ_E_STATE, "kuq_wait_flags timed out: a peer GPU never signalled (code %u)", err);
+  }
   CU(cudaMemcpy(&err, reinterpret_cast<uint32_t *>(s.d_scalars + 3), 4, cudaMemcpyDeviceToHost));
   if (err == 1) return fail(ctx, KUQ_E_TAXA_OVERFLOW, "the batch exhausted the hit-table pool for reads with more than 32 distinct taxa: use smaller batches");
   if (err == 4) return fail(ctx, KUQ_E_CAPACITY, "sparse-tier set saturated: raise kuq_config.sparse_set_slots (now %llu)", (unsigned long long)ctx->sparse_cap);
@@ -1312,11 +1327,75 @@ int fetch_counts(kuq_ctx *ctx, CountsHost &h) {
     CU(cudaMemcpyAsync(h.distinct.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost, ctx->aux));
     CU(cudaStreamSynchronize(ctx->aux));
     cudaFree(d_sh);
+    if (ctx->merged_summary) {             // sums over the code partitions of all GPUs (kuq_set_sparse_summary)
+      h.sparse_hist = ctx->merged_hist;
+      h.distinct = ctx->merged_distinct;
+    }
   }
   if (&h == &ctx->snap) ctx->snap_valid = true;
   return KUQ_OK;
 }
 }  // namespace
+
+namespace {
+// Histogram of the merged sketch of the member taxa (dense ids with k-mers): register-value histogram of the
+// register-wise max when any member is dense, else rank histogram of the union of the members' sparse code sets.
+// With a cross-GPU summary installed (kuq_set_sparse_summary) the local set is one code partition: the union
+// histogram of several sparse members is then a PARTIAL result the caller sums over GPUs (allow_partial).
+int clade_hist(kuq_ctx *ctx, const std::vector<uint32_t> &members, uint32_t *hist64, int *is_dense, bool allow_partial) {
+  const CountsHost &h = ctx->snap;
+  memset(hist64, 0, 64 * sizeof(uint32_t));
+  bool any_dense = ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY;
+  uint64_t sum_distinct = 0;
+  for (uint32_t d : members) { any_dense |= h.dense_flag[d] != 0; sum_distinct += h.distinct[d]; }
+  *is_dense = any_dense ? 1 : 0;
+  if (members.empty()) return KUQ_OK;
+  if (members.size() == 1 && !(allow_partial && ctx->merged_summary && !any_dense)) {
+    // a clade with a single contributing taxon has that taxon's sketch
+    const uint32_t d = members[0];
+    memcpy(hist64, any_dense ? &h.hist[(size_t)d * 64] : &h.sparse_hist[(size_t)d * 64], 64 * sizeof(uint32_t));
+    return KUQ_OK;
+  }
+  if (!any_dense) {
+    if (ctx->merged_summary && !allow_partial)
+      return fail(ctx, KUQ_E_STATE, "the sparse tier is partitioned over GPUs: sum kuq_clade_partial over the GPUs instead");
+    std::vector<uint8_t> member(ctx->n_sketch, 0);
+    for (uint32_t d : members) member[d] = 1;
+    uint64_t cap = 1024;
+    while (cap < 2 * sum_distinct + 16) cap <<= 1;
+    uint8_t *d_member; unsigned long long *d_set; uint32_t *d_hist;
+    CU(dmalloc(&d_member, ctx->n_sketch));
+    CU(dmalloc(&d_set, cap));
+    CU(dmalloc(&d_hist, 65));
+    CU(cudaMemcpyAsync(d_member, member.data(), ctx->n_sketch, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemsetAsync(d_set, 0, cap * 8, ctx->aux));
+    CU(cudaMemsetAsync(d_hist, 0, 65 * 4, ctx->aux));
+    launch_sparse_union(ctx->d_sparse_slots, ctx->sparse_cap, d_member, d_set, cap - 1, d_hist, d_hist + 64, ctx->aux);
+    ctx->launches++;
+    uint32_t hist[65];
+    CU(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->aux));
+    CU(cudaStreamSynchronize(ctx->aux));
+    cudaFree(d_member); cudaFree(d_set); cudaFree(d_hist);
+    if (hist[64]) return fail(ctx, KUQ_E_CAPACITY, "internal: clade union scratch overflow");
+    memcpy(hist64, hist, 64 * sizeof(uint32_t));
+    return KUQ_OK;
+  }
+  uint32_t *d_members; uint8_t *d_out; uint32_t *d_hist;
+  CU(dmalloc(&d_members, members.size()));
+  CU(dmalloc(&d_out, HLL_M));
+  CU(dmalloc(&d_hist, 64));
+  CU(cudaMemcpyAsync(d_members, members.data(), members.size() * 4, cudaMemcpyHostToDevice, ctx->aux));
+  launch_clade_max(ctx->d_regs, d_members, (uint32_t)members.size(), d_out, ctx->aux);
+  launch_register_histograms(d_out, 1, d_hist, ctx->aux);
+  ctx->launches += 2;
+  CU(cudaMemcpyAsync(hist64, d_hist, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  cudaFree(d_members); cudaFree(d_out); cudaFree(d_hist);
+  return KUQ_OK;
+}
+}  // namespace
+
+uint64_t kuq_ertl_sparse(const uint32_t *hist64, uint64_t n_observed);
 
 int kuq_counts_size(kuq_ctx *ctx, uint32_t *n) {
   if (!ctx || !n) return KUQ_E_INVALID_ARG;
@@ -1418,61 +1497,44 @@ int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t 
   }
   // clade sketch = merge of the members' sketches: dense as soon as one member is dense
   // (hyperloglogplus.cpp:604-621), else the union of the sparse sets (:600-603)
-  bool any_dense = ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY;
-  uint64_t sum_distinct = 0;
-  for (uint32_t d : members) { any_dense |= h.dense_flag[d] != 0; sum_distinct += h.distinct[d]; }
-  if (members.size() == 1) {
-    // a clade with a single contributing taxon has that taxon's sketch
-    const uint32_t d = members[0];
-    u = any_dense ? ertl_dense_hist(&h.hist[(size_t)d * 64], kmers)
-                  : ertl_sparse_hist(&h.sparse_hist[(size_t)d * 64], h.distinct[d], kmers);
-    if (n_reads) *n_reads = reads;
-    if (n_kmers) *n_kmers = kmers;
-    if (unique) *unique = u;
-    return KUQ_OK;
-  }
-  if (!members.empty() && !any_dense) {
-    std::vector<uint8_t> member(ctx->n_sketch, 0);
-    for (uint32_t d : members) member[d] = 1;
-    uint64_t cap = 1024;
-    while (cap < 2 * sum_distinct + 16) cap <<= 1;
-    uint8_t *d_member; unsigned long long *d_set; uint32_t *d_hist;
-    CU(dmalloc(&d_member, ctx->n_sketch));
-    CU(dmalloc(&d_set, cap));
-    CU(dmalloc(&d_hist, 65));
-    CU(cudaMemcpyAsync(d_member, member.data(), ctx->n_sketch, cudaMemcpyHostToDevice, ctx->aux));
-    CU(cudaMemsetAsync(d_set, 0, cap * 8, ctx->aux));
-    CU(cudaMemsetAsync(d_hist, 0, 65 * 4, ctx->aux));
-    launch_sparse_union(ctx->d_sparse_slots, ctx->sparse_cap, d_member, d_set, cap - 1, d_hist, d_hist + 64, ctx->aux);
-    ctx->launches++;
-    uint32_t hist[65];
-    CU(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->aux));
-    CU(cudaStreamSynchronize(ctx->aux));
-    cudaFree(d_member); cudaFree(d_set); cudaFree(d_hist);
-    if (hist[64]) return fail(ctx, KUQ_E_CAPACITY, "internal: clade union scratch overflow");
-    uint64_t n_codes = 0;
-    for (int i = 0; i < 64; i++) n_codes += hist[i];
-    u = ertl_sparse_hist(hist, n_codes, kmers);
-  } else if (!members.empty()) {
-    uint32_t *d_members; uint8_t *d_out; uint32_t *d_hist;
-    CU(dmalloc(&d_members, members.size()));
-    CU(dmalloc(&d_out, HLL_M));
-    CU(dmalloc(&d_hist, 64));
-    CU(cudaMemcpyAsync(d_members, members.data(), members.size() * 4, cudaMemcpyHostToDevice, ctx->aux));
-    launch_clade_max(ctx->d_regs, d_members, (uint32_t)members.size(), d_out, ctx->aux);
-    launch_register_histograms(d_out, 1, d_hist, ctx->aux);
-    ctx->launches += 2;
-    uint32_t hist[64];
-    CU(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->aux));
-    CU(cudaStreamSynchronize(ctx->aux));
-    cudaFree(d_members); cudaFree(d_out); cudaFree(d_hist);
-    u = ertl_dense_hist(hist, kmers);
-  }
+  uint32_t hist[64];
+  int is_dense = 0;
+  int rc = clade_hist(ctx, members, hist, &is_dense, /*allow_partial=*/false);
+  if (rc) return rc;
+  if (!members.empty()) u = is_dense ? ertl_dense_hist(hist, kmers) : kuq_ertl_sparse(hist, kmers);
   if (n_reads) *n_reads = reads;
   if (n_kmers) *n_kmers = kmers;
   if (unique) *unique = u;
   return KUQ_OK;
 }
+
+int kuq_clade_partial(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers, int *is_dense,
+                      uint32_t *hist64) {
+  if (!ctx || (!taxids && n) || !hist64 || !is_dense) return KUQ_E_INVALID_ARG;
+  if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
+  if (ctx->cfg.hll_mode == KUQ_HLL_EXACT) return fail(ctx, KUQ_E_STATE, "kuq_clade_partial is about sketches (not KUQ_HLL_EXACT)");
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  if (!ctx->snap_valid) {
+    int rc = fetch_counts(ctx, ctx->snap);
+    if (rc) return rc;
+  }
+  const CountsHost &h = ctx->snap;
+  std::vector<uint32_t> members;
+  uint64_t reads = 0, kmers = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    auto it = ctx->dense_of_raw.find(taxids[i]);
+    if (it == ctx->dense_of_raw.end()) continue;
+    const uint32_t d = it->second;
+    reads += h.n_reads[d];
+    if (d < ctx->n_sketch && h.n_kmers[d]) { kmers += h.n_kmers[d]; members.push_back(d); }
+  }
+  if (n_reads) *n_reads = reads;
+  if (n_kmers) *n_kmers = kmers;
+  return clade_hist(ctx, members, hist64, is_dense, /*allow_partial=*/true);
+}
+
+uint64_t kuq_ertl_dense_hist(const uint32_t *hist64, uint64_t n_observed) { return ertl_dense_hist(hist64, n_observed); }
 
 int kuq_get_registers(kuq_ctx *ctx, uint32_t taxid, uint8_t *regs) {
   if (!ctx || !regs) return KUQ_E_INVALID_ARG;
@@ -1522,6 +1584,176 @@ int kuq_sparse_export(kuq_ctx *ctx, uint64_t *d_keys_out, uint64_t cap, uint64_t
   cudaFree(d_n);
   *n = cnt;
   if (d_keys_out && cnt > cap) return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", cnt);
+  return KUQ_OK;
+}
+
+// ---- database sharded over GPUs: who counts, step flags, partitioned merge of the sparse tier ---------------------
+int kuq_set_shard_counting(kuq_ctx *ctx, int on) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  for (auto &s : ctx->slots)
+    if (s.busy) return fail(ctx, KUQ_E_STATE, "cannot change while a batch is in flight");
+  ctx->shard_counting = on != 0;
+  return KUQ_OK;
+}
+
+int kuq_signal_peers(kuq_ctx *ctx, uint32_t slot, uint64_t *const *d_flag_peers, uint32_t n_peers, uint32_t my_index,
+                     uint64_t value) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!d_flag_peers || n_peers == 0 || n_peers > 8 || my_index >= 8) return fail(ctx, KUQ_E_INVALID_ARG, "1..8 peers");
+  CU(cudaSetDevice(ctx->device));
+  launch_signal_peers(reinterpret_cast<unsigned long long *const *>(d_flag_peers), n_peers, my_index, value, ctx->slots[slot].stream);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return KUQ_OK;
+}
+
+int kuq_wait_flags(kuq_ctx *ctx, uint32_t slot, const uint64_t *d_flags, uint32_t n, uint64_t value, uint32_t timeout_ms) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!d_flags || n == 0 || n > 32) return fail(ctx, KUQ_E_INVALID_ARG, "1..32 flags");
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->d_sync_err) {
+    CU(dmalloc(&ctx->d_sync_err, 1));
+    CU(cudaMemset(ctx->d_sync_err, 0, 4));
+  }
+  launch_wait_flags(reinterpret_cast<const unsigned long long *>(d_flags), n, value, (unsigned long long)(timeout_ms ? timeout_ms : 20000) * 1000000ull,
+                    ctx->d_sync_err, ctx->slots[slot].stream);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return KUQ_OK;
+}
+
+int kuq_sparse_export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_keys_out, uint64_t cap, uint64_t *counts) {
+  if (!ctx || !counts || n_parts == 0 || n_parts > 8) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  for (uint32_t j = 0; j < n_parts; j++) counts[j] = 0;
+  if (!ctx->d_sparse_slots) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  rc = harvest_seen(ctx, false);
+  if (rc) return rc;
+  unsigned long long *d_cnt;
+  CU(dmalloc(&d_cnt, 8));
+  CU(cudaMemsetAsync(d_cnt, 0, 64, ctx->aux));
+  launch_sparse_parts(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, n_parts, d_cnt, nullptr, 0, ctx->aux);
+  ctx->launches++;
+  unsigned long long h[8];
+  CU(cudaMemcpyAsync(h, d_cnt, 64, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  uint64_t total = 0;
+  for (uint32_t j = 0; j < n_parts; j++) { counts[j] = h[j]; total += h[j]; }
+  if (d_keys_out && total) {
+    if (total > cap) { cudaFree(d_cnt); return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", (unsigned long long)total); }
+    unsigned long long cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t j = 1; j < n_parts; j++) cur[j] = cur[j - 1] + h[j - 1];
+    CU(cudaMemcpyAsync(d_cnt, cur, 64, cudaMemcpyHostToDevice, ctx->aux));
+    launch_sparse_parts(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, n_parts, d_cnt,
+                        reinterpret_cast<unsigned long long *>(d_keys_out), 1, ctx->aux);
+    ctx->launches++;
+    CU(cudaStreamSynchronize(ctx->aux));
+  }
+  cudaFree(d_cnt);
+  return KUQ_OK;
+}
+
+int kuq_sparse_replace(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
+  if (!ctx || (!d_keys && n)) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  if (!ctx->d_sparse_slots) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  rc = harvest_seen(ctx, true);                  // anything still flagged was exported before; drop the flags
+  if (rc) return rc;
+  ctx->snap_valid = false;
+  uint64_t cap = ctx->sparse_cap;
+  while (n * 10 > cap * 7) cap <<= 1;
+  if (cap != ctx->sparse_cap) {
+    cudaFree(ctx->d_sparse_slots);
+    ctx->d_sparse_slots = nullptr;
+    if (dmalloc(&ctx->d_sparse_slots, cap) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ctx->sparse_cap = 0;
+      return fail(ctx, KUQ_E_NOMEM, "sparse-tier set: no room for %llu slots", (unsigned long long)cap);
+    }
+    ctx->sparse_cap = cap;
+    ctx->sparse_grown++;
+  }
+  CU(cudaMemsetAsync(ctx->d_sparse_slots, 0, ctx->sparse_cap * 8ull, ctx->aux));
+  CU(cudaMemsetAsync(ctx->d_sparse_distinct, 0, ctx->n_sketch * 4ull, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
+  return kuq_sparse_import(ctx, d_keys, n);
+}
+
+int kuq_sparse_summary(kuq_ctx *ctx, uint32_t *d_hist_out, uint32_t *d_distinct_out) {
+  if (!ctx || !d_hist_out || !d_distinct_out) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  rc = harvest_seen(ctx, false);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(d_hist_out, 0, (uint64_t)ctx->n_sketch * 64 * 4, ctx->aux));
+  if (ctx->d_sparse_slots) {
+    launch_sparse_histograms(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, d_hist_out, ctx->aux);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(d_distinct_out, ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToDevice, ctx->aux));
+  } else {
+    CU(cudaMemsetAsync(d_distinct_out, 0, ctx->n_sketch * 4ull, ctx->aux));
+  }
+  CU(cudaStreamSynchronize(ctx->aux));
+  return KUQ_OK;
+}
+
+int kuq_set_sparse_summary(kuq_ctx *ctx, const uint32_t *d_hist, const uint32_t *d_distinct) {
+  if (!ctx || !d_hist || !d_distinct) return KUQ_E_INVALID_ARG;
+  int rc = ensure_ready(ctx);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  ctx->merged_hist.resize((size_t)ctx->n_sketch * 64);
+  ctx->merged_distinct.resize(ctx->n_sketch);
+  CU(cudaMemcpy(ctx->merged_hist.data(), d_hist, (uint64_t)ctx->n_sketch * 64 * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ctx->merged_distinct.data(), d_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost));
+  ctx->merged_summary = true;
+  ctx->snap_valid = false;
+  return KUQ_OK;
+}
+
+uint64_t kuq_ertl_sparse(const uint32_t *hist64, uint64_t n_observed) {
+  uint64_t n_codes = 0;
+  for (int i = 0; i < 64; i++) n_codes += hist64[i];
+  return ertl_sparse_hist(hist64, n_codes, n_observed);
+}
+
+int kuq_scan_device(kuq_ctx *ctx, uint32_t slot, uint32_t k, uint32_t nt, uint32_t idx_type, const char *d_bases,
+                    const uint64_t *d_read_offsets, uint32_t n_reads, uint64_t total_bases, uint64_t *d_canon_out,
+                    uint32_t *d_bins_out) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!d_bases || !d_read_offsets || !d_canon_out || !d_bins_out) return fail(ctx, KUQ_E_INVALID_ARG, "NULL device buffers");
+  if ((uintptr_t)d_bases & 15) return fail(ctx, KUQ_E_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (k < 2 || k > 31 || nt < 1 || nt > 15 || nt > k || (idx_type != 1 && idx_type != 2)) return fail(ctx, KUQ_E_INVALID_ARG, "bad k / minimizer length / index type");
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[slot];
+  if (n_reads > ctx->cfg.max_reads_per_batch || total_bases > ctx->cfg.max_bases_per_batch)
+    return fail(ctx, KUQ_E_CAPACITY, "batch exceeds the slot capacity");
+  Params p;
+  memset(&p, 0, sizeof p);
+  p.db.k = k; p.db.nt = nt;
+  p.db.key_mask = (1ull << (2 * k)) - 1;
+  p.db.xor_mask = (uint32_t)((idx_type == 1 ? 0ull : INDEX2_XOR_MASK) & ((1ull << (2 * nt)) - 1));
+  p.db.n_mini = k - nt + 1;
+  p.bases = d_bases; p.offsets = d_read_offsets; p.clean = s.d_clean;
+  p.n_reads = n_reads; p.n_chunks = (n_reads + CHUNK_READS - 1) / CHUNK_READS;
+  p.total_bases = total_bases;
+  p.n_windows = s.d_nwin; p.canon = d_canon_out; p.bins = d_bins_out;
+  p.chunk_counter = reinterpret_cast<uint32_t *>(s.d_scalars + 2);
+  p.error_flag = reinterpret_cast<uint32_t *>(s.d_scalars + 3);
+  CU(cudaMemsetAsync(s.d_scalars, 0, 8 * 8, s.stream));
+  ctx->launches += launch_scan_only(p, ctx->n_sm, s.stream);
+  CU(cudaGetLastError());
   return KUQ_OK;
 }
 

@@ -395,7 +395,11 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
   const bool counting = (MODE == MODE_FUSED) && !(p.flags & 4u);
   // hits of the fused path reach the sparse tier through the record flag (see below); dense-only / exact runs have
   // no sparse tier
-  const bool mark_seen = counting && p.hll_mode <= 1u;
+  // flag 32 (database sharded over GPUs, one database): the GPU that FINDS a hit owns its sketch work — register
+  // update and record flag happen in the lookup half, and the resolve half (on the GPU that owns the read) only adds
+  // the misses (taxon 0).  Valid because every looked-up window is counted exactly once in that layout.
+  const bool shard_counting = (p.flags & 32u) != 0;
+  const bool mark_seen = (counting || (MODE == MODE_LOOKUP && shard_counting)) && p.hll_mode <= 1u;
   // only the text of this call's reads (the scratch beyond it may hold windows of an earlier call on the slot)
   const uint64_t g_begin = p.offsets[0], g_end = p.offsets[p.n_reads];
   for (uint64_t g = g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g_end;
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
             // first sighting of a record issues the atomic.  k_harvest_seen turns flagged records into set keys
             // once per run.  A stale (non-coherent) load can only miss a flag another thread just set: the
             // atomicOr is then redundant, never wrong.
-            if (mark_seen && taxon != 0 && !(hiw & SEEN_BIT))
+            if (mark_seen && taxon != 0 && taxon != FOUND_ZERO && !(hiw & SEEN_BIT))
               atomicOr(const_cast<uint32_t *>(b + 3 * t + 1), SEEN_BIT);
             m = 0;
           }
@@ -474,7 +478,9 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
     } else if (MODE == MODE_RESOLVE || !p.only_hits || taxon != 0) {
       p.codes_dense[g] = taxon;
     }
-    if (counting || (MODE == MODE_RESOLVE && !(p.flags & 4u))) {
+    if (MODE == MODE_LOOKUP && shard_counting) {
+      if (taxon != 0 && taxon != FOUND_ZERO) hll_update(p.regs, taxon, fmix64(canon));
+    } else if ((counting || (MODE == MODE_RESOLVE && !(p.flags & 4u))) && !(MODE == MODE_RESOLVE && shard_counting && taxon != 0)) {
       const uint64_t h = fmix64(canon);
       hll_update(p.regs, taxon, h);
       // direct set insert: misses (taxon 0 has no record to flag) and the resolve half, which only sees merged ids
@@ -1278,6 +1284,17 @@ __global__ void __launch_bounds__(256) k_set_lcas(const __grid_constant__ Params
   }
 }
 
+// stage 1 alone: canonical k-mer + minimizer bin of every window into p.canon / p.bins (database build, workload tools)
+int launch_scan_only(const Params &p, int n_sm, cudaStream_t stream) {
+  if (p.n_reads == 0) return 0;
+  const int smem = classify_smem_bytes();
+  cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int grid = n_sm * 4;
+  if ((uint32_t)grid > p.n_chunks) grid = (int)p.n_chunks;
+  k_scan<<<grid, CTA_THREADS, smem, stream>>>(p);
+  return 1;
+}
+
 // scan the pieces, then fold their taxids into the record values; returns #kernels launched
 int launch_set_lcas(const Params &p, int n_sm, cudaStream_t stream) {
   if (p.n_reads == 0) return 0;
@@ -1451,6 +1468,77 @@ void launch_clade_max(const uint8_t *regs, const uint32_t *members, uint32_t n_m
 void launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream) {
   if (!n) return;
   k_fill_u32<<<(int)min((uint64_t)148 * 8, (n + 255) / 256), 256, 0, stream>>>(p, n, v);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Cross-GPU step synchronisation without the host (database sharded by minimizer range).
+// Flags are 64-bit counters in device memory every peer has mapped (CUDA IPC or peer access).  k_signal_peers runs
+// in stream order after the work it announces: the kernel boundary has made that work's peer stores visible at
+// system scope, the fence orders them before the flag stores.  k_wait_flags spins (one lane per flag) until every
+// flag has reached `value`; a peer that died shows up as a timeout (error code 6), not as a hung GPU.
+// ------------------------------------------------------------------------------------------------------
+struct PeerFlags { unsigned long long *ptr[8]; };
+__global__ void k_signal_peers(PeerFlags f, uint32_t n, uint32_t my_index, unsigned long long value) {
+  if (threadIdx.x < n) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(f.ptr[threadIdx.x] + my_index) = value;
+    __threadfence_system();
+  }
+}
+__global__ void k_wait_flags(const unsigned long long *flags, uint32_t n, unsigned long long value, unsigned long long timeout_ns,
+                             uint32_t *error_flag) {
+  if (threadIdx.x >= n) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const volatile unsigned long long *f = flags + threadIdx.x;
+  while (*f < value) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) { atomicExch(error_flag, 6u); break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+void launch_signal_peers(unsigned long long *const *flag_ptrs, uint32_t n, uint32_t my_index, unsigned long long value,
+                         cudaStream_t stream) {
+  PeerFlags f;
+  for (uint32_t j = 0; j < 8; j++) f.ptr[j] = j < n ? flag_ptrs[j] : nullptr;
+  k_signal_peers<<<1, 32, 0, stream>>>(f, n, my_index, value);
+}
+void launch_wait_flags(const unsigned long long *flags, uint32_t n, unsigned long long value, unsigned long long timeout_ns,
+                       uint32_t *error_flag, cudaStream_t stream) {
+  k_wait_flags<<<1, 32, 0, stream>>>(flags, n, value, timeout_ns, error_flag);
+}
+
+// Sparse-tier keys of the taxa that are still sparse, grouped by the rank that owns their CODE
+// (part = hash(code) % n_parts): all keys that can ever be duplicates of each other — the same (taxon, code) seen on
+// several GPUs, or the same code under two taxa of one clade — meet on one rank, so per-taxon distinct counts and
+// clade unions are sums of per-rank results.  pass 0 counts (counts[part]), pass 1 scatters through cursors[part].
+__device__ __forceinline__ uint32_t key_part(unsigned long long key, uint32_t n_parts) {
+  return (uint32_t)((mix64((uint32_t)key) >> 33) % n_parts);
+}
+__global__ void __launch_bounds__(256) k_sparse_parts(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag, uint32_t n_parts,
+                                                      unsigned long long *counters, unsigned long long *out, int pass) {
+  __shared__ unsigned long long s_cnt[8];
+  if (pass == 0) {
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+  }
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = slots[i];
+    if (!key || dense_flag[(uint32_t)(key >> 32) - 1]) continue;
+    const uint32_t part = key_part(key, n_parts);
+    if (pass == 0) atomicAdd(&s_cnt[part], 1ull);
+    else out[atomicAdd(counters + part, 1ull)] = key;
+  }
+  if (pass == 0) {
+    __syncthreads();
+    if (threadIdx.x < n_parts && s_cnt[threadIdx.x]) atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]);
+  }
+}
+void launch_sparse_parts(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag, uint32_t n_parts,
+                         unsigned long long *counters, unsigned long long *out, int pass, cudaStream_t stream) {
+  if (cap) k_sparse_parts<<<148 * 16, 256, 0, stream>>>(slots, cap, dense_flag, n_parts, counters, out, pass);
 }
 
 }  // namespace kuq

@@ -163,6 +163,7 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
 int classify_smem_bytes();
 // set_lcas: k_scan + k_set_lcas over library pieces (p.unit_id = dense taxid per piece, p.stats[0] += k-mers not found)
 int launch_set_lcas(const Params &p, int n_sm, cudaStream_t stream);
+int launch_scan_only(const Params &p, int n_sm, cudaStream_t stream);
 // db_sort on the device (kuq_dbbuild.cu)
 int dbsort_device(const uint8_t *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, uint8_t *kdb_out,
                   uint8_t *idx_out, char *err, size_t err_cap);
@@ -202,5 +203,13 @@ void launch_sparse_export(const unsigned long long *slots, uint64_t cap, const u
                           unsigned long long *out, uint64_t out_cap, unsigned long long *n_out, cudaStream_t stream);
 void launch_sparse_import(const unsigned long long *keys, uint64_t n, const SparseSet &s, const uint8_t *dense_flag,
                           uint32_t *error_flag, cudaStream_t stream);
+
+// cross-GPU flags (kuq_signal_peers / kuq_wait_flags) and the partitioned export of the sparse tier
+void launch_signal_peers(unsigned long long *const *flag_ptrs, uint32_t n, uint32_t my_index, unsigned long long value,
+                         cudaStream_t stream);
+void launch_wait_flags(const unsigned long long *flags, uint32_t n, unsigned long long value, unsigned long long timeout_ns,
+                       uint32_t *error_flag, cudaStream_t stream);
+void launch_sparse_parts(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag, uint32_t n_parts,
+                         unsigned long long *counters, unsigned long long *out, int pass, cudaStream_t stream);
 
 }  // namespace kuq
