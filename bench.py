@@ -51,8 +51,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--db-records", type=int, default=666_000_000, help="records of the synthetic database")
-    ap.add_argument("--db-passes", type=int, default=1, help="build the synthetic DB in this many minimizer ranges")
+    ap.add_argument("--db-records", type=int, default=0,
+                    help="records of the synthetic database (0 = 666 M for replicas / the configs[3] size for shards)")
+    ap.add_argument("--db-passes", type=int, default=0, help="build the synthetic DB in this many minimizer ranges (0 = auto)")
     ap.add_argument("--genomes", type=int, default=2000)
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads in the pool")
     ap.add_argument("--batch-reads", type=int, default=1_000_000, help="reads per step")
@@ -61,8 +62,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hll-mode", type=int, default=0, help="0 preload rule (reference default), 1 chunked, 2 dense only")
     ap.add_argument("--cache-dir", default=os.environ.get("KUQ_BENCH_CACHE", "/dev/shm"))
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "shards"],
-                    help="multi-GPU layout: replicas (DB on every GPU, reads partitioned) or minimizer-range shards")
+    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "shards"],
+                    help="multi-GPU layout: replicas (DB on every GPU, reads partitioned) or minimizer-range shards; "
+                         "auto = replicas on one GPU, on several GPUs the sharded configs[3] line with the replicas "
+                         "numbers under the key 'replicas'")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
                     help="shards: hits stored into the owner's buffer over NVLink (p2p) or ids all-reduced (nccl)")
     return ap.parse_args()
@@ -121,7 +124,7 @@ class ClockSampler:
 # workload
 # ------------------------------------------------------------------------------------------------------------
 def cache_dir(args):
-    return os.path.join(args.cache_dir, f"kuq_bench_r{args.db_records}_g{args.genomes}_k{K}m{NT}")
+    return os.path.join(args.cache_dir, f"kuq_bench_r{args.db_records or 666_000_000}_g{args.genomes}_k{K}m{NT}")
 
 
 def write_fastq(path, bases: np.ndarray, n_reads: int):
@@ -180,6 +183,59 @@ def host_threads(args=None):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def resolve_mode(args, world):
+    if args.mode != "auto":
+        return args.mode
+    return "shards" if world > 1 else "replicas"
+
+
+def shard_db_records(args, world):
+    """BASELINE configs[3]: a 300 GB database (25.0 G records) sharded by minimizer range.  Every card holds at most
+    75 GB of records here (the generator sorts a range next to the finished records), so 2 cards run a 150 GB database;
+    4 and 8 cards run the 300 GB one (75 / 37.5 GB per card)."""
+    if args.db_records:
+        return args.db_records
+    return min(25_000_000_000, world * 6_250_000_000)
+
+
+class Workload:
+    pass
+
+
+def build_workload(args, mode, rank, world, dev, dist, n_steps):
+    import torch
+    from krakenuniq_b200 import synth_gpu
+    w = Workload()
+    t_gen = time.time()
+    sharded = mode == "shards" and world > 1
+    records = shard_db_records(args, world) if sharded else (args.db_records or 666_000_000)
+    passes = args.db_passes or (max(1, -(-records // world // 800_000_000)) if sharded else max(1, records // 1_500_000_000))
+    torch.cuda.reset_peak_memory_stats()
+    w.db = synth_gpu.GpuDatabase(records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev, passes=passes,
+                                 shard=(rank, world) if sharded else None)
+    # every step classifies reads no earlier step has seen (a re-classified read finds its records already flagged /
+    # its sparse-tier keys already stored and would be cheaper): the pool covers all steps of the run
+    w.n_pool = max(args.reads, args.batch_reads * n_steps)
+    # replicas: every rank draws its own reads (seed + rank), reads are partitioned across GPUs;
+    # shards: every GPU scans the same reads
+    w.pool_bases, _ = w.db.sample_reads(w.n_pool, READ_LEN, seed=3 + (0 if sharded else 1000 * rank))
+    torch.cuda.synchronize()
+    w.gen_s = time.time() - t_gen
+    w.gen_peak_gb = torch.cuda.max_memory_allocated() / 1e9
+    total_records = w.db.key_ct
+    if sharded:
+        t = torch.tensor([w.db.key_ct], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        total_records = int(t.item())
+    tag = "configs[1]" if records == 666_000_000 and not sharded else ("configs[3]" if sharded and records == 25_000_000_000 else
+                                                                       ("scaled configs[3]" if sharded else "scaled configs[1]"))
+    w.workload = (f"{tag}: {total_records * 12 / 1e9:.1f} GB synthetic KrakenDB (k={K}, m={NT}, {total_records} records) "
+                  f"+ {8 * ((1 << (2 * NT)) + 1) / 1e9:.1f} GB index in HBM, {w.n_pool} x {READ_LEN} bp reads, "
+                  f"{args.batch_reads} reads per step")
+    w.records = records
+    return w
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -197,34 +253,14 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device(dev))
-
-    from krakenuniq_b200 import synth_gpu
-    t_gen = time.time()
-    sharded = args.mode == "shards" and world > 1
-    db = synth_gpu.GpuDatabase(args.db_records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev,
-                               passes=args.db_passes, shard=(rank, world) if sharded else None)
-    # every step classifies reads no earlier step has seen (a re-classified read finds its records already flagged /
-    # its sparse-tier keys already stored and would be cheaper): the pool covers all steps of the run
-    steps_total = (args.warmup + args.steps) + 4 + (max(args.warmup, 3) + args.steps)
-    n_pool = max(args.reads, args.batch_reads * steps_total) if args.impl == "ours" and args.mode != "shards" else max(args.reads, args.batch_reads)
-    # replicas: every rank draws its own reads (seed + rank), reads are partitioned across GPUs;
-    # shards: every GPU scans the same reads
-    pool_bases, _ = db.sample_reads(n_pool, READ_LEN, seed=3 + (0 if sharded else 1000 * rank))
-    torch.cuda.synchronize()
-    gen_s = time.time() - t_gen
-    total_records = db.key_ct
-    if sharded:
-        t = torch.tensor([db.key_ct], device=dev, dtype=torch.int64)
-        dist.all_reduce(t)
-        total_records = int(t.item())
-    workload = (f"{'configs[1]' if args.db_records == 666_000_000 else 'scaled configs[1]'}: {total_records * 12 / 1e9:.1f} GB synthetic KrakenDB (k={K}, m={NT}, {total_records} records) "
-                f"+ {8 * ((1 << (2 * NT)) + 1) / 1e9:.1f} GB index in HBM, {n_pool} x {READ_LEN} bp reads, "
-                f"{args.batch_reads} reads per step")
-    n_batches = n_pool // args.batch_reads
+    mode = resolve_mode(args, world if args.impl == "ours" else 1)
     B = args.batch_reads
+    steps_rep = (args.warmup + args.steps) + 4 + (max(args.warmup, 3) + args.steps)
 
     # ---------------- reference arm: the unmodified reference on the host cores ------------------------------
     if args.impl == "reference":
+        w = build_workload(args, "replicas", 0, 1, dev, None, 1)
+        db, pool_bases, workload = w.db, w.pool_bases, w.workload
         threads = host_threads(args)
         sample = pool_bases[:args.cpu_sample_reads * READ_LEN].cpu().numpy()
         d, fq = ensure_files(args, db, sample)
@@ -248,7 +284,38 @@ def main():
         return 0
 
     # ---------------- our arm ----------------------------------------------------------------------------------
-    from krakenuniq_b200 import binding
+    line, rep_line, cpu_baseline = None, None, None
+    if mode == "replicas" or (args.mode == "auto" and world > 1):
+        w = build_workload(args, "replicas", rank, world, dev, dist, steps_rep)
+        cpu_baseline = measure_cpu_baseline(args, w, rank)
+        rep_line = run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline)
+        del w
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        line = rep_line
+    if mode == "shards":
+        w = build_workload(args, "shards", rank, world, dev, dist, 2 * (args.warmup + args.steps) + 2)
+        extra = None
+        if rep_line is not None:
+            keep = ("value", "ms_per_step", "scaling", "e2e", "gpu_launches")
+            extra = {"replicas": dict({k: rep_line[k] for k in keep}, workload=rep_line["config"]["workload"],
+                                      end_of_run_merge_ms=rep_line["config"]["end_of_run_merge_ms"],
+                                      note="second layout, same run: the configs[1] database replicated on every GPU, reads "
+                                           "partitioned (weak scaling); merge of the per-taxon state timed separately")}
+        line = run_shards(args, w.db, w.pool_bases, rank, world, local_rank, dev, dist, w.workload, w.gen_s, cpu_baseline, extra)
+        if line is not None:
+            line["config"]["workload_gen_peak_gb"] = w.gen_peak_gb
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_cpu_baseline(args, w, rank):
+    """the unmodified reference on the host cores, rank 0 only, on a bounded sample of the configs[1] workload"""
+    db, pool_bases = w.db, w.pool_bases
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "classify")):
         try:
@@ -267,8 +334,16 @@ def main():
             cpu_baseline = {"value": None, "unit": "Mreads/s", "cores": host_threads(), "kind": "reference",
                             "sample": f"failed: {e}"[:300]}
 
-    if args.mode == "shards":
-        return run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workload, gen_s)
+    return cpu_baseline
+
+
+def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
+    """the database fits one card — every GPU holds it, reads are partitioned (weak scaling)."""
+    import torch
+    from krakenuniq_b200 import binding
+    db, pool_bases, n_pool, workload, gen_s = w.db, w.pool_bases, w.n_pool, w.workload, w.gen_s
+    B = args.batch_reads
+    n_batches = n_pool // B
     clf = binding.Classifier(device=local_rank, n_slots=3, max_reads=B, max_bases=B * READ_LEN + 4096,
                              hll_mode=args.hll_mode, sparse_set_slots=1 << 30)
     clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2)
@@ -312,7 +387,7 @@ def main():
         """end-of-run merge across replicas: NCCL allreduce MAX/SUM + sparse-tier union"""
         if dist:
             from krakenuniq_b200 import dist as kdist
-            kdist.merge_classifier_state(clf, dev)
+            kdist.merge_classifier_state_partitioned(clf, dev)
 
     # ---- value: device-resident inputs ----------------------------------------------------------------------------
     step = 0
@@ -370,7 +445,7 @@ def main():
     traffic, traffic_src = None, None
     try:    # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu capture of THIS build
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
-        if args.db_records == 666_000_000 and B == 1_000_000:
+        if w.records == 666_000_000 and B == 1_000_000:
             e = tj["k_lookup_dense_only" if args.hll_mode == 2 else "k_lookup_exact_hll"]
             traffic = e["dram_bytes"]
             traffic_src = {"capture": e["capture"], "kernel_ms_in_capture": e["kernel_ms"], "build": tj.get("build")}
@@ -487,83 +562,108 @@ def main():
                 "sanity": {"classified_fraction": sanity["classified"] / max(sanity["reads"], 1),
                            "expected": "about 0.80: 80 % of the reads are sampled from the database genomes (1 % substitutions)"},
                 "clocks": clocks}
-        print(json.dumps(line))
-    if dist:
-        dist.destroy_process_group()
-    return 0
+        return line
+    return None
 
 
-def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workload, gen_s):
-    """the database is split into `world` minimizer ranges (balanced by records, like
-    prepare_chunking); every GPU scans the SAME batch and looks up the k-mers whose minimizer it owns; read r is
-    resolved by one owner GPU.  Merge of the per-window ids: `p2p` = each hit is stored by the lookup kernel straight
-    into the owner's buffer over NVLink (fused lookup + scatter, CUDA IPC mapped peer memory); `nccl` = every rank
-    writes its own buffer and the buffers are max-all-reduced.  value = reads of the job / time."""
+def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workload, gen_s, cpu_baseline=None, extra=None):
+    """SURVEY §8(e).2 / BASELINE configs[3]: the database is split into `world` minimizer ranges (balanced by records,
+    like prepare_chunking); every GPU scans the SAME batch and looks up the k-mers whose minimizer it owns; read r is
+    resolved by one owner GPU.  Per step, all in stream order on each GPU — no host barrier inside the loop:
+        wait(ready)  → fused lookup + NVLink peer scatter of the hits (the finder also does the hit's sketch work)
+        signal(done) → wait(done) → resolve own share from the merged ids → zero own buffer → signal(ready)
+    `--merge nccl` replaces the peer scatter by a MAX all-reduce of the id buffers (stream-ordered NCCL).
+    End of run: code-partitioned merge of the per-taxon state (dist.merge_classifier_state_partitioned).
+    value = reads of the job / (time of the K steps + the end-of-run merge)."""
     import torch
     from krakenuniq_b200 import binding
     from krakenuniq_b200 import dist as kdist
     B = args.batch_reads
-    n_pool = max(args.reads, B)
+    n_pool = pool_bases.numel() // READ_LEN if pool_bases.numel() % READ_LEN == 0 else (pool_bases.numel() - 64) // READ_LEN
     n_batches = n_pool // B
-    n_bins = 1 << (2 * NT)
-    # every rank generated only its own minimizer range (GpuDatabase(shard=...)): ranges hold about equal records
     lo_bin, hi_bin = db.bin_lo, db.bin_hi
-    rec_lo, rec_hi = 0, db.key_ct
     clf = binding.Classifier(device=local_rank, n_slots=2, max_reads=B, max_bases=B * READ_LEN + 4096,
-                             hll_mode=args.hll_mode, sparse_set_slots=1 << 30)
+                             hll_mode=args.hll_mode, sparse_set_slots=1 << 26)
     clf.set_db_taxid_universe(np.array(db.species, np.uint32))
     clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2, lo_bin, hi_bin)
     clf.set_taxonomy(*db.parent_map())
+    clf.set_shard_counting(args.merge == "p2p")
     per_unit = -(-500000 // READ_LEN)
-    # owner shares: whole work units, contiguous
-    n_units = -(-B // per_unit)
+    n_units = -(-B // per_unit)                                  # owner shares: whole work units, contiguous
     share_units = [kdist.partition(n_units, world, r) for r in range(world)]
     shares = [(min(a * per_unit, B), min(b * per_unit, B)) for a, b in share_units]
     lo, hi = shares[rank]
+    assert lo % 2 == 0
     d_offsets = (torch.arange(B + 2, dtype=torch.int64, device=dev) * READ_LEN)
     unit_local = (torch.arange(B, dtype=torch.int64, device=dev) // per_unit).to(torch.int32)
     total = B * READ_LEN
     nbytes = (total + 64) * 4
-    my_buf = clf.device_alloc(nbytes)
-    bounds = np.array([s[0] * READ_LEN for s in shares] + [total], np.uint64)
+    bounds = np.array([s_[0] * READ_LEN for s_ in shares] + [total], np.uint64)
     bounds[0] = 0
-    peers = None
+    own_off, own_len = int(bounds[rank]) * 4, (int(bounds[rank + 1]) - int(bounds[rank])) * 4
+    bufs = [clf.device_alloc(nbytes) for _ in range(2)]           # double buffered by step parity
+    flags = clf.device_alloc(256)                                 # [0:8) done counters, [16:24) ready counters (u64)
+    flags_t = kdist.device_view(flags, 256, torch.int64, dev)
+    flags_t.zero_()
+    flags_t[16:24] = 2                                            # both buffers are clean for steps 0 and 1
+    for b_ in bufs:
+        clf.device_memset(0, b_, 0, nbytes)
+    clf.sync(0)
+    torch.cuda.synchronize()
+    peers_buf, peers_done, peers_ready, opened = [bufs, bufs], None, None, []
     if args.merge == "p2p":
         handles = [None] * world
-        dist.all_gather_object(handles, clf.ipc_export(my_buf))
-        peers = [my_buf if r == rank else clf.ipc_open(handles[r]) for r in range(world)]
-    my_t = kdist.device_view(my_buf, nbytes, torch.int32, dev)
+        dist.all_gather_object(handles, (clf.ipc_export(bufs[0]), clf.ipc_export(bufs[1]), clf.ipc_export(flags)))
+        pb0, pb1, pf = [], [], []
+        for r in range(world):
+            if r == rank:
+                pb0.append(bufs[0]); pb1.append(bufs[1]); pf.append(flags)
+            else:
+                m = [clf.ipc_open(h) for h in handles[r]]
+                opened += m
+                pb0.append(m[0]); pb1.append(m[1]); pf.append(m[2])
+        peers_buf = [pb0, pb1]
+        peers_done = pf                                           # flag arrays start with the done counters
+        peers_ready = [p + 128 for p in pf]
+    bufs_t = [kdist.device_view(b_, nbytes, torch.int32, dev) for b_ in bufs]
     stream = torch.cuda.ExternalStream(clf.slot_stream(0), device=dev)
+    dist.barrier()                                                # once: every rank's buffers and flags exist
     keep = {}
 
-    def step(i):
-        bptr = pool_bases.data_ptr() + (i % n_batches) * B * READ_LEN
-        clf.device_memset(0, my_buf, 0, nbytes)
-        clf.sync(0)
-        dist.barrier()                                       # all buffers zeroed
+    def step(i, bptr=None):
+        if bptr is None:
+            bptr = pool_bases.data_ptr() + (i % n_batches) * B * READ_LEN
+        par = i & 1
         if args.merge == "p2p":
-            clf.lookup_device_peers(0, bptr, d_offsets.data_ptr(), B, total, peers, bounds)
-            clf.sync(0)
-            dist.barrier()                                   # all hits landed
+            clf.wait_flags(0, flags + 128, world, i + 1)          # every owner has zeroed its buffer of this parity
+            clf.lookup_device_peers(0, bptr, d_offsets.data_ptr(), B, total, peers_buf[par], bounds)
+            clf.signal_peers(0, peers_done, rank, i + 1)
+            clf.wait_flags(0, flags, world, i + 1)                # every GPU's hits for my reads have landed
         else:
-            clf.lookup_device(0, bptr, d_offsets.data_ptr(), B, total, my_buf, only_hits=1)
-            clf.sync(0)
-            dist.all_reduce(my_t, op=dist.ReduceOp.MAX)
-            torch.cuda.synchronize()
+            clf.lookup_device(0, bptr, d_offsets.data_ptr(), B, total, bufs[par], only_hits=1)
+            with torch.cuda.stream(stream):
+                dist.all_reduce(bufs_t[par], op=dist.ReduceOp.MAX)
         if hi > lo:
             u = unit_local[lo:hi] + i * n_units
-            keep[i % 3] = u
-            clf.resolve_device(0, bptr, d_offsets.data_ptr() + lo * 8, hi - lo, total, my_buf,
+            keep[i % 4] = u
+            clf.resolve_device(0, bptr, d_offsets.data_ptr() + lo * 8, hi - lo, total, bufs[par],
                                u.data_ptr() if args.hll_mode == 0 else None)
+        if args.merge == "p2p":
+            clf.device_memset(0, bufs[par] + own_off, 0, own_len)
+            clf.signal_peers(0, peers_ready, rank, i + 3)
+        else:
+            clf.device_memset(0, bufs[par], 0, nbytes)
 
-    assert lo % 2 == 0
     sampler = ClockSampler(local_rank)
     sampler.start()
     s = 0
     for _ in range(args.warmup):
         step(s); s += 1
     clf.sync(0); torch.cuda.synchronize(); dist.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the warm-up's state (record flags included) is merged away outside the timed region
+    kdist.merge_classifier_state_partitioned(clf, dev)
+    torch.cuda.synchronize(); dist.barrier()
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t0 = time.time()
     launches0 = clf.launch_count()
     with torch.cuda.stream(stream):
@@ -572,43 +672,176 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
         step(s); s += 1
     with torch.cuda.stream(stream):
         ev1.record(stream)
+    clf.sync(0)
+    tm = {}
+    kdist.merge_classifier_state_partitioned(clf, dev, timings=tm)
+    with torch.cuda.stream(stream):
+        ev2.record(stream)
     clf.sync(0); torch.cuda.synchronize(); dist.barrier()
     sampler.mark(t0, time.time())
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    ms = torch.tensor([ev0.elapsed_time(ev1), ev0.elapsed_time(ev2)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    dev_ms = float(ms.item())
+    steps_ms, run_ms = float(ms[0].item()), float(ms[1].item())
     launches = clf.launch_count() - launches0
     st = clf.last_stage_ms(0)
-    tm0 = torch.cuda.Event(enable_timing=True); tm1 = torch.cuda.Event(enable_timing=True)
-    tm0.record(); kdist.merge_classifier_state(clf, dev); tm1.record(); torch.cuda.synchronize()
-    merge_ms = tm0.elapsed_time(tm1)
-    clocks = sampler.stop()
     cnt = clf.counts()
+
+    # ---- e2e: the same steps with HOST buffers — every GPU copies the batch from pinned host memory (copy stream,
+    # double buffered against the step before) and reads its share's calls / window counts / hit lists back ----------
+    dres = clf.device_result(0)
+    n_own = hi - lo
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_e2e = args.warmup + args.steps
+    h_in = [torch.empty(total + 64, dtype=torch.uint8).pin_memory() for _ in range(min(n_e2e, n_batches))]
+    first_b = s % n_batches
+    for j, hb in enumerate(h_in):
+        b_ = (first_b + j) % n_batches
+        hb[:total].copy_(pool_bases[b_ * total:(b_ + 1) * total])
+        hb[total:] = ord("N")
+    d_in = [torch.empty(total + 64, dtype=torch.uint8, device=dev) for _ in range(2)]
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    h_out = torch.empty(4 * max(n_own, 1) + 2, dtype=torch.int32).pin_memory()
+    h_runs = torch.empty((total // 2 + 64, 2), dtype=torch.int32).pin_memory()
+    views = None
+    if n_own:
+        views = [kdist.device_view(dres.d_call, n_own * 4, torch.int32, dev), kdist.device_view(dres.d_n_windows, n_own * 4, torch.int32, dev),
+                 kdist.device_view(dres.d_run_start, n_own * 4, torch.int32, dev), kdist.device_view(dres.d_run_count, n_own * 4, torch.int32, dev)]
+        runs_v = kdist.device_view(dres.d_runs, (total // 2 + 64) * 8, torch.int32, dev).view(-1, 2)
+        nruns_v = kdist.device_view(dres.d_n_runs, 8, torch.int64, dev)
+    d2h = [0]
+    est_runs = [min(8 * n_own + 64, total // 2)]
+
+    def step_e2e(i, j):
+        par = j & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[par])
+            d_in[par].copy_(h_in[j % len(h_in)], non_blocking=True)
+            ev_copied[par].record(copy_stream)
+        stream.wait_event(ev_copied[par])
+        step(i, d_in[par].data_ptr())
+        with torch.cuda.stream(stream):
+            ev_free[par].record(stream)
+            if n_own:
+                for q_, v in enumerate(views):
+                    h_out[q_ * n_own:(q_ + 1) * n_own].copy_(v, non_blocking=True)
+                h_runs[:est_runs[0]].copy_(runs_v[:est_runs[0]], non_blocking=True)
+        d2h[0] = 16 * n_own + 8 * est_runs[0]
+
+    for ev in ev_free:
+        ev.record(stream)
+    j = 0
+    for _ in range(args.warmup):
+        step_e2e(s, j); s += 1; j += 1
+    clf.sync(0); torch.cuda.synchronize()
+    if n_own:
+        est_runs[0] = min(int(nruns_v.item()) + 4096, total // 2)      # hit-list volume of a step (same workload every step)
+    kdist.merge_classifier_state_partitioned(clf, dev)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t1 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    for _ in range(args.steps):
+        step_e2e(s, j); s += 1; j += 1
+    clf.sync(0)
+    kdist.merge_classifier_state_partitioned(clf, dev)
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    clf.sync(0); torch.cuda.synchronize(); dist.barrier()
+    sampler.mark(t1, time.time())
+    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e2e.item())
+    d2h_t = torch.tensor([d2h[0]], device=dev, dtype=torch.int64)
+    dist.all_reduce(d2h_t)
+
+    # ---- roofline of the dominant kernel (k_lookup<MODE_LOOKUP> with peer scatter) on rank 0's range: one instrumented
+    # step for the algorithmic bytes, one plain step with a sync after the lookup for its duration -------------------
+    roofline = None
+    if args.merge == "p2p":
+        clf.set_stats(True)
+        bptr = pool_bases.data_ptr() + (s % n_batches) * B * READ_LEN
+        clf.wait_flags(0, flags + 128, world, s + 1)
+        clf.lookup_device_peers(0, bptr, d_offsets.data_ptr(), B, total, peers_buf[s & 1], bounds)
+        clf.sync(0)
+        n_lookups, sum_probes = clf.slot_stats(0)
+        clf.set_stats(False)
+        lk_ms = clf.last_stage_ms(0)
+        clf.signal_peers(0, peers_done, rank, s + 1)
+        clf.wait_flags(0, flags, world, s + 1)
+        clf.device_memset(0, bufs[s & 1] + own_off, 0, own_len)
+        clf.signal_peers(0, peers_ready, rank, s + 3)
+        s += 1
+        k_ms = []
+        for _ in range(2):
+            bptr = pool_bases.data_ptr() + (s % n_batches) * B * READ_LEN
+            clf.wait_flags(0, flags + 128, world, s + 1)
+            clf.lookup_device_peers(0, bptr, d_offsets.data_ptr(), B, total, peers_buf[s & 1], bounds)
+            clf.sync(0)
+            k_ms.append(clf.last_stage_ms(0)[1])
+            clf.signal_peers(0, peers_done, rank, s + 1)
+            clf.wait_flags(0, flags, world, s + 1)
+            clf.device_memset(0, bufs[s & 1] + own_off, 0, own_len)
+            clf.signal_peers(0, peers_ready, rank, s + 3)
+            s += 1
+        clf.sync(0); torch.cuda.synchronize(); dist.barrier()
+        kern_ms = float(np.mean(k_ms))
+        # SURVEY §8(d) for this GPU's range: 17 B per looked-up window of the range + 12 B per probe + the windows' scratch
+        # (12 B canonical k-mer + bin in) and 4 B out per hit are not counted: bin fetch + probes only, plus the read text share
+        algo_bytes = 17 * n_lookups + 12 * sum_probes + (B * (READ_LEN + 4 + 4 * (READ_LEN - 30))) // world
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = {"bound": "hbm", "achieved": algo_bytes / (kern_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": algo_bytes / (kern_ms / 1e3) / 1e9 / peak, "traffic": None,
+                    "kernel": "k_lookup<MODE_LOOKUP> (rank 0's minimizer range, hits stored over NVLink)", "kernel_ms": kern_ms,
+                    "algorithmic_bytes_per_launch": int(algo_bytes), "lookups_in_range": int(n_lookups), "sum_probes": int(sum_probes),
+                    "how": "SURVEY §8(d) per-unit bytes x the units of this GPU's range (17 B per window of the range + 12 B per "
+                           "bisection probe + 1/world of the per-read bytes), kernel duration from CUDA events on the slot stream",
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+    clocks = sampler.stop()
     tot_reads = int(cnt["n_reads"].sum())
     unclassified = int(cnt["n_reads"][cnt["taxid"] == 0].sum())
+    info = clf.sparse_tier_info()
+    line = None
     if rank == 0:
-        value = B * args.steps / (dev_ms / 1e3) / 1e6
-        print(json.dumps({
+        value = B * args.steps / (run_ms / 1e3) / 1e6
+        line = {
             "metric": METRIC, "value": value, "unit": "Mreads/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": run_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload, "parallelism": f"database sharded by minimizer range over {world} GPUs "
-                       f"({(rec_hi - rec_lo) * 12 / 1e9:.1f} GB of records on rank 0), every GPU scans every batch, "
-                       f"id merge = {args.merge}", "hll_mode": ["preload rule", "chunked rule", "dense only"][args.hll_mode],
-                       "timing": "CUDA events on the slot stream around the K steps (host barriers between the phases "
-                                 "included), max over ranks", "end_of_run_merge_ms": merge_ms, "workload_gen_s": gen_s,
-                       "owner_stage_ms_last_step": {"k_scan": st[0], "k_lookup(hll from merged ids)": st[1], "k_resolve": st[2]}},
+                       f"({db.key_ct * 12 / 1e9:.1f} GB of records on rank 0), every GPU scans every batch, the finder of a hit "
+                       f"does its sketch work, id merge = {args.merge}",
+                       "hll_mode": ["preload rule", "chunked rule", "dense only"][args.hll_mode],
+                       "timing": "CUDA events on the slot stream around the K steps AND the end-of-run merge of the per-taxon "
+                                 "state (run_ms); no host barrier inside the step loop (device flags over NVLink); max over ranks",
+                       "l2": "inputs larger than L2: 150 MB of reads per step, the database ranges are probed at random",
+                       "steps_ms": steps_ms, "run_ms": run_ms, "end_of_run_merge_ms": run_ms - steps_ms,
+                       "steps_only_mreads_s": B * args.steps / (steps_ms / 1e3) / 1e6,
+                       "merge": tm, "sparse_tier": info, "workload_gen_s": gen_s,
+                       "owner_stage_ms_last_step": {"k_scan": st[0], "k_lookup(misses + merged ids)": st[1], "k_resolve": st[2]}},
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": B * args.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mreads/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": world * (total + 64), "d2h_bytes_per_step": int(d2h_t.item()),
+                    "how": "every GPU copies the whole batch from pinned host memory (copy stream, double buffered), runs the "
+                           "sharded step through the C ABI, and copies its share's calls / window counts / RLE hit lists to pinned "
+                           "host memory; the end-of-run merge is inside the timed region; max over ranks"},
             "sanity": {"reads_counted": tot_reads, "classified_fraction": 1.0 - unclassified / max(tot_reads, 1),
                        "expected": "about 0.80 (80 % of the reads come from the database genomes)"},
-            "gpu_launches": int(launches), "clocks": clocks}))
+            "gpu_launches": int(launches), "clocks": clocks}
+        if extra:
+            line.update(extra)
     dist.barrier()
-    if peers:
-        for r in range(world):
-            if r != rank:
-                clf.ipc_close(peers[r])
+    for p_ in opened:
+        clf.ipc_close(p_)
     dist.barrier()
-    dist.destroy_process_group()
-    return 0
+    return line
 
 
 if __name__ == "__main__":

@@ -235,6 +235,8 @@ int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out);
 /* With KUQ_F_STATS: number of non-ambiguous windows looked up by the slot's last batch and the sum over them of
  * ceil(log2(bin size + 1)) — the textbook probe count SURVEY.md §8(d) defines the algorithmic bytes with. */
 int kuq_slot_stats(kuq_ctx *ctx, uint32_t slot, uint64_t *n_lookups, uint64_t *sum_probes);
+/* Turn KUQ_F_STATS on / off for every later call, including those that take no flags (kuq_lookup_device_peers). */
+int kuq_set_stats(kuq_ctx *ctx, int on);
 /* CUDA stream (cudaStream_t) of a slot, so callers can order their own work (e.g. NCCL) against it. */
 void *kuq_slot_stream(kuq_ctx *ctx, uint32_t slot);
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
@@ -310,6 +312,29 @@ uint64_t kuq_ertl_dense_hist(const uint32_t *hist64, uint64_t n_observed);
 int kuq_scan_device(kuq_ctx *ctx, uint32_t slot, uint32_t k, uint32_t nt, uint32_t idx_type, const char *d_bases,
                     const uint64_t *d_read_offsets, uint32_t n_reads, uint64_t total_bases, uint64_t *d_canon_out,
                     uint32_t *d_bins_out);
+
+/* ---- a database larger than HBM, streamed range by range (classify -x / --preload-size, krakendb.cpp:411-526) ------
+ * kuq_stage_db replaces the staged range synchronously.  The stream calls keep TWO device buffers and a copy stream, so
+ * the next minimizer range travels over PCIe while the lookups of the current one run:
+ *     kuq_set_db_taxid_universe(all taxids of the database); kuq_set_taxonomy(...);
+ *     kuq_stream_open(k, nt, idx_type, max records / bins of a range)
+ *     kuq_stream_load(0, range 0)
+ *     for r in ranges:  kuq_stream_use(r & 1);  kuq_stream_load((r + 1) & 1, range r + 1);      // order matters
+ *                       kuq_lookup_device(... only_hits = 1 ...) for every batch, ids merged in the caller's buffers
+ *     kuq_resolve_device(...) for every batch                                  // the final pass (classify.cpp:663-791)
+ * host_records = the range's records (12 bytes each, raw taxids, as in database.kdb), host_offsets = the bin_hi -
+ * bin_lo + 1 cumulative ABSOLUTE record offsets of its bins (a slice of database.idx); both should be pinned
+ * (kuq_host_alloc / kuq_host_register) or the copy will not overlap.  kuq_stream_load waits, on the device, for the
+ * work queued on the slots so far (the users of the buffer it overwrites), never for the host.  Record values are
+ * rewritten to dense ids on arrival; kuq_stream_check reports a taxid outside the declared universe. */
+int kuq_stream_open(kuq_ctx *ctx, uint32_t k, uint32_t nt, uint32_t idx_type, uint64_t max_records, uint64_t max_bins);
+int kuq_stream_load(kuq_ctx *ctx, uint32_t buf, const void *host_records, uint64_t n_records, const uint64_t *host_offsets,
+                    uint64_t bin_lo, uint64_t bin_hi);
+int kuq_stream_use(kuq_ctx *ctx, uint32_t buf);
+int kuq_stream_check(kuq_ctx *ctx);
+/* Pin / unpin caller memory (e.g. an mmap'ed database.kdb) for asynchronous copies. */
+int kuq_host_register(void *p, uint64_t bytes);
+int kuq_host_unregister(void *p);
 
 /* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);

@@ -130,6 +130,13 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_reset_counts": (C.c_int, [vp]),
         "kuq_sparse_tier_info": (C.c_int, [vp, u64p, u64p, u64p, C.POINTER(C.c_double)]),
         "kuq_set_shard_counting": (C.c_int, [vp, C.c_int]),
+        "kuq_set_stats": (C.c_int, [vp, C.c_int]),
+        "kuq_stream_open": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
+        "kuq_stream_load": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64]),
+        "kuq_stream_use": (C.c_int, [vp, C.c_uint32]),
+        "kuq_stream_check": (C.c_int, [vp]),
+        "kuq_host_register": (C.c_int, [vp, C.c_uint64]),
+        "kuq_host_unregister": (C.c_int, [vp]),
         "kuq_signal_peers": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint64]),
         "kuq_wait_flags": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint64, C.c_uint32]),
         "kuq_sparse_export_partitioned": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, u64p]),
@@ -435,6 +442,21 @@ class Classifier:
 
     def sparse_import(self, d_keys, n):
         self._ck(self.L.kuq_sparse_import(self.h, d_keys, n))
+
+    def stream_open(self, k, nt, idx_type, max_records, max_bins):
+        self._ck(self.L.kuq_stream_open(self.h, k, nt, idx_type, max_records, max_bins))
+
+    def stream_load(self, buf, host_records_ptr, n_records, host_offsets_ptr, bin_lo, bin_hi):
+        self._ck(self.L.kuq_stream_load(self.h, buf, host_records_ptr, n_records, host_offsets_ptr, bin_lo, bin_hi))
+
+    def stream_use(self, buf):
+        self._ck(self.L.kuq_stream_use(self.h, buf))
+
+    def stream_check(self):
+        self._ck(self.L.kuq_stream_check(self.h))
+
+    def set_stats(self, on=True):
+        self._ck(self.L.kuq_set_stats(self.h, 1 if on else 0))
 
     def set_shard_counting(self, on=True):
         self._ck(self.L.kuq_set_shard_counting(self.h, 1 if on else 0))

@@ -29,7 +29,7 @@ constexpr uint32_t USET_CAP = 1u << 22;                       // distinct (pair,
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_stage[2] = {nullptr, nullptr}, ev_sync = nullptr;
   double stage_ms[3] = {0, 0, 0};
   // device
   char *d_bases = nullptr, *d_clean = nullptr;
@@ -124,7 +124,20 @@ struct kuq_ctx {
   unsigned long long *d_exact_count = nullptr;
   uint64_t exact_cap = 0;
 
+  // database streamed through HBM range by range (kuq_stream_*): two device buffers, one copy stream
+  struct StreamBuf {
+    uint8_t *d_pairs = nullptr;
+    uint64_t *d_offsets = nullptr;
+    cudaEvent_t ready = nullptr;
+    uint64_t key_ct = 0, rec_base = 0, bin_lo = 0, bin_hi = 0;
+    bool loaded = false;
+  } sbuf[2];
+  bool stream_open = false;
+  uint64_t stream_cap_records = 0, stream_cap_bins = 0;
+  cudaStream_t copy_stream = nullptr;
+  uint32_t *d_stream_missing = nullptr;
   bool shard_counting = false;            // kuq_set_shard_counting: hits are counted by the GPU that finds them
+  uint32_t extra_flags = 0;               // kuq_set_stats: KUQ_F_STATS for calls that take no flags
   uint32_t *d_sync_err = nullptr;         // set by a kuq_wait_flags that timed out
   bool merged_summary = false;            // kuq_set_sparse_summary: snap.sparse_hist / distinct hold cross-GPU sums
   std::vector<uint32_t> merged_hist, merged_distinct;
@@ -138,6 +151,8 @@ struct kuq_ctx {
 };
 
 namespace {
+
+void stream_close(kuq_ctx *ctx);
 
 int fail(kuq_ctx *c, int code, const char *fmt, ...) {
   if (c) {
@@ -175,6 +190,7 @@ void free_slot(Slot &s) {
   if (s.ev_k1) cudaEventDestroy(s.ev_k1);
   if (s.ev_stage[0]) cudaEventDestroy(s.ev_stage[0]);
   if (s.ev_stage[1]) cudaEventDestroy(s.ev_stage[1]);
+  if (s.ev_sync) cudaEventDestroy(s.ev_sync);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Slot();
 }
@@ -244,6 +260,7 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   CU(cudaEventCreate(&s.ev_k1));
   CU(cudaEventCreate(&s.ev_stage[0]));
   CU(cudaEventCreate(&s.ev_stage[1]));
+  CU(cudaEventCreateWithFlags(&s.ev_sync, cudaEventDisableTiming));
   CU(dmalloc(&s.d_bases, mb + SLACK));
   CU(dmalloc(&s.d_clean, mb + SLACK));
   CU(dmalloc(&s.d_offsets, mr + 4));   // + slack: offsets slices are bulk-copied in 16-byte units
@@ -629,6 +646,7 @@ void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const ui
 int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
   if (ctx->lca_mode) return fail(ctx, KUQ_E_STATE, "this context built a database (kuq_set_lcas_batch): stage it anew to classify");
   ctx->snap_valid = false;
+  p.flags |= ctx->extra_flags;
   if (mode == MODE_LOOKUP && ctx->mark_zero_hits) p.flags |= 16u;
   if (ctx->shard_counting && mode != MODE_FUSED && !ctx->mark_zero_hits && !ctx->quick_min &&
       ctx->cfg.hll_mode != KUQ_HLL_EXACT) {
@@ -760,6 +778,7 @@ void kuq_destroy(kuq_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto &s : ctx->slots) free_slot(s);
+  stream_close(ctx);
   free_db(ctx);
   free_tax_state(ctx);
   cudaFree(ctx->d_sync_err);
@@ -811,6 +830,7 @@ int kuq_stage_db(kuq_ctx *ctx, const void *kdb_image, uint64_t kdb_bytes, const 
   if (rec_hi < rec_lo || rec_hi > key_ct) return fail(ctx, KUQ_E_DB_FORMAT, "index offsets inconsistent with key count");
   // taxonomy numbering survives a re-stage (chunked mode) as long as the new range only holds numbered taxids
   { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
+  stream_close(ctx);
   free_db(ctx);
   ctx->k = k; ctx->nt = nt; ctx->idx_type = idx_type;
   ctx->bin_lo = bin_lo; ctx->bin_hi = bin_hi;
@@ -1593,6 +1613,144 @@ int kuq_set_shard_counting(kuq_ctx *ctx, int on) {
   for (auto &s : ctx->slots)
     if (s.busy) return fail(ctx, KUQ_E_STATE, "cannot change while a batch is in flight");
   ctx->shard_counting = on != 0;
+  return KUQ_OK;
+}
+
+// ---- a database larger than HBM: ranges streamed from pinned host memory, copy overlapped with the lookups -------------
+extern "C++" {
+namespace {
+uint32_t host_hash_u32(uint32_t x) {                        // == hash_u32 of kuq_kernels.cu
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+void stream_close(kuq_ctx *ctx) {
+  for (auto &b : ctx->sbuf) {
+    cudaFree(b.d_pairs); cudaFree(b.d_offsets);
+    if (b.ready) cudaEventDestroy(b.ready);
+    b = kuq_ctx::StreamBuf();
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  ctx->copy_stream = nullptr;
+  cudaFree(ctx->d_stream_missing);
+  ctx->d_stream_missing = nullptr;
+  if (ctx->stream_open) { ctx->d_pairs = nullptr; ctx->d_offsets = nullptr; ctx->db_staged = false; }
+  ctx->stream_open = false;
+}
+}  // namespace
+}  // extern "C++"
+
+int kuq_stream_open(kuq_ctx *ctx, uint32_t k, uint32_t nt, uint32_t idx_type, uint64_t max_records, uint64_t max_bins) {
+  if (!ctx || !max_records || !max_bins) return KUQ_E_INVALID_ARG;
+  if (k < 29 || k > 31) return fail(ctx, KUQ_E_UNSUPPORTED_K, "k = %u: only 8-byte keys (k = 29..31)", k);
+  if (nt < 1 || nt > 15 || (idx_type != 1 && idx_type != 2)) return fail(ctx, KUQ_E_INVALID_ARG, "bad index parameters");
+  if (ctx->universe.empty()) return fail(ctx, KUQ_E_STATE, "declare the taxids of the whole database first (kuq_set_db_taxid_universe)");
+  if (!ctx->tax_set) return fail(ctx, KUQ_E_STATE, "no taxonomy set");
+  CU(cudaSetDevice(ctx->device));
+  { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
+  free_db(ctx);
+  stream_close(ctx);
+  ctx->k = k; ctx->nt = nt; ctx->idx_type = idx_type;
+  ctx->db_owned = false;
+  ctx->db_taxids = ctx->universe;
+  std::sort(ctx->db_taxids.begin(), ctx->db_taxids.end());
+  ctx->db_taxids.erase(std::unique(ctx->db_taxids.begin(), ctx->db_taxids.end()), ctx->db_taxids.end());
+  ctx->db_taxid_counts.assign(ctx->db_taxids.size(), 0);
+  ctx->db_staged = true;
+  int rc = finalize(ctx);
+  if (rc) { ctx->db_staged = false; return rc; }
+  // device table taxid → dense id over the whole universe (what collect_taxids builds per staged range otherwise)
+  uint32_t cap = 1u << 16;
+  while ((uint64_t)cap < 4ull * ctx->db_taxids.size()) cap <<= 1;
+  std::vector<uint32_t> keys(cap, 0), dense(cap, 0);
+  for (uint32_t t : ctx->db_taxids) {
+    uint32_t slot = host_hash_u32(t) & (cap - 1);
+    while (keys[slot]) slot = (slot + 1) & (cap - 1);
+    keys[slot] = t + 1;
+    dense[slot] = ctx->dense_of_raw[t];
+  }
+  CU(dmalloc(&ctx->d_tx_keys, cap));
+  CU(dmalloc(&ctx->d_tx_dense, cap));
+  CU(cudaMemcpy(ctx->d_tx_keys, keys.data(), cap * 4ull, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->d_tx_dense, dense.data(), cap * 4ull, cudaMemcpyHostToDevice));
+  ctx->tx_cap = cap;
+  ctx->db_remapped = true;                       // each range is remapped as it arrives
+  CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU(dmalloc(&ctx->d_stream_missing, 1));
+  CU(cudaMemset(ctx->d_stream_missing, 0, 4));
+  for (auto &b : ctx->sbuf) {
+    CU(cudaMalloc((void **)&b.d_pairs, max_records * 12 + SLACK));
+    CU(dmalloc(&b.d_offsets, max_bins + 1));
+    CU(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
+  }
+  ctx->stream_cap_records = max_records;
+  ctx->stream_cap_bins = max_bins;
+  ctx->stream_open = true;
+  ctx->key_ct = 0;
+  return KUQ_OK;
+}
+
+int kuq_stream_load(kuq_ctx *ctx, uint32_t buf, const void *host_records, uint64_t n_records, const uint64_t *host_offsets,
+                    uint64_t bin_lo, uint64_t bin_hi) {
+  if (!ctx || buf > 1 || !host_offsets || (!host_records && n_records)) return KUQ_E_INVALID_ARG;
+  if (!ctx->stream_open) return fail(ctx, KUQ_E_STATE, "kuq_stream_open first");
+  if (bin_lo >= bin_hi || bin_hi - bin_lo > ctx->stream_cap_bins || n_records > ctx->stream_cap_records)
+    return fail(ctx, KUQ_E_CAPACITY, "range of %llu records / %llu bins exceeds the stream buffers", (unsigned long long)n_records,
+                (unsigned long long)(bin_hi - bin_lo));
+  CU(cudaSetDevice(ctx->device));
+  kuq_ctx::StreamBuf &b = ctx->sbuf[buf];
+  // whoever still reads this buffer was queued before this call: the copy waits for the slots' streams as they stand
+  if (ctx->seen_dirty) { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
+  for (auto &s : ctx->slots) {
+    CU(cudaEventRecord(s.ev_sync, s.stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, s.ev_sync, 0));
+  }
+  if (n_records) CU(cudaMemcpyAsync(b.d_pairs, host_records, n_records * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU(cudaMemcpyAsync(b.d_offsets, host_offsets, (bin_hi - bin_lo + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+  launch_remap_values(b.d_pairs, n_records, ctx->d_tx_keys, ctx->d_tx_dense, ctx->tx_cap - 1, ctx->d_stream_missing,
+                      ctx->k >= 32 ? ~0ull : ((1ull << (2 * ctx->k)) - 1), ctx->copy_stream);
+  ctx->launches++;
+  CU(cudaEventRecord(b.ready, ctx->copy_stream));
+  b.key_ct = n_records; b.rec_base = host_offsets[0]; b.bin_lo = bin_lo; b.bin_hi = bin_hi; b.loaded = true;
+  return KUQ_OK;
+}
+
+int kuq_stream_use(kuq_ctx *ctx, uint32_t buf) {
+  if (!ctx || buf > 1) return KUQ_E_INVALID_ARG;
+  if (!ctx->stream_open || !ctx->sbuf[buf].loaded) return fail(ctx, KUQ_E_STATE, "stream buffer %u holds no range", buf);
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->seen_dirty) { int hrc = harvest_seen(ctx, false); if (hrc) return hrc; }
+  kuq_ctx::StreamBuf &b = ctx->sbuf[buf];
+  for (auto &s : ctx->slots) CU(cudaStreamWaitEvent(s.stream, b.ready, 0));
+  ctx->d_pairs = b.d_pairs; ctx->d_offsets = b.d_offsets;
+  ctx->key_ct = b.key_ct; ctx->rec_base = b.rec_base; ctx->bin_lo = b.bin_lo; ctx->bin_hi = b.bin_hi;
+  return KUQ_OK;
+}
+
+int kuq_stream_check(kuq_ctx *ctx) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  if (!ctx->stream_open) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  uint32_t missing = 0;
+  CU(cudaMemcpy(&missing, ctx->d_stream_missing, 4, cudaMemcpyDeviceToHost));
+  if (missing) return fail(ctx, KUQ_E_STATE, "a streamed range holds a taxid outside the declared universe");
+  return KUQ_OK;
+}
+
+int kuq_host_register(void *p, uint64_t bytes) {
+  if (!p || !bytes) return KUQ_E_INVALID_ARG;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { (void)cudaGetLastError(); return KUQ_E_CUDA; }
+  return KUQ_OK;
+}
+int kuq_host_unregister(void *p) {
+  if (!p) return KUQ_E_INVALID_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) { (void)cudaGetLastError(); return KUQ_E_CUDA; }
+  return KUQ_OK;
+}
+
+int kuq_set_stats(kuq_ctx *ctx, int on) {
+  if (!ctx) return KUQ_E_INVALID_ARG;
+  ctx->extra_flags = on ? KUQ_F_STATS : 0u;
   return KUQ_OK;
 }
 

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
         }
       }
     } else if (p.flags & 8u) {
-      atomicAdd(p.stats, 1ull);
+      atomicAdd(p.stats + 3, 1ull);                          // a window of another range: nothing fetched here
     }
     // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
     // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.

@@ -10,6 +10,7 @@ Works on CPU tensors with gloo (tests) and on HBM tensors with NCCL over NVLink 
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -47,6 +48,21 @@ def gather_sparse_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([out[r][:int(sizes[r].item())] for r in range(world) if r != rank]) if world > 1 else keys.new_zeros(0)
 
 
+def exchange_partitioned_keys(keys: torch.Tensor, counts, group=None) -> torch.Tensor:
+    """One all-to-all of key segments: `keys` holds the segment for rank 0, 1, ... back to back (`counts[r]` keys for
+    rank r); returns the keys every rank (this one included) sent to this rank.  O(keys / world) per rank."""
+    world = dist.get_world_size(group)
+    send = torch.tensor([int(c) for c in counts], dtype=torch.int64, device=keys.device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_l = [int(x) for x in recv.tolist()]
+    out = keys.new_empty(sum(recv_l))
+    dist.all_to_all_single(out, keys[:int(send.sum())], output_split_sizes=recv_l,
+                           input_split_sizes=[int(c) for c in counts], group=group)
+    assert len(recv_l) == world
+    return out
+
+
 def device_view(ptr: int, nbytes: int, dtype: torch.dtype, device):
     """torch view of library-owned device memory (for the collectives only)"""
     class _Holder:
@@ -79,3 +95,64 @@ def merge_classifier_state(clf, device, group=None):
     if others.numel():
         clf.sparse_import(others.data_ptr(), others.numel())
     torch.cuda.synchronize()
+
+
+def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | None = None):
+    """End-of-run merge in O(state / world) per rank (replicas or database shards):
+      1. all-reduce MAX of the dense flags FIRST, so that the harvest of the record flags skips taxa that are dense
+         anywhere (their codes are never needed: sparse + dense → dense, hyperloglogplus.cpp:604-612);
+      2. harvest (kuq_finish), all-reduce MAX of the registers, SUM of the counters;
+      3. sparse tier: keys grouped by the rank owning their code → one all-to-all → each rank dedups its slice
+         (kuq_sparse_replace) → all-reduce SUM of the per-taxon rank histograms and distinct counts
+         (kuq_set_sparse_summary).  Clade unions: `clade_counts_distributed`."""
+    import time
+    world = dist.get_world_size(group)
+    t0 = time.time()
+    sp = clf.state_ptrs()
+    regs = device_view(sp.d_regs, sp.regs_bytes, torch.uint8, device)
+    nk = device_view(sp.d_n_kmers, sp.n_sketch * 8, torch.int64, device)
+    nr = device_view(sp.d_n_reads, sp.n_taxa * 8, torch.int64, device)
+    flag = device_view(sp.d_dense_flag, sp.n_sketch, torch.uint8, device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    torch.cuda.synchronize()
+    clf.finish()
+    merge_state_tensors(regs, nk, nr, None, group)
+    n_max = clf.sparse_tier_info()["keys"]
+    keys = torch.empty(max(n_max, 1), dtype=torch.int64, device=device)
+    counts = clf.sparse_export_partitioned(world, keys.data_ptr(), keys.numel())
+    recv = exchange_partitioned_keys(keys, counts.tolist(), group)
+    torch.cuda.synchronize()
+    clf.sparse_replace(recv.data_ptr() if recv.numel() else None, recv.numel())
+    hist = torch.zeros(sp.n_sketch * 64, dtype=torch.int32, device=device)
+    distinct = torch.zeros(sp.n_sketch, dtype=torch.int32, device=device)
+    clf.sparse_summary(hist.data_ptr(), distinct.data_ptr())
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(distinct, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.synchronize()
+    clf.set_sparse_summary(hist.data_ptr(), distinct.data_ptr())
+    if timings is not None:
+        timings["merge_wall_ms"] = (time.time() - t0) * 1e3
+        timings["keys_exported"] = int(counts.sum())
+        timings["keys_after_dedup"] = int(recv.numel())
+
+
+def clade_counts_distributed(clf, clades, device, group=None):
+    """(unique, reads, kmers) per clade (list of taxid lists) after merge_classifier_state_partitioned: the union
+    histograms of the code partitions add up; one all-reduce for all clades."""
+    from . import binding
+    parts = [clf.clade_partial(c) for c in clades]
+    hist = torch.tensor(np.stack([p[3] for p in parts]).astype(np.int64) if parts else np.zeros((0, 64), np.int64), device=device)
+    dense = [p[2] for p in parts]
+    # dense clades: every rank holds the all-reduced registers, so its histogram is already the global one
+    for i, d in enumerate(dense):
+        if d and dist.get_rank(group) != 0:
+            hist[i] = 0
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    h = hist.cpu().numpy().astype(np.uint32)
+    out = []
+    for i, (r, k, d, _) in enumerate(parts):
+        u = 0
+        if k:
+            u = binding.ertl_dense_hist(h[i], k) if d else binding.ertl_sparse(h[i], k)
+        out.append((u, r, k))
+    return out

@@ -70,12 +70,54 @@ def make_taxonomy_rows(n_genomes: int, first_id: int = 100):
     return rows, sp
 
 
+class _DeviceScanner:
+    """canonical k-mer + minimizer bin of every window of a code tensor through the product's own scan stage
+    (kuq_scan_device → k_scan): two orders of magnitude faster than the elementwise torch loops above, which remain
+    the CPU / validation path (tests/test_synth_gpu.py compares both with the reference's db_sort)."""
+    PIECE = 352                                   # pseudo-read length (16-byte multiple): k_scan runs a warp per read
+
+    def __init__(self, device: torch.device, k: int, nt: int, idx_type: int, chunk: int):
+        from . import binding
+        self.k, self.nt, self.idx_type, self.dev = k, nt, idx_type, device
+        self.win = self.PIECE - (k - 1)
+        n_pieces = -(-chunk // self.win)
+        self.clf = binding.Classifier(device=device.index or 0, n_slots=1, max_reads=n_pieces + 64,
+                                      max_bases=n_pieces * self.PIECE + 4096, sparse_set_slots=1024)
+        self.lut = torch.tensor([ord(c) for c in "ACGT"], dtype=torch.uint8, device=device)
+
+    def scan(self, codes: torch.Tensor, start: int, count: int):
+        """windows [start, start+count) of `codes` → (canonical k-mers int64, bins int64)"""
+        k, win, P = self.k, self.win, self.PIECE
+        n_pieces = -(-count // win)
+        idx = (torch.arange(n_pieces, device=self.dev, dtype=torch.int64)[:, None] * win + start +
+               torch.arange(P, device=self.dev, dtype=torch.int64)[None, :])
+        idx.clamp_(max=codes.numel() - 1)
+        text = torch.empty(n_pieces * P + 64, dtype=torch.uint8, device=self.dev)
+        text[:n_pieces * P] = self.lut[codes[idx.reshape(-1)].to(torch.int64)]
+        text[n_pieces * P:] = ord("N")
+        del idx
+        offs = torch.arange(n_pieces + 2, dtype=torch.int64, device=self.dev) * P
+        offs[-1] = offs[-2]
+        canon = torch.empty(n_pieces * P + 64, dtype=torch.int64, device=self.dev)
+        bins = torch.empty(n_pieces * P + 64, dtype=torch.int32, device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        self.clf.scan_device(0, k, self.nt, self.idx_type, text.data_ptr(), offs.data_ptr(), n_pieces, n_pieces * P,
+                             canon.data_ptr(), bins.data_ptr())
+        self.clf.sync(0)
+        km = canon[:n_pieces * P].view(n_pieces, P)[:, :win].reshape(-1)[:count]
+        bn = bins[:n_pieces * P].view(n_pieces, P)[:, :win].reshape(-1)[:count].to(torch.int64)
+        return km, bn
+
+    def close(self):
+        self.clf.close()
+
+
 class GpuDatabase:
     """A synthetic database resident in HBM in the on-disk layout."""
 
     def __init__(self, n_records: int, n_genomes: int = 2000, k: int = 31, nt: int = 15, idx_type: int = 2,
                  seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26, passes: int = 1,
-                 shard: tuple[int, int] | None = None):
+                 shard: tuple[int, int] | None = None, use_kernel_scan: bool = True):
         """`passes` > 1 builds the database one minimizer range at a time (temporaries of one range only), for
         databases whose sort would not fit next to the result (tens of GB and more, > 2^32 records).
         `shard` = (rank, world): keep only this rank's minimizer range of a database cut into `world` ranges with
@@ -109,6 +151,7 @@ class GpuDatabase:
                 self.bin_lo, self.bin_hi = cuts[0], cuts[-1]
         else:
             cuts = [0, n_bins]
+        scanner = _DeviceScanner(dev, k, nt, idx_type, chunk) if dev.type == "cuda" and use_kernel_scan else None
         selective = n_parts > 1
         n_rows = n_pos if not shard else int(n_pos / shard[1] * 1.25) + (1 << 20)
         rec = torch.empty((n_rows, 3), dtype=torch.int32, device=dev)     # (n, 3) int32 == packed 12-byte records
@@ -121,8 +164,11 @@ class GpuDatabase:
             keys_l, bins_l, pos_l = [], [], []
             for a in range(0, n_pos, chunk):
                 c = min(chunk, n_pos - a)
-                km = canonical(forward_kmers(self.genome, a, c, k), k)
-                bn = bin_key(km, k, nt, idx_type)
+                if scanner is not None:
+                    km, bn = scanner.scan(self.genome, a, c)
+                else:
+                    km = canonical(forward_kmers(self.genome, a, c, k), k)
+                    bn = bin_key(km, k, nt, idx_type)
                 if selective:
                     sel = (bn >= lo) & (bn < hi)
                     keys_l.append(km[sel])
@@ -164,6 +210,8 @@ class GpuDatabase:
             counts += torch.bincount(bins.to(torch.int64) - self.bin_lo, minlength=self.bin_hi - self.bin_lo)
             del keys, taxa, bins
             torch.cuda.empty_cache() if dev.type == "cuda" else None
+        if scanner is not None:
+            scanner.close()
         self.key_ct = out
         self.records = rec[:out]
         off = torch.zeros(self.bin_hi - self.bin_lo + 1, dtype=torch.int64, device=dev)

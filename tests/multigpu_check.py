@@ -67,12 +67,19 @@ def main():
     rep.finish()
     if got_res is not None:
         assert np.array_equal(got_res["call"], want_res["call"][lo:hi])
-    kdist.merge_classifier_state(rep, dev)
+    kdist.merge_classifier_state_partitioned(rep, dev)
     got = rep.counts()
     for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
         assert np.array_equal(got[key], want[key]), (rank, "replicas", key, got[key], want[key])
     for t in want["taxid"].tolist():
         assert np.array_equal(rep.registers(t), single.registers(t))
+    # clade roll-ups over the code partitions (sum of the per-GPU union histograms) == the single-GPU clade sketches
+    from tests import util
+    members = util.clade_members(tax.rows, want["taxid"])
+    clades = [members[t] for t in sorted(members)]
+    got_cl = kdist.clade_counts_distributed(rep, clades, dev)
+    for c, g in zip(clades, got_cl):
+        assert g == single.clade(c), (rank, "replica clades", c, g, single.clade(c))
 
     # ---- minimizer-range shards ----------------------------------------------------------------------------------
     n_bins = 1 << 18
@@ -153,6 +160,77 @@ def main():
     dist.barrier()
     sp.device_free(my_buf)
 
+    # ---- shards as bench.py runs them: the finder of a hit does its sketch work, device flags instead of host
+    # barriers, double-buffered id buffers, several steps, code-partitioned merge at the end ------------------------
+    sf = fresh()
+    sf.set_db_taxid_universe(all_t)
+    sf.stage_db(kdb, idx, cuts[rank], cuts[rank + 1])
+    sf.set_shard_counting(True)
+    n_steps = 3
+    step_reads = [kdist.partition(n, n_steps, i) for i in range(n_steps)]
+    # cut the steps at unit boundaries too
+    def unit_cut(a):
+        while 0 < a < n and units[a] == units[a - 1]:
+            a += 1
+        return a
+    step_reads = [(unit_cut(a), unit_cut(b)) for a, b in step_reads]
+    bufs = [sf.device_alloc(nbytes) for _ in range(2)]
+    flg = sf.device_alloc(256)
+    ft = kdist.device_view(flg, 256, torch.int64, dev)
+    ft.zero_(); ft[16:24] = 2
+    for b_ in bufs:
+        sf.device_memset(0, b_, 0, nbytes)
+    sf.sync(0); torch.cuda.synchronize()
+    hs = [None] * world
+    dist.all_gather_object(hs, (sf.ipc_export(bufs[0]), sf.ipc_export(bufs[1]), sf.ipc_export(flg)))
+    opened, pb, pf = [], [[], []], []
+    for r in range(world):
+        if r == rank:
+            pb[0].append(bufs[0]); pb[1].append(bufs[1]); pf.append(flg)
+        else:
+            m = [sf.ipc_open(h) for h in hs[r]]
+            opened += m
+            pb[0].append(m[0]); pb[1].append(m[1]); pf.append(m[2])
+    dist.barrier()
+    for i, (sa, sb) in enumerate(step_reads):
+        # owners of this step's reads: contiguous shares cut at unit boundaries
+        cutsr = [unit_cut(sa + (sb - sa) * r // world) for r in range(world)] + [sb]
+        a, b = cutsr[rank], cutsr[rank + 1]
+        bnd = np.array([int(offs[c]) for c in cutsr], np.uint64)
+        bnd[0], bnd[-1] = int(offs[sa]), int(offs[sb])
+        sub = d_offs[sa:sb + 2].contiguous()
+        assert sub.data_ptr() % 16 == 0 or sa == sb
+        par = i & 1
+        sf.wait_flags(0, flg + 128, world, i + 1)
+        if sb > sa:
+            sf.lookup_device_peers(0, d_bases.data_ptr(), sub.data_ptr(), sb - sa, int(offs[-1]), pb[par], bnd)
+        sf.signal_peers(0, pf, rank, i + 1)
+        sf.wait_flags(0, flg, world, i + 1)
+        if b > a:
+            so = d_offs[a:b + 2].contiguous()
+            assert so.data_ptr() % 16 == 0
+            sf.resolve_device(0, d_bases.data_ptr(), so.data_ptr(), b - a, int(offs[-1]), bufs[par],
+                              d_units[a:b].contiguous().data_ptr())
+        sf.device_memset(0, bufs[par], 0, nbytes)
+        sf.signal_peers(0, [p_ + 128 for p_ in pf], rank, i + 3)
+        sf.sync(0)
+    kdist.merge_classifier_state_partitioned(sf, dev)
+    got = sf.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        if not np.array_equal(got[key], want[key]):
+            bad = np.nonzero(got[key] != want[key])[0]
+            raise AssertionError((rank, "flag shards", key, bad[:8].tolist(), got["taxid"][bad[:8]].tolist(),
+                                  got[key][bad[:8]].tolist(), want[key][bad[:8]].tolist()))
+    for t in want["taxid"].tolist():
+        assert np.array_equal(sf.registers(t), single.registers(t)), ("flag shards registers", t)
+    got_cl = kdist.clade_counts_distributed(sf, clades, dev)
+    for c, g in zip(clades, got_cl):
+        assert g == single.clade(c), (rank, "flag shard clades", c, g, single.clade(c))
+    dist.barrier()
+    for p_ in opened:
+        sf.ipc_close(p_)
+    dist.barrier()
+
     # and against the oracle (rank 0)
     if rank == 0:
         from oracle.oracle_py import Oracle
@@ -165,7 +243,8 @@ def main():
         assert 5 < int(want["sparse"].sum()) < len(want["taxid"]) - 2, "the case must mix sparse and dense taxa"
         for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
             assert np.array_equal(oc[key], want[key]), ("oracle", key)
-        print(f"multigpu_check OK on {world} GPUs: replicas, minimizer-range shards (NCCL id merge) and shards with NVLink peer scatter reproduce the single-GPU state "
+        print(f"multigpu_check OK on {world} GPUs: replicas (code-partitioned merge), minimizer-range shards (NCCL id merge), shards with NVLink "
+              f"peer scatter, and flag-synchronised shards with finder-side counting reproduce the single-GPU state "
               f"({len(want['taxid'])} taxa, {int(want['sparse'].sum())} sparse)")
     dist.barrier()
     dist.destroy_process_group()

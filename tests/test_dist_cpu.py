@@ -118,3 +118,42 @@ def test_two_rank_merge_equals_single_run(oracle):
     assert np.array_equal(nk, w_nk) and np.array_equal(nr, w_nr)
     assert np.array_equal(union, w_keys)
     assert flag[:2].tolist() == [1, 1] and flag[2:].sum() == 0
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    # keys (taxon + 1) << 32 | code; the owner of a key is a function of its CODE only
+    keys = ((rng.integers(1, 6, 5000, dtype=np.int64) << 32) | rng.integers(0, 3000, 5000, dtype=np.int64))
+    keys = np.unique(keys)
+    part = (keys & 0xFFFFFFFF) % world
+    order = np.argsort(part, kind="stable")
+    counts = np.bincount(part, minlength=world)
+    got = kdist.exchange_partitioned_keys(torch.from_numpy(keys[order]), counts.tolist()).numpy()
+    q.put((rank, keys, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partitioned_key_exchange_is_a_disjoint_cover():
+    """the all-to-all of the code-partitioned sparse-tier keys: every key reaches exactly the rank that owns its code,
+    so the union over ranks is the union of the inputs and no code lives on two ranks"""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sent = np.unique(np.concatenate([r[1] for r in res]))
+    for rank, _, got in res:
+        assert np.all((got & 0xFFFFFFFF) % world == rank)
+    assert np.array_equal(np.unique(np.concatenate([r[2] for r in res])), sent)

@@ -361,3 +361,76 @@ def test_database_ranges_through_the_halves(oracle, n_ranges):
     got = clf.counts()
     for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
         assert np.array_equal(got[key], want[key]), key
+
+
+@pytest.mark.parametrize("n_ranges,n_batches", [(3, 2), (6, 3)])
+def test_database_streamed_through_two_buffers(oracle, n_ranges, n_batches):
+    """kuq_stream_*: the database arrives range by range from pinned host memory into two device buffers while the
+    lookups of the previous range run; ids merge on the device (only_hits stores into one buffer per batch); the final
+    pass resolves.  Same calls, hit lists and chunked-rule counters as the oracle's one-pass run (classify -x)."""
+    import ctypes
+    import torch
+    tax, genomes, kdb, idx, bases, offs = _synthetic(93, 9, 2, n_genomes=6, n_reads=900)
+    db = oracle.open_db(kdb, idx)
+    pm = oracle.parent_map(*tax.parent_map())
+    run = oracle.run(db, pm, 500000, 1)
+    calls, codes, code_off = run.classify(bases, offs)
+    run.finish()
+    want = run.counts()
+
+    _, keys, taxa = synth.parse_kdb(kdb)
+    n_bins = 1 << 18
+    idx_off = np.frombuffer(idx[8:].tobytes(), np.uint64)
+    cuts = [int(np.searchsorted(idx_off, idx_off[-1] * r // n_ranges)) for r in range(n_ranges + 1)]
+    cuts[0], cuts[-1] = 0, n_bins
+    header = kdb.size - 12 * len(keys)
+    clf = _classifier(hll_mode=binding.HLL_CHUNKED, n_slots=2)
+    clf.set_taxonomy(*tax.parent_map())
+    clf.set_db_taxid_universe(np.unique(taxa))
+    max_rec = max(int(idx_off[cuts[r + 1]] - idx_off[cuts[r]]) for r in range(n_ranges))
+    max_bins = max(cuts[r + 1] - cuts[r] for r in range(n_ranges))
+    clf.stream_open(31, 9, 2, max(max_rec, 1), max_bins)
+    # pinned host copies of the record body and the offsets
+    L = clf.L
+    rec_bytes = kdb[header:]
+    h_rec = L.kuq_host_alloc(rec_bytes.size + 16)
+    ctypes.memmove(h_rec, rec_bytes.ctypes.data, rec_bytes.size)
+    h_off = L.kuq_host_alloc(idx_off.size * 8)
+    ctypes.memmove(h_off, idx_off.ctypes.data, idx_off.size * 8)
+
+    def load(buf, r):
+        a, b = int(idx_off[cuts[r]]), int(idx_off[cuts[r + 1]])
+        clf.stream_load(buf, h_rec + 12 * a, b - a, h_off + 8 * cuts[r], cuts[r], cuts[r + 1])
+
+    dev = "cuda:0"
+    total = int(offs[-1])
+    d_bases = torch.from_numpy(np.concatenate([bases, np.full(64, ord("N"), np.uint8)])).to(dev)
+    d_offs = torch.from_numpy(np.concatenate([offs, offs[-1:]]).astype(np.int64)).to(dev)
+    merged = torch.zeros(total + 64, dtype=torch.int32, device=dev)
+    n = len(offs) - 1
+    bcuts = [2 * (n * i // n_batches // 2) for i in range(n_batches)] + [n]     # even cuts: 16-byte aligned offset slices
+    ranges = [r for r in range(n_ranges) if cuts[r + 1] > cuts[r]]
+    load(0, ranges[0])
+    for j, r in enumerate(ranges):
+        clf.stream_use(j & 1)
+        if j + 1 < len(ranges):
+            load((j + 1) & 1, ranges[j + 1])
+        for bi in range(n_batches):
+            a, b = bcuts[bi], bcuts[bi + 1]
+            clf.lookup_device(bi & 1, d_bases.data_ptr(), d_offs.data_ptr() + 8 * a, b - a, total, merged.data_ptr(), only_hits=1)
+    clf.sync(0); clf.sync(1)
+    clf.stream_check()
+    call = np.zeros(n, np.uint32)
+    for bi in range(n_batches):
+        a, b = bcuts[bi], bcuts[bi + 1]
+        clf.resolve_device(0, d_bases.data_ptr(), d_offs.data_ptr() + 8 * a, b - a, total, merged.data_ptr(), None)
+        clf.sync(0)
+        r_ = clf.device_result(0)
+        from krakenuniq_b200 import dist as kdist
+        call[a:b] = kdist.device_view(r_.d_call, (b - a) * 4, torch.int32, dev).cpu().numpy().view(np.uint32)
+    clf.finish()
+    assert np.array_equal(call, calls)
+    got = clf.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        assert np.array_equal(got[key], want[key]), key
+    L.kuq_host_free(h_rec); L.kuq_host_free(h_off)

@@ -88,3 +88,16 @@ def test_sharded_generation_partitions_the_database():
         assert np.array_equal(sh.records.numpy(), full.records[a:b].numpy())
         n += sh.key_ct
     assert n == full.key_ct
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shard", [None, (1, 3)])
+def test_kernel_scan_generator_equals_torch_generator(shard):
+    """On a GPU the generator takes k-mers and minimizer bins from the product's scan stage (kuq_scan_device):
+    same database as the elementwise torch path that the CPU tests pin against the reference's db_sort."""
+    kw = dict(n_genomes=9, k=31, nt=7, seed=13, device="cuda:0", chunk=10000, passes=2, shard=shard)
+    a = synth_gpu.GpuDatabase(40000, use_kernel_scan=True, **kw)
+    b = synth_gpu.GpuDatabase(40000, use_kernel_scan=False, **kw)
+    assert a.key_ct == b.key_ct and (a.bin_lo, a.bin_hi) == (b.bin_lo, b.bin_hi)
+    assert np.array_equal(a.records.cpu().numpy(), b.records.cpu().numpy())
+    assert np.array_equal(a.offsets.cpu().numpy(), b.offsets.cpu().numpy())
