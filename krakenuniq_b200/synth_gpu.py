@@ -117,7 +117,7 @@ class GpuDatabase:
 
     def __init__(self, n_records: int, n_genomes: int = 2000, k: int = 31, nt: int = 15, idx_type: int = 2,
                  seed: int = 2, device: str = "cuda:0", chunk: int = 1 << 26, passes: int = 1,
-                 shard: tuple[int, int] | None = None, use_kernel_scan: bool = True):
+                 shard: tuple[int, int] | None = None, use_kernel_scan: bool = True, defer_build: bool = False):
         """`passes` > 1 builds the database one minimizer range at a time (temporaries of one range only), for
         databases whose sort would not fit next to the result (tens of GB and more, > 2^32 records).
         `shard` = (rank, world): keep only this rank's minimizer range of a database cut into `world` ranges with
@@ -151,9 +151,15 @@ class GpuDatabase:
                 self.bin_lo, self.bin_hi = cuts[0], cuts[-1]
         else:
             cuts = [0, n_bins]
+        self._chunk, self._n_pos, self._sp = chunk, n_pos, sp
         scanner = _DeviceScanner(dev, k, nt, idx_type, chunk) if dev.type == "cuda" and use_kernel_scan else None
         selective = n_parts > 1
-        n_rows = n_pos if not shard else int(n_pos / shard[1] * 1.25) + (1 << 20)
+        self.cuts = cuts
+        if defer_build:                                    # stream_ranges() builds and hands out one range at a time
+            self._scanner = scanner
+            self.key_ct, self.records, self.offsets = 0, None, None
+            return
+        n_rows = n_pos if not shard else int(n_pos / shard[1] * 1.10) + (1 << 20)
         rec = torch.empty((n_rows, 3), dtype=torch.int32, device=dev)     # (n, 3) int32 == packed 12-byte records
         counts = torch.zeros(self.bin_hi - self.bin_lo, dtype=torch.int64, device=dev)
         out = 0
@@ -161,46 +167,7 @@ class GpuDatabase:
             lo, hi = cuts[pi], cuts[pi + 1]
             if hi <= lo:
                 continue
-            keys_l, bins_l, pos_l = [], [], []
-            for a in range(0, n_pos, chunk):
-                c = min(chunk, n_pos - a)
-                if scanner is not None:
-                    km, bn = scanner.scan(self.genome, a, c)
-                else:
-                    km = canonical(forward_kmers(self.genome, a, c, k), k)
-                    bn = bin_key(km, k, nt, idx_type)
-                if selective:
-                    sel = (bn >= lo) & (bn < hi)
-                    keys_l.append(km[sel])
-                    bins_l.append(bn[sel].to(torch.int32))
-                    pos_l.append(torch.nonzero(sel).squeeze(1) + a)
-                    del sel
-                else:
-                    keys_l.append(km)
-                    bins_l.append(bn.to(torch.int32))
-                del km, bn
-            keys = torch.cat(keys_l); del keys_l
-            bins = torch.cat(bins_l); del bins_l
-            if selective:
-                pos = torch.cat(pos_l); del pos_l
-            # sort by (bin, key): key sort, then a stable bin sort
-            keys, order = torch.sort(keys)
-            bins = bins[order]
-            owner = (pos[order] if selective else order) // self.genome_len
-            taxa = sp[owner.to(torch.int64)]
-            del order, owner
-            if selective:
-                del pos
-            # drop duplicate keys (same k-mer at two positions / palindromes): keep the first owner
-            keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
-            keep[1:] = keys[1:] != keys[:-1]
-            if not bool(keep.all()):
-                keys, bins, taxa = keys[keep], bins[keep], taxa[keep]
-            del keep
-            bins, order = torch.sort(bins, stable=True)
-            keys = keys[order]
-            taxa = taxa[order]
-            del order
+            keys, taxa, bins = self._build_range(lo, hi, selective, scanner)
             n = keys.numel()
             assert out + n <= n_rows, "shard larger than planned: raise the row reserve"
             rec[out:out + n, 0] = (keys & 0xFFFFFFFF).to(torch.int32)      # wraps to the same 32 bits
@@ -220,6 +187,79 @@ class GpuDatabase:
         self.offsets = off
         if dev.type == "cuda":
             torch.cuda.empty_cache()
+
+    def _build_range(self, lo: int, hi: int, selective: bool, scanner):
+        """records of minimizer range [lo, hi): (keys int64, taxa int32, bins int32) sorted by (bin, key), deduplicated"""
+        k, nt, idx_type, chunk, n_pos, dev = self.k, self.nt, self.idx_type, self._chunk, self._n_pos, self.genome.device
+        keys_l, bins_l, pos_l = [], [], []
+        for a in range(0, n_pos, chunk):
+            c = min(chunk, n_pos - a)
+            if scanner is not None:
+                km, bn = scanner.scan(self.genome, a, c)
+            else:
+                km = canonical(forward_kmers(self.genome, a, c, k), k)
+                bn = bin_key(km, k, nt, idx_type)
+            if selective:
+                sel = (bn >= lo) & (bn < hi)
+                keys_l.append(km[sel])
+                bins_l.append(bn[sel].to(torch.int32))
+                pos_l.append(torch.nonzero(sel).squeeze(1) + a)
+                del sel
+            else:
+                keys_l.append(km)
+                bins_l.append(bn.to(torch.int32))
+            del km, bn
+        keys = torch.cat(keys_l); del keys_l
+        bins = torch.cat(bins_l); del bins_l
+        if selective:
+            pos = torch.cat(pos_l); del pos_l
+        # sort by (bin, key): key sort, then a stable bin sort
+        keys, order = torch.sort(keys)
+        bins = bins[order]
+        owner = (pos[order] if selective else order) // self.genome_len
+        taxa = self._sp[owner.to(torch.int64)]
+        del order, owner
+        if selective:
+            del pos
+        # drop duplicate keys (same k-mer at two positions / palindromes): keep the first owner
+        keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+        keep[1:] = keys[1:] != keys[:-1]
+        if not bool(keep.all()):
+            keys, bins, taxa = keys[keep], bins[keep], taxa[keep]
+        del keep
+        bins, order = torch.sort(bins, stable=True)
+        keys = keys[order]
+        taxa = taxa[order]
+        del order
+        return keys, taxa, bins
+
+    def stream_ranges(self):
+        """for a database built with defer_build=True: yields (bin_lo, bin_hi, records (n, 3) int32, offsets int64
+        [bin_hi - bin_lo + 1] ABSOLUTE record offsets) one minimizer range (= pass) at a time; nothing is kept"""
+        base = 0
+        for pi in range(len(self.cuts) - 1):
+            lo, hi = self.cuts[pi], self.cuts[pi + 1]
+            if hi <= lo:
+                continue
+            keys, taxa, bins = self._build_range(lo, hi, True, self._scanner)
+            n = keys.numel()
+            rec = torch.empty((n, 3), dtype=torch.int32, device=keys.device)
+            rec[:, 0] = (keys & 0xFFFFFFFF).to(torch.int32)
+            rec[:, 1] = (keys >> 32).to(torch.int32)
+            rec[:, 2] = taxa
+            off = torch.zeros(hi - lo + 1, dtype=torch.int64, device=keys.device)
+            torch.cumsum(torch.bincount(bins.to(torch.int64) - lo, minlength=hi - lo), 0, out=off[1:])
+            off += base
+            base += n
+            del keys, taxa, bins
+            yield lo, hi, rec, off
+            del rec, off
+            if self.genome.device.type == "cuda":
+                torch.cuda.empty_cache()
+        self.key_ct = base
+        if self._scanner is not None:
+            self._scanner.close()
+            self._scanner = None
 
     # ---- host images (for the reference binary / the oracle) --------------------------------------------------
     def kdb_header(self) -> np.ndarray:

@@ -101,3 +101,16 @@ def test_kernel_scan_generator_equals_torch_generator(shard):
     assert a.key_ct == b.key_ct and (a.bin_lo, a.bin_hi) == (b.bin_lo, b.bin_hi)
     assert np.array_equal(a.records.cpu().numpy(), b.records.cpu().numpy())
     assert np.array_equal(a.offsets.cpu().numpy(), b.offsets.cpu().numpy())
+
+
+def test_streamed_ranges_concatenate_to_the_database():
+    full = synth_gpu.GpuDatabase(30000, n_genomes=7, k=31, nt=7, seed=11, device="cpu", chunk=9000)
+    st = synth_gpu.GpuDatabase(30000, n_genomes=7, k=31, nt=7, seed=11, device="cpu", chunk=9000, passes=4, defer_build=True)
+    recs, prev_hi = [], 0
+    for lo, hi, rec, off in st.stream_ranges():
+        assert lo == prev_hi
+        prev_hi = hi
+        assert np.array_equal(off.numpy(), full.offsets[lo:hi + 1].numpy())
+        recs.append(rec.numpy().copy())
+    assert prev_hi == 1 << 14 and st.key_ct == full.key_ct
+    assert np.array_equal(np.concatenate(recs), full.records.numpy())
