@@ -37,7 +37,8 @@ struct Slot {
   uint32_t *d_unit = nullptr, *d_call = nullptr, *d_nwin = nullptr, *d_codes = nullptr;
   // HLL mode rule bookkeeping (KUQ_HLL_PRELOAD), allocated on first use
   unsigned long long *u_keys = nullptr, *u_last = nullptr, *u_set_keys = nullptr;
-  uint32_t *u_inserts = nullptr, *u_distinct = nullptr, *u_set_count = nullptr, *u_ncand = nullptr;
+  uint32_t *u_inserts = nullptr, *u_distinct = nullptr, *u_set_count = nullptr, *u_ncand = nullptr, *u_direct = nullptr;
+  uint32_t u_direct_rows = 0;
   uint8_t *u_cand = nullptr, *u_taxon_cand = nullptr;
   uint64_t *d_canon = nullptr;                 // scratch between the stages
   uint32_t *d_bins = nullptr, *d_dense = nullptr, *d_codes_in = nullptr;
@@ -183,7 +184,7 @@ void free_slot(Slot &s) {
   cudaFree(s.d_nwin); cudaFree(s.d_codes); cudaFree(s.d_run_start); cudaFree(s.d_run_count); cudaFree(s.d_runs);
   cudaFree(s.d_scalars); cudaFree(s.d_canon); cudaFree(s.d_bins); cudaFree(s.d_dense); cudaFree(s.d_codes_in); cudaFree(s.d_ovf);
   cudaFree(s.u_keys); cudaFree(s.u_last); cudaFree(s.u_set_keys); cudaFree(s.u_inserts); cudaFree(s.u_distinct);
-  cudaFree(s.u_set_count); cudaFree(s.u_ncand); cudaFree(s.u_cand); cudaFree(s.u_taxon_cand);
+  cudaFree(s.u_set_count); cudaFree(s.u_ncand); cudaFree(s.u_cand); cudaFree(s.u_taxon_cand); cudaFree(s.u_direct);
   cudaFreeHost(s.h_call); cudaFreeHost(s.h_nwin); cudaFreeHost(s.h_run_start); cudaFreeHost(s.h_run_count);
   cudaFreeHost(s.h_codes); cudaFreeHost(s.h_runs); cudaFreeHost(s.h_scalars); cudaFreeHost(s.h_unit);
   if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -516,8 +517,22 @@ int harvest_seen(kuq_ctx *ctx, bool discard) {
       ctx->sparse_grown++;
       ss = nb;
     }
-    launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 1, ctx->aux);
-    ctx->launches++;
+    // many keys: stage them by table slice first (L2 / TLB-resident inserts); few keys, or no room for the stage: insert
+    // in record order
+    unsigned long long *d_stage = nullptr, *d_part = nullptr;
+    const uint64_t stage_cap = ((uint64_t)(n_new * 1.05) + 256ull * 4096ull) / 256 * 256;
+    if (n_new >= (1ull << 22) && ctx->sparse_cap >= (1ull << 20) && !getenv("KUQ_HARVEST_DIRECT") &&
+        dmalloc(&d_stage, stage_cap) == cudaSuccess && dmalloc(&d_part, 3 * 256) == cudaSuccess) {
+      ctx->launches += launch_harvest_partitioned(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stage, stage_cap, d_part,
+                                                  reinterpret_cast<uint32_t *>(d_stat + 1), ctx->n_sm, ctx->aux);
+    } else {
+      (void)cudaGetLastError();
+      launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 1, ctx->aux);
+      ctx->launches++;
+    }
+    CU(cudaStreamSynchronize(ctx->aux));
+    cudaFree(d_stage);
+    cudaFree(d_part);
   }
   CU(cudaEventRecord(e1, ctx->aux));
   unsigned long long st[2] = {0, 0};
@@ -552,6 +567,11 @@ int prepare_unit_map(kuq_ctx *ctx, Slot &s) {
     CU(dmalloc(&s.u_ncand, 1));
     CU(dmalloc(&s.u_set_keys, USET_CAP));
     CU(dmalloc(&s.u_set_count, USET_CAP));
+    // dense (unit, taxon) table: the units a batch can hold when the library cuts them, at most 64 Mi counters
+    uint64_t rows = ctx->cfg.max_bases_per_batch / std::max<uint64_t>(ctx->cfg.work_unit_size, 1) + 8;
+    rows = std::min<uint64_t>(rows, (64ull << 20) / std::max<uint32_t>(ctx->n_sketch, 1));
+    s.u_direct_rows = (uint32_t)rows;
+    if (rows) CU(dmalloc(&s.u_direct, rows * ctx->n_sketch));
   }
   Params tmp;
   set_unit_ptrs(tmp, s);
@@ -582,6 +602,8 @@ void set_unit_ptrs(Params &p, Slot &s) {
   p.units.set_keys = s.u_set_keys;
   p.units.set_count = s.u_set_count;
   p.units.set_mask = USET_CAP - 1;
+  p.units.direct = s.u_direct;
+  p.units.direct_rows = s.u_direct_rows;
 }
 
 void fill_params(kuq_ctx *ctx, Slot &s, Params &p, const char *d_bases, const uint64_t *d_offsets,

@@ -570,9 +570,14 @@ __device__ uint32_t resolve_overflow(const Params &p, const OverflowPool &pool, 
     if (counting) {
       atomicAdd(p.n_kmers + t, (unsigned long long)c);
       if (units) {
-        uint32_t sl = umap_slot(p.units, unit, t, true);
-        if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
-        else atomicAdd(p.units.inserts + sl, c);
+        const uint32_t row = unit - p.unit_id[0];
+        if (row < p.units.direct_rows) {
+          atomicAdd(p.units.direct + (size_t)row * p.tax.n_sketch + t, c);
+        } else {
+          uint32_t sl = umap_slot(p.units, unit, t, true);
+          if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
+          else atomicAdd(p.units.inserts + sl, c);
+        }
       }
     }
     uint32_t score = 0;
@@ -630,12 +635,19 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
   uint32_t acc_miss = 0, acc_unclassified = 0, acc_classified = 0;
   uint32_t unit_cur = 0xFFFFFFFFu, unit_miss = 0;               // misses of the current work unit, not yet booked
   const bool units = counting && p.hll_mode == 0u && p.unit_id;
-  auto flush_unit = [&]() {
-    if (lane == 0 && unit_miss) {
-      uint32_t sl = umap_slot(p.units, unit_cur, 0, true);
+  const uint32_t unit_row0 = units ? p.unit_id[0] : 0u;
+  auto book_unit = [&](uint32_t unit, uint32_t taxon, uint32_t cnt) {          // N(unit, taxon) += cnt
+    const uint32_t row = unit - unit_row0;
+    if (row < p.units.direct_rows) {
+      atomicAdd(p.units.direct + (size_t)row * p.tax.n_sketch + taxon, cnt);
+    } else {
+      const uint32_t sl = umap_slot(p.units, unit, taxon, true);
       if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
-      else atomicAdd(p.units.inserts + sl, unit_miss);
+      else atomicAdd(p.units.inserts + sl, cnt);
     }
+  };
+  auto flush_unit = [&]() {
+    if (lane == 0 && unit_miss) book_unit(unit_cur, 0, unit_miss);
     unit_miss = 0;
   };
   // each warp takes a contiguous range of reads: consecutive reads share their work unit and their run block
@@ -792,11 +804,7 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
       // inserts per (work unit, taxon): the necessary condition for a per-unit sketch to convert
       if (unit != unit_cur) { flush_unit(); unit_cur = unit; }
       unit_miss += n_miss;
-      if (lane < n_hits) {
-        uint32_t sl = umap_slot(p.units, unit, my_t, true);
-        if (sl == 0xFFFFFFFFu) atomicExch(p.error_flag, 2u);
-        else atomicAdd(p.units.inserts + sl, my_c);
-      }
+      if (lane < n_hits) book_unit(unit, my_t, my_c);
     }
     if (counting) {
       if (lane < n_hits) atomicAdd(p.n_kmers + my_t, (unsigned long long)my_c);
@@ -879,11 +887,28 @@ __global__ void __launch_bounds__(256, 4) k_resolve(const __grid_constant__ Para
 // ---- HLL mode rule ------------------------------------------------------------------------
 __global__ void k_unit_mark(const __grid_constant__ Params p) {
   const UnitMap &u = p.units;
+  // dense table first: a pair with >= 1025 inserts moves to the hash map, where the candidate bookkeeping lives
+  if (u.direct_rows) {
+    const uint32_t row0 = p.unit_id[0];
+    const uint64_t n = (uint64_t)u.direct_rows * p.tax.n_sketch;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+      const uint32_t cnt = u.direct[e];
+      if (cnt < 1025u) continue;
+      const uint32_t taxon = (uint32_t)(e % p.tax.n_sketch), row = (uint32_t)(e / p.tax.n_sketch);
+      if (p.dense_flag[taxon]) continue;
+      const uint32_t sl = umap_slot(u, row0 + row, taxon, true);
+      if (sl == 0xFFFFFFFFu) { atomicExch(p.error_flag, 2u); continue; }
+      u.inserts[sl] = cnt;
+      u.cand[sl] = 1;
+      u.taxon_cand[taxon] = 1;
+      atomicAdd(u.n_cand, 1u);
+    }
+  }
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= u.mask; s += gridDim.x * blockDim.x) {
     const unsigned long long key = u.keys[s];
     if (!key) continue;
     const uint32_t taxon = (uint32_t)key;
-    if (u.inserts[s] >= 1025u && !p.dense_flag[taxon]) {
+    if (u.inserts[s] >= 1025u && !p.dense_flag[taxon] && !u.cand[s]) {
       u.cand[s] = 1;
       u.taxon_cand[taxon] = 1;
       atomicAdd(u.n_cand, 1u);
@@ -969,6 +994,8 @@ __global__ void __launch_bounds__(256) k_unit_clear(UnitMap u, uint32_t n_sketch
   for (uint64_t i = tid; i < scap / 2; i += nth) reinterpret_cast<uint4 *>(u.set_keys)[i] = z;
   for (uint64_t i = tid; i < scap / 4; i += nth) reinterpret_cast<uint4 *>(u.set_count)[i] = z;
   for (uint64_t i = tid; i < n_sketch; i += nth) u.taxon_cand[i] = 0;
+  const uint64_t nd = (uint64_t)u.direct_rows * n_sketch;
+  for (uint64_t i = tid; i < nd; i += nth) u.direct[i] = 0;
   if (tid == 0) *u.n_cand = 0;
 }
 void launch_unit_clear(const UnitMap &u, uint32_t n_sketch, int n_sm, cudaStream_t stream) {
@@ -1392,6 +1419,94 @@ void launch_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, cons
   if (!n_rec) return;
   const int grid = (int)min((uint64_t)148 * 16, (n_rec + 255) / 256);
   k_harvest_seen<<<grid, 256, 0, stream>>>(pairs, n_rec, (uint32_t)(key_mask >> 32), dense_flag, set, stats, error_flag, mode);
+}
+
+// The same harvest for millions of flagged records: inserting them in record order touches the (multi-GB) set at random
+// — one TLB miss and one DRAM sector per key, ~14 G keys/s measured.  Instead the keys are first staged, grouped by the
+// 1/256th of the table their home slot falls into (k_harvest_stage: shared-memory write combining, one global cursor
+// bump per flushed group), and then inserted slice by slice (k_harvest_insert): every CTA works on the same 1/256th of
+// the table at about the same time, so the slice (tens of MB) is L2- and TLB-resident while it is filled.
+constexpr int HP = 256;          // table slices
+constexpr int HW = 16;           // staged keys per slice and CTA between two flushes
+constexpr int HROUNDS = 8;       // records per thread between two flushes
+__global__ void __launch_bounds__(256) k_harvest_stage(uint8_t *pairs, uint64_t n_rec, uint32_t hi_mask, const uint8_t *dense_flag,
+                                                       uint64_t set_mask, uint32_t part_shift, unsigned long long *stage,
+                                                       unsigned long long *cursors /*[HP]*/, const unsigned long long *part_end /*[HP]*/,
+                                                       uint32_t *error_flag) {
+  __shared__ unsigned long long s_keys[HP][HW];
+  __shared__ uint32_t s_cnt[HP];
+  const uint32_t tid = threadIdx.x;
+  s_cnt[tid] = 0;
+  __syncthreads();
+  const uint64_t per_cta = (uint64_t)HROUNDS * blockDim.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * per_cta; base < n_rec; base += (uint64_t)gridDim.x * per_cta) {
+#pragma unroll 2
+    for (int r = 0; r < HROUNDS; r++) {
+      const uint64_t i = base + (uint64_t)r * blockDim.x + tid;
+      if (i >= n_rec) continue;
+      uint32_t *w = reinterpret_cast<uint32_t *>(pairs + i * 12);
+      const uint32_t hiw = w[1];
+      if (!(hiw & SEEN_BIT)) continue;
+      w[1] = hiw & ~SEEN_BIT;
+      const uint32_t taxon = w[2];
+      if (dense_flag[taxon]) continue;
+      const uint64_t kmer = ((uint64_t)(hiw & hi_mask) << 32) | w[0];
+      const unsigned long long key = ((unsigned long long)(taxon + 1) << 32) | encode_hash32(fmix64(kmer));
+      const uint32_t part = (uint32_t)((mix64(key) & set_mask) >> part_shift);
+      const uint32_t pos = atomicAdd(&s_cnt[part], 1u);
+      if (pos < (uint32_t)HW) {
+        s_keys[part][pos] = key;
+      } else {                                             // group full before the flush (rare): straight to the stage
+        const unsigned long long at = atomicAdd(cursors + part, 1ull);
+        if (at < part_end[part]) stage[at] = key; else atomicExch(error_flag, 7u);
+      }
+    }
+    __syncthreads();
+    {                                                      // thread t flushes slice t's group
+      const uint32_t n = min(s_cnt[tid], (uint32_t)HW);
+      if (n) {
+        const unsigned long long at = atomicAdd(cursors + tid, (unsigned long long)n);
+        if (at + n <= part_end[tid]) {
+          for (uint32_t j = 0; j < n; j++) stage[at + j] = s_keys[tid][j];
+        } else {
+          atomicExch(error_flag, 7u);
+        }
+      }
+      s_cnt[tid] = 0;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_harvest_insert(const unsigned long long *stage, const unsigned long long *part_begin,
+                                                        const unsigned long long *part_fill, SparseSet set, uint32_t *error_flag) {
+  for (int part = 0; part < HP; part++) {
+    const unsigned long long a = part_begin[part], b = part_fill[part];
+    for (unsigned long long i = a + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < b;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+      const unsigned long long key = stage[i];
+      const uint32_t taxon = (uint32_t)(key >> 32) - 1;
+      const int ins = sparse_insert(set, taxon, (uint32_t)key);
+      if (ins > 0) atomicAdd(set.distinct + taxon, 1u);
+      else if (ins < 0) atomicExch(error_flag, 4u);
+    }
+  }
+}
+// stage: room for n_keys * 1.05 + HP * 4096 keys; d_part: 3 * HP words (begin, cursor, end) set up here
+int launch_harvest_partitioned(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
+                               unsigned long long *stage, uint64_t stage_cap, unsigned long long *d_part, uint32_t *error_flag,
+                               int n_sm, cudaStream_t stream) {
+  if (!n_rec) return 0;
+  unsigned long long h[3 * HP];
+  const uint64_t per = stage_cap / HP;
+  for (int p = 0; p < HP; p++) { h[p] = (unsigned long long)p * per; h[HP + p] = h[p]; h[2 * HP + p] = h[p] + per; }
+  cudaMemcpyAsync(d_part, h, sizeof h, cudaMemcpyHostToDevice, stream);   // pageable source: copied before the call returns
+  uint32_t shift = 0;
+  while (((set.mask + 1) >> shift) > (uint64_t)HP) shift++;
+  const int grid = (int)min((uint64_t)n_sm * 8, (n_rec + 2047) / 2048);
+  k_harvest_stage<<<grid, 256, 0, stream>>>(pairs, n_rec, (uint32_t)(key_mask >> 32), dense_flag, set.mask, shift, stage, d_part + HP,
+                                            d_part + 2 * HP, error_flag);
+  k_harvest_insert<<<n_sm * 8, 256, 0, stream>>>(stage, d_part, d_part + HP, set, error_flag);
+  return 2;
 }
 
 // re-insert the keys of an outgrown table into its successor (no per-taxon counting: the keys were counted before)

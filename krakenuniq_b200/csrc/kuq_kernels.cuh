@@ -86,6 +86,11 @@ struct UnitMap {
   unsigned long long *set_keys;  // distinct (pair slot, code): 0 = empty; (slot + 1) << 32 | code
   uint32_t *set_count;           // occurrences of the key
   uint32_t set_mask;
+  // fast path for the insert counts: units of a batch are (nearly always) consecutive ids, so N(unit, taxon) lives in a
+  // dense table direct[(unit - unit_id[0]) * n_sketch + taxon] — one fire-and-forget atomic per (read, taxon), no probe.
+  // Pairs outside the table (rows >= direct_rows) use the hash map above; k_unit_mark moves the candidates there.
+  uint32_t *direct;
+  uint32_t direct_rows;
 };
 
 // classifyExact (EXACT_COUNTING, classify.cpp:46-49): the per-taxon container is a set of canonical k-mers.  All
@@ -176,6 +181,10 @@ void launch_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, c
 // flagged records → sparse-tier keys: mode 0 count (stats[0]), 1 insert + clear, 2 clear only
 void launch_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
                          unsigned long long *stats, uint32_t *error_flag, int mode, cudaStream_t stream);
+// the same for many flagged records: keys staged by table slice, then inserted slice by slice (L2 / TLB resident)
+int launch_harvest_partitioned(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
+                               unsigned long long *stage, uint64_t stage_cap, unsigned long long *d_part, uint32_t *error_flag,
+                               int n_sm, cudaStream_t stream);
 void launch_sparse_rehash(const unsigned long long *old_slots, uint64_t old_cap, const SparseSet &s, uint32_t *error_flag,
                           cudaStream_t stream);
 void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist /*[n_sketch][64]*/,

@@ -222,14 +222,20 @@ def test_sparse_tier_grows_at_the_harvest_and_survives_several_readouts(oracle):
     """The fused path only flags the records of its hits; kuq_finish / kuq_read_counts harvest the flags into the
     (taxon, code) set.  Start with a set far too small (1024 slots): the harvest must grow it, and reading the
     counts between batches (harvest, more batches, harvest again) must not change the final state."""
-    tax, genomes, kdb, idx, bases, offs = _synthetic(21, 8, 2, n_genomes=6, glen=3000, n_reads=900)
+    rng = np.random.default_rng(21)
+    tax = synth.make_taxonomy(6)
+    genomes = synth.random_genomes(rng, 6, 3000, shared_frac=0.25)
+    km, tx = synth.label_kmers(genomes, synth.species_ids(tax), tax, K)
+    kdb, idx = synth.build_db_images(km, tx, K, 8, 2)
+    # few misses (they go straight into the set, which must not saturate before the first harvest), many hits
+    bases, offs = synth.sample_reads(rng, genomes, 900, 150, 0.0005, 0.2, 0.01)
     db = oracle.open_db(kdb, idx)
     pm = oracle.parent_map(*tax.parent_map())
     run = oracle.run(db, pm, 500000, 0)
     run.classify(bases, offs, want_codes=False)
     run.finish()
     want = run.counts()
-    clf = _classifier(hll_mode=binding.HLL_PRELOAD, sparse_set_slots=1024)
+    clf = _classifier(hll_mode=binding.HLL_PRELOAD, sparse_set_slots=1 << 13)
     clf.stage_db(kdb, idx)
     clf.set_taxonomy(*tax.parent_map())
     n = len(offs) - 1
@@ -241,7 +247,7 @@ def test_sparse_tier_grows_at_the_harvest_and_survives_several_readouts(oracle):
     clf.finish()
     got = clf.counts()
     info = clf.sparse_tier_info()
-    assert info["times_grown"] >= 1 and info["slots"] > 1024 and info["keys"] <= info["slots"] * 0.7 + 1
+    assert info["times_grown"] >= 1 and info["slots"] > (1 << 13) and info["keys"] <= info["slots"] * 0.7 + 1
     assert np.array_equal(got["taxid"], want["taxid"])
     assert np.array_equal(got["n_kmers"], want["n_kmers"]) and np.array_equal(got["n_reads"], want["n_reads"])
     assert np.array_equal(got["sparse"], want["sparse"])
