@@ -135,6 +135,8 @@ const char *kuq_strerror(int code);
 const char *kuq_last_error(const kuq_ctx *ctx);
 /* Build identification: "libkuq <version> sm_100a" */
 const char *kuq_version(void);
+/* Number of device ordinals [0, n) among which sm_100 devices were found (0 without a usable GPU). */
+int kuq_device_count(void);
 
 /* ---- database -------------------------------------------------------------------------------------------- */
 /* Stage (a minimizer range of) the database into HBM.  kdb_image / idx_image are the bytes of database.kdb and
@@ -335,6 +337,12 @@ int kuq_stream_check(kuq_ctx *ctx);
 /* Pin / unpin caller memory (e.g. an mmap'ed database.kdb) for asynchronous copies. */
 int kuq_host_register(void *p, uint64_t bytes);
 int kuq_host_unregister(void *p);
+
+/* Several GPUs in one process (what the drop-in `classify` does when it sees more than one device: every GPU holds the
+ * database, batches go round-robin): fold the per-taxon state of `src` into `dst` — counters add, registers max, dense
+ * anywhere = dense, sparse-tier keys united (classify.cpp:542-544 across devices; cudaMemcpyPeer, no NCCL).  Both
+ * contexts must have been given the same database and taxonomy.  `src` keeps its state. */
+int kuq_merge_into(kuq_ctx *dst, kuq_ctx *src);
 
 /* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);

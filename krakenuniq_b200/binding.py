@@ -82,6 +82,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_strerror": (C.c_char_p, [C.c_int]),
         "kuq_last_error": (C.c_char_p, [vp]),
         "kuq_version": (C.c_char_p, []),
+        "kuq_device_count": (C.c_int, []),
         "kuq_stage_db": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64]),
         "kuq_attach_db_device": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                            C.c_uint64]),
@@ -131,6 +132,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_sparse_tier_info": (C.c_int, [vp, u64p, u64p, u64p, C.POINTER(C.c_double)]),
         "kuq_set_shard_counting": (C.c_int, [vp, C.c_int]),
         "kuq_set_stats": (C.c_int, [vp, C.c_int]),
+        "kuq_merge_into": (C.c_int, [vp, vp]),
         "kuq_stream_open": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
         "kuq_stream_load": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64]),
         "kuq_stream_use": (C.c_int, [vp, C.c_uint32]),
@@ -454,6 +456,10 @@ class Classifier:
 
     def stream_check(self):
         self._ck(self.L.kuq_stream_check(self.h))
+
+    def merge_from(self, other):
+        """kuq_merge_into(self, other): fold another context's per-taxon state (another GPU of this process) into this one"""
+        self._ck(self.L.kuq_merge_into(self.h, other.h))
 
     def set_stats(self, on=True):
         self._ck(self.L.kuq_set_stats(self.h, 1 if on else 0))

@@ -674,7 +674,12 @@ static const char *next_record_start(const char *p, const char *file_begin, cons
   return file_end;
 }
 
-static bool process_file_parallel(kuq_ctx *ctx, const char *filename) {
+// Several GPUs (replicas: every device holds the database): batches go round-robin over the contexts; results come back
+// in submission order, so the Kraken output stays in file order whatever the number of devices.
+static vector<kuq_ctx *> All_ctx;
+static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
+  const vector<kuq_ctx *> ctxs = All_ctx.empty() ? vector<kuq_ctx *>{ctx0} : All_ctx;
+  const int G = (int)ctxs.size();
   int fd = ::open(filename, O_RDONLY);
   if (fd < 0) return false;
   struct stat sb;
@@ -758,7 +763,7 @@ static bool process_file_parallel(kuq_ctx *ctx, const char *filename) {
   double t_fill = 0, t_emit = 0, t_wait = 0, t_submit = 0;
   // two host staging sets, filled / formatted by all threads while the GPU works on the other one
   struct Stage { char *bases = NULL; uint64_t cap = 0; uint64_t *offs = NULL; size_t offs_cap = 0; size_t begin = 0, end = 0; };
-  Stage st[2];
+  vector<Stage> st(2 * G);
   auto fill = [&](Stage &s, const Cut &b) {
     if (s.cap < b.bases + 64) {
       if (s.bases) kuq_host_free(s.bases);
@@ -847,38 +852,39 @@ static bool process_file_parallel(kuq_ctx *ctx, const char *filename) {
     total_bases += s.offs[n];
     fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
   };
-  int inflight = -1;
-  for (size_t bi = 0; bi < batches.size(); bi++) {
-    const int cur = (int)(bi & 1);
-    double a = now_s();
-    fill(st[cur], batches[bi]);
-    double b = now_s();
-    if (kuq_submit_batch(ctx, (uint32_t)cur, st[cur].bases, st[cur].offs, (uint32_t)(st[cur].end - st[cur].begin), NULL, 0))
-      die(EX_SOFTWARE, kuq_last_error(ctx));
-    double c = now_s();
-    t_fill += b - a; t_submit += c - b;
-    if (inflight >= 0) {
-      kuq_batch_result res;
-      if (kuq_wait_batch(ctx, (uint32_t)inflight, &res)) die(EX_SOFTWARE, kuq_last_error(ctx));
-      double d = now_s();
-      emit(st[inflight], res);
-      t_wait += d - c; t_emit += now_s() - d;
-    }
-    inflight = cur;
-  }
-  if (inflight >= 0) {
+  // batch bi runs on device bi % G, slot (bi / G) & 1, staged in st[bi % 2G]; at most 2G batches are in flight and
+  // the oldest one is collected before its staging set is reused
+  auto collect = [&](size_t bj) {
+    const int k = (int)(bj % (2 * G));
+    kuq_ctx *c = ctxs[bj % G];
     kuq_batch_result res;
-    double c = now_s();
-    if (kuq_wait_batch(ctx, (uint32_t)inflight, &res)) die(EX_SOFTWARE, kuq_last_error(ctx));
+    double c0 = now_s();
+    if (kuq_wait_batch(c, (uint32_t)((bj / G) & 1), &res)) die(EX_SOFTWARE, kuq_last_error(c));
     double d = now_s();
-    emit(st[inflight], res);
-    t_wait += d - c; t_emit += now_s() - d;
+    emit(st[k], res);
+    t_wait += d - c0; t_emit += now_s() - d;
+  };
+  size_t collected = 0;
+  for (size_t bi = 0; bi < batches.size(); bi++) {
+    const int k = (int)(bi % (2 * G));
+    kuq_ctx *c = ctxs[bi % G];
+    while (bi - collected >= (size_t)(2 * G)) collect(collected++);     // the staging set st[k] is free again
+    double a = now_s();
+    fill(st[k], batches[bi]);
+    double b = now_s();
+    if (kuq_submit_batch(c, (uint32_t)((bi / G) & 1), st[k].bases, st[k].offs, (uint32_t)(st[k].end - st[k].begin), NULL, 0))
+      die(EX_SOFTWARE, kuq_last_error(c));
+    t_fill += b - a; t_submit += now_s() - b;
+    // keep one batch per device in flight while the host formats the older ones
+    while (bi + 1 - collected > (size_t)G) collect(collected++);
   }
+  while (collected < batches.size()) collect(collected++);
   { double w0 = now_s(); writer.finish(); if (Timing) fprintf(stderr, "\n[timing] writer drain %.3f s\n", now_s() - w0); }
-  if (Timing) fprintf(stderr, "\n[timing] fill %.3f submit %.3f wait %.3f emit %.3f s over %zu batches\n", t_fill, t_submit, t_wait, t_emit, batches.size());
-  if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
+  if (Timing) fprintf(stderr, "\n[timing] fill %.3f submit %.3f wait %.3f emit %.3f s over %zu batches on %d device(s)\n", t_fill, t_submit, t_wait, t_emit, batches.size(), G);
+  for (kuq_ctx *c : ctxs) if (kuq_finish(c)) die(EX_SOFTWARE, kuq_last_error(c));
   for (auto &s : st) { if (s.bases) kuq_host_free(s.bases); if (s.offs) kuq_host_free(s.offs); }
   munmap((void *)base, size);
+  (void)ctx0;
   return true;
 }
 
@@ -1215,17 +1221,45 @@ int main(int argc, char **argv) {
     cerr << "classify: database larger than the HBM budget: processing it in ranges (unique k-mer counts follow the -x rule)" << endl;
   if (getenv("KUQ_SPARSE_SLOTS")) cfg.sparse_set_slots = strtoull(getenv("KUQ_SPARSE_SLOTS"), NULL, 10);
   if (getenv("KUQ_DEVICE")) cfg.device = atoi(getenv("KUQ_DEVICE"));
+  // devices: KUQ_DEVICES=0,2,3 (or "all"); default = every visible sm_100 GPU when the database is replicated (one
+  // database that fits a card), else one device (KUQ_DEVICE).  Ranges / several databases run on the first device.
+  vector<int> devices;
+  {
+    const char *dl = getenv("KUQ_DEVICES");
+    const bool replicable = !chunk_budget && n_db == 1 && cfg.hll_mode != KUQ_HLL_EXACT;   // exact k-mer sets are not merged across devices
+    if (dl && strcmp(dl, "all") != 0) {
+      for (const char *q = dl; *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; }
+    } else if ((dl || !getenv("KUQ_DEVICE")) && replicable) {
+      for (int d = 0; d < kuq_device_count(); d++) devices.push_back(d);
+    }
+    if (devices.empty() || !replicable) devices.assign(1, devices.empty() ? cfg.device : devices[0]);
+    cfg.device = devices[0];
+  }
   kuq_ctx *ctx = NULL;
   int rc = kuq_create(&cfg, &ctx);
   if (rc) die(EX_UNAVAILABLE, string("libkuq: ") + kuq_strerror(rc));
+  All_ctx.assign(1, ctx);
+  for (size_t g = 1; g < devices.size(); g++) {
+    kuq_config c2 = cfg;
+    c2.device = devices[g];
+    kuq_ctx *cx = NULL;
+    int r2 = kuq_create(&c2, &cx);
+    if (r2) { fprintf(stderr, "classify: device %d not usable (%s): continuing without it\n", devices[g], kuq_strerror(r2)); continue; }
+    All_ctx.push_back(cx);
+  }
+  if (All_ctx.size() > 1) fprintf(stderr, "classify: %zu GPUs, database replicated, batches round-robin\n", All_ctx.size());
   // -q: the preloaded path leaves a read at its -m'th hit; with -x every k-mer is counted (classify.cpp:943-944 / :701-738)
-  if (Quick_mode && kuq_set_quick_mode(ctx, Minimum_hit_count, Populate_memory_size == 0)) die(EX_SOFTWARE, kuq_last_error(ctx));
+  for (kuq_ctx *c : All_ctx)
+    if (Quick_mode && kuq_set_quick_mode(c, Minimum_hit_count, Populate_memory_size == 0)) die(EX_SOFTWARE, kuq_last_error(c));
   map<uint32_t, uint64_t> chunk_db_counts;
   vector<map<uint32_t, uint64_t>> multi_db_counts;
   if (!chunk_budget && n_db == 1) {
     double T0__ = now_s();
-    rc = kuq_stage_db(ctx, kdb.p, kdb.size, idx.p, idx.size, 0, 0);
-    if (rc) die(EX_DATAERR, kuq_last_error(ctx));
+    // every device stages the database from the same mapped files, in parallel
+    vector<int> rcs(All_ctx.size(), 0);
+#pragma omp parallel for num_threads((int)All_ctx.size()) schedule(static, 1)
+    for (int g = 0; g < (int)All_ctx.size(); g++) rcs[g] = kuq_stage_db(All_ctx[g], kdb.p, kdb.size, idx.p, idx.size, 0, 0);
+    for (size_t g = 0; g < All_ctx.size(); g++) if (rcs[g]) die(EX_DATAERR, kuq_last_error(All_ctx[g]));
     TICK("stage_db");
   }
   if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;
@@ -1237,7 +1271,8 @@ int main(int argc, char **argv) {
   {
     vector<uint32_t> ids, parents;
     tax.parent_map(ids, parents);
-    if (kuq_set_taxonomy(ctx, ids.data(), parents.data(), (uint32_t)ids.size())) die(EX_SOFTWARE, kuq_last_error(ctx));
+    for (kuq_ctx *c : All_ctx)
+      if (kuq_set_taxonomy(c, ids.data(), parents.data(), (uint32_t)ids.size())) die(EX_SOFTWARE, kuq_last_error(c));
   }
   if (Print_classified) Classified_out.open(Classified_output_file);
   if (Print_unclassified) Unclassified_out.open(Unclassified_output_file);
@@ -1253,6 +1288,9 @@ int main(int argc, char **argv) {
   if (n_db > 1) run_multi_db(ctx, kdbs, idxs, argc, argv, multi_db_counts);
   else if (chunk_budget) run_chunked(ctx, kdb, idx, chunk_budget, argc, argv, chunk_db_counts);
   else for (int i = optind; i < argc; i++) process_file(ctx, argv[i]);
+  // the other devices' per-taxon state joins the first one's (classify.cpp:542-544 across GPUs)
+  for (size_t g = 1; g < All_ctx.size(); g++)
+    if (kuq_merge_into(ctx, All_ctx[g])) die(EX_SOFTWARE, kuq_last_error(ctx));
   gettimeofday(&tv2, NULL);
   {                                                                 // report_stats, classify.cpp:361-375
     double seconds = get_seconds(tv1, tv2);
@@ -1323,6 +1361,6 @@ int main(int argc, char **argv) {
   Kraken_out.close();
   Classified_out.close();
   Unclassified_out.close();
-  kuq_destroy(ctx);
+  for (kuq_ctx *c : All_ctx) kuq_destroy(c);
   return 0;
 }

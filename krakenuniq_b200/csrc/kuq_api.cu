@@ -718,7 +718,18 @@ int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
 // ===========================================================================================================
 extern "C" {
 
-const char *kuq_version(void) { return "libkuq 0.1.0 sm_100a"; }
+const char *kuq_version(void) { return "libkuq 0.2.0 sm_100a"; }
+
+int kuq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  int usable = 0;
+  for (int d = 0; d < n; d++) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major >= 10) usable = d + 1;
+  }
+  return usable;
+}
 
 const char *kuq_strerror(int code) {
   switch (code) {
@@ -1768,6 +1779,90 @@ int kuq_host_unregister(void *p) {
   if (!p) return KUQ_E_INVALID_ARG;
   if (cudaHostUnregister(p) != cudaSuccess) { (void)cudaGetLastError(); return KUQ_E_CUDA; }
   return KUQ_OK;
+}
+
+// Several GPUs in ONE process (the drop-in `classify` with replicas): fold the per-taxon state of `src` into `dst`.
+int kuq_merge_into(kuq_ctx *dst, kuq_ctx *src) {
+  kuq_ctx *ctx = dst;
+  if (!dst || !src || dst == src) return KUQ_E_INVALID_ARG;
+  if (!src->finalized) return KUQ_OK;                       // src never classified anything: nothing to add
+  if (!dst->finalized) return fail(ctx, KUQ_E_STATE, "the destination context has not classified anything yet");
+  if (dst->n_taxa != src->n_taxa || dst->n_sketch != src->n_sketch || dst->raw_of_dense != src->raw_of_dense ||
+      dst->cfg.hll_mode != src->cfg.hll_mode)
+    return fail(ctx, KUQ_E_STATE, "the contexts number their taxa differently (different database / taxonomy / HLL mode)");
+  if (dst->cfg.hll_mode == KUQ_HLL_EXACT) return fail(ctx, KUQ_E_STATE, "kuq_merge_into does not merge exact k-mer sets");
+  // src: flagged records → its set (skipping what dst already knows to be dense is a refinement left out)
+  CU(cudaSetDevice(src->device));
+  for (auto &s : src->slots) CU(cudaStreamSynchronize(s.stream));
+  { int rc = harvest_seen(src, false); if (rc) { dst->err = src->err; return rc; } }
+  uint64_t n_keys = 0;
+  uint64_t *d_keys_src = nullptr;
+  if (src->d_sparse_slots) {
+    int rc = kuq_sparse_export(src, nullptr, 0, &n_keys);
+    if (rc) { dst->err = src->err; return rc; }
+    if (n_keys) {
+      if (cudaMalloc((void **)&d_keys_src, n_keys * 8) != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, KUQ_E_NOMEM, "no room for %llu keys", (unsigned long long)n_keys); }
+      uint64_t n2 = 0;
+      rc = kuq_sparse_export(src, d_keys_src, n_keys, &n2);
+      if (rc) { cudaFree(d_keys_src); dst->err = src->err; return rc; }
+      n_keys = n2;
+    }
+  }
+  CU(cudaSetDevice(dst->device));
+  for (auto &s : dst->slots) CU(cudaStreamSynchronize(s.stream));
+  { int rc = harvest_seen(dst, false); if (rc) return rc; }
+  dst->snap_valid = false;
+  dst->merged_summary = false;
+  uint8_t *t_regs, *t_dense; unsigned long long *t_nk, *t_nr;
+  const uint64_t reg_bytes = (uint64_t)dst->n_sketch * HLL_M;
+  CU(cudaMalloc((void **)&t_regs, reg_bytes));
+  CU(dmalloc(&t_dense, dst->n_sketch));
+  CU(dmalloc(&t_nk, dst->n_sketch));
+  CU(dmalloc(&t_nr, dst->n_taxa));
+  CU(cudaMemcpyPeer(t_regs, dst->device, src->d_regs, src->device, reg_bytes));
+  CU(cudaMemcpyPeer(t_dense, dst->device, src->d_dense_flag, src->device, dst->n_sketch));
+  CU(cudaMemcpyPeer(t_nk, dst->device, src->d_n_kmers, src->device, dst->n_sketch * 8ull));
+  CU(cudaMemcpyPeer(t_nr, dst->device, src->d_n_reads, src->device, dst->n_taxa * 8ull));
+  launch_merge_state(dst->d_regs, t_regs, dst->d_n_kmers, t_nk, dst->n_sketch, dst->d_n_reads, t_nr, dst->n_taxa, dst->d_dense_flag,
+                     t_dense, dst->aux);
+  dst->launches++;
+  CU(cudaStreamSynchronize(dst->aux));
+  cudaFree(t_regs); cudaFree(t_dense); cudaFree(t_nk); cudaFree(t_nr);
+  int rc = KUQ_OK;
+  if (n_keys && dst->d_sparse_slots) {
+    uint64_t *d_keys_dst = nullptr;
+    if (cudaMalloc((void **)&d_keys_dst, n_keys * 8) != cudaSuccess) { (void)cudaGetLastError(); cudaSetDevice(src->device); cudaFree(d_keys_src); return fail(ctx, KUQ_E_NOMEM, "no room for %llu keys", (unsigned long long)n_keys); }
+    CU(cudaMemcpyPeer(d_keys_dst, dst->device, d_keys_src, src->device, n_keys * 8));
+    // make room first: the import itself cannot grow the set
+    std::vector<uint32_t> distinct(dst->n_sketch);
+    CU(cudaMemcpy(distinct.data(), dst->d_sparse_distinct, dst->n_sketch * 4ull, cudaMemcpyDeviceToHost));
+    uint64_t used = 0;
+    for (uint32_t v : distinct) used += v;
+    if ((used + n_keys) * 10 > dst->sparse_cap * 7) {
+      uint64_t cap = dst->sparse_cap;
+      while ((used + n_keys) * 2 > cap) cap <<= 1;
+      unsigned long long *bigger = nullptr;
+      uint32_t *d_err;
+      if (dmalloc(&bigger, cap) != cudaSuccess) { (void)cudaGetLastError(); cudaFree(d_keys_dst); return fail(ctx, KUQ_E_NOMEM, "sparse-tier set cannot grow to %llu slots", (unsigned long long)cap); }
+      CU(dmalloc(&d_err, 1));
+      CU(cudaMemsetAsync(d_err, 0, 4, dst->aux));
+      CU(cudaMemsetAsync(bigger, 0, cap * 8ull, dst->aux));
+      SparseSet nb;
+      nb.slots = bigger; nb.mask = cap - 1; nb.n_used = dst->d_sparse_used; nb.distinct = dst->d_sparse_distinct;
+      launch_sparse_rehash(dst->d_sparse_slots, dst->sparse_cap, nb, d_err, dst->aux);
+      dst->launches++;
+      CU(cudaStreamSynchronize(dst->aux));
+      cudaFree(d_err);
+      cudaFree(dst->d_sparse_slots);
+      dst->d_sparse_slots = bigger;
+      dst->sparse_cap = cap;
+      dst->sparse_grown++;
+    }
+    rc = kuq_sparse_import(dst, d_keys_dst, n_keys);
+    cudaFree(d_keys_dst);
+  }
+  if (d_keys_src) { cudaSetDevice(src->device); cudaFree(d_keys_src); cudaSetDevice(dst->device); }
+  return rc;
 }
 
 int kuq_set_stats(kuq_ctx *ctx, int on) {

@@ -1585,6 +1585,24 @@ void launch_fill_u32(uint32_t *p, uint64_t n, uint32_t v, cudaStream_t stream) {
   k_fill_u32<<<(int)min((uint64_t)148 * 8, (n + 255) / 256), 256, 0, stream>>>(p, n, v);
 }
 
+// `taxon_counts[t] += other[t]` (classify.cpp:542-544) for the state of another context copied next to ours:
+// registers max (hyperloglogplus.cpp:614-620), counters add (readcounts.hpp:76-88), dense anywhere = dense (:604-612)
+__global__ void k_merge_state(uint32_t *regs, const uint32_t *regs2, uint64_t n_words, unsigned long long *n_kmers,
+                              const unsigned long long *n_kmers2, uint32_t n_sketch, unsigned long long *n_reads,
+                              const unsigned long long *n_reads2, uint32_t n_taxa, uint8_t *dense, const uint8_t *dense2) {
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < n_words; i += nth) regs[i] = __vmaxu4(regs[i], regs2[i]);
+  for (uint64_t i = tid; i < n_sketch; i += nth) { n_kmers[i] += n_kmers2[i]; dense[i] |= dense2[i]; }
+  for (uint64_t i = tid; i < n_taxa; i += nth) n_reads[i] += n_reads2[i];
+}
+void launch_merge_state(uint8_t *regs, const uint8_t *regs2, unsigned long long *n_kmers, const unsigned long long *n_kmers2,
+                        uint32_t n_sketch, unsigned long long *n_reads, const unsigned long long *n_reads2, uint32_t n_taxa,
+                        uint8_t *dense, const uint8_t *dense2, cudaStream_t stream) {
+  k_merge_state<<<148 * 4, 256, 0, stream>>>(reinterpret_cast<uint32_t *>(regs), reinterpret_cast<const uint32_t *>(regs2),
+                                             (uint64_t)n_sketch * (HLL_M / 4), n_kmers, n_kmers2, n_sketch, n_reads, n_reads2, n_taxa,
+                                             dense, dense2);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Cross-GPU step synchronisation without the host (database sharded by minimizer range).
 // Flags are 64-bit counters in device memory every peer has mapped (CUDA IPC or peer access).  k_signal_peers runs

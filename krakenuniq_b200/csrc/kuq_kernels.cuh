@@ -213,6 +213,9 @@ void launch_sparse_export(const unsigned long long *slots, uint64_t cap, const u
 void launch_sparse_import(const unsigned long long *keys, uint64_t n, const SparseSet &s, const uint8_t *dense_flag,
                           uint32_t *error_flag, cudaStream_t stream);
 
+void launch_merge_state(uint8_t *regs, const uint8_t *regs2, unsigned long long *n_kmers, const unsigned long long *n_kmers2,
+                        uint32_t n_sketch, unsigned long long *n_reads, const unsigned long long *n_reads2, uint32_t n_taxa,
+                        uint8_t *dense, const uint8_t *dense2, cudaStream_t stream);
 // cross-GPU flags (kuq_signal_peers / kuq_wait_flags) and the partitioned export of the sparse tier
 void launch_signal_peers(unsigned long long *const *flag_ptrs, uint32_t n, uint32_t my_index, unsigned long long value,
                          cudaStream_t stream);

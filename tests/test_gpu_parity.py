@@ -440,3 +440,38 @@ def test_database_streamed_through_two_buffers(oracle, n_ranges, n_batches):
     for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
         assert np.array_equal(got[key], want[key]), key
     L.kuq_host_free(h_rec); L.kuq_host_free(h_off)
+
+
+def test_two_contexts_merge_into_one(oracle):
+    """kuq_merge_into: what the multi-GPU `classify` does with its per-device contexts (replicas) — here both contexts
+    live on one device.  Each classifies every other work unit; the merged state equals the oracle's single run."""
+    tax, genomes, kdb, idx, bases, offs = _synthetic(33, 8, 2, n_genomes=6, glen=3000, n_reads=1200)
+    unit = 6000
+    db = oracle.open_db(kdb, idx)
+    pm = oracle.parent_map(*tax.parent_map())
+    run = oracle.run(db, pm, unit, 0)
+    calls, _, _ = run.classify(bases, offs, want_codes=False)
+    run.finish()
+    want = run.counts()
+    units, _, _ = synth.work_unit_ids(offs, unit)
+    n = len(offs) - 1
+    a, b = _classifier(hll_mode=binding.HLL_PRELOAD, work_unit_size=unit, sparse_set_slots=1 << 14), \
+        _classifier(hll_mode=binding.HLL_PRELOAD, work_unit_size=unit, sparse_set_slots=1 << 14)
+    for c in (a, b):
+        c.stage_db(kdb, idx)
+        c.set_taxonomy(*tax.parent_map())
+    got_calls = np.zeros(n, np.uint32)
+    # runs of whole units alternate between the two contexts
+    bounds = [0] + [i for i in range(1, n) if units[i] != units[i - 1]] + [n]
+    for j, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+        res = (a, b)[j & 1].classify(bases, np.ascontiguousarray(offs[lo:hi + 1]), unit_id=units[lo:hi])
+        got_calls[lo:hi] = res["call"]
+    assert np.array_equal(got_calls, calls)
+    a.finish(); b.finish()
+    a.merge_from(b)
+    got = a.counts()
+    for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
+        assert np.array_equal(got[key], want[key]), key
+    members = util.clade_members(tax.rows, want["taxid"])
+    for taxid, mem in members.items():
+        assert a.clade(mem) == run.clade(mem), taxid
