@@ -729,6 +729,8 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
   vector<Cut> batches;
   {
     const uint64_t BATCH_NT = 96ull << 20;
+    // KUQ_BATCH_READS: close a batch at the first unit boundary after this many reads (tests: small batches)
+    const size_t batch_reads = getenv("KUQ_BATCH_READS") ? std::max<size_t>(1, strtoull(getenv("KUQ_BATCH_READS"), NULL, 10)) : (1u << 20) - 4096;
     uint64_t unit_nt = 0, batch_nt = 0;
     size_t begin = 0, unit_first = 0;
     int c = 0;
@@ -743,7 +745,7 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
       unit_nt += len; batch_nt += len;
       bool close_unit = unit_nt >= Work_unit_size;
       if (close_unit) { unit_nt = 0; unit_first = i + 1; }
-      if ((close_unit && (batch_nt >= BATCH_NT || i + 1 - begin >= (1u << 20) - 4096)) ||
+      if ((close_unit && (batch_nt >= BATCH_NT || i + 1 - begin >= std::min<size_t>(batch_reads, (1u << 20) - 4096))) ||
           (!close_unit && (i + 1 - begin >= (1u << 20) - 1 || batch_nt >= (150ull << 20)))) {
         batches.push_back({begin, i + 1, batch_nt});
         begin = i + 1; batch_nt = 0;

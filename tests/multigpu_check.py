@@ -246,6 +246,34 @@ def main():
         print(f"multigpu_check OK on {world} GPUs: replicas (code-partitioned merge), minimizer-range shards (NCCL id merge), shards with NVLink "
               f"peer scatter, and flag-synchronised shards with finder-side counting reproduce the single-GPU state "
               f"({len(want['taxid'])} taxa, {int(want['sparse'].sum())} sparse)")
+    # ---- the drop-in executable on several GPUs of one process (replicas, round-robin batches, kuq_merge_into) -----------
+    if rank == 0:
+        import subprocess
+        import tempfile
+        from krakenuniq_b200 import build
+        G = util.GOLDEN
+        exe = build.build_classify()
+        with tempfile.TemporaryDirectory() as td:
+            for tag, extra in (("preload", ["-M"]), ("preload_u20000", ["-M", "-u", "20000"])):
+                out, rep = os.path.join(td, tag + ".kraken"), os.path.join(td, tag + ".report.tsv")
+                cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a", os.path.join(G, "taxDB"),
+                       "-t", "4", "-r", rep, "-o", out] + extra + [os.path.join(G, "reads.fa")]
+                env = dict(os.environ, KUQ_DEVICES=",".join(str(d) for d in range(world)), KUQ_SPARSE_SLOTS=str(1 << 22),
+                           KUQ_BATCH_READS="200")        # small batches so that every device gets work
+                r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+                assert r.returncode == 0, r.stderr[-2000:]
+                assert f"{world} GPUs" in r.stderr, r.stderr[-500:]
+                assert open(out).read() == open(os.path.join(G, tag + ".kraken")).read(), tag
+
+                def rows(path):
+                    d = {}
+                    for line in open(path):
+                        if not line.startswith("#") and not line.startswith("%"):
+                            f = line.rstrip("\n").split("\t")
+                            d[f[6]] = f
+                    return d
+                assert rows(rep) == rows(os.path.join(G, tag + ".report.tsv")), tag
+        print(f"multigpu_check OK: classify on {world} GPUs reproduces the reference's golden Kraken output and report")
     dist.barrier()
     dist.destroy_process_group()
 
