@@ -350,8 +350,9 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
     db, pool_bases, n_pool, workload, gen_s = w.db, w.pool_bases, w.n_pool, w.workload, w.gen_s
     B = args.batch_reads
     n_batches = n_pool // B
+    # sparse-tier set sized for the worst case of this workload (no taxon ever converts: one key per database record)
     clf = binding.Classifier(device=local_rank, n_slots=3, max_reads=B, max_bases=B * READ_LEN + 4096,
-                             hll_mode=args.hll_mode, sparse_set_slots=1 << 30)
+                             hll_mode=args.hll_mode, sparse_set_slots=1 << 31)
     clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2)
     clf.set_taxonomy(*db.parent_map())
 
@@ -871,7 +872,9 @@ def run_stream(args, local_rank, dev):
     B = args.batch_reads // 2 if args.paired else args.batch_reads
     n_batches = args.steps
     n_reads = n_batches * B
-    hll_mode = 1 if args.paired else args.hll_mode
+    # a database that does not fit is the reference's -x path: one global sketch per taxon (classify.cpp:719), i.e. the
+    # chunked HLL rule for both stream configurations (2 = dense only on request)
+    hll_mode = 2 if args.hll_mode == 2 else 1
     t_gen = time.time()
     db = synth_gpu.GpuDatabase(records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev, passes=passes, defer_build=True)
     if args.paired:
@@ -912,7 +915,7 @@ def run_stream(args, local_rank, dev):
     gen_s = time.time() - t_gen
     total_b = B * L
     clf = binding.Classifier(device=local_rank, n_slots=2, max_reads=B, max_bases=total_b + 4096, hll_mode=hll_mode,
-                             sparse_set_slots=1 << 28)
+                             sparse_set_slots=1 << 27)
     clf.set_db_taxid_universe(species)
     clf.set_taxonomy(*pmap)
     clf.stream_open(K, NT, 2, max(m[2] for m in meta), max(m[1] - m[0] for m in meta))

@@ -496,13 +496,10 @@ int harvest_seen(kuq_ctx *ctx, bool discard) {
     CU(cudaStreamSynchronize(ctx->aux));
     uint64_t used = 0;
     for (uint32_t v : distinct) used += v;
-    if ((used + n_new) * 10 > ctx->sparse_cap * 7) {             // keep the load factor below 0.7
-      uint64_t cap = ctx->sparse_cap;
-      while ((used + n_new) * 2 > cap) cap <<= 1;
+    auto grow_to = [&](uint64_t cap) -> int {                    // re-allocate the set with `cap` slots and re-insert its keys
       unsigned long long *bigger = nullptr;
       if (dmalloc(&bigger, cap) != cudaSuccess) {
         (void)cudaGetLastError();
-        cudaFree(d_stat);
         return fail(ctx, KUQ_E_NOMEM, "sparse-tier set: no room to grow from %llu to %llu slots", (unsigned long long)ctx->sparse_cap, (unsigned long long)cap);
       }
       CU(cudaMemsetAsync(bigger, 0, cap * 8ull, ctx->aux));
@@ -516,21 +513,54 @@ int harvest_seen(kuq_ctx *ctx, bool discard) {
       ctx->sparse_cap = cap;
       ctx->sparse_grown++;
       ss = nb;
+      return KUQ_OK;
+    };
+    if ((used + n_new) * 10 > ctx->sparse_cap * 8) {             // keep the load factor below 0.8
+      uint64_t cap = ctx->sparse_cap;
+      while ((used + n_new) * 10 > cap * 6) cap <<= 1;
+      int grc = grow_to(cap);
+      if (grc) { cudaFree(d_stat); return grc; }
     }
     // many keys: stage them by table slice first (L2 / TLB-resident inserts); few keys, or no room for the stage: insert
     // in record order
     unsigned long long *d_stage = nullptr, *d_part = nullptr;
-    const uint64_t stage_cap = ((uint64_t)(n_new * 1.05) + 256ull * 4096ull) / 256 * 256;
-    if (n_new >= (1ull << 22) && ctx->sparse_cap >= (1ull << 20) && !getenv("KUQ_HARVEST_DIRECT") &&
-        dmalloc(&d_stage, stage_cap) == cudaSuccess && dmalloc(&d_part, 3 * 256) == cudaSuccess) {
-      ctx->launches += launch_harvest_partitioned(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stage, stage_cap, d_part,
-                                                  reinterpret_cast<uint32_t *>(d_stat + 1), ctx->n_sm, ctx->aux);
+    const uint32_t n_parts = harvest_parts(ctx->sparse_cap);
+    const uint64_t stage_cap = ((uint64_t)(n_new * 1.05) + (uint64_t)n_parts * 4096ull) / n_parts * n_parts;
+    cudaEvent_t em;
+    CU(cudaEventCreate(&em));
+    if (n_new >= (1ull << 22) && ctx->sparse_cap >= (1ull << 22) && !getenv("KUQ_HARVEST_DIRECT") &&
+        dmalloc(&d_stage, stage_cap) == cudaSuccess && dmalloc(&d_part, 3 * (uint64_t)n_parts) == cudaSuccess) {
+      launch_harvest_stage(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stage, stage_cap, d_part,
+                           reinterpret_cast<uint32_t *>(d_stat + 1), ctx->n_sm, ctx->aux);
+      CU(cudaEventRecord(em, ctx->aux));
+      ctx->launches++;
+      for (int attempt = 0; attempt < 4; attempt++) {
+        launch_harvest_insert(ss, d_stage, d_part, n_parts, reinterpret_cast<uint32_t *>(d_stat + 1), ctx->n_sm, ctx->aux);
+        ctx->launches++;
+        uint32_t err = 0;
+        CU(cudaMemcpyAsync(&err, d_stat + 1, 4, cudaMemcpyDeviceToHost, ctx->aux));
+        CU(cudaStreamSynchronize(ctx->aux));
+        if (err != 4u) break;
+        // saturated (the estimate was off): double the set and run the insert phase again — the keys are still staged
+        CU(cudaMemsetAsync(d_stat + 1, 0, 8, ctx->aux));
+        int grc = grow_to(ctx->sparse_cap << 1);
+        if (grc) { cudaFree(d_stat); cudaFree(d_stage); cudaFree(d_part); return grc; }
+      }
+      float ms1 = 0, ms2 = 0;
+      CU(cudaEventRecord(e1, ctx->aux));
+      CU(cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&ms1, e0, em);
+      cudaEventElapsedTime(&ms2, em, e1);
+      if (getenv("KUQ_TIMING"))
+        fprintf(stderr, "[timing] harvest: %llu flagged records, count+stage %.2f ms, insert %.2f ms (%u slices, %llu slots)\n",
+                n_new, ms1, ms2, n_parts, (unsigned long long)ctx->sparse_cap);
     } else {
       (void)cudaGetLastError();
       launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 1, ctx->aux);
       ctx->launches++;
     }
     CU(cudaStreamSynchronize(ctx->aux));
+    cudaEventDestroy(em);
     cudaFree(d_stage);
     cudaFree(d_part);
   }

@@ -231,16 +231,17 @@ def test_sparse_tier_grows_at_the_harvest_and_survives_several_readouts(oracle):
     bases, offs = synth.sample_reads(rng, genomes, 900, 150, 0.0005, 0.2, 0.01)
     db = oracle.open_db(kdb, idx)
     pm = oracle.parent_map(*tax.parent_map())
-    run = oracle.run(db, pm, 500000, 0)
-    run.classify(bases, offs, want_codes=False)
+    run = oracle.run(db, pm, 1200, 0)                  # work units of 8 reads: no (unit, taxon) sketch ever converts,
+    run.classify(bases, offs, want_codes=False)        # so every taxon stays in the sparse tier
     run.finish()
     want = run.counts()
-    clf = _classifier(hll_mode=binding.HLL_PRELOAD, sparse_set_slots=1 << 13)
+    assert want["sparse"].all()
+    clf = _classifier(hll_mode=binding.HLL_PRELOAD, sparse_set_slots=1 << 13, work_unit_size=1200)
     clf.stage_db(kdb, idx)
     clf.set_taxonomy(*tax.parent_map())
     n = len(offs) - 1
-    cuts = [0, n // 3, n // 3, 2 * n // 3, n]                       # includes an empty batch
-    unit = np.zeros(n, np.uint32)                                   # one work unit, as the oracle saw it
+    cuts = [0, 296, 296, 600, n]                                    # unit boundaries; includes an empty batch
+    unit = (np.arange(n) // 8).astype(np.uint32)                    # the units the oracle cut
     for a, b in zip(cuts[:-1], cuts[1:]):
         clf.classify(bases, offs[a:b + 1], unit_id=unit[a:b])
         clf.counts()                                                # readout in the middle of the run = a harvest
