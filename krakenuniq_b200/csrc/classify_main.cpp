@@ -720,10 +720,28 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
   }
   vector<size_t> first_of(last_chunk + 1, 0);
   for (int c = 0; c < last_chunk; c++) first_of[c + 1] = first_of[c] + parsed[c].reads.size();
-  auto view = [&](size_t i, int &c) -> const View & {
-    while (first_of[c + 1] <= i) c++;
-    return parsed[c].reads[i - first_of[c]];
-  };
+  n_total = first_of[last_chunk];
+  // flat views of all reads + cumulative sequence length (parallel per chunk, chunk bases from a short serial scan)
+  vector<const View *> rv(n_total);
+  vector<uint64_t> cum(n_total + 1);
+  {
+    vector<uint64_t> chunk_nt(last_chunk + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+    for (int c = 0; c < last_chunk; c++) {
+      uint64_t nt = 0;
+      for (const View &v : parsed[c].reads) nt += v.seq_len;
+      chunk_nt[c + 1] = nt;
+    }
+    for (int c = 0; c < last_chunk; c++) chunk_nt[c + 1] += chunk_nt[c];
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+    for (int c = 0; c < last_chunk; c++) {
+      uint64_t run = chunk_nt[c];
+      size_t i = first_of[c];
+      for (const View &v : parsed[c].reads) { rv[i] = &v; cum[i] = run; run += v.seq_len; i++; }
+    }
+    cum[n_total] = chunk_nt[last_chunk];
+  }
+  auto chunk_of = [&](size_t i) { return (int)(std::upper_bound(first_of.begin(), first_of.end(), i) - first_of.begin()) - 1; };
   // work units and batches (classify.cpp:506-521): batches end at unit boundaries
   struct Cut { size_t begin, end; uint64_t bases; };
   vector<Cut> batches;
@@ -733,10 +751,9 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
     const size_t batch_reads = getenv("KUQ_BATCH_READS") ? std::max<size_t>(1, strtoull(getenv("KUQ_BATCH_READS"), NULL, 10)) : (1u << 20) - 4096;
     uint64_t unit_nt = 0, batch_nt = 0;
     size_t begin = 0, unit_first = 0;
-    int c = 0;
     const uint64_t SLOT_NT = 280ull << 20;            // below the slot capacity (288 MiB)
     for (size_t i = 0; i < n_total; i++) {
-      const uint32_t len = view(i, c).seq_len;
+      const uint64_t len = cum[i + 1] - cum[i];
       if (len > SLOT_NT) die(EX_DATAERR, "a single sequence is longer than 280 Mbp: not supported");
       if (batch_nt + len > SLOT_NT && i > begin) {    // a very long sequence is coming: close the batch before it
         batches.push_back({begin, i, batch_nt});
@@ -754,18 +771,18 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
     }
     size_t end = n_total;
     if (unit_nt == 0 && unit_first < n_total) end = unit_first;    // last unit with zero length is dropped (:523-524)
-    if (end > begin) {
-      uint64_t nt = 0;
-      int c2 = 0;
-      for (size_t i = begin; i < end; i++) nt += view(i, c2).seq_len;
-      batches.push_back({begin, end, nt});
-    }
+    if (end > begin) batches.push_back({begin, end, cum[end] - cum[begin]});
   }
   TICK("units+batches");
-  double t_fill = 0, t_emit = 0, t_wait = 0, t_submit = 0;
-  // two host staging sets, filled / formatted by all threads while the GPU works on the other one
+  // ---- pipeline: a filler thread gathers batch b + 2 into pinned memory and submits it while the GPUs classify batch
+  // b + 1 and this thread formats batch b.  Batch b runs on device b % G in slot (b / G) % NS and is staged in
+  // st[b % (NS * G)]; a slot (and its staging set) is reused only after its batch has been formatted, because the
+  // results live in the slot's pinned buffers until then.
+  const int NS = 3;
+  const int Tf = std::max(1, T / 4), Te = std::max(1, T - Tf);
   struct Stage { char *bases = NULL; uint64_t cap = 0; uint64_t *offs = NULL; size_t offs_cap = 0; size_t begin = 0, end = 0; };
-  vector<Stage> st(2 * G);
+  vector<Stage> st((size_t)NS * G);
+  double t_fill = 0, t_emit = 0, t_wait = 0, t_submit = 0;
   auto fill = [&](Stage &s, const Cut &b) {
     if (s.cap < b.bases + 64) {
       if (s.bases) kuq_host_free(s.bases);
@@ -781,72 +798,82 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
       s.offs = (uint64_t *)kuq_host_alloc(s.offs_cap * 8);
       if (!s.offs) die(EX_OSERR, "pinned allocation failed");
     }
-    s.offs[0] = 0;
-    { int c = 0; for (size_t i = 0; i < n; i++) s.offs[i + 1] = s.offs[i] + view(b.begin + i, c).seq_len; }
-#pragma omp parallel num_threads(T)
-    {
-      int c = 0;
-#pragma omp for schedule(static)
-      for (size_t i = 0; i < n; i++) {
-        int cc = c;
-        const View &v = view(b.begin + i, cc);
-        c = cc;
-        const char *src = v.owned >= 0 ? parsed[cc].arena[v.owned].data() : v.seq;
-        memcpy(s.bases + s.offs[i], src, v.seq_len);
-      }
+    const uint64_t c0 = cum[b.begin];
+#pragma omp parallel for schedule(static) num_threads(Tf)
+    for (size_t i = 0; i < n; i++) {
+      const View &v = *rv[b.begin + i];
+      s.offs[i] = cum[b.begin + i] - c0;
+      const char *src = v.owned >= 0 ? parsed[chunk_of(b.begin + i)].arena[v.owned].data() : v.seq;
+      memcpy(s.bases + s.offs[i], src, v.seq_len);
     }
+    s.offs[n] = cum[b.end] - c0;
   };
   Writer writer;
   writer.start();
+  // upper bound of the Kraken line of read i (so that a part formats into one exactly sized buffer, no growth checks)
   auto emit = [&](Stage &s, const kuq_batch_result &res) {
     const size_t n = s.end - s.begin;
-    const int parts = T;
+    const int parts = Te;
     OutJob job = writer.take(parts);
     vector<string> &kr = job.kraken, &cl = job.classified, &un = job.unclassified;
-#pragma omp parallel for schedule(static, 1) num_threads(T)
+#pragma omp parallel for schedule(static, 1) num_threads(Te)
     for (int pi = 0; pi < parts; pi++) {
       const size_t a = n * pi / parts, b = n * (pi + 1) / parts;
       string &out = kr[pi];
-      out.reserve((b - a) * 64);
-      int c = 0;
+      if (Print_kraken) {
+        size_t need = 0;
+        for (size_t i = a; i < b; i++) {
+          const View &v = *rv[s.begin + i];
+          need += 2 + v.hdr_len + 1 + 10 + 1 + 10 + 1 + 4 + 22ull * res.run_count[i] + 1 + (Print_sequence ? v.seq_len + 1 : 0);
+        }
+        out.resize(need);
+      }
+      char *o = Print_kraken ? &out[0] : NULL;
+      auto put_u32 = [&](uint32_t v) {
+        char buf[10];
+        int k = 0;
+        do { buf[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (k) *o++ = buf[--k];
+      };
       for (size_t i = a; i < b; i++) {
-        const View &v = view(s.begin + i, c);
+        const View &v = *rv[s.begin + i];
         const uint32_t call = res.call[i];
         const char *seq = s.bases + s.offs[i];
         if ((Print_unclassified && !call) || (Print_classified && call)) {       // print_sequence, :794-805
-          string &o = call ? cl[pi] : un[pi];
-          o += fastq ? '@' : '>';
-          o.append(v.hdr, v.hdr_len); o += '\n';
-          o.append(seq, v.seq_len); o += '\n';
-          if (fastq) { o += "+\n"; o.append(v.qual, v.qual_len); o += '\n'; }
+          string &oo = call ? cl[pi] : un[pi];
+          oo += fastq ? '@' : '>';
+          oo.append(v.hdr, v.hdr_len); oo += '\n';
+          oo.append(seq, v.seq_len); oo += '\n';
+          if (fastq) { oo += "+\n"; oo.append(v.qual, v.qual_len); oo += '\n'; }
         }
         if (!Print_kraken) continue;
         if (!call && Only_classified_kraken_output) continue;
-        out += call ? "C\t" : "U\t";
+        *o++ = call ? 'C' : 'U'; *o++ = '\t';
         {   // id = first whitespace-delimited token of the header line
           uint32_t x = 0;
           while (x < v.hdr_len && isspace((unsigned char)v.hdr[x])) x++;
           uint32_t y = x;
           while (y < v.hdr_len && !isspace((unsigned char)v.hdr[y])) y++;
-          out.append(v.hdr + x, y - x);
+          memcpy(o, v.hdr + x, y - x); o += y - x;
         }
-        out += '\t';
-        append_u32(out, call);
-        out += '\t';
-        append_u32(out, v.seq_len);
-        out += '\t';
-        if (Quick_mode) { out += "Q:"; append_u32(out, res.run_count[i]); }
-        else if (res.run_count[i] == 0) out += "0:0";
+        *o++ = '\t';
+        put_u32(call);
+        *o++ = '\t';
+        put_u32(v.seq_len);
+        *o++ = '\t';
+        if (Quick_mode) { *o++ = 'Q'; *o++ = ':'; put_u32(res.run_count[i]); }
+        else if (res.run_count[i] == 0) { *o++ = '0'; *o++ = ':'; *o++ = '0'; }
         for (uint32_t j = 0; !Quick_mode && j < res.run_count[i]; j++) {
           const kuq_run &run = res.runs[res.run_start[i] + j];
-          if (j) out += ' ';
-          if (run.code == KUQ_CODE_AMBIG) out += 'A'; else append_u32(out, run.code);
-          out += ':';
-          append_u32(out, run.count);
+          if (j) *o++ = ' ';
+          if (run.code == KUQ_CODE_AMBIG) *o++ = 'A'; else put_u32(run.code);
+          *o++ = ':';
+          put_u32(run.count);
         }
-        if (Print_sequence) { out += '\t'; out.append(seq, v.seq_len); }
-        out += '\n';
+        if (Print_sequence) { *o++ = '\t'; memcpy(o, seq, v.seq_len); o += v.seq_len; }
+        *o++ = '\n';
       }
+      if (Print_kraken) out.resize(o - &out[0]);
     }
     writer.push(std::move(job));
     total_classified += res.n_classified;
@@ -854,38 +881,61 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
     total_bases += s.offs[n];
     fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
   };
-  // batch bi runs on device bi % G, slot (bi / G) & 1, staged in st[bi % 2G]; at most 2G batches are in flight and
-  // the oldest one is collected before its staging set is reused
-  auto collect = [&](size_t bj) {
-    const int k = (int)(bj % (2 * G));
+  // batch bi: device bi % G, slot (bi / G) % NS, staging set bi % (NS * G)
+  std::mutex pm;
+  std::condition_variable pcv;
+  size_t submitted = 0, collected = 0;
+  string filler_error;
+  std::thread filler([&] {
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+      {
+        std::unique_lock<std::mutex> l(pm);
+        pcv.wait(l, [&] { return bi - collected < (size_t)(NS * G); });        // the slot's previous batch is formatted
+      }
+      const int k = (int)(bi % ((size_t)NS * G));
+      kuq_ctx *c = ctxs[bi % G];
+      double a = now_s();
+      fill(st[k], batches[bi]);
+      double b = now_s();
+      if (kuq_submit_batch(c, (uint32_t)((bi / G) % NS), st[k].bases, st[k].offs, (uint32_t)(st[k].end - st[k].begin), NULL, 0)) {
+        std::lock_guard<std::mutex> l(pm);
+        filler_error = kuq_last_error(c);
+        submitted = batches.size() + 1;
+        pcv.notify_all();
+        return;
+      }
+      t_fill += b - a; t_submit += now_s() - b;
+      { std::lock_guard<std::mutex> l(pm); submitted = bi + 1; }
+      pcv.notify_all();
+    }
+  });
+  for (size_t bj = 0; bj < batches.size(); bj++) {
+    {
+      std::unique_lock<std::mutex> l(pm);
+      pcv.wait(l, [&] { return submitted > bj; });
+      if (!filler_error.empty()) { l.unlock(); filler.join(); die(EX_SOFTWARE, filler_error); }
+    }
+    const int k = (int)(bj % ((size_t)NS * G));
     kuq_ctx *c = ctxs[bj % G];
     kuq_batch_result res;
     double c0 = now_s();
-    if (kuq_wait_batch(c, (uint32_t)((bj / G) & 1), &res)) die(EX_SOFTWARE, kuq_last_error(c));
+    if (kuq_wait_batch(c, (uint32_t)((bj / G) % NS), &res)) { filler.detach(); die(EX_SOFTWARE, kuq_last_error(c)); }
     double d = now_s();
     emit(st[k], res);
     t_wait += d - c0; t_emit += now_s() - d;
-  };
-  size_t collected = 0;
-  for (size_t bi = 0; bi < batches.size(); bi++) {
-    const int k = (int)(bi % (2 * G));
-    kuq_ctx *c = ctxs[bi % G];
-    while (bi - collected >= (size_t)(2 * G)) collect(collected++);     // the staging set st[k] is free again
-    double a = now_s();
-    fill(st[k], batches[bi]);
-    double b = now_s();
-    if (kuq_submit_batch(c, (uint32_t)((bi / G) & 1), st[k].bases, st[k].offs, (uint32_t)(st[k].end - st[k].begin), NULL, 0))
-      die(EX_SOFTWARE, kuq_last_error(c));
-    t_fill += b - a; t_submit += now_s() - b;
-    // keep one batch per device in flight while the host formats the older ones
-    while (bi + 1 - collected > (size_t)G) collect(collected++);
+    { std::lock_guard<std::mutex> l(pm); collected = bj + 1; }
+    pcv.notify_all();
   }
-  while (collected < batches.size()) collect(collected++);
+  filler.join();
+  TICK("pipeline");
   { double w0 = now_s(); writer.finish(); if (Timing) fprintf(stderr, "\n[timing] writer drain %.3f s\n", now_s() - w0); }
-  if (Timing) fprintf(stderr, "\n[timing] fill %.3f submit %.3f wait %.3f emit %.3f s over %zu batches on %d device(s)\n", t_fill, t_submit, t_wait, t_emit, batches.size(), G);
+  if (Timing) fprintf(stderr, "\n[timing] fill %.3f submit %.3f (filler thread, %d threads) | wait %.3f emit %.3f s (%d threads) over %zu batches on %d device(s)\n",
+                      t_fill, t_submit, Tf, t_wait, t_emit, Te, batches.size(), G);
   for (kuq_ctx *c : ctxs) if (kuq_finish(c)) die(EX_SOFTWARE, kuq_last_error(c));
+  TICK("kuq_finish (harvest)");
   for (auto &s : st) { if (s.bases) kuq_host_free(s.bases); if (s.offs) kuq_host_free(s.offs); }
   munmap((void *)base, size);
+  TICK("free + munmap");
   (void)ctx0;
   return true;
 }
@@ -1209,7 +1259,7 @@ int main(int argc, char **argv) {
   if (Populate_memory_size > 0 && getenv("KUQ_FORCE_CHUNKS")) chunk_budget = Populate_memory_size;
   kuq_config cfg;
   kuq_config_default(&cfg);
-  cfg.n_slots = 2;
+  cfg.n_slots = 3;                             // classify b + 1 on the GPU, format b, gather b + 2 (process_file_parallel)
   cfg.max_bases_per_batch = 288ull << 20;      // one read may be a whole chromosome (the largest human one is 248 Mbp)
   cfg.work_unit_size = Work_unit_size;
   // -x (or a database that has to be split) → one global sketch per taxon (classify.cpp:719); else per work unit
