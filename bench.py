@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--cache-dir", default=os.environ.get("KUQ_BENCH_CACHE", "/dev/shm"))
     ap.add_argument("--range-gb", type=float, default=0.0, help="stream mode: GB of records per streamed range (0 = 24, paired 32)")
     ap.add_argument("--paired", action="store_true", help="stream mode: configs[4], 2 x 150 bp mates merged with N")
+    ap.add_argument("--stream-both", action="store_true", help="stream mode: configs[2] and configs[4] against one generated database")
     ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "shards", "stream"],
                     help="multi-GPU layout: replicas (DB on every GPU, reads partitioned) or minimizer-range shards; "
                          "auto = replicas on one GPU, on several GPUs the sharded configs[3] line with the replicas "
@@ -857,38 +858,42 @@ def run_stream(args, local_rank, dev):
     overlapping the current range's lookups; per-window ids are merged on the device (hits only); the final pass
     resolves every batch.  The whole job is the timed region (DB traffic over PCIe included: it IS the hot path here);
     a 'step' is one batch of reads carried through all ranges and the final pass.  `--paired` = configs[4]: 2 x 150 bp
-    mates merged `mate1 + N + mate2` (scripts/read_merger.pl:187-191), 32 GB ranges, chunked HLL rule (classify -x)."""
+    mates merged `mate1 + N + mate2` (scripts/read_merger.pl:187-191); `--stream-both` runs configs[2] and configs[4]
+    against one generated database.  HLL: the chunked rule, as the reference's -x path (classify.cpp:719)."""
     import torch
     from krakenuniq_b200 import binding, synth_gpu
     from krakenuniq_b200 import dist as kdist
     records = args.db_records or 25_000_000_000
-    range_gb = args.range_gb or (32.0 if args.paired else 24.0)
+    range_gb = args.range_gb or 24.0
     # the generator builds the database in passes of <= ~0.9 G records (its sorts stay below 2^31 elements); a streamed
     # range is a run of consecutive passes
     passes = max(2, int(np.ceil(records / 0.9e9)))
     ppr = max(1, int((range_gb * 1e9 / 12) // (records / passes)))          # passes per streamed range
-    n_ranges = -(-passes // ppr)
-    L = 2 * READ_LEN + 1 if args.paired else READ_LEN
-    B = args.batch_reads // 2 if args.paired else args.batch_reads
+    variants = [False, True] if args.stream_both else [bool(args.paired)]
     n_batches = args.steps
-    n_reads = n_batches * B
-    # a database that does not fit is the reference's -x path: one global sketch per taxon (classify.cpp:719), i.e. the
-    # chunked HLL rule for both stream configurations (2 = dense only on request)
     hll_mode = 2 if args.hll_mode == 2 else 1
     t_gen = time.time()
     db = synth_gpu.GpuDatabase(records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev, passes=passes, defer_build=True)
-    if args.paired:
-        mates, _ = db.sample_reads(2 * n_reads, READ_LEN, seed=5)
-        pool = torch.full((n_reads * L + 64,), ord("N"), dtype=torch.uint8, device=dev)
-        pv = pool[:n_reads * L].view(n_reads, L)
-        mv = mates[:2 * n_reads * READ_LEN].view(n_reads, 2, READ_LEN)
-        pv[:, :READ_LEN] = mv[:, 0]
-        pv[:, READ_LEN + 1:] = mv[:, 1]
-        del mates, mv, pv
-    else:
-        pool, _ = db.sample_reads(n_reads, READ_LEN, seed=3)
-    host_pool = torch.empty(n_reads * L + 64, dtype=torch.uint8).pin_memory()
-    host_pool.copy_(pool)
+    host_pools = {}
+    for paired in variants:                                 # reads first (they need the genome), parked in pinned host memory
+        L = 2 * READ_LEN + 1 if paired else READ_LEN
+        B = args.batch_reads // 2 if paired else args.batch_reads
+        n_reads = n_batches * B
+        if paired:
+            mates, _ = db.sample_reads(2 * n_reads, READ_LEN, seed=5)
+            pool = torch.full((n_reads * L + 64,), ord("N"), dtype=torch.uint8, device=dev)
+            pv = pool[:n_reads * L].view(n_reads, L)
+            mv = mates[:2 * n_reads * READ_LEN].view(n_reads, 2, READ_LEN)
+            pv[:, :READ_LEN] = mv[:, 0]
+            pv[:, READ_LEN + 1:] = mv[:, 1]
+            del mates, mv, pv
+        else:
+            pool, _ = db.sample_reads(n_reads, READ_LEN, seed=3)
+        hp = torch.empty(n_reads * L + 64, dtype=torch.uint8).pin_memory()
+        hp.copy_(pool)
+        host_pools[paired] = hp
+        del pool
+        torch.cuda.empty_cache()
     # the database: generated range by range on the GPU, parked in pinned host memory (where a real run mmaps the file)
     h_rec, h_off, meta = [], [], []
     cap_rows = int(records / passes * ppr * 1.15) + (1 << 20)
@@ -913,7 +918,24 @@ def run_stream(args, local_rank, dev):
     del db.genome
     torch.cuda.empty_cache()
     gen_s = time.time() - t_gen
+    for paired in variants:
+        _stream_job(args, local_rank, dev, paired, host_pools[paired], h_rec, h_off, meta, key_ct, species, pmap, records, range_gb,
+                    hll_mode, gen_s)
+        torch.cuda.empty_cache()
+    return 0
+
+
+def _stream_job(args, local_rank, dev, paired, host_pool, h_rec, h_off, meta, key_ct, species, pmap, records, range_gb, hll_mode, gen_s):
+    import torch
+    from krakenuniq_b200 import binding
+    from krakenuniq_b200 import dist as kdist
+    L = 2 * READ_LEN + 1 if paired else READ_LEN
+    B = args.batch_reads // 2 if paired else args.batch_reads
+    n_batches = args.steps
+    n_reads = n_batches * B
     total_b = B * L
+    pool = torch.empty(n_reads * L + 64, dtype=torch.uint8, device=dev)
+    pool.copy_(host_pool)
     clf = binding.Classifier(device=local_rank, n_slots=2, max_reads=B, max_bases=total_b + 4096, hll_mode=hll_mode,
                              sparse_set_slots=1 << 27)
     clf.set_db_taxid_universe(species)
@@ -921,15 +943,13 @@ def run_stream(args, local_rank, dev):
     clf.stream_open(K, NT, 2, max(m[2] for m in meta), max(m[1] - m[0] for m in meta))
     d_offsets = torch.arange(B + 2, dtype=torch.int64, device=dev) * L
     merged = torch.zeros(n_reads * L + 64, dtype=torch.int32, device=dev)
-    per_unit = -(-500000 // L)
-    unit_all = (torch.arange(n_reads, dtype=torch.int64, device=dev) // per_unit).to(torch.int32)
     streams = [torch.cuda.ExternalStream(clf.slot_stream(i), device=dev) for i in range(2)]
-    d_in = torch.empty(n_reads * L + 64, dtype=torch.uint8, device=dev)
+    h_call = torch.empty(n_reads, dtype=torch.int32).pin_memory()
 
     def load(buf, r):
         clf.stream_load(buf, h_rec[r].data_ptr(), meta[r][2], h_off[r].data_ptr(), meta[r][0], meta[r][1])
 
-    def job(bases_t, from_host):
+    def job(from_host):
         """the whole job; with from_host the reads are copied from pinned host memory as the first range reaches them"""
         merged.zero_()
         torch.cuda.synchronize()
@@ -942,15 +962,14 @@ def run_stream(args, local_rank, dev):
                 sl = bi & 1
                 if from_host and r == 0:
                     with torch.cuda.stream(streams[sl]):
-                        bases_t[bi * total_b:(bi + 1) * total_b].copy_(host_pool[bi * total_b:(bi + 1) * total_b], non_blocking=True)
-                clf.lookup_device(sl, bases_t.data_ptr() + bi * total_b, d_offsets.data_ptr(), B, total_b,
+                        pool[bi * total_b:(bi + 1) * total_b].copy_(host_pool[bi * total_b:(bi + 1) * total_b], non_blocking=True)
+                clf.lookup_device(sl, pool.data_ptr() + bi * total_b, d_offsets.data_ptr(), B, total_b,
                                   merged.data_ptr() + 4 * bi * total_b, only_hits=1)
-        outs = []
         for bi in range(n_batches):
             sl = bi & 1
-            clf.resolve_device(sl, bases_t.data_ptr() + bi * total_b, d_offsets.data_ptr(), B, total_b,
-                               merged.data_ptr() + 4 * bi * total_b, unit_all[bi * B:(bi + 1) * B].data_ptr() if hll_mode == 0 else None)
-            if from_host:                                      # D2H of the calls of the batch (16-byte results per read stay simple)
+            clf.resolve_device(sl, pool.data_ptr() + bi * total_b, d_offsets.data_ptr(), B, total_b,
+                               merged.data_ptr() + 4 * bi * total_b, None)
+            if from_host:                                      # D2H of the calls of the batch
                 r_ = clf.device_result(sl)
                 with torch.cuda.stream(streams[sl]):
                     h_call[bi * B:(bi + 1) * B].copy_(kdist.device_view(r_.d_call, B * 4, torch.int32, dev), non_blocking=True)
@@ -958,7 +977,6 @@ def run_stream(args, local_rank, dev):
         clf.finish()
         clf.stream_check()
 
-    h_call = torch.empty(n_reads, dtype=torch.int32).pin_memory()
     sampler = ClockSampler(local_rank)
     sampler.start()
     # warm-up: a few batches against the first range (kernels, clocks), state wiped afterwards
@@ -967,7 +985,7 @@ def run_stream(args, local_rank, dev):
         clf.lookup_device(bi & 1, pool.data_ptr() + bi * total_b, d_offsets.data_ptr(), B, total_b, merged.data_ptr() + 4 * bi * total_b, only_hits=1)
     clf.sync(0); clf.sync(1)
     res = {}
-    for name, src, from_host in (("value", pool, False), ("e2e", d_in, True)):
+    for name, from_host in (("value", False), ("e2e", True)):
         clf.reset_counts()
         launches0 = clf.launch_count()
         torch.cuda.synchronize()
@@ -975,7 +993,7 @@ def run_stream(args, local_rank, dev):
         t0 = time.time()
         with torch.cuda.stream(streams[0]):
             e0.record(streams[0])
-        job(src, from_host)
+        job(from_host)
         with torch.cuda.stream(streams[0]):
             e1.record(streams[0])
         torch.cuda.synchronize()
@@ -987,12 +1005,13 @@ def run_stream(args, local_rank, dev):
     uncl = int(cnt["n_reads"][cnt["taxid"] == 0].sum())
     ms, launches = res["value"]
     db_bytes = key_ct * 12 + 8 * ((1 << (2 * NT)) + 1)
-    unit_name = "pairs" if args.paired else "reads"
-    line = {"metric": METRIC if not args.paired else "Mpairs/s (2 x 150 bp)", "value": n_reads / (ms / 1e3) / 1e6,
-            "unit": "Mreads/s" if not args.paired else "Mpairs/s", "n_gpus": 1, "steps": n_batches, "warmup": args.warmup,
+    unit_name = "pairs" if paired else "reads"
+    unit = "Mreads/s" if not paired else "Mpairs/s"
+    line = {"metric": METRIC if not paired else "Mpairs/s (2 x 150 bp)", "value": n_reads / (ms / 1e3) / 1e6,
+            "unit": unit, "n_gpus": 1, "steps": n_batches, "warmup": args.warmup,
             "ms_per_step": ms / n_batches, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": f"{'configs[4]' if args.paired else 'configs[2]'}{'' if records == 25_000_000_000 else ' (scaled)'}: "
+            "config": {"workload": f"{'configs[4]' if paired else 'configs[2]'}{'' if records == 25_000_000_000 else ' (scaled)'}: "
                                    f"{key_ct * 12 / 1e9:.1f} GB synthetic KrakenDB ({key_ct} records) + 8.6 GB index in PINNED HOST memory, streamed "
                                    f"through one GPU in {len(meta)} minimizer ranges of <= {range_gb:.0f} GB, {n_reads} {unit_name} "
                                    f"({L} chars each), {B} per step",
@@ -1006,18 +1025,19 @@ def run_stream(args, local_rank, dev):
                        "l2": "inputs larger than L2", "workload_gen_s": gen_s},
             "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
                          "note": "PCIe-bound configuration: see config.pcie_bound; the kernels are those of the configs[1] line"},
-            "cpu_baseline": {"value": None, "unit": "Mreads/s", "cores": host_threads(), "kind": "reference",
+            "cpu_baseline": {"value": None, "unit": unit, "cores": host_threads(), "kind": "reference",
                              "sample": "not run: the reference needs the 309 GB of database files in tmpfs plus the same again for -M"},
-            "e2e": {"value": n_reads / (res["e2e"][0] / 1e3) / 1e6, "unit": "Mreads/s" if not args.paired else "Mpairs/s",
+            "e2e": {"value": n_reads / (res["e2e"][0] / 1e3) / 1e6, "unit": unit,
                     "h2d_bytes_per_step": int(total_b + db_bytes / n_batches), "d2h_bytes_per_step": 4 * B,
                     "ms_per_step": res["e2e"][0] / n_batches,
                     "how": "reads copied from pinned host memory as the first range reaches them, calls copied back after the final pass"},
             "gpu_launches": int(launches),
             "sanity": {"reads_counted": tot, "classified_fraction": 1.0 - uncl / max(tot, 1),
-                       "expected": "about 0.80" if not args.paired else "about 0.96 (a pair is classified if either mate is)"},
+                       "expected": "about 0.80" if not paired else "about 0.96 (a pair is classified if either mate is)"},
             "clocks": clocks}
-    print(json.dumps(line))
-    return 0
+    print(json.dumps(line), flush=True)
+    clf.close()
+    del pool, merged
 
 
 if __name__ == "__main__":

@@ -51,13 +51,23 @@ H = {}
 for i, h in enumerate(hdr):
     H.setdefault(h, i)
 samp, inst = H["# Samples"], H["Instructions Executed"]
+
+
+def num(x):
+    try:
+        return int(x)
+    except ValueError:
+        return 0
+
+
+
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-tot = {s: sum(int(r[H[s]] or 0) for r in lines) for s in stalls}
+tot = {s: sum(num(r[H[s]]) for r in lines) for s in stalls}
 T = sum(tot.values()) or 1
 print(f"\n== {cur}")
 print("stall mix:", ", ".join(f"{s[6:]} {100 * v / T:.1f}%" for s, v in sorted(tot.items(), key=lambda x: -x[1])[:8]))
-ts, ti = sum(int(r[samp] or 0) for r in lines) or 1, sum(int(r[inst] or 0) for r in lines) or 1
+ts, ti = sum(num(r[samp]) for r in lines) or 1, sum(num(r[inst]) for r in lines) or 1
 print(f"{'line':>5} {'samples%':>8} {'inst%':>6}  top stall      source")
-for r in sorted(lines, key=lambda r: -int(r[samp] or 0))[:topn]:
-    st = max(stalls, key=lambda s: int(r[H[s]] or 0))
-    print(f"{r[0]:>5} {100 * int(r[samp] or 0) / ts:8.1f} {100 * int(r[inst] or 0) / ti:6.1f}  {st[6:]:<14} {r[1].strip()[:110]}")
+for r in sorted(lines, key=lambda r: -num(r[samp]))[:topn]:
+    st = max(stalls, key=lambda s: num(r[H[s]]))
+    print(f"{r[0]:>5} {100 * num(r[samp]) / ts:8.1f} {100 * num(r[inst]) / ti:6.1f}  {st[6:]:<14} {r[1].strip()[:110]}")
