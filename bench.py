@@ -668,8 +668,8 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     for _ in range(args.warmup):
         step(s); s += 1
     clf.sync(0); torch.cuda.synchronize(); dist.barrier()
-    # the warm-up's state (record flags included) is merged away outside the timed region
-    kdist.merge_classifier_state_partitioned(clf, dev)
+    # the warm-up's state (record flags included) is wiped outside the timed region: the timed run starts like a fresh run
+    clf.reset_counts()
     torch.cuda.synchronize(); dist.barrier()
     ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t0 = time.time()
@@ -744,7 +744,7 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     clf.sync(0); torch.cuda.synchronize()
     if n_own:
         est_runs[0] = min(int(nruns_v.item()) + 4096, total // 2)      # hit-list volume of a step (same workload every step)
-    kdist.merge_classifier_state_partitioned(clf, dev)
+    clf.reset_counts()
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t1 = time.time()
