@@ -181,7 +181,8 @@ __device__ __forceinline__ Block64 load_block(const char *seq, uint32_t len, uin
   b.codes = ((uint64_t)hi << 32) | lo;
   b.amb = __ballot_sync(0xFFFFFFFFu, !ok);
   b.mark = marks ? __ballot_sync(0xFFFFFFFFu, mk != 0) : 0u;
-  b.skip = !marks && __any_sync(0xFFFFFFFFu, !ok && (c == '\n' || c == '\r'));
+  // a skipped character is first of all a non-ACGT one: blocks without any (the common case) need no second vote
+  b.skip = !marks && b.amb != 0 && __any_sync(0xFFFFFFFFu, !ok && (c == '\n' || c == '\r'));
   return b;
 }
 
@@ -404,15 +405,21 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
   const bool mark_seen = (counting || (MODE == MODE_LOOKUP && shard_counting)) && p.hll_mode <= 1u;
   // only the text of this call's reads (the scratch beyond it may hold windows of an earlier call on the slot)
   const uint64_t g_begin = p.offsets[0], g_end = p.offsets[p.n_reads];
-  for (uint64_t g = g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < g_end;
-       g += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t bin = __ldg(p.bins + g);
+  // the scratch of the NEXT position of this thread is fetched while the current window is searched: the grid-stride
+  // loop would otherwise start every window with an exposed (streaming, but still ~1 us) load
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t g = g_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bin_n = g < g_end ? __ldg(p.bins + g) : BIN_NONE;
+  uint64_t canon_n = g < g_end ? __ldg(p.canon + g) : 0ull;
+  for (; g < g_end; g += stride) {
+    const uint32_t bin = bin_n;
+    const uint64_t canon = canon_n;
+    if (g + stride < g_end) { bin_n = __ldg(p.bins + g + stride); canon_n = __ldg(p.canon + g + stride); }
     if (bin == BIN_NONE) continue;
     if (bin == BIN_AMBIG) {
       if (!p.only_hits && !(MODE == MODE_LOOKUP && p.n_peers)) p.codes_dense[g] = AMBIG;
       continue;
     }
-    const uint64_t canon = __ldg(p.canon + g);
     uint32_t taxon = 0;
     if (MODE == MODE_RESOLVE) {
       taxon = p.codes_in[g];                                 // merged dense ids of all database ranges
