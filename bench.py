@@ -590,8 +590,12 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     n_pool = pool_bases.numel() // READ_LEN if pool_bases.numel() % READ_LEN == 0 else (pool_bases.numel() - 64) // READ_LEN
     n_batches = n_pool // B
     lo_bin, hi_bin = db.bin_lo, db.bin_hi
+    # the owner of a code keeps its keys after the merge: at most one per record of the whole database / world
+    want_slots = 1 << 26
+    while want_slots < (1 << 31) and want_slots < 2.5 * min(db.key_ct, (args.warmup + args.steps) * B * 100 / world):
+        want_slots <<= 1
     clf = binding.Classifier(device=local_rank, n_slots=2, max_reads=B, max_bases=B * READ_LEN + 4096,
-                             hll_mode=args.hll_mode, sparse_set_slots=1 << 26)
+                             hll_mode=args.hll_mode, sparse_set_slots=want_slots)
     clf.set_db_taxid_universe(np.array(db.species, np.uint32))
     clf.attach_db_device(db.records.data_ptr(), db.key_ct, db.offsets.data_ptr(), K, NT, 2, lo_bin, hi_bin)
     clf.set_taxonomy(*db.parent_map())
@@ -636,6 +640,15 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     bufs_t = [kdist.device_view(b_, nbytes, torch.int32, dev) for b_ in bufs]
     stream = torch.cuda.ExternalStream(clf.slot_stream(0), device=dev)
     dist.barrier()                                                # once: every rank's buffers and flags exist
+    # NCCL builds its all-to-all / all-reduce channels on first use: do that before anything is timed
+    wa = torch.zeros(world * 1024, dtype=torch.int64, device=dev)
+    wb = torch.empty_like(wa)
+    dist.all_to_all_single(wb, wa)
+    for dt in (torch.uint8, torch.int32, torch.int64):
+        t_ = torch.zeros(1024, dtype=dt, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
     keep = {}
 
     def step(i, bptr=None):

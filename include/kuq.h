@@ -292,7 +292,9 @@ int kuq_wait_flags(kuq_ctx *ctx, uint32_t slot, const uint64_t *d_flags, uint32_
 /* End-of-run merge of the sparse tier across GPUs in O(keys / GPUs) per GPU (replicas or shards): the keys of the
  * still-sparse taxa are grouped by the GPU that owns their CODE (hash(code) % n_parts; counts[j] keys for part j,
  * parts stored back to back in d_keys_out; pass d_keys_out = NULL to get the counts only), exchanged with one
- * all-to-all, and kuq_sparse_replace makes the received keys this GPU's set (duplicates collapse there).  Every key
+ * all-to-all, and kuq_sparse_replace makes the received keys this GPU's set (duplicates collapse there).  The export
+ * covers the local set and the database records flagged since the last harvest; with a buffer it CONSUMES those
+ * flags (their keys exist only in the buffer afterwards), so it must be followed by kuq_sparse_replace.  Every key
  * that can duplicate another — the same (taxon, code) from two GPUs, the same code under two taxa of a clade — lands
  * on one GPU, so global per-taxon numbers are SUMS: kuq_sparse_summary writes this GPU's rank histograms
  * ([n_sketch][64] uint32) and distinct counts ([n_sketch] uint32) to device buffers for an all-reduce(SUM), and

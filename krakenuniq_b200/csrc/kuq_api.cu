@@ -283,6 +283,7 @@ int alloc_slot(kuq_ctx *ctx, Slot &s) {
   if (s.runs_cap > 0xFFFFFF00ull) s.runs_cap = 0xFFFFFF00ull;   // run indices are 32-bit
   CU(dmalloc(&s.d_runs, s.runs_cap));
   CU(dmalloc(&s.d_scalars, 8));
+  CU(cudaMemset(s.d_scalars, 0, 8 * 8));           // kuq_sync_slot reads the error word even before the first batch
   CU(hmalloc(&s.h_call, mr));
   CU(hmalloc(&s.h_nwin, mr));
   CU(hmalloc(&s.h_run_start, mr));
@@ -818,6 +819,10 @@ int kuq_create(const kuq_config *cfg_in, kuq_ctx **out) {
   if (cudaGetDeviceProperties(&prop, cfg.device) != cudaSuccess) return KUQ_E_NO_DEVICE;
   if (prop.major < 10) return KUQ_E_NO_DEVICE;     // kernels are built for sm_100a only
   if (cudaSetDevice(cfg.device) != cudaSuccess) return KUQ_E_NO_DEVICE;
+  if (getenv("KUQ_L2_FETCH")) {           // experiment knob: L2 fetch granularity hint in bytes (32 / 64 / 128)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("KUQ_L2_FETCH")));
+    (void)cudaGetLastError();
+  }
   kuq_ctx *ctx = new kuq_ctx();
   ctx->cfg = cfg;
   ctx->device = cfg.device;
@@ -1937,29 +1942,47 @@ int kuq_sparse_export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_ke
   if (!ctx->d_sparse_slots) return KUQ_OK;
   CU(cudaSetDevice(ctx->device));
   for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
-  rc = harvest_seen(ctx, false);
-  if (rc) return rc;
+  // Two sources: the keys already in the local set (misses, resolve-half inserts, earlier harvests) and the records
+  // flagged since the last harvest.  The flagged records are NOT inserted locally first: their keys go straight into
+  // the export buffer (and the flags are cleared) — after the exchange every key is inserted exactly once, by its owner.
+  const uint64_t key_mask = ctx->k >= 32 ? ~0ull : ((1ull << (2 * ctx->k)) - 1);
+  const bool records = ctx->seen_dirty && ctx->d_pairs && ctx->key_ct;
   unsigned long long *d_cnt;
-  CU(dmalloc(&d_cnt, 8));
-  CU(cudaMemsetAsync(d_cnt, 0, 64, ctx->aux));
-  launch_sparse_parts(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, n_parts, d_cnt, nullptr, 0, ctx->aux);
+  CU(dmalloc(&d_cnt, 24));                       // [0:8) counts / cursors, [8:16) part ends, [16] error word
+  CU(cudaMemsetAsync(d_cnt, 0, 24 * 8, ctx->aux));
+  uint32_t *d_err = reinterpret_cast<uint32_t *>(d_cnt + 16);
+  launch_keys_parts(0, ctx->d_sparse_slots, nullptr, ctx->sparse_cap, key_mask, ctx->d_dense_flag, n_parts, d_cnt, nullptr, nullptr, d_err, 0, ctx->aux);
   ctx->launches++;
+  if (records) {
+    launch_keys_parts(1, nullptr, ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, n_parts, d_cnt, nullptr, nullptr, d_err, 0, ctx->aux);
+    ctx->launches++;
+  }
   unsigned long long h[8];
   CU(cudaMemcpyAsync(h, d_cnt, 64, cudaMemcpyDeviceToHost, ctx->aux));
   CU(cudaStreamSynchronize(ctx->aux));
   uint64_t total = 0;
   for (uint32_t j = 0; j < n_parts; j++) { counts[j] = h[j]; total += h[j]; }
-  if (d_keys_out && total) {
-    if (total > cap) { cudaFree(d_cnt); return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", (unsigned long long)total); }
-    unsigned long long cur[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (uint32_t j = 1; j < n_parts; j++) cur[j] = cur[j - 1] + h[j - 1];
-    CU(cudaMemcpyAsync(d_cnt, cur, 64, cudaMemcpyHostToDevice, ctx->aux));
-    launch_sparse_parts(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, n_parts, d_cnt,
-                        reinterpret_cast<unsigned long long *>(d_keys_out), 1, ctx->aux);
+  if (!d_keys_out) { cudaFree(d_cnt); return KUQ_OK; }     // counts only: nothing was consumed
+  if (total > cap) { cudaFree(d_cnt); return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", (unsigned long long)total); }
+  unsigned long long lay[16];
+  lay[0] = 0;
+  for (uint32_t j = 1; j < 8; j++) lay[j] = lay[j - 1] + (j - 1 < n_parts ? h[j - 1] : 0);
+  for (uint32_t j = 0; j < 8; j++) lay[8 + j] = lay[j] + (j < n_parts ? h[j] : 0);
+  CU(cudaMemcpyAsync(d_cnt, lay, 128, cudaMemcpyHostToDevice, ctx->aux));
+  launch_keys_parts(0, ctx->d_sparse_slots, nullptr, ctx->sparse_cap, key_mask, ctx->d_dense_flag, n_parts, d_cnt,
+                    reinterpret_cast<unsigned long long *>(d_keys_out), d_cnt + 8, d_err, 1, ctx->aux);
+  ctx->launches++;
+  if (records) {
+    launch_keys_parts(1, nullptr, ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, n_parts, d_cnt,
+                      reinterpret_cast<unsigned long long *>(d_keys_out), d_cnt + 8, d_err, 1, ctx->aux);
     ctx->launches++;
-    CU(cudaStreamSynchronize(ctx->aux));
+    ctx->seen_dirty = false;                     // the flags are gone: their keys live in the export buffer now
   }
+  uint32_t err = 0;
+  CU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, ctx->aux));
+  CU(cudaStreamSynchronize(ctx->aux));
   cudaFree(d_cnt);
+  if (err) return fail(ctx, KUQ_E_CAPACITY, "internal: partitioned export overran a segment");
   return KUQ_OK;
 }
 

@@ -225,7 +225,10 @@ void launch_signal_peers(unsigned long long *const *flag_ptrs, uint32_t n, uint3
                          cudaStream_t stream);
 void launch_wait_flags(const unsigned long long *flags, uint32_t n, unsigned long long value, unsigned long long timeout_ns,
                        uint32_t *error_flag, cudaStream_t stream);
-void launch_sparse_parts(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag, uint32_t n_parts,
-                         unsigned long long *counters, unsigned long long *out, int pass, cudaStream_t stream);
+// keys of the still-sparse taxa grouped by owner part: src 0 = slots of the local set, src 1 = flagged records (pass 1
+// clears the flags); pass 0 counts into counters[part], pass 1 scatters through counters[part] (cursors), bounded by part_end
+void launch_keys_parts(int src, const unsigned long long *slots, uint8_t *pairs, uint64_t n_items, uint64_t key_mask,
+                       const uint8_t *dense_flag, uint32_t n_parts, unsigned long long *counters, unsigned long long *out,
+                       const unsigned long long *part_end, uint32_t *error_flag, int pass, cudaStream_t stream);
 
 }  // namespace kuq

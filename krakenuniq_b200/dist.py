@@ -101,8 +101,9 @@ def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | 
     """End-of-run merge in O(state / world) per rank (replicas or database shards):
       1. all-reduce MAX of the dense flags FIRST, so that the harvest of the record flags skips taxa that are dense
          anywhere (their codes are never needed: sparse + dense → dense, hyperloglogplus.cpp:604-612);
-      2. harvest (kuq_finish), all-reduce MAX of the registers, SUM of the counters;
-      3. sparse tier: keys grouped by the rank owning their code → one all-to-all → each rank dedups its slice
+      2. all-reduce MAX of the registers, SUM of the counters;
+      3. sparse tier: keys (of the local set AND of the still-flagged records, which are not inserted locally first)
+         grouped by the rank owning their code → one all-to-all → each rank dedups its slice
          (kuq_sparse_replace) → all-reduce SUM of the per-taxon rank histograms and distinct counts
          (kuq_set_sparse_summary).  Clade unions: `clade_counts_distributed`."""
     import time
@@ -115,9 +116,9 @@ def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | 
     flag = device_view(sp.d_dense_flag, sp.n_sketch, torch.uint8, device)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
     torch.cuda.synchronize()
-    clf.finish()
     merge_state_tensors(regs, nk, nr, None, group)
-    n_max = clf.sparse_tier_info()["keys"]
+    # no local harvest: the keys of the flagged records go straight into the export buffer (kuq.h)
+    n_max = int(clf.sparse_export_partitioned(world).sum())
     keys = torch.empty(max(n_max, 1), dtype=torch.int64, device=device)
     counts = clf.sparse_export_partitioned(world, keys.data_ptr(), keys.numel())
     recv = exchange_partitioned_keys(keys, counts.tolist(), group)
