@@ -186,6 +186,19 @@ def host_threads(args=None):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def warm_collectives(dist, dev, world):
+    """NCCL builds its all-to-all / all-reduce channels on first use: do that before anything is timed"""
+    import torch
+    wa = torch.zeros(world * 1024, dtype=torch.int64, device=dev)
+    wb = torch.empty_like(wa)
+    dist.all_to_all_single(wb, wa)
+    for dt in (torch.uint8, torch.int32, torch.int64):
+        t_ = torch.zeros(1024, dtype=dt, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+
+
 def resolve_mode(args, world):
     if args.mode != "auto":
         return args.mode
@@ -391,6 +404,9 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if dist:
+        warm_collectives(dist, dev, world)
+
     def merge_state():
         """end-of-run merge across replicas: NCCL allreduce MAX/SUM + sparse-tier union"""
         if dist:
@@ -556,6 +572,7 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
                            "timing": "CUDA events on the slot stream around K steps + the end-of-run harvest (kuq_finish), max over "
                                      "ranks; the once-per-run NCCL merge of the per-taxon state across ranks is timed separately",
                            "end_of_run_merge_ms": merge_ms,
+                           "value_including_merge": world * B * args.steps / ((dev_ms + merge_ms) / 1e3) / 1e6,
                            "harvest_ms_in_timed_region": harvest_ms_value,
                            "read_pool": f"{n_pool} reads: every step of the run classifies reads no earlier step saw",
                            "sparse_tier": clf.sparse_tier_info(),
@@ -640,15 +657,7 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     bufs_t = [kdist.device_view(b_, nbytes, torch.int32, dev) for b_ in bufs]
     stream = torch.cuda.ExternalStream(clf.slot_stream(0), device=dev)
     dist.barrier()                                                # once: every rank's buffers and flags exist
-    # NCCL builds its all-to-all / all-reduce channels on first use: do that before anything is timed
-    wa = torch.zeros(world * 1024, dtype=torch.int64, device=dev)
-    wb = torch.empty_like(wa)
-    dist.all_to_all_single(wb, wa)
-    for dt in (torch.uint8, torch.int32, torch.int64):
-        t_ = torch.zeros(1024, dtype=dt, device=dev)
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t_, op=dist.ReduceOp.SUM)
-    torch.cuda.synchronize()
+    warm_collectives(dist, dev, world)
     keep = {}
 
     def step(i, bptr=None):
