@@ -233,6 +233,14 @@ int kuq_ipc_export(kuq_ctx *ctx, void *d_ptr, uint8_t handle64[64]);
 int kuq_ipc_open(kuq_ctx *ctx, const uint8_t handle64[64], void **d_ptr_out);
 int kuq_ipc_close(kuq_ctx *ctx, void *d_ptr);
 int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot);
+/* Helpers for callers that keep their batches in HBM across several passes (a database streamed in ranges): an
+ * asynchronous host → device copy on the slot's stream (pageable memory is fine), the free device memory, and the
+ * second half of kuq_classify_batch for device inputs: after kuq_classify_device / kuq_resolve_device on `slot`,
+ * kuq_collect_device_batch copies the batch's calls / window counts / hit lists to the slot's pinned host buffers,
+ * waits, and fills `out` exactly like kuq_wait_batch. */
+int kuq_copy_to_device(kuq_ctx *ctx, uint32_t slot, void *d_dst, const void *h_src, uint64_t bytes);
+uint64_t kuq_device_free_bytes(kuq_ctx *ctx);
+int kuq_collect_device_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out);
 int kuq_slot_device_result(kuq_ctx *ctx, uint32_t slot, kuq_device_result *out);
 /* With KUQ_F_STATS: number of non-ambiguous windows looked up by the slot's last batch and the sum over them of
  * ceil(log2(bin size + 1)) — the textbook probe count SURVEY.md §8(d) defines the algorithmic bytes with. */

@@ -113,6 +113,9 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_ipc_open": (C.c_int, [vp, u8p, C.POINTER(vp)]),
         "kuq_ipc_close": (C.c_int, [vp, vp]),
         "kuq_sync_slot": (C.c_int, [vp, C.c_uint32]),
+        "kuq_copy_to_device": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint64]),
+        "kuq_device_free_bytes": (C.c_uint64, [vp]),
+        "kuq_collect_device_batch": (C.c_int, [vp, C.c_uint32, C.POINTER(BatchResult)]),
         "kuq_slot_device_result": (C.c_int, [vp, C.c_uint32, C.POINTER(DeviceResult)]),
         "kuq_slot_stream": (vp, [vp, C.c_uint32]),
         "kuq_slot_stats": (C.c_int, [vp, C.c_uint32, u64p, u64p]),

@@ -1110,6 +1110,96 @@ static void run_chunked(kuq_ctx *ctx, const Mapped &kdb, const Mapped &idx, uint
   }
   vector<Batch> batches;
   for (int i = optind; i < argc; i++) load_file_batches(argv[i], batches);
+  // Preferred path: reads and per-window ids stay in HBM for the whole run and the ranges stream through two device
+  // buffers from the (pinned, if the mapping can be registered) database file while the previous range is looked up
+  // (kuq_stream_*).  Needs 5 bytes per base + 8 per read of device memory next to the two range buffers; a run that does
+  // not fit falls back to the host-side merge below.
+  if (!getenv("KUQ_CHUNKS_ON_HOST")) {
+    uint64_t need = 0, max_rec = 1, max_bins = 1;
+    for (auto &b : batches) need += (b.bases.size() + 64) * 5 + (b.reads.size() + 4) * 8 + 1024;
+    const uint64_t key_len_rec = 12;
+    for (auto &rg : ranges) {
+      max_rec = std::max<uint64_t>(max_rec, offsets[rg.second] - offsets[rg.first]);
+      max_bins = std::max<uint64_t>(max_bins, rg.second - rg.first);
+    }
+    const uint64_t range_bytes = 2 * (max_rec * key_len_rec + (max_bins + 1) * 8 + 4096);
+    const uint64_t free_b = kuq_device_free_bytes(ctx);
+    if (need + range_bytes + (2ull << 30) < free_b || getenv("KUQ_FORCE_CHUNKS")) {
+      uint64_t key_bits;
+      memcpy(&key_bits, (const uint8_t *)kdb.p + 8, 8);
+      const uint64_t header = 72 + 2 * (4 + 8 * key_bits);
+      const uint8_t *rec0 = (const uint8_t *)kdb.p + header;
+      const uint32_t k = (uint32_t)(key_bits / 2), idx_type = memcmp(q, "KRAKIDX", 7) == 0 ? 1 : 2;
+      // taxonomy must be known before the stream opens (the dense numbering is fixed there): main() sets it before us
+      if (kuq_stream_open(ctx, k, nt, idx_type, max_rec, max_bins)) die(EX_DATAERR, kuq_last_error(ctx));
+      const bool pinned = kuq_host_register(kdb.p, kdb.size) == KUQ_OK && kuq_host_register(idx.p, idx.size) == KUQ_OK;
+      if (Timing) fprintf(stderr, "[timing] chunked: %zu ranges, database mapping %s\n", ranges.size(), pinned ? "pinned" : "pageable");
+      struct DevBatch { void *bases, *offs, *codes; };
+      vector<DevBatch> dev(batches.size());
+      for (size_t bi = 0; bi < batches.size(); bi++) {
+        Batch &b = batches[bi];
+        DevBatch &d = dev[bi];
+        d.bases = kuq_device_alloc(ctx, b.bases.size() + 64);
+        d.offs = kuq_device_alloc(ctx, (b.reads.size() + 4) * 8);
+        d.codes = kuq_device_alloc(ctx, (b.bases.size() + 64) * 4);
+        if (!d.bases || !d.offs || !d.codes) die(EX_OSERR, "device allocation for the read batches failed");
+        vector<uint64_t> offs(b.offs);
+        offs.push_back(offs.back()); offs.push_back(offs.back());
+        if (kuq_device_memset(ctx, 0, (char *)d.bases + b.bases.size(), 'N', 64) ||
+            kuq_copy_to_device(ctx, 0, d.bases, b.bases.data(), b.bases.size()) ||
+            kuq_copy_to_device(ctx, 0, d.offs, offs.data(), offs.size() * 8) ||
+            kuq_device_memset(ctx, 0, d.codes, 0, (b.bases.size() + 64) * 4) || kuq_sync_slot(ctx, 0))
+          die(EX_SOFTWARE, kuq_last_error(ctx));
+      }
+      auto load = [&](uint32_t buf, size_t c) {
+        const uint64_t lo = ranges[c].first, hi = ranges[c].second;
+        if (kuq_stream_load(ctx, buf, rec0 + offsets[lo] * key_len_rec, offsets[hi] - offsets[lo], offsets + lo, lo, hi))
+          die(EX_DATAERR, kuq_last_error(ctx));
+      };
+      load(0, 0);
+      for (size_t c = 0; c < ranges.size(); c++) {
+        if (kuq_stream_use(ctx, (uint32_t)(c & 1))) die(EX_SOFTWARE, kuq_last_error(ctx));
+        if (c + 1 < ranges.size()) load((uint32_t)((c + 1) & 1), c + 1);
+        uint64_t seqs = 0;
+        for (size_t bi = 0; bi < batches.size(); bi++) {
+          Batch &b = batches[bi];
+          if (kuq_lookup_device(ctx, (uint32_t)(bi & 1), (const char *)dev[bi].bases, (const uint64_t *)dev[bi].offs,
+                                (uint32_t)b.reads.size(), b.bases.size(), (uint32_t *)dev[bi].codes, 1))
+            die(EX_SOFTWARE, kuq_last_error(ctx));
+          seqs += b.reads.size();
+        }
+        fprintf(stderr, "\r Processed %llu sequences (database chunk %zu of %zu)\n", (unsigned long long)seqs, c + 1, ranges.size());
+      }
+      if (kuq_sync_slot(ctx, 0) || kuq_sync_slot(ctx, 1) || kuq_stream_check(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
+      for (size_t bi = 0; bi < batches.size(); bi++) {              // final pass (classify.cpp:663-791)
+        Batch &b = batches[bi];
+        kuq_batch_result res;
+        if (kuq_resolve_device(ctx, 0, (const char *)dev[bi].bases, (const uint64_t *)dev[bi].offs, (uint32_t)b.reads.size(),
+                               b.bases.size(), (const uint32_t *)dev[bi].codes, NULL, 0) ||
+            kuq_collect_device_batch(ctx, 0, &res))
+          die(EX_SOFTWARE, kuq_last_error(ctx));
+        Fastq_input = b.fastq;
+        emit_results(b, res);
+        total_classified += res.n_classified;
+        total_sequences += b.reads.size();
+        total_bases += b.bases.size();
+        fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
+      }
+      if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
+      for (auto &d : dev) { kuq_device_free(ctx, d.bases); kuq_device_free(ctx, d.offs); kuq_device_free(ctx, d.codes); }
+      if (pinned) { kuq_host_unregister(kdb.p); kuq_host_unregister(idx.p); }
+      return;
+    }
+    cerr << "classify: the reads (" << need / (1 << 20) << " MiB on the device) do not fit next to the database ranges: merging on the host" << endl;
+  }
+  {
+    // host-side merge needs 5 x the input in RAM: say so instead of running into the OOM killer
+    uint64_t bytes = 0;
+    for (auto &b : batches) bytes += b.bases.size() * 5;
+    const uint64_t avail = (uint64_t)sysconf(_SC_AVPHYS_PAGES) * (uint64_t)sysconf(_SC_PAGESIZE);
+    if (bytes > avail) die(EX_OSERR, "the host-side merge of the database chunks needs about " + std::to_string(bytes >> 30) +
+                                     " GiB of RAM, " + std::to_string(avail >> 30) + " GiB are available: split the input");
+  }
   for (auto &b : batches) b.codes.assign(b.bases.size() + 1, 0);
   vector<uint32_t> tmp;
   for (size_t c = 0; c < ranges.size(); c++) {

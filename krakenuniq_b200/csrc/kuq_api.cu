@@ -1291,6 +1291,46 @@ int kuq_ipc_close(kuq_ctx *ctx, void *d_ptr) {
   return KUQ_OK;
 }
 
+int kuq_copy_to_device(kuq_ctx *ctx, uint32_t slot, void *d_dst, const void *h_src, uint64_t bytes) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!bytes) return KUQ_OK;
+  if (!d_dst || !h_src) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->slots[slot].stream));
+  return KUQ_OK;
+}
+
+uint64_t kuq_device_free_bytes(kuq_ctx *ctx) {
+  if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return 0;
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return fr;
+}
+
+// after kuq_classify_device / kuq_resolve_device on `slot`: bring the batch's results to the slot's pinned host
+// buffers and wait — the device-input counterpart of kuq_classify_batch's second half
+int kuq_collect_device_batch(kuq_ctx *ctx, uint32_t slot, kuq_batch_result *out) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!out) return KUQ_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  Slot &s = ctx->slots[slot];
+  if (s.busy) return fail(ctx, KUQ_E_STATE, "slot %u still has an unread batch", slot);
+  const uint32_t n_reads = s.n_reads;
+  if (n_reads) {
+    CU(cudaMemcpyAsync(s.h_call, s.d_call, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaMemcpyAsync(s.h_nwin, s.d_nwin, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    if (!(s.flags & KUQ_F_NO_RUNS) || ctx->quick_min) {
+      CU(cudaMemcpyAsync(s.h_run_start, s.d_run_start, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+      CU(cudaMemcpyAsync(s.h_run_count, s.d_run_count, n_reads * 4ull, cudaMemcpyDeviceToHost, s.stream));
+    }
+  }
+  CU(cudaMemcpyAsync(s.h_scalars, s.d_scalars, 8 * 8, cudaMemcpyDeviceToHost, s.stream));
+  s.busy = true;
+  return kuq_wait_batch(ctx, slot, out);
+}
+
 int kuq_sync_slot(kuq_ctx *ctx, uint32_t slot) {
   int rc = check_slot(ctx, slot);
   if (rc) return rc;
@@ -1807,8 +1847,12 @@ int kuq_stream_check(kuq_ctx *ctx) {
 
 int kuq_host_register(void *p, uint64_t bytes) {
   if (!p || !bytes) return KUQ_E_INVALID_ARG;
-  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { (void)cudaGetLastError(); return KUQ_E_CUDA; }
-  return KUQ_OK;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) return KUQ_OK;
+  (void)cudaGetLastError();
+  // a read-only mapping (mmap PROT_READ of database.kdb) can only be pinned read-only
+  if (cudaHostRegister(p, bytes, cudaHostRegisterReadOnly) == cudaSuccess) return KUQ_OK;
+  (void)cudaGetLastError();
+  return KUQ_E_CUDA;
 }
 int kuq_host_unregister(void *p) {
   if (!p) return KUQ_E_INVALID_ARG;
