@@ -310,6 +310,8 @@ int kuq_wait_flags(kuq_ctx *ctx, uint32_t slot, const uint64_t *d_flags, uint32_
  * unions of several sparse taxa: sum kuq_clade_partial's hist64 over the GPUs and evaluate kuq_ertl_sparse /
  * kuq_ertl_dense_hist (is_dense is the same on every GPU once dense flags and registers were all-reduced). */
 int kuq_sparse_export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_keys_out, uint64_t cap, uint64_t *counts);
+/* the same with the buffer sized and allocated by the library after its counting pass (release with kuq_device_free) */
+int kuq_sparse_export_partitioned_alloc(kuq_ctx *ctx, uint32_t n_parts, uint64_t **d_keys_out, uint64_t *counts);
 int kuq_sparse_replace(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n);
 int kuq_sparse_summary(kuq_ctx *ctx, uint32_t *d_hist_out, uint32_t *d_distinct_out);
 int kuq_set_sparse_summary(kuq_ctx *ctx, const uint32_t *d_hist, const uint32_t *d_distinct);

@@ -145,6 +145,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_signal_peers": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint64]),
         "kuq_wait_flags": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.c_uint64, C.c_uint32]),
         "kuq_sparse_export_partitioned": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, u64p]),
+        "kuq_sparse_export_partitioned_alloc": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), u64p]),
         "kuq_sparse_replace": (C.c_int, [vp, vp, C.c_uint64]),
         "kuq_sparse_summary": (C.c_int, [vp, vp, vp]),
         "kuq_set_sparse_summary": (C.c_int, [vp, vp, vp]),
@@ -481,6 +482,13 @@ class Classifier:
         counts = np.zeros(n_parts, np.uint64)
         self._ck(self.L.kuq_sparse_export_partitioned(self.h, n_parts, d_out, cap, _p(counts, u64p)))
         return counts
+
+    def sparse_export_partitioned_alloc(self, n_parts):
+        """→ (device pointer of the keys grouped by part — release with device_free —, counts per part)"""
+        counts = np.zeros(n_parts, np.uint64)
+        ptr = C.c_void_p()
+        self._ck(self.L.kuq_sparse_export_partitioned_alloc(self.h, n_parts, C.byref(ptr), _p(counts, u64p)))
+        return ptr.value, counts
 
     def sparse_replace(self, d_keys, n):
         self._ck(self.L.kuq_sparse_replace(self.h, d_keys, n))

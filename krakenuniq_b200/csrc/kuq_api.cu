@@ -1978,7 +1978,18 @@ int kuq_wait_flags(kuq_ctx *ctx, uint32_t slot, const uint64_t *d_flags, uint32_
   return KUQ_OK;
 }
 
+static int export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_keys_out, uint64_t cap, uint64_t *counts, uint64_t **alloc_out);
+
 int kuq_sparse_export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_keys_out, uint64_t cap, uint64_t *counts) {
+  return export_partitioned(ctx, n_parts, d_keys_out, cap, counts, nullptr);
+}
+int kuq_sparse_export_partitioned_alloc(kuq_ctx *ctx, uint32_t n_parts, uint64_t **d_keys_out, uint64_t *counts) {
+  if (!d_keys_out) return KUQ_E_INVALID_ARG;
+  *d_keys_out = nullptr;
+  return export_partitioned(ctx, n_parts, nullptr, 0, counts, d_keys_out);
+}
+
+static int export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_keys_out, uint64_t cap, uint64_t *counts, uint64_t **alloc_out) {
   if (!ctx || !counts || n_parts == 0 || n_parts > 8) return KUQ_E_INVALID_ARG;
   int rc = ensure_ready(ctx);
   if (rc) return rc;
@@ -2006,6 +2017,15 @@ int kuq_sparse_export_partitioned(kuq_ctx *ctx, uint32_t n_parts, uint64_t *d_ke
   CU(cudaStreamSynchronize(ctx->aux));
   uint64_t total = 0;
   for (uint32_t j = 0; j < n_parts; j++) { counts[j] = h[j]; total += h[j]; }
+  if (alloc_out) {                                         // the library sizes the buffer (one counting pass instead of two)
+    if (cudaMalloc((void **)&d_keys_out, (total ? total : 1) * 8) != cudaSuccess) {
+      (void)cudaGetLastError();
+      cudaFree(d_cnt);
+      return fail(ctx, KUQ_E_NOMEM, "no room for %llu exported keys", (unsigned long long)total);
+    }
+    *alloc_out = d_keys_out;
+    cap = total;
+  }
   if (!d_keys_out) { cudaFree(d_cnt); return KUQ_OK; }     // counts only: nothing was consumed
   if (total > cap) { cudaFree(d_cnt); return fail(ctx, KUQ_E_CAPACITY, "need room for %llu keys", (unsigned long long)total); }
   unsigned long long lay[16];

@@ -118,11 +118,13 @@ def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | 
     torch.cuda.synchronize()
     merge_state_tensors(regs, nk, nr, None, group)
     # no local harvest: the keys of the flagged records go straight into the export buffer (kuq.h)
-    n_max = int(clf.sparse_export_partitioned(world).sum())
-    keys = torch.empty(max(n_max, 1), dtype=torch.int64, device=device)
-    counts = clf.sparse_export_partitioned(world, keys.data_ptr(), keys.numel())
+    kptr, counts = clf.sparse_export_partitioned_alloc(world)
+    n_keys = int(counts.sum())
+    keys = device_view(kptr, max(n_keys, 1) * 8, torch.int64, device)
     recv = exchange_partitioned_keys(keys, counts.tolist(), group)
     torch.cuda.synchronize()
+    del keys
+    clf.device_free(kptr)
     clf.sparse_replace(recv.data_ptr() if recv.numel() else None, recv.numel())
     hist = torch.zeros(sp.n_sketch * 64, dtype=torch.int32, device=device)
     distinct = torch.zeros(sp.n_sketch, dtype=torch.int32, device=device)
