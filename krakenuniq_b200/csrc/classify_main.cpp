@@ -674,6 +674,24 @@ static const char *next_record_start(const char *p, const char *file_begin, cons
   return file_end;
 }
 
+struct Stage { char *bases = NULL; uint64_t cap = 0; uint64_t *offs = NULL; size_t offs_cap = 0; size_t begin = 0, end = 0; };
+// pinned staging of one batch; prepare_stage() is also called up front, while the database is being staged
+static vector<Stage> Prealloc_stages;
+static void prepare_stage(Stage &s, uint64_t bases, size_t reads) {
+  if (s.cap < bases + 64) {
+    if (s.bases) kuq_host_free(s.bases);
+    s.cap = std::max<uint64_t>(bases + 64, 160ull << 20);
+    s.bases = (char *)kuq_host_alloc(s.cap);
+    if (!s.bases) die(EX_OSERR, "pinned allocation failed");
+  }
+  if (s.offs_cap < reads + 2) {
+    if (s.offs) kuq_host_free(s.offs);
+    s.offs_cap = std::max<size_t>(reads + 2, (1u << 20) + 8);
+    s.offs = (uint64_t *)kuq_host_alloc(s.offs_cap * 8);
+    if (!s.offs) die(EX_OSERR, "pinned allocation failed");
+  }
+}
+
 // Several GPUs (replicas: every device holds the database): batches go round-robin over the contexts; results come back
 // in submission order, so the Kraken output stays in file order whatever the number of devices.
 static vector<kuq_ctx *> All_ctx;
@@ -780,24 +798,15 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
   // results live in the slot's pinned buffers until then.
   const int NS = 3;
   const int Tf = std::max(1, T / 4), Te = std::max(1, T - Tf);
-  struct Stage { char *bases = NULL; uint64_t cap = 0; uint64_t *offs = NULL; size_t offs_cap = 0; size_t begin = 0, end = 0; };
-  vector<Stage> st((size_t)NS * G);
+  // staging sets live for the whole process: pinned allocations cost tens of ms each, the second input file reuses them
+  static vector<Stage> st;
+  if (st.empty() && !Prealloc_stages.empty()) st.swap(Prealloc_stages);
+  if (st.size() < (size_t)NS * G) st.resize((size_t)NS * G);
   double t_fill = 0, t_emit = 0, t_wait = 0, t_submit = 0;
   auto fill = [&](Stage &s, const Cut &b) {
-    if (s.cap < b.bases + 64) {
-      if (s.bases) kuq_host_free(s.bases);
-      s.cap = std::max<uint64_t>(b.bases + 64, 160ull << 20);
-      s.bases = (char *)kuq_host_alloc(s.cap);
-      if (!s.bases) die(EX_OSERR, "pinned allocation failed");
-    }
     s.begin = b.begin; s.end = b.end;
     const size_t n = b.end - b.begin;
-    if (s.offs_cap < n + 2) {
-      if (s.offs) kuq_host_free(s.offs);
-      s.offs_cap = std::max<size_t>(n + 2, (1u << 20) + 8);
-      s.offs = (uint64_t *)kuq_host_alloc(s.offs_cap * 8);
-      if (!s.offs) die(EX_OSERR, "pinned allocation failed");
-    }
+    prepare_stage(s, b.bases, n);
     const uint64_t c0 = cum[b.begin];
 #pragma omp parallel for schedule(static) num_threads(Tf)
     for (size_t i = 0; i < n; i++) {
@@ -933,9 +942,9 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
                       t_fill, t_submit, Tf, t_wait, t_emit, Te, batches.size(), G);
   for (kuq_ctx *c : ctxs) if (kuq_finish(c)) die(EX_SOFTWARE, kuq_last_error(c));
   TICK("kuq_finish (harvest)");
-  for (auto &s : st) { if (s.bases) kuq_host_free(s.bases); if (s.offs) kuq_host_free(s.offs); }
-  munmap((void *)base, size);
-  TICK("free + munmap");
+  // tearing down a multi-GB mapping takes ~0.1 s of page-table work nobody has to wait for
+  std::thread([base, size] { munmap((void *)base, size); }).detach();
+  TICK("unmap (detached)");
   (void)ctx0;
   return true;
 }
@@ -1309,7 +1318,6 @@ static void run_multi_db(kuq_ctx *ctx, const vector<Mapped> &kdbs, const vector<
 int main(int argc, char **argv) {
   parse_command_line(argc, argv);
   if (Map_UIDs) die(EX_USAGE, "-I (UID mapping) is not supported by the GPU classify");
-  if (Quick_mode && DB_filenames.size() > 1) die(EX_USAGE, "-q with several databases is not supported by the GPU classify");
   if (DB_filenames.size() != Index_filenames.size()) die(EX_USAGE, "Must specify a index file for each database file");
   const size_t n_db = DB_filenames.size();
   if (n_db > 1 && Populate_memory_size > 0) die(EX_USAGE, "-x with several databases is not supported by the GPU classify");
@@ -1397,11 +1405,19 @@ int main(int argc, char **argv) {
   vector<map<uint32_t, uint64_t>> multi_db_counts;
   if (!chunk_budget && n_db == 1) {
     double T0__ = now_s();
+    // the pinned staging sets of the ingest pipeline are allocated while the database travels to the GPUs
+    std::thread prealloc([] {
+      const size_t want = 3 * All_ctx.size();
+      vector<Stage> tmp(want);
+      for (auto &s : tmp) prepare_stage(s, 150ull << 20, 1u << 20);
+      Prealloc_stages.swap(tmp);
+    });
     // every device stages the database from the same mapped files, in parallel
     vector<int> rcs(All_ctx.size(), 0);
 #pragma omp parallel for num_threads((int)All_ctx.size()) schedule(static, 1)
     for (int g = 0; g < (int)All_ctx.size(); g++) rcs[g] = kuq_stage_db(All_ctx[g], kdb.p, kdb.size, idx.p, idx.size, 0, 0);
     for (size_t g = 0; g < All_ctx.size(); g++) if (rcs[g]) die(EX_DATAERR, kuq_last_error(All_ctx[g]));
+    prealloc.join();
     TICK("stage_db");
   }
   if (Populate_memory && Populate_memory_size == 0) cerr << "\ncomplete." << endl;

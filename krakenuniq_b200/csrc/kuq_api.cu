@@ -522,48 +522,13 @@ int harvest_seen(kuq_ctx *ctx, bool discard) {
       int grc = grow_to(cap);
       if (grc) { cudaFree(d_stat); return grc; }
     }
-    // many keys: stage them by table slice first (L2 / TLB-resident inserts); few keys, or no room for the stage: insert
-    // in record order
-    unsigned long long *d_stage = nullptr, *d_part = nullptr;
-    const uint32_t n_parts = harvest_parts(ctx->sparse_cap);
-    const uint64_t stage_cap = ((uint64_t)(n_new * 1.05) + (uint64_t)n_parts * 4096ull) / n_parts * n_parts;
-    cudaEvent_t em;
-    CU(cudaEventCreate(&em));
-    if (n_new >= (1ull << 22) && ctx->sparse_cap >= (1ull << 22) && !getenv("KUQ_HARVEST_DIRECT") &&
-        dmalloc(&d_stage, stage_cap) == cudaSuccess && dmalloc(&d_part, 3 * (uint64_t)n_parts) == cudaSuccess) {
-      launch_harvest_stage(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stage, stage_cap, d_part,
-                           reinterpret_cast<uint32_t *>(d_stat + 1), ctx->n_sm, ctx->aux);
-      CU(cudaEventRecord(em, ctx->aux));
-      ctx->launches++;
-      for (int attempt = 0; attempt < 4; attempt++) {
-        launch_harvest_insert(ss, d_stage, d_part, n_parts, reinterpret_cast<uint32_t *>(d_stat + 1), ctx->n_sm, ctx->aux);
-        ctx->launches++;
-        uint32_t err = 0;
-        CU(cudaMemcpyAsync(&err, d_stat + 1, 4, cudaMemcpyDeviceToHost, ctx->aux));
-        CU(cudaStreamSynchronize(ctx->aux));
-        if (err != 4u) break;
-        // saturated (the estimate was off): double the set and run the insert phase again — the keys are still staged
-        CU(cudaMemsetAsync(d_stat + 1, 0, 8, ctx->aux));
-        int grc = grow_to(ctx->sparse_cap << 1);
-        if (grc) { cudaFree(d_stat); cudaFree(d_stage); cudaFree(d_part); return grc; }
-      }
-      float ms1 = 0, ms2 = 0;
-      CU(cudaEventRecord(e1, ctx->aux));
-      CU(cudaEventSynchronize(e1));
-      cudaEventElapsedTime(&ms1, e0, em);
-      cudaEventElapsedTime(&ms2, em, e1);
-      if (getenv("KUQ_TIMING"))
-        fprintf(stderr, "[timing] harvest: %llu flagged records, count+stage %.2f ms, insert %.2f ms (%u slices, %llu slots)\n",
-                n_new, ms1, ms2, n_parts, (unsigned long long)ctx->sparse_cap);
-    } else {
-      (void)cudaGetLastError();
-      launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 1, ctx->aux);
-      ctx->launches++;
-    }
+    // Insert in record order.  (Round 2 also tried staging the keys by table slice so that the inserts of a slice are
+    // L2-resident — profiles/README.md: read-only probes got 3x faster, but NEW keys did not (each one still costs a
+    // DRAM sector fetch and a dirty sector write-back), and new keys are what a harvest mostly sees.)
+    launch_harvest_seen(ctx->d_pairs, ctx->key_ct, key_mask, ctx->d_dense_flag, ss, d_stat, reinterpret_cast<uint32_t *>(d_stat + 1), 1, ctx->aux);
+    ctx->launches++;
     CU(cudaStreamSynchronize(ctx->aux));
-    cudaEventDestroy(em);
-    cudaFree(d_stage);
-    cudaFree(d_part);
+    if (getenv("KUQ_TIMING")) fprintf(stderr, "[timing] harvest: %llu flagged records, %llu slots\n", n_new, (unsigned long long)ctx->sparse_cap);
   }
   CU(cudaEventRecord(e1, ctx->aux));
   unsigned long long st[2] = {0, 0};
@@ -819,10 +784,6 @@ int kuq_create(const kuq_config *cfg_in, kuq_ctx **out) {
   if (cudaGetDeviceProperties(&prop, cfg.device) != cudaSuccess) return KUQ_E_NO_DEVICE;
   if (prop.major < 10) return KUQ_E_NO_DEVICE;     // kernels are built for sm_100a only
   if (cudaSetDevice(cfg.device) != cudaSuccess) return KUQ_E_NO_DEVICE;
-  if (getenv("KUQ_L2_FETCH")) {           // experiment knob: L2 fetch granularity hint in bytes (32 / 64 / 128)
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("KUQ_L2_FETCH")));
-    (void)cudaGetLastError();
-  }
   kuq_ctx *ctx = new kuq_ctx();
   ctx->cfg = cfg;
   ctx->device = cfg.device;

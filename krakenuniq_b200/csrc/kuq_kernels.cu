@@ -2,8 +2,6 @@
 // Design history: round 1 first fused all stages into one persistent warp-per-read kernel; at 128 registers it ran
 // at 25 % occupancy and was bound by exposed latency (profiles/README.md), so the path is now three kernels that
 // each keep a small register footprint and hand windows over through HBM scratch (12 B per window, streamed).
-#include <vector>
-
 #include "kuq_kernels.cuh"
 
 namespace kuq {
@@ -1428,107 +1426,6 @@ void launch_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, cons
   if (!n_rec) return;
   const int grid = (int)min((uint64_t)148 * 16, (n_rec + 255) / 256);
   k_harvest_seen<<<grid, 256, 0, stream>>>(pairs, n_rec, (uint32_t)(key_mask >> 32), dense_flag, set, stats, error_flag, mode);
-}
-
-// The same harvest for millions of flagged records: inserting them in record order touches the (multi-GB) set at random
-// — one TLB miss and one DRAM sector per key, ~14 G keys/s measured.  Instead the keys are first staged, grouped by the
-// 1/256th of the table their home slot falls into (k_harvest_stage: shared-memory write combining, one global cursor
-// bump per flushed group), and then inserted slice by slice (k_harvest_insert): every CTA works on the same 1/256th of
-// the table at about the same time, so the slice (tens of MB) is L2- and TLB-resident while it is filled.
-constexpr int HW = 8;            // staged keys per slice and CTA between two flushes (+1 word of padding per row)
-constexpr int HROUNDS = 16;      // records per thread between two flushes
-constexpr int HP_MAX = 1024;     // table slices (a power of two chosen so that a slice is <= 16 MB: it has to stay in L2
-                                 // while 148 SMs fill it, and B200's L2 is two ~60 MB halves that mirror remote lines)
-__global__ void __launch_bounds__(256) k_harvest_stage(uint8_t *pairs, uint64_t n_rec, uint32_t hi_mask, const uint8_t *dense_flag,
-                                                       uint64_t set_mask, uint32_t part_shift, uint32_t n_parts, unsigned long long *stage,
-                                                       unsigned long long *cursors /*[n_parts]*/, const unsigned long long *part_end,
-                                                       uint32_t *error_flag) {
-  extern __shared__ __align__(16) uint8_t h_smem[];
-  unsigned long long(*s_keys)[HW + 1] = reinterpret_cast<unsigned long long(*)[HW + 1]>(h_smem);
-  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(h_smem + (size_t)n_parts * (HW + 1) * 8);
-  const uint32_t tid = threadIdx.x;
-  for (uint32_t q = tid; q < n_parts; q += blockDim.x) s_cnt[q] = 0;
-  __syncthreads();
-  const uint64_t per_cta = (uint64_t)HROUNDS * blockDim.x;
-  for (uint64_t base = (uint64_t)blockIdx.x * per_cta; base < n_rec; base += (uint64_t)gridDim.x * per_cta) {
-#pragma unroll 4
-    for (int r = 0; r < HROUNDS; r++) {
-      const uint64_t i = base + (uint64_t)r * blockDim.x + tid;
-      if (i >= n_rec) continue;
-      uint32_t *w = reinterpret_cast<uint32_t *>(pairs + i * 12);
-      const uint32_t hiw = w[1];
-      if (!(hiw & SEEN_BIT)) continue;
-      w[1] = hiw & ~SEEN_BIT;
-      const uint32_t taxon = w[2];
-      if (dense_flag[taxon]) continue;
-      const uint64_t kmer = ((uint64_t)(hiw & hi_mask) << 32) | w[0];
-      const unsigned long long key = ((unsigned long long)(taxon + 1) << 32) | encode_hash32(fmix64(kmer));
-      const uint32_t part = (uint32_t)((mix64(key) & set_mask) >> part_shift);
-      const uint32_t pos = atomicAdd(&s_cnt[part], 1u);
-      if (pos < (uint32_t)HW) {
-        s_keys[part][pos] = key;
-      } else {                                             // group full before the flush (rare): straight to the stage
-        const unsigned long long at = atomicAdd(cursors + part, 1ull);
-        if (at < part_end[part]) stage[at] = key; else atomicExch(error_flag, 7u);
-      }
-    }
-    __syncthreads();
-    for (uint32_t q = tid; q < n_parts; q += blockDim.x) {   // thread t flushes the groups of slices t, t + 256, ...
-      const uint32_t n = min(s_cnt[q], (uint32_t)HW);
-      if (n) {
-        const unsigned long long at = atomicAdd(cursors + q, (unsigned long long)n);
-        if (at + n <= part_end[q]) {
-          for (uint32_t j = 0; j < n; j++) stage[at + j] = s_keys[q][j];
-        } else {
-          atomicExch(error_flag, 7u);
-        }
-      }
-      s_cnt[q] = 0;
-    }
-    __syncthreads();
-  }
-}
-__global__ void __launch_bounds__(256) k_harvest_insert(const unsigned long long *stage, const unsigned long long *part_begin,
-                                                        const unsigned long long *part_fill, uint32_t n_parts, SparseSet set,
-                                                        uint32_t *error_flag) {
-  for (uint32_t part = 0; part < n_parts; part++) {
-    const unsigned long long a = part_begin[part], b = part_fill[part];
-    for (unsigned long long i = a + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < b;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-      const unsigned long long key = stage[i];
-      const uint32_t taxon = (uint32_t)(key >> 32) - 1;
-      const int ins = sparse_insert(set, taxon, (uint32_t)key);
-      if (ins > 0) atomicAdd(set.distinct + taxon, 1u);
-      else if (ins < 0) atomicExch(error_flag, 4u);
-    }
-  }
-}
-uint32_t harvest_parts(uint64_t set_cap) {
-  uint32_t n = 64;
-  while (n < (uint32_t)HP_MAX && set_cap * 8 / n > (16ull << 20)) n <<= 1;
-  return n;
-}
-// phase 1: stage (d_part: 3 * n_parts words = segment begin, cursor, end — set up here); stage: room for stage_cap keys
-void launch_harvest_stage(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
-                          unsigned long long *stage, uint64_t stage_cap, unsigned long long *d_part, uint32_t *error_flag,
-                          int n_sm, cudaStream_t stream) {
-  const uint32_t n_parts = harvest_parts(set.mask + 1);
-  std::vector<unsigned long long> h(3 * (size_t)n_parts);
-  const uint64_t per = stage_cap / n_parts;
-  for (uint32_t p = 0; p < n_parts; p++) { h[p] = (unsigned long long)p * per; h[n_parts + p] = h[p]; h[2 * n_parts + p] = h[p] + per; }
-  cudaMemcpy(d_part, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
-  uint32_t shift = 0;
-  while (((set.mask + 1) >> shift) > (uint64_t)n_parts) shift++;
-  const int smem = (int)(n_parts * (HW + 1) * 8 + n_parts * 4);
-  cudaFuncSetAttribute(k_harvest_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int grid = (int)min((uint64_t)n_sm * 2, (n_rec + 4095) / 4096);
-  k_harvest_stage<<<grid, 256, smem, stream>>>(pairs, n_rec, (uint32_t)(key_mask >> 32), dense_flag, set.mask, shift, n_parts, stage,
-                                               d_part + n_parts, d_part + 2 * n_parts, error_flag);
-}
-// phase 2: insert slice by slice; can be repeated after the set grew (the staged keys stay where they are)
-void launch_harvest_insert(const SparseSet &set, const unsigned long long *stage, const unsigned long long *d_part, uint32_t n_parts,
-                           uint32_t *error_flag, int n_sm, cudaStream_t stream) {
-  k_harvest_insert<<<n_sm * 8, 256, 0, stream>>>(stage, d_part, d_part + n_parts, n_parts, set, error_flag);
 }
 
 // re-insert the keys of an outgrown table into its successor (no per-taxon counting: the keys were counted before)

@@ -181,14 +181,6 @@ void launch_remap_values(uint8_t *pairs, uint64_t n_rec, const uint32_t *keys, c
 // flagged records → sparse-tier keys: mode 0 count (stats[0]), 1 insert + clear, 2 clear only
 void launch_harvest_seen(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
                          unsigned long long *stats, uint32_t *error_flag, int mode, cudaStream_t stream);
-// the same for many flagged records: keys staged by table slice (phase 1), then inserted slice by slice while the slice
-// is L2 / TLB resident (phase 2, repeatable after the set grew)
-uint32_t harvest_parts(uint64_t set_cap);
-void launch_harvest_stage(uint8_t *pairs, uint64_t n_rec, uint64_t key_mask, const uint8_t *dense_flag, const SparseSet &set,
-                          unsigned long long *stage, uint64_t stage_cap, unsigned long long *d_part, uint32_t *error_flag,
-                          int n_sm, cudaStream_t stream);
-void launch_harvest_insert(const SparseSet &set, const unsigned long long *stage, const unsigned long long *d_part, uint32_t n_parts,
-                           uint32_t *error_flag, int n_sm, cudaStream_t stream);
 void launch_sparse_rehash(const unsigned long long *old_slots, uint64_t old_cap, const SparseSet &s, uint32_t *error_flag,
                           cudaStream_t stream);
 void launch_register_histograms(const uint8_t *regs, uint32_t n_sketch, uint32_t *hist /*[n_sketch][64]*/,

@@ -172,17 +172,19 @@ def test_cli_long_contigs_match_oracle(tmp_path, oracle):
         assert open(out).read() == want
 
 
-@pytest.mark.parametrize("tag", ["ab", "ba"])
+@pytest.mark.parametrize("tag", ["ab", "ba", "ab_q2", "ba_q1"])
 def test_cli_two_databases_first_hit(tmp_path, tag):
     """classify -d A -d B (both orders): the first database holding a k-mer decides, a stored taxon 0 included
-    (classify.cpp:928-936); the report adds up the genome sizes of both .counts files (classify.cpp:262-285)."""
+    (classify.cpp:928-936); the report adds up the genome sizes of both .counts files (classify.cpp:262-285).
+    `_q*`: the same with -q -m N (the read ends at its N-th hit, :943-944), golden files from the reference too."""
     M = os.path.join(util.ROOT, "tests", "golden", "multidb")
     a = ["-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx")]
     b = ["-d", os.path.join(M, "db2.kdb"), "-i", os.path.join(M, "db2.idx")]
     exe = build.build_classify()
     out, rep = tmp_path / f"{tag}.kraken", tmp_path / f"{tag}.report.tsv"
-    cmd = [exe] + (a + b if tag == "ab" else b + a) + ["-a", os.path.join(G, "taxDB"), "-t", "1", "-M", "-u", "20000",
-                                                      "-r", str(rep), "-o", str(out), os.path.join(G, "reads.fa")]
+    quick = {"ab_q2": ["-q", "-m", "2"], "ba_q1": ["-q", "-m", "1"]}.get(tag, [])     # quick mode over two databases
+    cmd = [exe] + (a + b if tag.startswith("ab") else b + a) + ["-a", os.path.join(G, "taxDB"), "-t", "1", "-M", "-u", "20000"] + \
+        quick + ["-r", str(rep), "-o", str(out), os.path.join(G, "reads.fa")]
     r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22)))
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(out).read() == open(os.path.join(M, f"{tag}.kraken")).read()
