@@ -576,6 +576,7 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
                                      "per-taxon state across ranks is timed separately",
                            "end_of_run_merge_ms": merge_ms,
                            "value_including_merge": world * B * args.steps / ((dev_ms + merge_ms) / 1e3) / 1e6,
+                           "steps_only_mreads_s": world * B * args.steps / (max(dev_ms - harvest_ms_value, 1e-3) / 1e3) / 1e6,
                            "harvest_ms_in_timed_region": harvest_ms_value,
                            "read_pool": f"{n_pool} reads: every step of the run classifies reads no earlier step saw",
                            "sparse_tier": clf.sparse_tier_info(),

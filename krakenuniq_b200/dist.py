@@ -109,6 +109,13 @@ def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | 
     import time
     world = dist.get_world_size(group)
     t0 = time.time()
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            torch.cuda.synchronize()
+            marks.append((name, time.time()))
+
     sp = clf.state_ptrs()
     regs = device_view(sp.d_regs, sp.regs_bytes, torch.uint8, device)
     nk = device_view(sp.d_n_kmers, sp.n_sketch * 8, torch.int64, device)
@@ -117,26 +124,36 @@ def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | 
     dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
     torch.cuda.synchronize()
     merge_state_tensors(regs, nk, nr, None, group)
+    mark("allreduce_state")
     # no local harvest: the keys of the flagged records go straight into the export buffer (kuq.h)
     kptr, counts = clf.sparse_export_partitioned_alloc(world)
     n_keys = int(counts.sum())
     keys = device_view(kptr, max(n_keys, 1) * 8, torch.int64, device)
+    mark("export_partitioned")
     recv = exchange_partitioned_keys(keys, counts.tolist(), group)
     torch.cuda.synchronize()
     del keys
     clf.device_free(kptr)
+    mark("all_to_all")
     clf.sparse_replace(recv.data_ptr() if recv.numel() else None, recv.numel())
+    mark("replace_import")
     hist = torch.zeros(sp.n_sketch * 64, dtype=torch.int32, device=device)
     distinct = torch.zeros(sp.n_sketch, dtype=torch.int32, device=device)
     clf.sparse_summary(hist.data_ptr(), distinct.data_ptr())
+    mark("summary")
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(distinct, op=dist.ReduceOp.SUM, group=group)
     torch.cuda.synchronize()
     clf.set_sparse_summary(hist.data_ptr(), distinct.data_ptr())
+    mark("allreduce_summary")
     if timings is not None:
         timings["merge_wall_ms"] = (time.time() - t0) * 1e3
         timings["keys_exported"] = int(counts.sum())
         timings["keys_after_dedup"] = int(recv.numel())
+        prev = t0
+        for name, t in marks:
+            timings[name + "_ms"] = (t - prev) * 1e3
+            prev = t
 
 
 def clade_counts_distributed(clf, clades, device, group=None):
