@@ -142,6 +142,7 @@ struct kuq_ctx {
   uint32_t *d_sync_err = nullptr;         // set by a kuq_wait_flags that timed out
   bool merged_summary = false;            // kuq_set_sparse_summary: snap.sparse_hist / distinct hold cross-GPU sums
   std::vector<uint32_t> merged_hist, merged_distinct;
+  uint64_t direct_upper = 0;              // upper bound of the keys in the sparse-tier set (reserve_direct_inserts)
   bool seen_dirty = false;                // counted hits flagged records since the last harvest (SEEN_BIT)
   uint64_t sparse_grown = 0;              // times the sparse-tier set was re-allocated at a harvest
   double harvest_ms = 0;                  // device time of the last harvest
@@ -468,6 +469,53 @@ int remap_db(kuq_ctx *ctx) {
 // records of the staged range become (taxon, encoded hash) keys of the device set — the union the reference builds
 // with `taxon_counts[t] += ...` over sparse sketches (hyperloglogplus.cpp:600-603) — and the flags are cleared.
 // The number of keys is known before they are inserted, so the set grows here instead of failing mid-batch.
+// Re-allocate the sparse-tier set with `cap` slots and re-insert its keys.  All slots must be idle.
+int grow_sparse_set(kuq_ctx *ctx, uint64_t cap) {
+  unsigned long long *bigger = nullptr;
+  uint32_t *d_err = nullptr;
+  if (dmalloc(&bigger, cap) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(ctx, KUQ_E_NOMEM, "sparse-tier set: no room to grow from %llu to %llu slots", (unsigned long long)ctx->sparse_cap, (unsigned long long)cap);
+  }
+  CU(dmalloc(&d_err, 1));
+  CU(cudaMemsetAsync(d_err, 0, 4, ctx->aux));
+  CU(cudaMemsetAsync(bigger, 0, cap * 8ull, ctx->aux));
+  SparseSet nb;
+  nb.slots = bigger; nb.mask = cap - 1; nb.n_used = ctx->d_sparse_used; nb.distinct = ctx->d_sparse_distinct;
+  launch_sparse_rehash(ctx->d_sparse_slots, ctx->sparse_cap, nb, d_err, ctx->aux);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->aux));
+  cudaFree(d_err);
+  cudaFree(ctx->d_sparse_slots);
+  ctx->d_sparse_slots = bigger;
+  ctx->sparse_cap = cap;
+  ctx->sparse_grown++;
+  return KUQ_OK;
+}
+
+// The resolve half inserts (taxon, code) pairs straight into the set — at most one per window of the batch.  Make room
+// BEFORE the batch instead of failing in the middle of it: `direct_upper` bounds the keys inserted that way since the
+// last exact count; when the bound says the set could pass a load factor of 0.8 the exact fill is read back, and only
+// if that still does not fit the set doubles (all slots drained first).
+int reserve_direct_inserts(kuq_ctx *ctx, uint64_t windows) {
+  if (!ctx->d_sparse_slots) return KUQ_OK;
+  if ((ctx->direct_upper + windows) * 10 <= ctx->sparse_cap * 8) { ctx->direct_upper += windows; return KUQ_OK; }
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  std::vector<uint32_t> distinct(ctx->n_sketch);
+  CU(cudaMemcpy(distinct.data(), ctx->d_sparse_distinct, ctx->n_sketch * 4ull, cudaMemcpyDeviceToHost));
+  uint64_t used = 0;
+  for (uint32_t v : distinct) used += v;
+  ctx->direct_upper = used;
+  if ((used + windows) * 10 > ctx->sparse_cap * 8) {
+    uint64_t cap = ctx->sparse_cap;
+    while ((used + windows) * 10 > cap * 6) cap <<= 1;
+    int rc = grow_sparse_set(ctx, cap);
+    if (rc) return rc;
+  }
+  ctx->direct_upper += windows;
+  return KUQ_OK;
+}
+
 int harvest_seen(kuq_ctx *ctx, bool discard) {
   if (!ctx->seen_dirty) return KUQ_OK;
   CU(cudaSetDevice(ctx->device));
@@ -497,31 +545,14 @@ int harvest_seen(kuq_ctx *ctx, bool discard) {
     CU(cudaStreamSynchronize(ctx->aux));
     uint64_t used = 0;
     for (uint32_t v : distinct) used += v;
-    auto grow_to = [&](uint64_t cap) -> int {                    // re-allocate the set with `cap` slots and re-insert its keys
-      unsigned long long *bigger = nullptr;
-      if (dmalloc(&bigger, cap) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return fail(ctx, KUQ_E_NOMEM, "sparse-tier set: no room to grow from %llu to %llu slots", (unsigned long long)ctx->sparse_cap, (unsigned long long)cap);
-      }
-      CU(cudaMemsetAsync(bigger, 0, cap * 8ull, ctx->aux));
-      SparseSet nb = ss;
-      nb.slots = bigger; nb.mask = cap - 1;
-      launch_sparse_rehash(ctx->d_sparse_slots, ctx->sparse_cap, nb, reinterpret_cast<uint32_t *>(d_stat + 1), ctx->aux);
-      ctx->launches++;
-      CU(cudaStreamSynchronize(ctx->aux));
-      cudaFree(ctx->d_sparse_slots);
-      ctx->d_sparse_slots = bigger;
-      ctx->sparse_cap = cap;
-      ctx->sparse_grown++;
-      ss = nb;
-      return KUQ_OK;
-    };
     if ((used + n_new) * 10 > ctx->sparse_cap * 8) {             // keep the load factor below 0.8
       uint64_t cap = ctx->sparse_cap;
       while ((used + n_new) * 10 > cap * 6) cap <<= 1;
-      int grc = grow_to(cap);
+      int grc = grow_sparse_set(ctx, cap);
       if (grc) { cudaFree(d_stat); return grc; }
+      ss.slots = ctx->d_sparse_slots; ss.mask = ctx->sparse_cap - 1;
     }
+    ctx->direct_upper = used + n_new;
     // Insert in record order.  (Round 2 also tried staging the keys by table slice so that the inserts of a slice are
     // L2-resident — profiles/README.md: read-only probes got 3x faster, but NEW keys did not (each one still costs a
     // DRAM sector fetch and a dirty sector write-back), and new keys are what a harvest mostly sees.)
@@ -677,6 +708,13 @@ int launch_on_slot(kuq_ctx *ctx, Slot &s, int mode, Params &p) {
     p.quick_stop = ctx->quick_stop;
     p.flags |= KUQ_F_NO_RUNS;
     s.flags |= KUQ_F_NO_RUNS;
+  }
+  if (mode == MODE_RESOLVE && !(p.flags & 4u) && ctx->cfg.hll_mode <= KUQ_HLL_CHUNKED && p.n_reads) {
+    int rrc = reserve_direct_inserts(ctx, s.total_bases);
+    if (rrc) return rrc;
+    // the set may have moved
+    p.sparse.slots = ctx->d_sparse_slots;
+    p.sparse.mask = ctx->sparse_cap ? ctx->sparse_cap - 1 : 0;
   }
   const bool units = mode != MODE_LOOKUP && ctx->cfg.hll_mode == KUQ_HLL_PRELOAD && p.unit_id && !(p.flags & 4u);
   if (units) {
@@ -1878,26 +1916,13 @@ int kuq_merge_into(kuq_ctx *dst, kuq_ctx *src) {
     CU(cudaMemcpy(distinct.data(), dst->d_sparse_distinct, dst->n_sketch * 4ull, cudaMemcpyDeviceToHost));
     uint64_t used = 0;
     for (uint32_t v : distinct) used += v;
-    if ((used + n_keys) * 10 > dst->sparse_cap * 7) {
+    if ((used + n_keys) * 10 > dst->sparse_cap * 8) {
       uint64_t cap = dst->sparse_cap;
-      while ((used + n_keys) * 2 > cap) cap <<= 1;
-      unsigned long long *bigger = nullptr;
-      uint32_t *d_err;
-      if (dmalloc(&bigger, cap) != cudaSuccess) { (void)cudaGetLastError(); cudaFree(d_keys_dst); return fail(ctx, KUQ_E_NOMEM, "sparse-tier set cannot grow to %llu slots", (unsigned long long)cap); }
-      CU(dmalloc(&d_err, 1));
-      CU(cudaMemsetAsync(d_err, 0, 4, dst->aux));
-      CU(cudaMemsetAsync(bigger, 0, cap * 8ull, dst->aux));
-      SparseSet nb;
-      nb.slots = bigger; nb.mask = cap - 1; nb.n_used = dst->d_sparse_used; nb.distinct = dst->d_sparse_distinct;
-      launch_sparse_rehash(dst->d_sparse_slots, dst->sparse_cap, nb, d_err, dst->aux);
-      dst->launches++;
-      CU(cudaStreamSynchronize(dst->aux));
-      cudaFree(d_err);
-      cudaFree(dst->d_sparse_slots);
-      dst->d_sparse_slots = bigger;
-      dst->sparse_cap = cap;
-      dst->sparse_grown++;
+      while ((used + n_keys) * 10 > cap * 6) cap <<= 1;
+      int grc = grow_sparse_set(dst, cap);
+      if (grc) { cudaFree(d_keys_dst); return grc; }
     }
+    dst->direct_upper = used + n_keys;
     rc = kuq_sparse_import(dst, d_keys_dst, n_keys);
     cudaFree(d_keys_dst);
   }
@@ -2037,6 +2062,7 @@ int kuq_sparse_replace(kuq_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
   CU(cudaMemsetAsync(ctx->d_sparse_slots, 0, ctx->sparse_cap * 8ull, ctx->aux));
   CU(cudaMemsetAsync(ctx->d_sparse_distinct, 0, ctx->n_sketch * 4ull, ctx->aux));
   CU(cudaStreamSynchronize(ctx->aux));
+  ctx->direct_upper = n;
   return kuq_sparse_import(ctx, d_keys, n);
 }
 
@@ -2180,6 +2206,7 @@ int kuq_reset_counts(kuq_ctx *ctx) {
     CU(cudaMemset(ctx->d_sparse_slots, 0, ctx->sparse_cap * 8ull));
     CU(cudaMemset(ctx->d_sparse_used, 0, 8));
     CU(cudaMemset(ctx->d_sparse_distinct, 0, ctx->n_sketch * 4ull));
+    ctx->direct_upper = 0;
   }
   if (ctx->d_exact) {
     CU(cudaMemset(ctx->d_exact, 0, ctx->exact_cap * 16ull));
