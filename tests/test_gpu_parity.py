@@ -325,8 +325,8 @@ def test_paired_reads_merged_with_N(oracle):
     _check_against_oracle(oracle, kdb, idx, tax, bases, offs, hll_mode=binding.HLL_PRELOAD, unit=30000)
 
 
-@pytest.mark.parametrize("n_ranges", [2, 5])
-def test_database_ranges_through_the_halves(oracle, n_ranges):
+@pytest.mark.parametrize("n_ranges,slots", [(2, 1 << 22), (5, 1 << 10)])
+def test_database_ranges_through_the_halves(oracle, n_ranges, slots):
     """chunked database (classify.cpp:566-791) through the C ABI halves: stage one minimizer range at a time,
     kuq_lookup_batch for every range, element-wise max merge, kuq_resolve_batch — same calls, hit lists and
     (chunked-rule) counters as the oracle's one-pass run."""
@@ -342,7 +342,8 @@ def test_database_ranges_through_the_halves(oracle, n_ranges):
     idx_off = np.frombuffer(idx[8:].tobytes(), np.uint64)
     cuts = [int(np.searchsorted(idx_off, idx_off[-1] * r // n_ranges)) for r in range(n_ranges + 1)]
     cuts[0], cuts[-1] = 0, n_bins
-    clf = _classifier(hll_mode=binding.HLL_CHUNKED)
+    # slots = 1024: the resolve half inserts its (taxon, code) pairs directly; the set must grow before the batch
+    clf = _classifier(hll_mode=binding.HLL_CHUNKED, sparse_set_slots=slots)
     clf.set_taxonomy(*tax.parent_map())
     universe = set()
     for r in range(n_ranges):                       # pass 0: the taxids of every range
@@ -368,6 +369,8 @@ def test_database_ranges_through_the_halves(oracle, n_ranges):
     got = clf.counts()
     for key in ("taxid", "n_reads", "n_kmers", "sparse", "unique"):
         assert np.array_equal(got[key], want[key]), key
+    if slots < (1 << 12):
+        assert clf.sparse_tier_info()["times_grown"] >= 1
 
 
 @pytest.mark.parametrize("n_ranges,n_batches", [(3, 2), (6, 3)])
