@@ -355,6 +355,9 @@ int kuq_host_unregister(void *p);
  * anywhere = dense, sparse-tier keys united (classify.cpp:542-544 across devices; cudaMemcpyPeer, no NCCL).  Both
  * contexts must have been given the same database and taxonomy.  `src` keeps its state. */
 int kuq_merge_into(kuq_ctx *dst, kuq_ctx *src);
+/* In one process the GPUs of a sharded database need no CUDA IPC: after kuq_enable_peer_access(ctx, peer) the device
+ * pointers of `peer` (kuq_device_alloc) can be handed to kuq_lookup_device_peers / kuq_signal_peers of `ctx` as they are. */
+int kuq_enable_peer_access(kuq_ctx *ctx, kuq_ctx *peer);
 
 /* Dense id ↔ taxid tables (n_taxa entries) for callers that exchange dense ids between GPUs. */
 int kuq_dense_taxids(kuq_ctx *ctx, uint32_t *taxid_of_dense, uint32_t cap, uint32_t *n);

@@ -136,6 +136,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_set_shard_counting": (C.c_int, [vp, C.c_int]),
         "kuq_set_stats": (C.c_int, [vp, C.c_int]),
         "kuq_merge_into": (C.c_int, [vp, vp]),
+        "kuq_enable_peer_access": (C.c_int, [vp, vp]),
         "kuq_stream_open": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
         "kuq_stream_load": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64]),
         "kuq_stream_use": (C.c_int, [vp, C.c_uint32]),

@@ -478,12 +478,14 @@ static void print_sequence(OutStream &o, const Read &r, const string &bases) {  
   o.write(s);
 }
 
-static void emit_results(const Batch &b, const kuq_batch_result &res) {
+// reads [first, first + n) of the batch; the result arrays are indexed from 0 (a share of the batch resolved on one GPU)
+static void emit_results(const Batch &b, const kuq_batch_result &res, size_t first = 0, size_t n = (size_t)-1) {
   string out;
-  out.reserve(b.reads.size() * 64);
+  if (n == (size_t)-1) n = b.reads.size() - first;
+  out.reserve(n * 64);
   char num[32];
-  for (size_t i = 0; i < b.reads.size(); i++) {
-    const Read &r = b.reads[i];
+  for (size_t i = 0; i < n; i++) {
+    const Read &r = b.reads[first + i];
     uint32_t call = res.call[i];
     if (Print_unclassified && !call) print_sequence(Unclassified_out, r, b.bases);
     if (Print_classified && call) print_sequence(Classified_out, r, b.bases);
@@ -1247,6 +1249,135 @@ static void run_chunked(kuq_ctx *ctx, const Mapped &kdb, const Mapped &idx, uint
   if (kuq_finish(ctx)) die(EX_SOFTWARE, kuq_last_error(ctx));
 }
 
+// ---- a database that fits the GPUs of the node together but not one of them: minimizer-range shards ---
+// GPU g stages range g.  Every GPU scans every batch and looks up the k-mers whose minimizer it owns; each hit is stored
+// straight into the id buffer of the GPU that resolves the read (peer stores over NVLink, kuq_lookup_device_peers), which
+// also does the hit's sketch work; device flags order the phases (no host barrier between GPUs); every GPU resolves a
+// contiguous share of the batch cut at work-unit boundaries.  One process, so peer access instead of CUDA IPC.  The
+// sketches follow the chunked rule, as for any database the reference could only run with -x.
+static void run_sharded(const vector<kuq_ctx *> &ctxs, const Mapped &kdb, const Mapped &idx, int argc, char **argv,
+                        map<uint32_t, uint64_t> &db_counts) {
+  const int G = (int)ctxs.size();
+  const uint8_t *q = (const uint8_t *)idx.p;
+  const uint32_t nt = q[7];
+  const uint64_t n_bins = 1ull << (2 * nt);
+  const uint64_t *offsets = (const uint64_t *)(q + 8);
+  const uint64_t key_ct = offsets[n_bins];
+  vector<uint64_t> cut(G + 1, 0);
+  cut[G] = n_bins;
+  for (int g = 1; g < G; g++) cut[g] = std::lower_bound(offsets, offsets + n_bins, key_ct / G * g) - offsets;
+  for (int g = 1; g <= G; g++) if (cut[g] < cut[g - 1]) cut[g] = cut[g - 1];
+  cerr << "Database sharded over " << G << " GPUs by minimizer range" << endl;
+  {
+    vector<int> rcs(G, 0);
+#pragma omp parallel for num_threads(G) schedule(static, 1)
+    for (int g = 0; g < G; g++)
+      rcs[g] = cut[g + 1] > cut[g] ? kuq_stage_db(ctxs[g], kdb.p, kdb.size, idx.p, idx.size, cut[g], cut[g + 1]) : 0;
+    for (int g = 0; g < G; g++) if (rcs[g]) die(EX_DATAERR, kuq_last_error(ctxs[g]));
+  }
+  for (int g = 0; g < G; g++) {
+    if (cut[g + 1] <= cut[g]) die(EX_DATAERR, "more GPUs than non-empty minimizer ranges: use fewer devices (KUQ_DEVICES)");
+    uint32_t m = 0;
+    kuq_db_taxids(ctxs[g], NULL, NULL, 0, &m);
+    vector<uint32_t> tt(m);
+    vector<uint64_t> cc(m);
+    if (m) kuq_db_taxids(ctxs[g], tt.data(), cc.data(), m, &m);
+    for (uint32_t i = 0; i < m; i++) db_counts[tt[i]] += cc[i];
+  }
+  vector<uint32_t> all;
+  for (auto &kv : db_counts) all.push_back(kv.first);
+  for (int g = 0; g < G; g++) {
+    if (kuq_set_db_taxid_universe(ctxs[g], all.data(), (uint32_t)all.size()) || kuq_set_shard_counting(ctxs[g], 1))
+      die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+    for (int h = 0; h < G; h++) if (h != g && kuq_enable_peer_access(ctxs[g], ctxs[h])) die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+  }
+  vector<Batch> batches;
+  for (int i = optind; i < argc; i++) load_file_batches(argv[i], batches, /*unit_aligned=*/true);
+  uint64_t max_bases = 64, max_reads = 4;
+  for (auto &b : batches) { max_bases = std::max<uint64_t>(max_bases, b.bases.size()); max_reads = std::max<uint64_t>(max_reads, b.reads.size()); }
+  struct Dev { void *bases[2], *offs[2], *ids[2], *flags; };
+  vector<Dev> dev(G);
+  const uint64_t id_bytes = (max_bases + 64) * 4;
+  for (int g = 0; g < G; g++) {
+    Dev &d = dev[g];
+    for (int k = 0; k < 2; k++) {
+      d.bases[k] = kuq_device_alloc(ctxs[g], max_bases + 64);
+      d.offs[k] = kuq_device_alloc(ctxs[g], (max_reads + 4) * 8);
+      d.ids[k] = kuq_device_alloc(ctxs[g], id_bytes);
+      if (!d.bases[k] || !d.offs[k] || !d.ids[k]) die(EX_OSERR, "device allocation for the sharded batches failed");
+      if (kuq_device_memset(ctxs[g], 0, d.ids[k], 0, id_bytes)) die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+    }
+    d.flags = kuq_device_alloc(ctxs[g], 256);            // [0:8) done counters, [16:24) ready counters
+    if (!d.flags || kuq_device_memset(ctxs[g], 0, d.flags, 0, 256)) die(EX_OSERR, "device allocation failed");
+    const uint64_t two[8] = {2, 2, 2, 2, 2, 2, 2, 2};     // both id buffers are clean for steps 0 and 1
+    if (kuq_copy_to_device(ctxs[g], 0, (char *)d.flags + 128, two, 64) || kuq_sync_slot(ctxs[g], 0)) die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+  }
+  uint64_t step = 0;
+  for (auto &b : batches) {
+    const size_t n = b.reads.size();
+    const int par = (int)(step & 1);
+    // shares: contiguous, cut where a work unit ends (the chunked rule does not depend on units; even cuts keep the
+    // offset slices 16-byte aligned)
+    vector<size_t> first(G + 1, 0);
+    first[G] = n;
+    for (int g = 1; g < G; g++) first[g] = std::min(n, (n * g / G) & ~(size_t)1);
+    vector<uint64_t> bounds(G + 1);
+    for (int g = 0; g <= G; g++) bounds[g] = b.offs[first[g]];
+    bounds[0] = 0;
+    vector<uint64_t> offs(b.offs);
+    offs.push_back(offs.back()); offs.push_back(offs.back());
+    // phase 1: the batch goes to every GPU (a pageable copy may wait for the stream: everything it can wait for is queued)
+    for (int g = 0; g < G; g++) {
+      if (kuq_copy_to_device(ctxs[g], 0, dev[g].bases[par], b.bases.data(), b.bases.size()) ||
+          kuq_device_memset(ctxs[g], 0, (char *)dev[g].bases[par] + b.bases.size(), 'N', 64) ||
+          kuq_copy_to_device(ctxs[g], 0, dev[g].offs[par], offs.data(), offs.size() * 8))
+        die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+    }
+    // phase 2: lookups with peer scatter; phase 3: owners resolve — all stream ordered, flags between the GPUs
+    for (int g = 0; g < G; g++) {
+      vector<uint32_t *> peer_ids(G);
+      vector<uint64_t *> peer_done(G);
+      for (int h = 0; h < G; h++) { peer_ids[h] = (uint32_t *)dev[h].ids[par]; peer_done[h] = (uint64_t *)dev[h].flags; }
+      if (kuq_wait_flags(ctxs[g], 0, (const uint64_t *)((char *)dev[g].flags + 128), (uint32_t)G, step + 1, 0) ||
+          kuq_lookup_device_peers(ctxs[g], 0, (const char *)dev[g].bases[par], (const uint64_t *)dev[g].offs[par], (uint32_t)n,
+                                  b.bases.size(), peer_ids.data(), bounds.data(), (uint32_t)G) ||
+          kuq_signal_peers(ctxs[g], 0, peer_done.data(), (uint32_t)G, (uint32_t)g, step + 1))
+        die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+    }
+    for (int g = 0; g < G; g++) {
+      vector<uint64_t *> peer_ready(G);
+      for (int h = 0; h < G; h++) peer_ready[h] = (uint64_t *)((char *)dev[h].flags + 128);
+      const size_t share = first[g + 1] - first[g];
+      if (kuq_wait_flags(ctxs[g], 0, (const uint64_t *)dev[g].flags, (uint32_t)G, step + 1, 0)) die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+      if (share && kuq_resolve_device(ctxs[g], 0, (const char *)dev[g].bases[par], (const uint64_t *)dev[g].offs[par] + first[g],
+                                      (uint32_t)share, b.bases.size(), (const uint32_t *)dev[g].ids[par], NULL, 0))
+        die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+      if (kuq_device_memset(ctxs[g], 0, (char *)dev[g].ids[par] + bounds[g] * 4, 0, (bounds[g + 1] - bounds[g]) * 4) ||
+          kuq_signal_peers(ctxs[g], 0, peer_ready.data(), (uint32_t)G, (uint32_t)g, step + 3))
+        die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+    }
+    // phase 4: results of the shares, in read order
+    Fastq_input = b.fastq;
+    for (int g = 0; g < G; g++) {
+      const size_t share = first[g + 1] - first[g];
+      if (!share) { if (kuq_sync_slot(ctxs[g], 0)) die(EX_SOFTWARE, kuq_last_error(ctxs[g])); continue; }
+      kuq_batch_result res;
+      if (kuq_collect_device_batch(ctxs[g], 0, &res)) die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+      emit_results(b, res, first[g], share);
+      total_classified += res.n_classified;
+    }
+    total_sequences += n;
+    total_bases += b.bases.size();
+    fprintf(stderr, "\r Processed %llu sequences (%.2f%% classified)", total_sequences, total_classified * 100.0 / total_sequences);
+    step++;
+  }
+  for (int g = 0; g < G; g++) {
+    if (kuq_finish(ctxs[g])) die(EX_SOFTWARE, kuq_last_error(ctxs[g]));
+    for (int k = 0; k < 2; k++) { kuq_device_free(ctxs[g], dev[g].bases[k]); kuq_device_free(ctxs[g], dev[g].offs[k]); kuq_device_free(ctxs[g], dev[g].ids[k]); }
+    kuq_device_free(ctxs[g], dev[g].flags);
+  }
+}
+
 // ---- several databases: `-d a -d b` (classify.cpp:928-936) ----------------------------------------------------
 // For every k-mer the reference asks the databases in command-line order and keeps the value of the first one
 // that holds the key — a stored taxon 0 included.  One database is resident in HBM at a time: the reads are
@@ -1348,27 +1479,38 @@ int main(int argc, char **argv) {
   uint64_t hbm_budget = 150ull << 30;
   if (getenv("KUQ_HBM_BUDGET")) hbm_budget = strtoull(getenv("KUQ_HBM_BUDGET"), NULL, 10);
   uint64_t chunk_budget = 0;
-  if (kdb.size + idx.size > hbm_budget) chunk_budget = hbm_budget;
+  // a database larger than one card: sharded over the visible GPUs when they hold it together (run_sharded), else
+  // streamed through one GPU in ranges of at most 40 GB (two range buffers + the reads have to fit, run_chunked)
+  bool want_shards = false;
+  if (n_db == 1 && (kdb.size + idx.size > hbm_budget || getenv("KUQ_FORCE_SHARDS"))) {
+    int n_vis = 0;
+    if (const char *dl = getenv("KUQ_DEVICES")) { if (strcmp(dl, "all") == 0) n_vis = kuq_device_count(); else { n_vis = 1; for (const char *c = dl; *c; c++) n_vis += *c == ','; } }
+    else if (!getenv("KUQ_DEVICE")) n_vis = kuq_device_count();
+    want_shards = n_vis > 1 && (getenv("KUQ_FORCE_SHARDS") || (kdb.size + idx.size) / n_vis + (16ull << 30) < hbm_budget);
+  }
+  if (kdb.size + idx.size > hbm_budget && !want_shards) chunk_budget = std::min<uint64_t>(hbm_budget / 4, 40ull << 30);
   if (n_db > 1) {
     for (size_t i = 0; i < n_db; i++)
       if (kdbs[i].size + idxs[i].size > hbm_budget) die(EX_USAGE, "with several databases each one has to fit the HBM budget");
     chunk_budget = 0;
   }
-  if (Populate_memory_size > 0 && getenv("KUQ_FORCE_CHUNKS")) chunk_budget = Populate_memory_size;
+  if (Populate_memory_size > 0 && getenv("KUQ_FORCE_CHUNKS")) { chunk_budget = Populate_memory_size; want_shards = false; }
   kuq_config cfg;
   kuq_config_default(&cfg);
   cfg.n_slots = 3;                             // classify b + 1 on the GPU, format b, gather b + 2 (process_file_parallel)
   cfg.max_bases_per_batch = 288ull << 20;      // one read may be a whole chromosome (the largest human one is 248 Mbp)
   cfg.work_unit_size = Work_unit_size;
   // -x (or a database that has to be split) → one global sketch per taxon (classify.cpp:719); else per work unit
-  cfg.hll_mode = (Populate_memory_size > 0 || chunk_budget) ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;
+  cfg.hll_mode = (Populate_memory_size > 0 || chunk_budget || want_shards) ? KUQ_HLL_CHUNKED : KUQ_HLL_PRELOAD;
 #ifdef EXACT_COUNTING
   // classifyExact (classify.cpp:46-49): sets of k-mers instead of sketches; work units and chunks make no difference
   cfg.hll_mode = KUQ_HLL_EXACT;
+  if (want_shards) { want_shards = false; chunk_budget = std::min<uint64_t>(hbm_budget / 4, 40ull << 30); }   // exact sets are not merged across devices
   if (Quick_mode) die(EX_USAGE, "-q is not supported by the GPU classifyExact");
 #endif
-  if (chunk_budget && !Populate_memory_size)
-    cerr << "classify: database larger than the HBM budget: processing it in ranges (unique k-mer counts follow the -x rule)" << endl;
+  if ((chunk_budget || want_shards) && !Populate_memory_size)
+    cerr << "classify: database larger than one GPU's HBM budget: " << (want_shards ? "sharding it over the GPUs" : "processing it in ranges")
+         << " (unique k-mer counts follow the -x rule)" << endl;
   if (getenv("KUQ_SPARSE_SLOTS")) cfg.sparse_set_slots = strtoull(getenv("KUQ_SPARSE_SLOTS"), NULL, 10);
   if (getenv("KUQ_DEVICE")) cfg.device = atoi(getenv("KUQ_DEVICE"));
   // devices: KUQ_DEVICES=0,2,3 (or "all"); default = every visible sm_100 GPU when the database is replicated (one
@@ -1377,6 +1519,7 @@ int main(int argc, char **argv) {
   {
     const char *dl = getenv("KUQ_DEVICES");
     const bool replicable = !chunk_budget && n_db == 1 && cfg.hll_mode != KUQ_HLL_EXACT;   // exact k-mer sets are not merged across devices
+    // (replicas when the database fits a card, shards when it only fits the cards together)
     if (dl && strcmp(dl, "all") != 0) {
       for (const char *q = dl; *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; }
     } else if ((dl || !getenv("KUQ_DEVICE")) && replicable) {
@@ -1397,13 +1540,14 @@ int main(int argc, char **argv) {
     if (r2) { fprintf(stderr, "classify: device %d not usable (%s): continuing without it\n", devices[g], kuq_strerror(r2)); continue; }
     All_ctx.push_back(cx);
   }
-  if (All_ctx.size() > 1) fprintf(stderr, "classify: %zu GPUs, database replicated, batches round-robin\n", All_ctx.size());
+  if (want_shards && All_ctx.size() < 2) { want_shards = false; chunk_budget = std::min<uint64_t>(hbm_budget / 4, 40ull << 30); }
+  if (All_ctx.size() > 1 && !want_shards) fprintf(stderr, "classify: %zu GPUs, database replicated, batches round-robin\n", All_ctx.size());
   // -q: the preloaded path leaves a read at its -m'th hit; with -x every k-mer is counted (classify.cpp:943-944 / :701-738)
   for (kuq_ctx *c : All_ctx)
     if (Quick_mode && kuq_set_quick_mode(c, Minimum_hit_count, Populate_memory_size == 0)) die(EX_SOFTWARE, kuq_last_error(c));
   map<uint32_t, uint64_t> chunk_db_counts;
   vector<map<uint32_t, uint64_t>> multi_db_counts;
-  if (!chunk_budget && n_db == 1) {
+  if (!chunk_budget && !want_shards && n_db == 1) {
     double T0__ = now_s();
     // the pinned staging sets of the ingest pipeline are allocated while the database travels to the GPUs
     std::thread prealloc([] {
@@ -1444,6 +1588,7 @@ int main(int argc, char **argv) {
   struct timeval tv1, tv2;
   gettimeofday(&tv1, NULL);
   if (n_db > 1) run_multi_db(ctx, kdbs, idxs, argc, argv, multi_db_counts);
+  else if (want_shards) run_sharded(All_ctx, kdb, idx, argc, argv, chunk_db_counts);
   else if (chunk_budget) run_chunked(ctx, kdb, idx, chunk_budget, argc, argv, chunk_db_counts);
   else for (int i = optind; i < argc; i++) process_file(ctx, argv[i]);
   // the other devices' per-taxon state joins the first one's (classify.cpp:542-544 across GPUs)
@@ -1478,7 +1623,7 @@ int main(int argc, char **argv) {
       ofstream ofs(fname);
       if (n_db > 1) {
         for (auto &kv : multi_db_counts[d]) ofs << kv.first << '\t' << kv.second << '\n';
-      } else if (chunk_budget) {
+      } else if (chunk_budget || want_shards) {
         for (auto &kv : chunk_db_counts) ofs << kv.first << '\t' << kv.second << '\n';
       } else {
         uint32_t m = 0;

@@ -1930,6 +1930,19 @@ int kuq_merge_into(kuq_ctx *dst, kuq_ctx *src) {
   return rc;
 }
 
+int kuq_enable_peer_access(kuq_ctx *ctx, kuq_ctx *peer) {
+  if (!ctx || !peer) return KUQ_E_INVALID_ARG;
+  if (ctx->device == peer->device) return KUQ_OK;
+  CU(cudaSetDevice(ctx->device));
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+  if (!can) return fail(ctx, KUQ_E_STATE, "device %d cannot map the memory of device %d", ctx->device, peer->device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, KUQ_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+  (void)cudaGetLastError();
+  return KUQ_OK;
+}
+
 int kuq_set_stats(kuq_ctx *ctx, int on) {
   if (!ctx) return KUQ_E_INVALID_ARG;
   ctx->extra_flags = on ? KUQ_F_STATS : 0u;

@@ -254,15 +254,18 @@ def main():
         G = util.GOLDEN
         exe = build.build_classify()
         with tempfile.TemporaryDirectory() as td:
-            for tag, extra in (("preload", ["-M"]), ("preload_u20000", ["-M", "-u", "20000"])):
+            # replicas (database on every GPU) and shards (one minimizer range per GPU: the layout classify picks for a
+            # database that only fits the cards together; its sketches follow the -x rule → the reference's -x goldens)
+            for tag, extra, more_env in (("preload", ["-M"], {}), ("preload_u20000", ["-M", "-u", "20000"], {}),
+                                         ("chunked", ["-M"], {"KUQ_FORCE_SHARDS": "1"})):
                 out, rep = os.path.join(td, tag + ".kraken"), os.path.join(td, tag + ".report.tsv")
                 cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a", os.path.join(G, "taxDB"),
                        "-t", "4", "-r", rep, "-o", out] + extra + [os.path.join(G, "reads.fa")]
                 env = dict(os.environ, KUQ_DEVICES=",".join(str(d) for d in range(world)), KUQ_SPARSE_SLOTS=str(1 << 22),
-                           KUQ_BATCH_READS="200")        # small batches so that every device gets work
+                           KUQ_BATCH_READS="200", **more_env)        # small batches so that every device gets work
                 r = subprocess.run(cmd, capture_output=True, text=True, env=env)
                 assert r.returncode == 0, r.stderr[-2000:]
-                assert f"{world} GPUs" in r.stderr, r.stderr[-500:]
+                assert (f"sharded over {world} GPUs" if more_env else f"{world} GPUs") in r.stderr, r.stderr[-500:]
                 assert open(out).read() == open(os.path.join(G, tag + ".kraken")).read(), tag
 
                 def rows(path):
