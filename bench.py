@@ -225,7 +225,7 @@ def build_workload(args, mode, rank, world, dev, dist, n_steps):
     t_gen = time.time()
     sharded = mode == "shards" and world > 1
     records = shard_db_records(args, world) if sharded else (args.db_records or 666_000_000)
-    passes = args.db_passes or (max(1, -(-records // world // 800_000_000)) if sharded else max(1, records // 1_500_000_000))
+    passes = args.db_passes or (max(1, -(-records // world // 600_000_000)) if sharded else max(1, records // 1_500_000_000))
     torch.cuda.reset_peak_memory_stats()
     w.db = synth_gpu.GpuDatabase(records, n_genomes=args.genomes, k=K, nt=NT, seed=2, device=dev, passes=passes,
                                  shard=(rank, world) if sharded else None)
