@@ -889,8 +889,22 @@ def run_stream(args, local_rank, dev):
     import torch
     from krakenuniq_b200 import binding, synth_gpu
     from krakenuniq_b200 import dist as kdist
-    records = args.db_records or 25_000_000_000
-    range_gb = args.range_gb or 24.0
+    # The configurations are quoted on a 300 GB database (25 G records).  The whole database has to sit in pinned host
+    # memory here, and this pool's boxes give a container 200 GiB of host memory (cgroup memory.max) — a 300 GB run
+    # takes the box down.  Default = what is safe there: 60 GB of records in ranges of 6 GB (the behaviour is the same,
+    # PCIe-bound: one pass moves the database once); --db-records 25000000000 --range-gb 24 is the real thing on a
+    # host that has the memory, and the guard below refuses sizes the container cannot hold.
+    records = args.db_records or 5_000_000_000
+    range_gb = args.range_gb or (24.0 if records >= 20_000_000_000 else 6.0)
+    need_host = records * 12 * 1.10 + (1 << (2 * NT)) * 8 + 2 * args.steps * args.batch_reads * READ_LEN * (2 if args.stream_both else 1) + (8 << 30)
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        lim = int(lim) if lim != "max" else None
+    except Exception:
+        lim = None
+    if lim is not None and need_host > 0.7 * lim:
+        raise SystemExit(f"bench.py --mode stream: about {need_host / 2**30:.0f} GiB of pinned host memory needed, the container "
+                         f"allows {lim / 2**30:.0f} GiB: use a smaller --db-records / fewer --steps")
     # the generator builds the database in passes of <= ~0.9 G records (its sorts stay below 2^31 elements); a streamed
     # range is a run of consecutive passes
     passes = max(2, int(np.ceil(records / 0.9e9)))
@@ -922,7 +936,7 @@ def run_stream(args, local_rank, dev):
         torch.cuda.empty_cache()
     # the database: generated range by range on the GPU, parked in pinned host memory (where a real run mmaps the file)
     h_rec, h_off, meta = [], [], []
-    cap_rows = int(records / passes * ppr * 1.15) + (1 << 20)
+    cap_rows = int(records / passes * ppr * 1.08) + (1 << 20)
     pi = 0
     for lo, hi, rec, off in db.stream_ranges():
         if pi % ppr == 0:
