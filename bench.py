@@ -414,12 +414,12 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
             kdist.merge_classifier_state_partitioned(clf, dev)
 
     # ---- value: device-resident inputs ----------------------------------------------------------------------------
-    # consecutive batches alternate between two of the context's slots (streams): the ALU-bound scan of batch i+1 and the
-    # latency-bound resolve of batch i-1 fill the gaps of the memory-bound lookup of batch i
+    # one slot (stream): alternating the batches over two slots was measured 25 % SLOWER per step (4.67 vs 3.70 ms) —
+    # the lookups of one batch and the scan / resolve of its neighbours evict each other's sectors from L2
     step = 0
     for _ in range(args.warmup):
-        clf.classify_device(step & 1, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
-    clf.sync(0); clf.sync(1)
+        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
+    clf.sync(0)
     clf.finish()                                  # the warm-up's flagged records are harvested outside the timed region
     barrier()
     launches0 = clf.launch_count()
@@ -429,13 +429,13 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
     with torch.cuda.stream(stream):
         ev0.record(stream)
     for _ in range(args.steps):
-        clf.classify_device(step & 1, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
-    # end of the run: the records flagged by the K steps become sparse-tier keys (kuq_finish waits for both slots and
-    # harvests) — part of the job, so inside the timed region
+        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
+    # end of the run: the records flagged by the K steps become sparse-tier keys (kuq_finish) — part of the job, so
+    # inside the timed region
     clf.finish()
     with torch.cuda.stream(stream):
         ev1.record(stream)
-    clf.sync(0); clf.sync(1)
+    clf.sync(0)
     barrier()
     harvest_ms_value = clf.sparse_tier_info()["last_harvest_ms"]
     sampler.mark(t0, time.time())
@@ -571,9 +571,8 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
                 "config": {"workload": workload, "parallelism": f"replicas x{world} (reads partitioned, DB replicated)",
                            "l2": "inputs larger than L2: 150 MB of reads per step, 16.6 GB database probed at random",
                            "hll_mode": ["preload rule", "chunked rule", "dense only"][args.hll_mode],
-                           "timing": "CUDA events around K steps (alternating over two slots / streams of the context) + the end-of-run "
-                                     "harvest (kuq_finish, which waits for both), max over ranks; the once-per-run NCCL merge of the "
-                                     "per-taxon state across ranks is timed separately",
+                           "timing": "CUDA events on the slot stream around K steps + the end-of-run harvest (kuq_finish), max over "
+                                     "ranks; the once-per-run NCCL merge of the per-taxon state across ranks is timed separately",
                            "end_of_run_merge_ms": merge_ms,
                            "value_including_merge": world * B * args.steps / ((dev_ms + merge_ms) / 1e3) / 1e6,
                            "steps_only_mreads_s": world * B * args.steps / (max(dev_ms - harvest_ms_value, 1e-3) / 1e3) / 1e6,
