@@ -1574,59 +1574,70 @@ __device__ __forceinline__ uint32_t key_part(unsigned long long key, uint32_t n_
 // scatters through the per-part cursors.  Same-address atomics would serialise hundreds of millions of keys on
 // n_parts counters, so a warp votes per part (ballot), its leader adds the warp's count to a shared-memory counter,
 // and only one thread per part and CTA touches the global cursor per tile.
+constexpr int KP_E = 8;      // keys per thread and tile: four block-wide barriers per 2048 items instead of per 256
 template <int SRC>
 __global__ void __launch_bounds__(256) k_keys_parts(const unsigned long long *slots, uint8_t *pairs, uint64_t n_items, uint32_t hi_mask,
                                                     const uint8_t *dense_flag, uint32_t n_parts, unsigned long long *counters,
                                                     unsigned long long *out, const unsigned long long *part_end, uint32_t *error_flag,
                                                     int pass) {
   __shared__ unsigned long long s_total[8];      // pass 0: the CTA's counts
-  __shared__ uint32_t s_cnt[8];                  // pass 1: keys of the tile per part, then fill cursor
+  __shared__ uint32_t s_cnt[8];                  // pass 1: keys of the tile per part
   __shared__ unsigned long long s_base[8];
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   if (tid < 8) { s_total[tid] = 0; s_cnt[tid] = 0; }
   __syncthreads();
-  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n_items; base += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = base + tid;
-    unsigned long long key = 0;
-    if (i < n_items) {
-      if (SRC == 0) {
-        key = slots[i];
-        if (key && dense_flag[(uint32_t)(key >> 32) - 1]) key = 0;
-      } else {
-        uint32_t *w = reinterpret_cast<uint32_t *>(pairs + i * 12);
-        const uint32_t hiw = w[1];
-        if (hiw & SEEN_BIT) {
-          if (pass == 1) w[1] = hiw & ~SEEN_BIT;
-          const uint32_t taxon = w[2];
-          if (!dense_flag[taxon]) {
-            const uint64_t kmer = ((uint64_t)(hiw & hi_mask) << 32) | w[0];
-            key = ((unsigned long long)(taxon + 1) << 32) | encode_hash32(fmix64(kmer));
+  const uint64_t tile = (uint64_t)blockDim.x * KP_E;
+  for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n_items; base += (uint64_t)gridDim.x * tile) {
+    unsigned long long key[KP_E];
+    uint32_t where[KP_E];                        // part << 28 | rank inside the tile's group of that part
+#pragma unroll
+    for (int j = 0; j < KP_E; j++) {
+      const uint64_t i = base + (uint64_t)j * blockDim.x + tid;
+      unsigned long long k = 0;
+      if (i < n_items) {
+        if (SRC == 0) {
+          k = slots[i];
+          if (k && dense_flag[(uint32_t)(k >> 32) - 1]) k = 0;
+        } else {
+          uint32_t *w = reinterpret_cast<uint32_t *>(pairs + i * 12);
+          const uint32_t hiw = w[1];
+          if (hiw & SEEN_BIT) {
+            if (pass == 1) w[1] = hiw & ~SEEN_BIT;
+            const uint32_t taxon = w[2];
+            if (!dense_flag[taxon]) {
+              const uint64_t kmer = ((uint64_t)(hiw & hi_mask) << 32) | w[0];
+              k = ((unsigned long long)(taxon + 1) << 32) | encode_hash32(fmix64(kmer));
+            }
           }
         }
       }
-    }
-    const uint32_t part = key ? key_part(key, n_parts) : 0xFFFFFFFFu;
-    uint32_t my_rank = 0;
-    for (uint32_t q = 0; q < n_parts; q++) {
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, part == q);
-      if (!m) continue;
-      uint32_t wbase = 0;
-      if (lane == (uint32_t)(__ffs(m) - 1)) {
-        if (pass == 0) atomicAdd(&s_total[q], (unsigned long long)__popc(m));
-        else wbase = atomicAdd(&s_cnt[q], (uint32_t)__popc(m));
-      }
-      if (pass == 1) {
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, __ffs(m) - 1);
-        if (part == q) my_rank = wbase + __popc(m & ((1u << lane) - 1));
+      key[j] = k;
+      const uint32_t part = k ? key_part(k, n_parts) : 0xFu;
+      where[j] = part << 28;
+      for (uint32_t q = 0; q < n_parts; q++) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, part == q);
+        if (!m) continue;
+        uint32_t wbase = 0;
+        if (lane == (uint32_t)(__ffs(m) - 1)) {
+          if (pass == 0) atomicAdd(&s_total[q], (unsigned long long)__popc(m));
+          else wbase = atomicAdd(&s_cnt[q], (uint32_t)__popc(m));
+        }
+        if (pass == 1) {
+          wbase = __shfl_sync(0xFFFFFFFFu, wbase, __ffs(m) - 1);
+          if (part == q) where[j] |= wbase + __popc(m & ((1u << lane) - 1));
+        }
       }
     }
     if (pass == 1) {
       __syncthreads();
       if (tid < n_parts && s_cnt[tid]) s_base[tid] = atomicAdd(counters + tid, (unsigned long long)s_cnt[tid]);
       __syncthreads();
-      if (key) {
-        const unsigned long long at = s_base[part] + my_rank;
-        if (at < part_end[part]) out[at] = key; else atomicExch(error_flag, 7u);
+#pragma unroll
+      for (int j = 0; j < KP_E; j++) {
+        if (!key[j]) continue;
+        const uint32_t part = where[j] >> 28;
+        const unsigned long long at = s_base[part] + (where[j] & 0x0FFFFFFFu);
+        if (at < part_end[part]) out[at] = key[j]; else atomicExch(error_flag, 7u);
       }
       __syncthreads();
       if (tid < 8) s_cnt[tid] = 0;
@@ -1642,7 +1653,7 @@ void launch_keys_parts(int src, const unsigned long long *slots, uint8_t *pairs,
                        const uint8_t *dense_flag, uint32_t n_parts, unsigned long long *counters, unsigned long long *out,
                        const unsigned long long *part_end, uint32_t *error_flag, int pass, cudaStream_t stream) {
   if (!n_items) return;
-  const int grid = (int)min((uint64_t)148 * 16, (n_items + 255) / 256);
+  const int grid = (int)min((uint64_t)148 * 8, (n_items + 256 * KP_E - 1) / (256 * KP_E));
   if (src == 0) k_keys_parts<0><<<grid, 256, 0, stream>>>(slots, pairs, n_items, (uint32_t)(key_mask >> 32), dense_flag, n_parts, counters, out, part_end, error_flag, pass);
   else k_keys_parts<1><<<grid, 256, 0, stream>>>(slots, pairs, n_items, (uint32_t)(key_mask >> 32), dense_flag, n_parts, counters, out, part_end, error_flag, pass);
 }
