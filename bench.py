@@ -1075,8 +1075,12 @@ def _stream_job(args, local_rank, dev, paired, host_pool, h_rec, h_off, meta, ke
                        "expected": "about 0.80" if not paired else "about 0.96 (a pair is classified if either mate is)"},
             "clocks": clocks}
     print(json.dumps(line), flush=True)
+    # tensors that were used on the slots' streams go first: torch's allocator records an event on those streams when
+    # it frees them, and kuq_destroy takes the streams away
+    del pool, merged, h_call, d_offsets
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     clf.close()
-    del pool, merged
 
 
 if __name__ == "__main__":
