@@ -958,14 +958,15 @@ def run_stream(args, local_rank, dev):
     torch.cuda.empty_cache()
     gen_s = time.time() - t_gen
     for paired in variants:
-        _stream_job(args, local_rank, dev, paired, host_pools[paired], h_rec, h_off, meta, key_ct, species, pmap, records, range_gb,
+        _stream_job(args, local_rank, dev, paired, [host_pools.pop(paired)], h_rec, h_off, meta, key_ct, species, pmap, records, range_gb,
                     hll_mode, gen_s)
         torch.cuda.empty_cache()
     return 0
 
 
-def _stream_job(args, local_rank, dev, paired, host_pool, h_rec, h_off, meta, key_ct, species, pmap, records, range_gb, hll_mode, gen_s):
+def _stream_job(args, local_rank, dev, paired, host_pool_box, h_rec, h_off, meta, key_ct, species, pmap, records, range_gb, hll_mode, gen_s):
     import torch
+    host_pool = host_pool_box.pop()              # owned here: it is freed below, while the slots' streams still exist
     from krakenuniq_b200 import binding
     from krakenuniq_b200 import dist as kdist
     L = 2 * READ_LEN + 1 if paired else READ_LEN
@@ -1077,7 +1078,7 @@ def _stream_job(args, local_rank, dev, paired, host_pool, h_rec, h_off, meta, ke
     print(json.dumps(line), flush=True)
     # tensors that were used on the slots' streams go first: torch's allocator records an event on those streams when
     # it frees them, and kuq_destroy takes the streams away
-    del pool, merged, h_call, d_offsets
+    del pool, merged, h_call, d_offsets, host_pool
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     clf.close()
