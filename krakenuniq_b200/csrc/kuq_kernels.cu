@@ -123,7 +123,7 @@ __device__ __forceinline__ int sparse_insert(const SparseSet &s, uint32_t taxon,
   unsigned long long key = ((unsigned long long)(taxon + 1) << 32) | code;
   uint64_t slot = mix64(key) & s.mask;
   for (uint32_t probe = 0; probe < 512; probe++) {
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(s.slots + slot);
+    unsigned long long cur = __ldcg(s.slots + slot);          // L2 is where the CAS of other threads lands
     if (cur == key) return 0;
     if (cur == 0) {
       unsigned long long prev = atomicCAS(s.slots + slot, 0ull, key);
