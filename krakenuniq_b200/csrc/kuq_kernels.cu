@@ -1572,19 +1572,20 @@ __device__ __forceinline__ uint32_t key_part(unsigned long long key, uint32_t n_
 // One kernel for both sources of keys — SRC 0: the slots of the local set, SRC 1: the records a counted hit flagged
 // (pass 1 clears the flag: the key leaves this GPU instead of entering its set).  pass 0 counts per part, pass 1
 // scatters through the per-part cursors.  Same-address atomics would serialise hundreds of millions of keys on
-// n_parts counters, so a warp votes per part (ballot), its leader adds the warp's count to a shared-memory counter,
-// and only one thread per part and CTA touches the global cursor per tile.
+// n_parts counters, so keys are counted / ranked on shared-memory counters (only real keys touch them — most slots are
+// empty and most records unflagged, and a per-part warp vote for every item made the kernel instruction bound), and
+// only one thread per part and CTA touches the global cursor per tile.
 constexpr int KP_E = 8;      // keys per thread and tile: four block-wide barriers per 2048 items instead of per 256
 template <int SRC>
 __global__ void __launch_bounds__(256) k_keys_parts(const unsigned long long *slots, uint8_t *pairs, uint64_t n_items, uint32_t hi_mask,
                                                     const uint8_t *dense_flag, uint32_t n_parts, unsigned long long *counters,
                                                     unsigned long long *out, const unsigned long long *part_end, uint32_t *error_flag,
                                                     int pass) {
-  __shared__ unsigned long long s_total[8];      // pass 0: the CTA's counts
+  __shared__ uint32_t s_total32[8];              // pass 0: the CTA's counts (a CTA sees far fewer than 2^32 items)
   __shared__ uint32_t s_cnt[8];                  // pass 1: keys of the tile per part
   __shared__ unsigned long long s_base[8];
-  const uint32_t tid = threadIdx.x, lane = tid & 31;
-  if (tid < 8) { s_total[tid] = 0; s_cnt[tid] = 0; }
+  const uint32_t tid = threadIdx.x;
+  if (tid < 8) { s_total32[tid] = 0; s_cnt[tid] = 0; }
   __syncthreads();
   const uint64_t tile = (uint64_t)blockDim.x * KP_E;
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n_items; base += (uint64_t)gridDim.x * tile) {
@@ -1612,20 +1613,11 @@ __global__ void __launch_bounds__(256) k_keys_parts(const unsigned long long *sl
         }
       }
       key[j] = k;
-      const uint32_t part = k ? key_part(k, n_parts) : 0xFu;
-      where[j] = part << 28;
-      for (uint32_t q = 0; q < n_parts; q++) {
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, part == q);
-        if (!m) continue;
-        uint32_t wbase = 0;
-        if (lane == (uint32_t)(__ffs(m) - 1)) {
-          if (pass == 0) atomicAdd(&s_total[q], (unsigned long long)__popc(m));
-          else wbase = atomicAdd(&s_cnt[q], (uint32_t)__popc(m));
-        }
-        if (pass == 1) {
-          wbase = __shfl_sync(0xFFFFFFFFu, wbase, __ffs(m) - 1);
-          if (part == q) where[j] |= wbase + __popc(m & ((1u << lane) - 1));
-        }
+      where[j] = 0;
+      if (k) {                                   // only real keys cost anything: one shared-memory atomic on the part's counter
+        const uint32_t part = key_part(k, n_parts);
+        if (pass == 0) atomicAdd(&s_total32[part], 1u);
+        else where[j] = (part << 28) | atomicAdd(&s_cnt[part], 1u);
       }
     }
     if (pass == 1) {
@@ -1646,7 +1638,7 @@ __global__ void __launch_bounds__(256) k_keys_parts(const unsigned long long *sl
   }
   if (pass == 0) {
     __syncthreads();
-    if (tid < n_parts && s_total[tid]) atomicAdd(counters + tid, s_total[tid]);
+    if (tid < n_parts && s_total32[tid]) atomicAdd(counters + tid, (unsigned long long)s_total32[tid]);
   }
 }
 void launch_keys_parts(int src, const unsigned long long *slots, uint8_t *pairs, uint64_t n_items, uint64_t key_mask,
