@@ -1591,17 +1591,29 @@ __global__ void __launch_bounds__(256) k_keys_parts(const unsigned long long *sl
   for (uint64_t base = (uint64_t)blockIdx.x * tile; base < n_items; base += (uint64_t)gridDim.x * tile) {
     unsigned long long key[KP_E];
     uint32_t where[KP_E];                        // part << 28 | rank inside the tile's group of that part
+    // all loads of the tile first (KP_E independent requests per thread in flight: the scan is bandwidth work), then
+    // the per-key arithmetic
+    uint32_t hiws[KP_E];
+#pragma unroll
+    for (int j = 0; j < KP_E; j++) {
+      const uint64_t i = base + (uint64_t)j * blockDim.x + tid;
+      key[j] = 0; hiws[j] = 0;
+      if (i < n_items) {
+        if (SRC == 0) key[j] = __ldg(slots + i);
+        else hiws[j] = __ldg(reinterpret_cast<const uint32_t *>(pairs + i * 12) + 1);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < KP_E; j++) {
       const uint64_t i = base + (uint64_t)j * blockDim.x + tid;
       unsigned long long k = 0;
       if (i < n_items) {
         if (SRC == 0) {
-          k = slots[i];
+          k = key[j];
           if (k && dense_flag[(uint32_t)(k >> 32) - 1]) k = 0;
         } else {
           uint32_t *w = reinterpret_cast<uint32_t *>(pairs + i * 12);
-          const uint32_t hiw = w[1];
+          const uint32_t hiw = hiws[j];
           if (hiw & SEEN_BIT) {
             if (pass == 1) w[1] = hiw & ~SEEN_BIT;
             const uint32_t taxon = w[2];
