@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -909,14 +910,45 @@ int kuq_stage_db(kuq_ctx *ctx, const void *kdb_image, uint64_t kdb_bytes, const 
   CU(cudaMalloc((void **)&ctx->d_pairs, ctx->key_ct * 12 + SLACK));
   CU(dmalloc(&ctx->d_offsets_owned, bin_hi - bin_lo + 1));
   ctx->d_offsets = ctx->d_offsets_owned;
-  // bulk H2D: the images may be pageable / mmap'ed file memory; the driver stages them
-  const uint64_t step = 1ull << 30;
-  const uint8_t *src = p + header + rec_lo * 12;
-  for (uint64_t off = 0; off < ctx->key_ct * 12; off += step) {
-    uint64_t n = std::min(step, ctx->key_ct * 12 - off);
-    CU(cudaMemcpy(ctx->d_pairs + off, src + off, n, cudaMemcpyHostToDevice));
+  // bulk H2D.  The images are usually mmap'ed files: a plain cudaMemcpy from pageable memory goes through the driver's
+  // single-threaded staging (~7 GB/s, page faults included).  Instead a few threads fault the pages in and copy 64 MB
+  // pieces into two pinned bounce buffers while the previous piece travels (cudaMemcpyAsync on the aux stream).
+  {
+    const uint64_t CH = 64ull << 20;
+    const int NT = 8;
+    uint8_t *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    bool ok = cudaHostAlloc((void **)&bounce[0], CH, cudaHostAllocPortable) == cudaSuccess &&
+              cudaHostAlloc((void **)&bounce[1], CH, cudaHostAllocPortable) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();
+    for (int b = 0; b < 2; b++) CU(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+    auto piece_copy = [&](uint8_t *d_dst, const uint8_t *h_src, uint64_t bytes) -> int {
+      if (!ok) { CU(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice)); return KUQ_OK; }
+      uint64_t i = 0;
+      for (uint64_t off = 0; off < bytes; off += CH, i++) {
+        const uint64_t n = std::min(CH, bytes - off);
+        const int b = (int)(i & 1);
+        CU(cudaEventSynchronize(ev[b]));                       // the bounce buffer's previous piece has left
+        std::vector<std::thread> th;
+        const uint64_t per = (n + NT - 1) / NT;
+        for (int t = 0; t < NT; t++) {
+          const uint64_t a = std::min(n, per * t), e = std::min(n, per * (t + 1));
+          if (e > a) th.emplace_back([=] { memcpy(bounce[b] + a, h_src + off + a, e - a); });
+        }
+        for (auto &x : th) x.join();
+        CU(cudaMemcpyAsync(d_dst + off, bounce[b], n, cudaMemcpyHostToDevice, ctx->aux));
+        CU(cudaEventRecord(ev[b], ctx->aux));
+      }
+      CU(cudaStreamSynchronize(ctx->aux));
+      return KUQ_OK;
+    };
+    const uint8_t *src = p + header + rec_lo * 12;
+    int crc = piece_copy(ctx->d_pairs, src, ctx->key_ct * 12);
+    if (!crc) crc = piece_copy(reinterpret_cast<uint8_t *>(ctx->d_offsets_owned), reinterpret_cast<const uint8_t *>(offsets + bin_lo),
+                               (bin_hi - bin_lo + 1) * 8);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(ev[b]); if (bounce[b]) cudaFreeHost(bounce[b]); }
+    if (crc) return crc;
   }
-  CU(cudaMemcpy(ctx->d_offsets_owned, offsets + bin_lo, (bin_hi - bin_lo + 1) * 8, cudaMemcpyHostToDevice));
   ctx->db_staged = true;
   int rc = collect_taxids(ctx);
   if (rc) return rc;
