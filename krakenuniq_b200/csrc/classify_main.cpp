@@ -799,7 +799,10 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
   // st[b % (NS * G)]; a slot (and its staging set) is reused only after its batch has been formatted, because the
   // results live in the slot's pinned buffers until then.
   const int NS = 3;
-  const int Tf = std::max(1, T / 4), Te = std::max(1, T - Tf);
+  // Worker teams of the pipeline: more than ~32 OpenMP threads spinning at their barriers starve the thread that talks
+  // to the CUDA driver (measured with -t 64 on 8 M reads: 1.47 s; OMP_WAIT_POLICY=passive 0.58 s; -t 32 0.55 s; -t 16
+  // 0.56 s — profiles/cli_variants_r02.log), and the formatting is not the bottleneck beyond that anyway.
+  const int Tf = std::min(8, std::max(1, T / 4)), Te = std::min(24, std::max(1, T - Tf));
   // staging sets live for the whole process: pinned allocations cost tens of ms each, the second input file reuses them
   static vector<Stage> st;
   if (st.empty() && !Prealloc_stages.empty()) st.swap(Prealloc_stages);
