@@ -664,6 +664,11 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     stream = torch.cuda.ExternalStream(clf.slot_stream(0), device=dev)
     dist.barrier()                                                # once: every rank's buffers and flags exist
     warm_collectives(dist, dev, world)
+    # merge buffers, allocated once: a rank exports at most one key per hit it found (+ its misses' keys), and receives
+    # about as many
+    n_run_steps = args.warmup + args.steps
+    key_bound = int(min(db.key_ct + (1 << 26), 1.3 * n_run_steps * B * 100 / world + (1 << 26)))
+    merge_bufs = (torch.empty(key_bound, dtype=torch.int64, device=dev), torch.empty(key_bound, dtype=torch.int64, device=dev))
     keep = {}
 
     def step(i, bptr=None):
@@ -699,7 +704,7 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     # dress rehearsal of the end-of-run merge on the warm-up's state: NCCL sets up its all-to-all channels for real message
     # sizes and the allocators see the big buffers once (both are first-use costs of a process, not of a run); then the
     # state is wiped — the timed run starts like a fresh run
-    kdist.merge_classifier_state_partitioned(clf, dev)
+    kdist.merge_classifier_state_partitioned(clf, dev, buffers=merge_bufs)
     clf.reset_counts()
     torch.cuda.synchronize(); dist.barrier()
     ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -713,7 +718,7 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
         ev1.record(stream)
     clf.sync(0)
     tm = {}
-    kdist.merge_classifier_state_partitioned(clf, dev, timings=tm)
+    kdist.merge_classifier_state_partitioned(clf, dev, timings=tm, buffers=merge_bufs)
     with torch.cuda.stream(stream):
         ev2.record(stream)
     clf.sync(0); torch.cuda.synchronize(); dist.barrier()
@@ -784,7 +789,7 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     for _ in range(args.steps):
         step_e2e(s, j); s += 1; j += 1
     clf.sync(0)
-    kdist.merge_classifier_state_partitioned(clf, dev)
+    kdist.merge_classifier_state_partitioned(clf, dev, buffers=merge_bufs)
     with torch.cuda.stream(stream):
         e1.record(stream)
     clf.sync(0); torch.cuda.synchronize(); dist.barrier()

@@ -48,7 +48,7 @@ def gather_sparse_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([out[r][:int(sizes[r].item())] for r in range(world) if r != rank]) if world > 1 else keys.new_zeros(0)
 
 
-def exchange_partitioned_keys(keys: torch.Tensor, counts, group=None) -> torch.Tensor:
+def exchange_partitioned_keys(keys: torch.Tensor, counts, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """One all-to-all of key segments: `keys` holds the segment for rank 0, 1, ... back to back (`counts[r]` keys for
     rank r); returns the keys every rank (this one included) sent to this rank.  O(keys / world) per rank."""
     world = dist.get_world_size(group)
@@ -56,7 +56,10 @@ def exchange_partitioned_keys(keys: torch.Tensor, counts, group=None) -> torch.T
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
     recv_l = [int(x) for x in recv.tolist()]
-    out = keys.new_empty(sum(recv_l))
+    if out is not None and out.numel() >= sum(recv_l):
+        out = out[:sum(recv_l)]
+    else:
+        out = keys.new_empty(sum(recv_l))
     dist.all_to_all_single(out, keys[:int(send.sum())], output_split_sizes=recv_l,
                            input_split_sizes=[int(c) for c in counts], group=group)
     assert len(recv_l) == world
@@ -97,7 +100,7 @@ def merge_classifier_state(clf, device, group=None):
     torch.cuda.synchronize()
 
 
-def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | None = None):
+def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | None = None, buffers=None):
     """End-of-run merge in O(state / world) per rank (replicas or database shards):
       1. all-reduce MAX of the dense flags FIRST, so that the harvest of the record flags skips taxa that are dense
          anywhere (their codes are never needed: sparse + dense → dense, hyperloglogplus.cpp:604-612);
@@ -125,15 +128,25 @@ def merge_classifier_state_partitioned(clf, device, group=None, timings: dict | 
     torch.cuda.synchronize()
     merge_state_tensors(regs, nk, nr, None, group)
     mark("allreduce_state")
-    # no local harvest: the keys of the flagged records go straight into the export buffer (kuq.h)
-    kptr, counts = clf.sparse_export_partitioned_alloc(world)
-    n_keys = int(counts.sum())
-    keys = device_view(kptr, max(n_keys, 1) * 8, torch.int64, device)
+    # no local harvest: the keys of the flagged records go straight into the export buffer (kuq.h).
+    # `buffers` = (export tensor, receive tensor), int64, allocated once by the caller: multi-GB cudaMallocs inside the
+    # merge cost tens of ms and vary wildly when the card is nearly full
+    kptr = None
+    if buffers is not None:
+        try:
+            counts = clf.sparse_export_partitioned(world, buffers[0].data_ptr(), buffers[0].numel())
+            keys = buffers[0]
+        except Exception:                       # buffer too small: nothing was consumed yet, let the library allocate
+            buffers = None
+    if buffers is None:
+        kptr, counts = clf.sparse_export_partitioned_alloc(world)
+        keys = device_view(kptr, max(int(counts.sum()), 1) * 8, torch.int64, device)
     mark("export_partitioned")
-    recv = exchange_partitioned_keys(keys, counts.tolist(), group)
+    recv = exchange_partitioned_keys(keys, counts.tolist(), group, out=None if buffers is None else buffers[1])
     torch.cuda.synchronize()
     del keys
-    clf.device_free(kptr)
+    if kptr is not None:
+        clf.device_free(kptr)
     mark("all_to_all")
     clf.sparse_replace(recv.data_ptr() if recv.numel() else None, recv.numel())
     mark("replace_import")
