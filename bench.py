@@ -271,7 +271,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     mode = resolve_mode(args, world if args.impl == "ours" else 1)
     B = args.batch_reads
-    steps_rep = (args.warmup + args.steps) + 4 + (max(args.warmup, 3) + args.steps)
+    steps_rep = (args.warmup + args.steps) + 5 + (max(args.warmup, 3) + args.steps)
 
     # ---------------- reference arm: the unmodified reference on the host cores ------------------------------
     if args.impl == "reference":
@@ -315,7 +315,7 @@ def main():
         torch.cuda.empty_cache()
         line = rep_line
     if mode == "shards":
-        w = build_workload(args, "shards", rank, world, dev, dist, 2 * (args.warmup + args.steps) + 2)
+        w = build_workload(args, "shards", rank, world, dev, dist, 2 * (args.warmup + args.steps) + 6)
         extra = None
         if rep_line is not None:
             keep = ("value", "ms_per_step", "scaling", "e2e", "gpu_launches")
@@ -424,6 +424,11 @@ def run_replicas(args, w, rank, world, local_rank, dev, dist, cpu_baseline):
     if dist:                                      # rehearsal of the cross-rank merge (first-use costs of NCCL / allocators)
         merge_state()
         clf.reset_counts()
+        # one more untimed step: like at N = 1, the timed steps start with the run's start-up behind them (the misses'
+        # taxon converts to dense in the first batch of any run)
+        clf.classify_device(0, batch_ptr(step), d_offsets.data_ptr(), B, B * READ_LEN, d_units(step)); step += 1
+        clf.sync(0)
+        clf.finish()
     barrier()
     launches0 = clf.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -706,6 +711,8 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     # state is wiped — the timed run starts like a fresh run
     kdist.merge_classifier_state_partitioned(clf, dev, buffers=merge_bufs)
     clf.reset_counts()
+    step(s); s += 1                               # one more untimed step: the run's start-up (the misses' taxon converts to
+    clf.sync(0)                                   # dense in the first batch of any run) stays outside, as at N = 1
     torch.cuda.synchronize(); dist.barrier()
     ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t0 = time.time()
@@ -735,7 +742,7 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     dres = clf.device_result(0)
     n_own = hi - lo
     copy_stream = torch.cuda.Stream(device=dev)
-    n_e2e = args.warmup + args.steps
+    n_e2e = args.warmup + args.steps + 1
     h_in = [torch.empty(total + 64, dtype=torch.uint8).pin_memory() for _ in range(min(n_e2e, n_batches))]
     first_b = s % n_batches
     for j, hb in enumerate(h_in):
@@ -781,6 +788,8 @@ def run_shards(args, db, pool_bases, rank, world, local_rank, dev, dist, workloa
     if n_own:
         est_runs[0] = min(int(nruns_v.item()) + 4096, total // 2)      # hit-list volume of a step (same workload every step)
     clf.reset_counts()
+    step_e2e(s, j); s += 1; j += 1                # start-up step of the fresh state, untimed (see above)
+    clf.sync(0)
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t1 = time.time()
