@@ -376,6 +376,38 @@ uint64_t kuq_ertl_dense(const uint8_t *regs4096, uint64_t n_observed);
 int kuq_random_gather_peak(int device, uint64_t buffer_bytes, uint64_t n_sectors_to_read, uint32_t bytes_per_access,
                            double *gsectors_per_s, double *gbytes_per_s, double *kernel_ms);
 
+/* Record-layout / search-shape experiment for the bin search (kmer_query, krakendb.cpp:250-321) — measurement aid.
+ * Transcodes the staged 12-byte records once into 8-byte minimizer-relative records (the 16 bases outside the bin's
+ * minimizer + minimizer position / orientation + 24-bit dense taxon; k = 31, m = 15 only) and times a lookup-only
+ * kernel over the windows the LAST batch of `slot` left in the slot's scratch (text positions [0, n_positions), i.e.
+ * a batch whose first read starts at offset 0), for both layouts x {4, 8, 16}-ary narrowing x final scans of <= 8 /
+ * <= 16 records.  Every variant's per-window dense ids are compared with the ids the product's k_lookup wrote for
+ * that batch (mismatches[] must be 0).  On the product's layout and search it also times other launch SHAPES:
+ * shape 0 = thread per window with the next window's scratch prefetched (the product's), 1 = the product's own
+ * k_lookup<MODE_LOOKUP> in the same harness, 2 / 3 = the next window's index entry prefetched too (8 / 6 CTAs per SM),
+ * 4 / 5 / 6 = two windows per thread in lock step (8 / 6 / 4 CTAs per SM), 7 = four windows per thread (4 CTAs),
+ * 8 = the product's k_lookup<MODE_LOOKUP> with its launch-uniform switches compiled out, 9 / 10 = the product's
+ * k_lookup<MODE_FUSED> (search + register update) with / without those switches — these two run only on a
+ * KUQ_HLL_DENSE_ONLY context (they count the batch's windows into its sketches once per launch; use a throwaway
+ * context) and are reported as 0 ms otherwise; 11 = shape 0 with the narrowing step as an if / else-if chain instead
+ * of a count of the pivots <= key, 12 = shape 0 fed through the product's parameter block.
+ * Needs 8 bytes per record + 4 bytes per position of free device memory.
+ * Times: CUDA events on the slot's stream, one warm-up launch then `reps` timed ones per variant. */
+#define KUQ_LAYOUT_VARIANTS 22
+typedef struct kuq_layout_result {
+  uint64_t n_records, n_positions;
+  uint64_t n_windows;                         /* windows looked up in the staged range */
+  uint64_t sum_probes;                        /* sum of ceil(log2(bin size + 1)) over them (SURVEY.md §8(d)'s P) */
+  uint64_t bin_class[6];                      /* windows whose bin holds <= 8, <= 16, <= 64, <= 256, <= 1024, more records */
+  double transcode_ms;
+  uint32_t n_variants;
+  uint32_t rec_bytes[KUQ_LAYOUT_VARIANTS], arity[KUQ_LAYOUT_VARIANTS], window[KUQ_LAYOUT_VARIANTS];
+  uint32_t shape[KUQ_LAYOUT_VARIANTS];        /* see below */
+  double best_ms[KUQ_LAYOUT_VARIANTS], mean_ms[KUQ_LAYOUT_VARIANTS];
+  uint64_t mismatches[KUQ_LAYOUT_VARIANTS];
+} kuq_layout_result;
+int kuq_layout_experiment(kuq_ctx *ctx, uint32_t slot, uint64_t n_positions, uint32_t reps, kuq_layout_result *out);
+
 /* ---- database build ---------------------------------------------------------------------- */
 /* db_sort [-z] -n nt (db_sort.cpp:41-116 + KrakenDB::make_index, krakendb.cpp:118-148): unsorted Jellyfish-style
  * image → database.kdb image (kdb_out: header + key_ct * (key_len + 4) bytes) and KRAKIX2 index image (idx_out:

@@ -50,6 +50,24 @@ class DeviceResult(C.Structure):
                 ("d_n_runs", C.c_void_p)]
 
 
+LAYOUT_VARIANTS = 22
+LAYOUT_SHAPES = ["thread per window", "product k_lookup<MODE_LOOKUP>", "index prefetch, 8 CTAs/SM", "index prefetch, 6 CTAs/SM",
+                 "2 windows per thread, 8 CTAs/SM", "2 windows per thread, 6 CTAs/SM", "2 windows per thread, 4 CTAs/SM",
+                 "4 windows per thread, 4 CTAs/SM", "product k_lookup<MODE_LOOKUP>, lean", "product k_lookup<MODE_FUSED>",
+                 "product k_lookup<MODE_FUSED>, lean", "thread per window, if-chain narrowing",
+                 "thread per window, product parameter block"]
+
+
+class LayoutResult(C.Structure):                     # kuq_layout_result
+    _fields_ = [("n_records", C.c_uint64), ("n_positions", C.c_uint64), ("n_windows", C.c_uint64),
+                ("sum_probes", C.c_uint64), ("bin_class", C.c_uint64 * 6), ("transcode_ms", C.c_double),
+                ("n_variants", C.c_uint32), ("rec_bytes", C.c_uint32 * LAYOUT_VARIANTS),
+                ("arity", C.c_uint32 * LAYOUT_VARIANTS), ("window", C.c_uint32 * LAYOUT_VARIANTS),
+                ("shape", C.c_uint32 * LAYOUT_VARIANTS),
+                ("best_ms", C.c_double * LAYOUT_VARIANTS), ("mean_ms", C.c_double * LAYOUT_VARIANTS),
+                ("mismatches", C.c_uint64 * LAYOUT_VARIANTS)]
+
+
 class StatePtrs(C.Structure):
     _fields_ = [("d_regs", C.c_void_p), ("regs_bytes", C.c_uint64), ("d_n_kmers", C.c_void_p),
                 ("d_n_reads", C.c_void_p), ("d_dense_flag", C.c_void_p), ("n_sketch", C.c_uint32),
@@ -155,6 +173,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_ertl_dense_hist": (C.c_uint64, [u32p, C.c_uint64]),
         "kuq_scan_device": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint64, vp, vp]),
         "kuq_ertl_dense": (C.c_uint64, [u8p, C.c_uint64]),
+        "kuq_layout_experiment": (C.c_int, [vp, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(LayoutResult)]),
         "kuq_random_gather_peak": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_double),
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
@@ -515,6 +534,21 @@ class Classifier:
         a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
         self._ck(self.L.kuq_sparse_tier_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"slots": a.value, "keys": b.value, "times_grown": c.value, "last_harvest_ms": d.value}
+
+    def layout_experiment(self, slot, n_positions, reps=5):
+        """kuq_layout_experiment: record layout x search shape of the bin search, timed on the windows of the slot's
+        last batch and checked against the ids the product wrote for it"""
+        r = LayoutResult()
+        self._ck(self.L.kuq_layout_experiment(self.h, slot, n_positions, reps, C.byref(r)))
+        out = {"n_records": r.n_records, "n_positions": r.n_positions, "n_windows": r.n_windows,
+               "probes_per_window": r.sum_probes / max(r.n_windows, 1), "transcode_ms": r.transcode_ms,
+               "windows_by_bin_size": dict(zip(["<=8", "<=16", "<=64", "<=256", "<=1024", ">1024"], list(r.bin_class))),
+               "variants": []}
+        for v in range(r.n_variants):
+            out["variants"].append({"record_bytes": r.rec_bytes[v], "arity": r.arity[v], "scan_window": r.window[v],
+                                    "shape": LAYOUT_SHAPES[r.shape[v]],
+                                    "best_ms": r.best_ms[v], "mean_ms": r.mean_ms[v], "mismatches": r.mismatches[v]})
+        return out
 
     def reset_counts(self):
         self._ck(self.L.kuq_reset_counts(self.h))

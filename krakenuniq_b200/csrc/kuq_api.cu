@@ -2183,6 +2183,30 @@ int kuq_scan_device(kuq_ctx *ctx, uint32_t slot, uint32_t k, uint32_t nt, uint32
   return KUQ_OK;
 }
 
+int kuq_layout_experiment(kuq_ctx *ctx, uint32_t slot, uint64_t n_positions, uint32_t reps, kuq_layout_result *out) {
+  int rc = check_slot(ctx, slot);
+  if (rc) return rc;
+  if (!out) return fail(ctx, KUQ_E_INVALID_ARG, "NULL result");
+  CU(cudaSetDevice(ctx->device));
+  rc = ensure_ready(ctx);
+  if (rc) return rc;
+  if (!ctx->db_staged || ctx->stream_open || !ctx->d_pairs) return fail(ctx, KUQ_E_STATE, "the experiment needs a staged (not streamed) database");
+  if (ctx->k != 31 || ctx->nt != 15) return fail(ctx, KUQ_E_INVALID_ARG, "the 8-byte record code is defined for k = 31, m = 15");
+  Slot &s = ctx->slots[slot];
+  if (!s.timed || n_positions == 0 || n_positions > s.total_bases)
+    return fail(ctx, KUQ_E_STATE, "run a batch on the slot first; n_positions must not exceed its text length");
+  Params p;
+  fill_params(ctx, s, p, nullptr, nullptr, nullptr, 0, 0);
+  const int erc = layout_experiment(p, ctx->key_ct, s.d_canon, s.d_bins, s.d_dense, n_positions, ctx->n_sm, s.stream, reps,
+                                    ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY, out);
+  ctx->snap_valid = false;
+  ctx->launches += 2 + (uint64_t)KUQ_LAYOUT_VARIANTS * (reps + 2ull);
+  if (erc == 1) return fail(ctx, KUQ_E_NOMEM, "not enough free device memory for the transcoded records");
+  if (erc == 3) return fail(ctx, KUQ_E_CAPACITY, "dense taxon ids need more than 24 bits");
+  if (erc) return fail(ctx, KUQ_E_CUDA, "layout experiment: %s", cudaGetErrorString(cudaGetLastError()));
+  return KUQ_OK;
+}
+
 int kuq_sparse_tier_info(kuq_ctx *ctx, uint64_t *slots, uint64_t *keys, uint64_t *times_grown, double *last_harvest_ms) {
   if (!ctx) return KUQ_E_INVALID_ARG;
   int rc = ensure_ready(ctx);

@@ -389,17 +389,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) k_scan(const __grid_constant__
 // lookups belong to one range of a sharded database — the HLL insert of ReadCounts::add_kmer (classify.cpp:939).
 // Threads of a warp hold consecutive windows of a read: windows that share a minimizer read the same index
 // sector and the same pivots, which the load unit coalesces.
-template <int MODE>
+// LEAN = the launch uses none of: probe statistics (flag 8), stored-zero marking (16), shard counting (32), hits-only
+// output, peer buffers.  Those are launch-uniform run-time switches; compiled out, the common path of the fused kernel
+// is a third shorter and measurably faster (profiles/layout_probe_r02.log: the search alone 1.87 -> 1.62 ms).
+template <int MODE, bool LEAN>
 __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Params p) {
   const DbView &db = p.db;
+  const uint32_t flags = LEAN ? (p.flags & 4u) : p.flags;
+  const uint32_t only_hits = LEAN ? 0u : p.only_hits;
+  const uint32_t n_peers = LEAN ? 0u : p.n_peers;
   const uint32_t hi_mask = (uint32_t)(db.key_mask >> 32);
-  const bool counting = (MODE == MODE_FUSED) && !(p.flags & 4u);
+  const bool counting = (MODE == MODE_FUSED) && !(flags & 4u);
   // hits of the fused path reach the sparse tier through the record flag (see below); dense-only / exact runs have
   // no sparse tier
   // flag 32 (database sharded over GPUs, one database): the GPU that FINDS a hit owns its sketch work — register
   // update and record flag happen in the lookup half, and the resolve half (on the GPU that owns the read) only adds
   // the misses (taxon 0).  Valid because every looked-up window is counted exactly once in that layout.
-  const bool shard_counting = (p.flags & 32u) != 0;
+  const bool shard_counting = (flags & 32u) != 0;
   const bool mark_seen = (counting || (MODE == MODE_LOOKUP && shard_counting)) && p.hll_mode <= 1u;
   // only the text of this call's reads (the scratch beyond it may hold windows of an earlier call on the slot)
   const uint64_t g_begin = p.offsets[0], g_end = p.offsets[p.n_reads];
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
     if (g + stride < g_end) { bin_n = __ldg(p.bins + g + stride); canon_n = __ldg(p.canon + g + stride); }
     if (bin == BIN_NONE) continue;
     if (bin == BIN_AMBIG) {
-      if (!p.only_hits && !(MODE == MODE_LOOKUP && p.n_peers)) p.codes_dense[g] = AMBIG;
+      if (!only_hits && !(MODE == MODE_LOOKUP && n_peers)) p.codes_dense[g] = AMBIG;
       continue;
     }
     uint32_t taxon = 0;
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
       const uint64_t o0 = __ldg(o), o1 = __ldg(o + 1);
       uint64_t lo = o0 - db.rec_base;
       uint32_t n = (uint32_t)(o1 - o0);
-      if (p.flags & 8u) {   // measurement aid: algorithmic probe count of SURVEY.md §8(d)
+      if (flags & 8u) {   // measurement aid: algorithmic probe count of SURVEY.md §8(d)
         atomicAdd(p.stats, 1ull);
         atomicAdd(p.stats + 1, (unsigned long long)(n ? 32 - __clz(n) : 0));
       }
@@ -436,10 +442,10 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
         const uint64_t k1 = load_key(db.pairs, lo + q, db.key_mask);
         const uint64_t k2 = load_key(db.pairs, lo + 2 * q, db.key_mask);
         const uint64_t k3 = load_key(db.pairs, lo + 3 * q, db.key_mask);
-        if (canon >= k3) { lo += 3 * q; n -= 3 * q; }
-        else if (canon >= k2) { lo += 2 * q; n = q; }
-        else if (canon >= k1) { lo += q; n = q; }
-        else { n = q; }
+        // pivots <= the key: the quarter that can hold it (branch-free; the lanes of a warp disagree here all the time)
+        const uint32_t c = (canon >= k1 ? 1u : 0u) + (canon >= k2 ? 1u : 0u) + (canon >= k3 ? 1u : 0u);
+        lo += (uint64_t)c * q;
+        n = (c == 3u) ? n - 3 * q : q;
       }
       if (n) {
         // compare the low key words of the window first, confirm the (rare) matches on the high word
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
           const uint32_t hiw = __ldg(b + 3 * t + 1);
           if ((hiw & hi_mask) == chi) {
             taxon = __ldg(b + 3 * t + 2);                        // value = dense id
-            if (MODE == MODE_LOOKUP && taxon == 0 && (p.flags & 16u)) taxon = FOUND_ZERO;
+            if (MODE == MODE_LOOKUP && taxon == 0 && (flags & 16u)) taxon = FOUND_ZERO;
             // Sparse HLL tier of a hit (hyperloglogplus.cpp:499-512): the (taxon, encoded hash) pair is a function
             // of the RECORD, so instead of probing a hash set per window the record itself is flagged in the free
             // top bit of its key word — the sector is in L1/L2 already, the flag costs no DRAM read, and only the
@@ -470,24 +476,24 @@ __global__ void __launch_bounds__(256, 8) k_lookup(const __grid_constant__ Param
           }
         }
       }
-    } else if (p.flags & 8u) {
+    } else if (flags & 8u) {
       atomicAdd(p.stats + 3, 1ull);                          // a window of another range: nothing fetched here
     }
     // only_hits: several DB ranges (GPUs) write their hits into one zero-initialised buffer, possibly over
     // NVLink; a key lives in exactly one range (classify.cpp:447), so no two writers touch the same word.
-    if (MODE == MODE_LOOKUP && p.n_peers) {
+    if (MODE == MODE_LOOKUP && n_peers) {
       // fused lookup + scatter: the hit goes to the GPU that resolves this read, as a peer store over NVLink
       if (taxon != 0) {
         uint32_t j = 0;
-        while (j + 1 < p.n_peers && g >= p.peer_bounds[j + 1]) j++;
+        while (j + 1 < n_peers && g >= p.peer_bounds[j + 1]) j++;
         p.peer_codes[j][g] = taxon;
       }
-    } else if (MODE == MODE_RESOLVE || !p.only_hits || taxon != 0) {
+    } else if (MODE == MODE_RESOLVE || !only_hits || taxon != 0) {
       p.codes_dense[g] = taxon;
     }
     if (MODE == MODE_LOOKUP && shard_counting) {
       if (taxon != 0 && taxon != FOUND_ZERO) hll_update(p.regs, taxon, fmix64(canon));
-    } else if ((counting || (MODE == MODE_RESOLVE && !(p.flags & 4u))) && !(MODE == MODE_RESOLVE && shard_counting && taxon != 0)) {
+    } else if ((counting || (MODE == MODE_RESOLVE && !(flags & 4u))) && !(MODE == MODE_RESOLVE && shard_counting && taxon != 0)) {
       const uint64_t h = fmix64(canon);
       hll_update(p.regs, taxon, h);
       // direct set insert: misses (taxon 0 has no record to flag) and the resolve half, which only sees merged ids
@@ -1213,6 +1219,14 @@ int classify_smem_bytes() { return N_STAGES * STAGE_BYTES + (int)sizeof(SharedSt
 // mode MODE_FUSED : scan → lookup (+HLL) → resolve            (whole database on this GPU)
 //      MODE_LOOKUP: scan → lookup into p.codes_dense            (one range of a sharded / chunked database)
 //      MODE_RESOLVE: scan → HLL from merged codes → resolve    (owner of the reads after the merge)
+// picks the lean instantiation when the launch uses none of the rare switches (see k_lookup)
+template <int MODE>
+static void launch_lookup(const Params &q, int lgrid, cudaStream_t stream) {
+  const bool lean = !(q.flags & (8u | 16u | 32u)) && !q.only_hits && !q.n_peers;
+  if (lean) k_lookup<MODE, true><<<lgrid, 256, 0, stream>>>(q);
+  else k_lookup<MODE, false><<<lgrid, 256, 0, stream>>>(q);
+}
+
 int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cudaEvent_t *stage_events) {
   const int smem = classify_smem_bytes();
   // per device (function attributes belong to the current context): cheap enough to set on every call
@@ -1232,10 +1246,10 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
     Params q = p;
     if (mode == MODE_FUSED) {
       q.only_hits = 0; q.n_peers = 0; q.flags &= ~16u;
-      k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(q);
+      launch_lookup<MODE_LOOKUP>(q, lgrid, stream);
     } else {
       q.flags |= 4u;                                         // merged codes → codes_dense, no sketches
-      k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(q);
+      launch_lookup<MODE_RESOLVE>(q, lgrid, stream);
     }
     if (!(p.flags & 4u)) { k_exact_insert<<<lgrid, 256, 0, stream>>>(p); launches++; }
   } else if (quick && p.quick_stop) {
@@ -1243,18 +1257,18 @@ int launch_classify(int mode, const Params &p, int n_sm, cudaStream_t stream, cu
     Params q = p;
     if (mode == MODE_FUSED) {
       q.only_hits = 0; q.n_peers = 0; q.flags &= ~16u;
-      k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(q);
+      launch_lookup<MODE_LOOKUP>(q, lgrid, stream);
       launches++;
       q.codes_in = p.codes_dense;
     }
     const int cgrid = (int)min((uint32_t)n_sm * 8, (p.n_reads + 7) / 8);
     k_quick_cut<<<cgrid, 256, 0, stream>>>(p, q.codes_in);
     q.flags = p.flags;
-    k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(q);
+    launch_lookup<MODE_RESOLVE>(q, lgrid, stream);
     launches += 2;
-  } else if (mode == MODE_FUSED) k_lookup<MODE_FUSED><<<lgrid, 256, 0, stream>>>(p);
-  else if (mode == MODE_LOOKUP) k_lookup<MODE_LOOKUP><<<lgrid, 256, 0, stream>>>(p);
-  else k_lookup<MODE_RESOLVE><<<lgrid, 256, 0, stream>>>(p);
+  } else if (mode == MODE_FUSED) launch_lookup<MODE_FUSED>(p, lgrid, stream);
+  else if (mode == MODE_LOOKUP) launch_lookup<MODE_LOOKUP>(p, lgrid, stream);
+  else launch_lookup<MODE_RESOLVE>(p, lgrid, stream);
   if (exact || !(quick && p.quick_stop)) launches++;
   if (stage_events) cudaEventRecord(stage_events[1], stream);
   if (mode != MODE_LOOKUP) {
@@ -1326,6 +1340,21 @@ int launch_scan_only(const Params &p, int n_sm, cudaStream_t stream) {
   int grid = n_sm * 4;
   if ((uint32_t)grid > p.n_chunks) grid = (int)p.n_chunks;
   k_scan<<<grid, CTA_THREADS, smem, stream>>>(p);
+  return 1;
+}
+
+// stage 2 alone over scratch that is already there (kuq_layout_exp.cu times the product's kernel next to its variants):
+// p.offsets = {first, last + 1} text positions with p.n_reads = 1
+// fused = 1: k_lookup<MODE_FUSED> (counts into the sketches of p); lean: see k_lookup (the caller vouches for the flags)
+int launch_lookup_only(const Params &p, int n_sm, cudaStream_t stream, int fused, int lean) {
+  const int lgrid = (int)max((uint64_t)1, min((uint64_t)n_sm * 8 * 8, (p.total_bases + 255) / 256));
+  if (fused) {
+    if (lean) k_lookup<MODE_FUSED, true><<<lgrid, 256, 0, stream>>>(p);
+    else k_lookup<MODE_FUSED, false><<<lgrid, 256, 0, stream>>>(p);
+  } else {
+    if (lean) k_lookup<MODE_LOOKUP, true><<<lgrid, 256, 0, stream>>>(p);
+    else k_lookup<MODE_LOOKUP, false><<<lgrid, 256, 0, stream>>>(p);
+  }
   return 1;
 }
 

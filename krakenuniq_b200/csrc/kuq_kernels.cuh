@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct kuq_layout_result;
+
 namespace kuq {
 
 constexpr uint32_t AMBIG = 0xFFFFFFFFu;
@@ -169,6 +171,7 @@ int classify_smem_bytes();
 // set_lcas: k_scan + k_set_lcas over library pieces (p.unit_id = dense taxid per piece, p.stats[0] += k-mers not found)
 int launch_set_lcas(const Params &p, int n_sm, cudaStream_t stream);
 int launch_scan_only(const Params &p, int n_sm, cudaStream_t stream);
+int launch_lookup_only(const Params &p, int n_sm, cudaStream_t stream, int fused, int lean);
 // db_sort on the device (kuq_dbbuild.cu)
 int dbsort_device(const uint8_t *jdb_image, uint64_t jdb_bytes, uint32_t nt, int zero_vals, uint8_t *kdb_out,
                   uint8_t *idx_out, char *err, size_t err_cap);
@@ -222,5 +225,10 @@ void launch_wait_flags(const unsigned long long *flags, uint32_t n, unsigned lon
 void launch_keys_parts(int src, const unsigned long long *slots, uint8_t *pairs, uint64_t n_items, uint64_t key_mask,
                        const uint8_t *dense_flag, uint32_t n_parts, unsigned long long *counters, unsigned long long *out,
                        const unsigned long long *part_end, uint32_t *error_flag, int pass, cudaStream_t stream);
+
+// kuq_layout_exp.cu: record-layout / search-shape experiment (0 ok, 1 no memory, 2 CUDA error, 3 taxon ids > 24 bits);
+// `product` = parameters of a k_lookup<MODE_LOOKUP> launch on the same database (scratch / output pointers are set there)
+int layout_experiment(const Params &product, uint64_t n_records, const uint64_t *canon, const uint32_t *bins, const uint32_t *ref,
+                      uint64_t n_pos, int n_sm, cudaStream_t st, uint32_t reps, int allow_fused, ::kuq_layout_result *res);
 
 }  // namespace kuq
