@@ -269,6 +269,15 @@ int kuq_read_counts(kuq_ctx *ctx, uint32_t *taxid, uint64_t *n_reads, uint64_t *
  * of the listed taxa; returns reads / kmers / unique of the union. */
 int kuq_clade_counts(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers,
                      uint64_t *unique);
+/* The same roll-up for many clades in one call: clade(taxids[i]) = that taxon and all its descendants in the taxonomy
+ * given to kuq_set_taxonomy (what the TaxReport constructor builds for every node, taxdb.hpp:928-982).  Counters by
+ * one pass up the tree; dense clades (a member's sketch is dense: register-wise max, hyperloglogplus.cpp:604-621) by
+ * one launch per 8192 clades; sparse clades (union of the members' code sets, :600-603) from ONE sort of the sparse
+ * tier's keys by (code, preorder of the taxon) — a subtree is a preorder interval, so its distinct codes are its
+ * keys minus the adjacent equal-code pairs whose lowest common ancestor lies inside it.  Results equal
+ * kuq_clade_counts() of the member list, clade by clade.  Unknown taxids and taxa without counted descendants give 0. */
+int kuq_clade_counts_tree(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers,
+                          uint64_t *unique);
 /* The 4096 p=12 registers of one taxon (all zero if it received no k-mer). */
 int kuq_get_registers(kuq_ctx *ctx, uint32_t taxid, uint8_t *regs4096);
 int kuq_state_ptrs_get(kuq_ctx *ctx, kuq_state_ptrs *out);

@@ -144,6 +144,7 @@ def load_library(rebuild_if_stale: bool = False):
         "kuq_counts_size": (C.c_int, [vp, u32p]),
         "kuq_read_counts": (C.c_int, [vp, u32p, u64p, u64p, u64p, u8p, C.c_uint32]),
         "kuq_clade_counts": (C.c_int, [vp, u32p, C.c_uint32, u64p, u64p, u64p]),
+        "kuq_clade_counts_tree": (C.c_int, [vp, u32p, C.c_uint32, u64p, u64p, u64p]),
         "kuq_get_registers": (C.c_int, [vp, C.c_uint32, u8p]),
         "kuq_state_ptrs_get": (C.c_int, [vp, C.POINTER(StatePtrs)]),
         "kuq_dense_taxids": (C.c_int, [vp, u32p, C.c_uint32, u32p]),
@@ -518,6 +519,13 @@ class Classifier:
 
     def set_sparse_summary(self, d_hist, d_distinct):
         self._ck(self.L.kuq_set_sparse_summary(self.h, d_hist, d_distinct))
+
+    def clade_counts_tree(self, taxids):
+        """kuq_clade_counts_tree: (reads, kmers, unique) arrays for clade(taxid) = the taxon and all its descendants"""
+        t = np.ascontiguousarray(taxids, np.uint32)
+        r, k, u = (np.zeros(len(t), np.uint64) for _ in range(3))
+        self._ck(self.L.kuq_clade_counts_tree(self.h, _p(t, u32p), len(t), _p(r, u64p), _p(k, u64p), _p(u, u64p)))
+        return r, k, u
 
     def clade_partial(self, taxids):
         """(reads, kmers, is_dense, hist64) of the listed taxa's merged sketch on THIS GPU (see kuq.h)"""

@@ -116,6 +116,7 @@ static void parse_command_line(int argc, char **argv) {
       case 't':
         sig = atoll(optarg);
         if (sig <= 0) die(EX_USAGE, "can't use nonpositive thread count");
+        if (sig > omp_get_num_procs()) die(EX_USAGE, "thread count exceeds number of processors");   // classify.cpp:1087-1088
         Num_threads = (int)sig;                  // host threads: parallel FASTA/FASTQ parsing and text formatting
         break;
       case 'p': HLL_PRECISION = atoi(optarg); break;
@@ -374,11 +375,29 @@ static void print_report(kuq_ctx *ctx, TaxDB &tax, ostream &out) {
     for (int x = it->second; x >= 0; x = tax.e[x].parent) members[x].push_back(t[i]);
   }
   unordered_map<int, Clade> clade;
-  for (auto &kv : members) {
-    Clade c;
-    if (kuq_clade_counts(ctx, kv.second.data(), (uint32_t)kv.second.size(), &c.reads, &c.kmers, &c.unique))
-      die(EX_SOFTWARE, kuq_last_error(ctx));
-    clade[kv.first] = c;
+  // A handful of clades: one merge per clade.  A real taxonomy (thousands of rows): all clades in one call — the
+  // library walks its own copy of the tree, which is this one as long as nothing hangs below the "unclassified" entry.
+  size_t batch_min = 32;
+  if (const char *v = getenv("KUQ_REPORT_BATCH_MIN")) batch_min = (size_t)strtoull(v, NULL, 10);
+  bool batch = getenv("KUQ_REPORT_PER_CLADE") == NULL && members.size() >= batch_min;
+  {
+    auto z = tax.idx.find(0);
+    if (z != tax.idx.end() && !tax.e[z->second].children.empty()) batch = false;
+  }
+  if (batch) {
+    vector<uint32_t> ids;
+    vector<int> node;
+    for (auto &kv : members) { ids.push_back(tax.e[kv.first].id); node.push_back(kv.first); }
+    vector<uint64_t> r(ids.size()), k(ids.size()), u(ids.size());
+    if (kuq_clade_counts_tree(ctx, ids.data(), (uint32_t)ids.size(), r.data(), k.data(), u.data())) die(EX_SOFTWARE, kuq_last_error(ctx));
+    for (size_t i = 0; i < ids.size(); i++) { Clade c; c.reads = r[i]; c.kmers = k[i]; c.unique = u[i]; clade[node[i]] = c; }
+  } else {
+    for (auto &kv : members) {
+      Clade c;
+      if (kuq_clade_counts(ctx, kv.second.data(), (uint32_t)kv.second.size(), &c.reads, &c.kmers, &c.unique))
+        die(EX_SOFTWARE, kuq_last_error(ctx));
+      clade[kv.first] = c;
+    }
   }
   cerr << " done" << endl;
   cerr << "Printing classification report ... ";

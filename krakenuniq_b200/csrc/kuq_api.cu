@@ -111,6 +111,7 @@ struct kuq_ctx {
   bool mark_zero_hits = false;            // kuq_mark_zero_hits: lookups report stored taxon 0 as KUQ_CODE_FOUND_ZERO
   std::vector<uint32_t> tax_ids, tax_parents;
   std::vector<uint32_t> raw_of_dense;
+  std::vector<uint32_t> parent_dense;     // host copy of d_parent (dense id of the parent, 0 = none)
   std::unordered_map<uint32_t, uint32_t> dense_of_raw;
   uint32_t n_taxa = 0, n_sketch = 0;
   uint32_t *d_parent = nullptr, *d_raw = nullptr;
@@ -405,6 +406,7 @@ int finalize(kuq_ctx *ctx) {
     }
   }
   free_tax_state(ctx);
+  ctx->parent_dense = parent;
   CU(dmalloc(&ctx->d_parent, ctx->n_taxa));
   CU(dmalloc(&ctx->d_raw, ctx->n_taxa));
   CU(dmalloc(&ctx->d_depth, ctx->n_taxa));
@@ -1693,6 +1695,237 @@ int kuq_clade_partial(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t
   if (n_reads) *n_reads = reads;
   if (n_kmers) *n_kmers = kmers;
   return clade_hist(ctx, members, hist64, is_dense, /*allow_partial=*/true);
+}
+
+// All clades at once (kuq.h).  Host: one pass up the tree for the counters and for which clades are dense / sparse /
+// carried by a single taxon; device: kuq_clades.cu.
+int kuq_clade_counts_tree(kuq_ctx *ctx, const uint32_t *taxids, uint32_t n, uint64_t *n_reads, uint64_t *n_kmers,
+                          uint64_t *unique) {
+  if (!ctx || (!taxids && n)) return KUQ_E_INVALID_ARG;
+  if (!ctx->finalized) return fail(ctx, KUQ_E_STATE, "nothing classified yet");
+  CU(cudaSetDevice(ctx->device));
+  for (auto &s : ctx->slots) CU(cudaStreamSynchronize(s.stream));
+  if (!ctx->snap_valid) {
+    int rc = fetch_counts(ctx, ctx->snap);
+    if (rc) return rc;
+  }
+  const CountsHost &h = ctx->snap;
+  const uint32_t NT = ctx->n_taxa, NS = ctx->n_sketch;
+  const std::vector<uint32_t> &par = ctx->parent_dense;
+  const uint32_t NONE = 0xFFFFFFFFu;
+  auto has_kmers = [&](uint32_t d) { return d < NS && h.n_kmers[d] != 0; };
+  // ---- the nodes on a path from a counted taxon to its root, children before parents ----------------------------
+  std::vector<uint32_t> cid(NT, NONE), nodes;
+  for (uint32_t d = 0; d < NT; d++) {
+    if (!(h.n_reads[d] || has_kmers(d))) continue;
+    for (uint32_t x = d; cid[x] == NONE;) {
+      cid[x] = (uint32_t)nodes.size();
+      nodes.push_back(x);
+      if (x == 0 || par[x] == 0) break;
+      x = par[x];
+    }
+  }
+  const uint32_t NC = (uint32_t)nodes.size();
+  std::vector<uint32_t> parent_c(NC, NONE), depth_c(NC, 0), order(NC);
+  for (uint32_t c = 0; c < NC; c++) {
+    const uint32_t x = nodes[c];
+    if (x != 0 && par[x] != 0) parent_c[c] = cid[par[x]];
+  }
+  {  // depth in the compact forest (roots 0); a node's chain was appended root-last, so walk it explicitly
+    std::vector<uint32_t> chain;
+    std::vector<uint8_t> done(NC, 0);
+    for (uint32_t c = 0; c < NC; c++) {
+      chain.clear();
+      uint32_t x = c;
+      while (x != NONE && !done[x]) { chain.push_back(x); x = parent_c[x]; }
+      uint32_t d = x == NONE ? 0 : depth_c[x] + 1;
+      for (size_t i = chain.size(); i-- > 0;) { depth_c[chain[i]] = d++; done[chain[i]] = 1; }
+    }
+    for (uint32_t c = 0; c < NC; c++) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return depth_c[a] > depth_c[b]; });
+  }
+  const bool all_dense = ctx->cfg.hll_mode == KUQ_HLL_DENSE_ONLY;
+  std::vector<uint64_t> c_reads(NC, 0), c_kmers(NC, 0);
+  std::vector<uint32_t> c_members(NC, 0), c_single(NC, NONE);
+  std::vector<uint8_t> c_dense(NC, 0);
+  for (uint32_t c = 0; c < NC; c++) {
+    const uint32_t d = nodes[c];
+    c_reads[c] = h.n_reads[d];
+    if (has_kmers(d)) { c_kmers[c] = h.n_kmers[d]; c_members[c] = 1; c_single[c] = d; c_dense[c] = all_dense || h.dense_flag[d]; }
+  }
+  for (uint32_t c : order) {
+    const uint32_t q = parent_c[c];
+    if (q == NONE) continue;
+    c_reads[q] += c_reads[c];
+    c_kmers[q] += c_kmers[c];
+    if (c_members[c]) {
+      if (c_members[q] == 0) c_single[q] = c_single[c];
+      c_members[q] += c_members[c];
+      c_dense[q] |= c_dense[c];
+    }
+  }
+  // ---- what was asked for ---------------------------------------------------------------------------------------
+  std::vector<uint32_t> req(n, NONE);
+  std::vector<uint8_t> wanted(NC, 0);
+  for (uint32_t i = 0; i < n; i++) {
+    auto it = ctx->dense_of_raw.find(taxids[i]);
+    if (it != ctx->dense_of_raw.end() && cid[it->second] != NONE) { req[i] = cid[it->second]; wanted[req[i]] = 1; }
+  }
+  std::vector<uint64_t> c_unique(NC, 0);
+  const bool per_clade = ctx->cfg.hll_mode == KUQ_HLL_EXACT || ctx->merged_summary;
+  bool sparse_fallback = false;
+  std::vector<uint32_t> dense_list, sparse_multi;          // compact ids
+  if (!per_clade) {
+    for (uint32_t c = 0; c < NC; c++) {
+      if (c_members[c] == 0) continue;
+      if (c_members[c] == 1) {
+        if (!wanted[c]) continue;
+        const uint32_t d = c_single[c];
+        c_unique[c] = c_dense[c] ? ertl_dense_hist(&h.hist[(size_t)d * 64], c_kmers[c]) : kuq_ertl_sparse(&h.sparse_hist[(size_t)d * 64], c_kmers[c]);
+      } else if (c_dense[c]) {
+        if (wanted[c]) dense_list.push_back(c);
+      } else {
+        sparse_multi.push_back(c);                          // needed for the sums up the tree whether asked for or not
+      }
+    }
+  }
+  // ---- dense clades: register-wise max of the members, in chunks ---------------------------------------------------
+  if (!dense_list.empty()) {
+    std::vector<uint32_t> dix(NC, NONE);
+    for (uint32_t i = 0; i < dense_list.size(); i++) dix[dense_list[i]] = i;
+    std::vector<uint32_t> offs(dense_list.size() + 1, 0), mem;
+    for (int pass = 0; pass < 2; pass++) {
+      std::vector<uint32_t> fill(offs.begin(), offs.end() - 1);
+      for (uint32_t c = 0; c < NC; c++) {
+        if (!has_kmers(nodes[c])) continue;
+        for (uint32_t x = c; x != NONE; x = parent_c[x])
+          if (dix[x] != NONE) { if (pass == 0) offs[dix[x] + 1]++; else mem[fill[dix[x]]++] = nodes[c]; }
+      }
+      if (pass == 0) { for (size_t i = 1; i < offs.size(); i++) offs[i] += offs[i - 1]; mem.resize(offs.back()); }
+    }
+    const uint32_t CH = 8192;                                // clades per launch: 32 MB of folded registers
+    uint32_t *d_offs = nullptr, *d_mem = nullptr, *d_hist = nullptr;
+    uint8_t *d_out = nullptr;
+    std::vector<uint32_t> hist((size_t)CH * 64), loc;
+    CU(dmalloc(&d_offs, CH + 1));
+    CU(dmalloc(&d_mem, std::max<size_t>(mem.size(), 1)));
+    CU(dmalloc(&d_out, (uint64_t)CH * HLL_M));
+    CU(dmalloc(&d_hist, (uint64_t)CH * 64));
+    CU(cudaMemcpyAsync(d_mem, mem.data(), mem.size() * 4, cudaMemcpyHostToDevice, ctx->aux));
+    for (uint32_t a = 0; a < dense_list.size(); a += CH) {
+      const uint32_t m = std::min<uint32_t>(CH, (uint32_t)dense_list.size() - a);
+      loc.assign(offs.begin() + a, offs.begin() + a + m + 1);           // absolute offsets into d_mem
+      CU(cudaMemcpyAsync(d_offs, loc.data(), (m + 1) * 4ull, cudaMemcpyHostToDevice, ctx->aux));
+      launch_clade_max_batch(ctx->d_regs, d_offs, d_mem, m, d_out, ctx->aux);
+      launch_register_histograms(d_out, m, d_hist, ctx->aux);
+      ctx->launches += 2;
+      CU(cudaMemcpyAsync(hist.data(), d_hist, (uint64_t)m * 64 * 4, cudaMemcpyDeviceToHost, ctx->aux));
+      CU(cudaStreamSynchronize(ctx->aux));
+      for (uint32_t i = 0; i < m; i++) {
+        const uint32_t c = dense_list[a + i];
+        c_unique[c] = ertl_dense_hist(&hist[(size_t)i * 64], c_kmers[c]);
+      }
+    }
+    cudaFree(d_offs); cudaFree(d_mem); cudaFree(d_out); cudaFree(d_hist);
+  }
+  // ---- sparse clades with several members: distinct codes of every subtree from one sort ------------------------------
+  if (!sparse_multi.empty()) {
+    std::vector<int32_t> sid(NC, -1);
+    for (uint32_t i = 0; i < sparse_multi.size(); i++) sid[sparse_multi[i]] = (int32_t)i;
+    // preorder numbers: children lists from the parent pointers, explicit stack
+    std::vector<uint32_t> first_child(NC + 1, 0), child(NC), pre(NC, NONE), node_of_pre(NC, 0);
+    for (uint32_t c = 0; c < NC; c++) if (parent_c[c] != NONE) first_child[parent_c[c] + 1]++;
+    for (uint32_t c = 0; c < NC; c++) first_child[c + 1] += first_child[c];
+    {
+      std::vector<uint32_t> fill(first_child.begin(), first_child.end() - 1);
+      for (uint32_t c = 0; c < NC; c++) if (parent_c[c] != NONE) child[fill[parent_c[c]]++] = c;
+      std::vector<uint32_t> stack;
+      uint32_t counter = 0;
+      for (uint32_t r = 0; r < NC; r++) {
+        if (parent_c[r] != NONE) continue;
+        stack.push_back(r);
+        while (!stack.empty()) {
+          const uint32_t x = stack.back();
+          stack.pop_back();
+          pre[x] = counter;
+          node_of_pre[counter++] = x;
+          for (uint32_t i = first_child[x]; i < first_child[x + 1]; i++) stack.push_back(child[i]);
+        }
+      }
+    }
+    std::vector<uint32_t> pre_of_taxon(NS, NONE);
+    uint64_t n_keys = 0;
+    for (uint32_t c = 0; c < NC; c++) {
+      const uint32_t d = nodes[c];
+      if (d < NS) { pre_of_taxon[d] = pre[c]; if (has_kmers(d) && !h.dense_flag[d]) n_keys += h.distinct[d]; }
+    }
+    uint32_t *d_pre = nullptr, *d_nop = nullptr, *d_par = nullptr, *d_dep = nullptr, *d_dup = nullptr;
+    int32_t *d_sid = nullptr;
+    CU(dmalloc(&d_pre, NS)); CU(dmalloc(&d_nop, NC)); CU(dmalloc(&d_par, NC)); CU(dmalloc(&d_dep, NC)); CU(dmalloc(&d_sid, NC));
+    CU(dmalloc(&d_dup, sparse_multi.size() * 64));
+    CU(cudaMemcpyAsync(d_pre, pre_of_taxon.data(), NS * 4ull, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemcpyAsync(d_nop, node_of_pre.data(), NC * 4ull, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemcpyAsync(d_par, parent_c.data(), NC * 4ull, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemcpyAsync(d_dep, depth_c.data(), NC * 4ull, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemcpyAsync(d_sid, sid.data(), NC * 4ull, cudaMemcpyHostToDevice, ctx->aux));
+    CU(cudaMemsetAsync(d_dup, 0, sparse_multi.size() * 64 * 4ull, ctx->aux));
+    const int src = sparse_clade_dups(ctx->d_sparse_slots, ctx->sparse_cap, ctx->d_dense_flag, n_keys, d_pre, d_nop, d_par, d_dep,
+                                      d_sid, d_dup, ctx->n_sm, ctx->aux);
+    ctx->launches += 3;
+    std::vector<uint32_t> dup(sparse_multi.size() * 64, 0);
+    cudaError_t ce = cudaSuccess;
+    if (src == 0) {
+      ce = cudaMemcpyAsync(dup.data(), d_dup, dup.size() * 4, cudaMemcpyDeviceToHost, ctx->aux);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->aux);
+    }
+    cudaFree(d_pre); cudaFree(d_nop); cudaFree(d_par); cudaFree(d_dep); cudaFree(d_sid); cudaFree(d_dup);
+    if (src == 2 || ce != cudaSuccess) return fail(ctx, KUQ_E_CUDA, "clade roll-up (sparse tier) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (src == 1) {
+      sparse_fallback = true;                                // no room for the sort: one union per clade instead
+    } else {
+      // rank histogram of every sparse subtree: own codes + children's − the pairs booked at the node
+      std::vector<std::vector<uint32_t>> H(NC);
+      for (uint32_t c : order) {
+        if (c_members[c] == 0 || c_dense[c]) continue;
+        std::vector<uint32_t> &hc = H[c];
+        if (hc.empty()) hc.assign(64, 0);
+        const uint32_t d = nodes[c];
+        if (has_kmers(d)) for (int r = 0; r < 64; r++) hc[r] += h.sparse_hist[(size_t)d * 64 + r];
+        if (sid[c] >= 0) for (int r = 0; r < 64; r++) hc[r] -= dup[(size_t)sid[c] * 64 + r];
+        if (wanted[c] && c_members[c] > 1) c_unique[c] = kuq_ertl_sparse(hc.data(), c_kmers[c]);
+        const uint32_t q = parent_c[c];
+        if (q != NONE && !c_dense[q]) {
+          std::vector<uint32_t> &hq = H[q];
+          if (hq.empty()) hq.assign(64, 0);
+          for (int r = 0; r < 64; r++) hq[r] += hc[r];
+        }
+        std::vector<uint32_t>().swap(hc);
+      }
+    }
+  }
+  // ---- exact counting / partitioned sparse tier / no memory for the sort: one merge per clade ------------------------
+  if (per_clade || sparse_fallback) {
+    std::vector<std::vector<uint32_t>> lists(NC);
+    for (uint32_t c = 0; c < NC; c++) {
+      if (!(h.n_reads[nodes[c]] || has_kmers(nodes[c]))) continue;
+      for (uint32_t x = c; x != NONE; x = parent_c[x])
+        if (wanted[x] && (per_clade || (c_members[x] > 1 && !c_dense[x]))) lists[x].push_back(ctx->raw_of_dense[nodes[c]]);
+    }
+    for (uint32_t c = 0; c < NC; c++) {
+      if (lists[c].empty()) continue;
+      uint64_t r = 0, k = 0, u = 0;
+      int rc = kuq_clade_counts(ctx, lists[c].data(), (uint32_t)lists[c].size(), &r, &k, &u);
+      if (rc) return rc;
+      c_unique[c] = u;
+    }
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t c = req[i];
+    if (n_reads) n_reads[i] = c == NONE ? 0 : c_reads[c];
+    if (n_kmers) n_kmers[i] = c == NONE ? 0 : c_kmers[c];
+    if (unique) unique[i] = c == NONE ? 0 : c_unique[c];
+  }
+  return KUQ_OK;
 }
 
 uint64_t kuq_ertl_dense_hist(const uint32_t *hist64, uint64_t n_observed) { return ertl_dense_hist(hist64, n_observed); }

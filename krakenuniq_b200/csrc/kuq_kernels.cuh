@@ -226,6 +226,12 @@ void launch_keys_parts(int src, const unsigned long long *slots, uint8_t *pairs,
                        const uint8_t *dense_flag, uint32_t n_parts, unsigned long long *counters, unsigned long long *out,
                        const unsigned long long *part_end, uint32_t *error_flag, int pass, cudaStream_t stream);
 
+// kuq_clades.cu: all clades of the report at once
+void launch_clade_max_batch(const uint8_t *regs, const uint32_t *d_offs, const uint32_t *d_members, uint32_t n_clades,
+                            uint8_t *d_out, cudaStream_t stream);
+int sparse_clade_dups(const unsigned long long *slots, uint64_t cap, const uint8_t *dense_flag, uint64_t n_keys_upper,
+                      const uint32_t *d_pre_of_taxon, const uint32_t *d_node_of_pre, const uint32_t *d_parent_c,
+                      const uint32_t *d_depth_c, const int32_t *d_sid_of_node, uint32_t *d_dup, int n_sm, cudaStream_t stream);
 // kuq_layout_exp.cu: record-layout / search-shape experiment (0 ok, 1 no memory, 2 CUDA error, 3 taxon ids > 24 bits);
 // `product` = parameters of a k_lookup<MODE_LOOKUP> launch on the same database (scratch / output pointers are set there)
 int layout_experiment(const Params &product, uint64_t n_records, const uint64_t *canon, const uint32_t *bins, const uint32_t *ref,

@@ -92,3 +92,6 @@ def test_executables_fail_loudly_without_a_gpu(tmp_path):
         assert "no CPU path" in r.stderr
         assert r.stdout == ""
     assert not os.path.exists(tmp_path / "t.kdb")
+    # argument errors come first and are the reference's: more threads than processors (classify.cpp:1087-1088)
+    r = subprocess.run(cmds[0][:1] + ["-t", "1000000"] + cmds[0][1:], capture_output=True, text=True)
+    assert r.returncode == 64 and "thread count exceeds number of processors" in r.stderr

@@ -479,3 +479,76 @@ def test_two_contexts_merge_into_one(oracle):
     members = util.clade_members(tax.rows, want["taxid"])
     for taxid, mem in members.items():
         assert a.clade(mem) == run.clade(mem), taxid
+
+
+def _clade_tree_equals_per_clade(clf, tax_rows):
+    cnt = clf.counts()
+    members = util.clade_members(tax_rows, cnt["taxid"])
+    ids = np.array(sorted(members), np.uint32)
+    extra = np.array([4000000000, 7], np.uint32)                    # unknown / uncounted taxids give zeros
+    r, k, u = clf.clade_counts_tree(np.concatenate([ids, extra]))
+    assert not r[len(ids):].any() and not u[len(ids):].any()
+    kinds = set()
+    for i, t in enumerate(ids.tolist()):
+        assert (int(u[i]), int(r[i]), int(k[i])) == clf.clade(members[t]), (t, members[t])
+        with_kmers = [m for m in members[t] if cnt["n_kmers"][list(cnt["taxid"]).index(m)]]
+        if len(with_kmers) > 1:
+            sp = [bool(cnt["sparse"][list(cnt["taxid"]).index(m)]) for m in with_kmers]
+            kinds.add("sparse" if all(sp) else "dense")
+    return kinds
+
+
+@pytest.mark.parametrize("case", ["all_sparse", "mixed", "dense_only", "forest", "chunked", "collisions"])
+def test_all_clades_in_one_call_equal_the_per_clade_merge(case):
+    """kuq_clade_counts_tree (one sort of the sparse tier + one fold of the registers for ALL clades) against
+    kuq_clade_counts clade by clade, which the tests above hold against the oracle and the reference's report."""
+    rng = np.random.default_rng(91)
+    if case == "forest":
+        rows = [(1, 1, "root", "no rank"), (10, 1, "a", "genus"), (11, 10, "a1", "species"), (12, 10, "a2", "species"),
+                (20, 1, "b", "genus"), (21, 20, "b1", "species"), (500, 500, "other root", "no rank"),
+                (501, 500, "c1", "species"), (502, 500, "c2", "species"), (600, 999, "dangling parent", "species")]
+        tax = synth.Taxonomy(rows)
+        labels = [11, 12, 21, 501, 502, 600, 4242]
+        genomes = [rng.integers(0, 4, 1500, dtype=np.uint8) for _ in labels]
+        # a shared stretch puts the same k-mers' hashes under several taxa's clades only through the LCA labels;
+        # equal codes under different taxa come from the reads below hitting shared prefixes
+        ks, ts = [], []
+        for gseq, t in zip(genomes, labels):
+            km, ok = synth.forward_kmers(gseq, K)
+            c = np.unique(synth.canonical(km[ok], K))
+            ks.append(c); ts.append(np.full(len(c), t, np.uint32))
+        km, first = np.unique(np.concatenate(ks), return_index=True)
+        tx = np.concatenate(ts)[first]
+        kdb, idx = synth.build_db_images(km, tx, K, 7, 2)
+        g = [synth.decode(x).tobytes() for x in genomes]
+        seqs = [g[i % len(g)][s:s + 150] for i, s in enumerate(rng.integers(0, 1300, 400).tolist())]
+        bases, offs = synth.pack_reads(seqs)
+        mode, unit, tax_rows = binding.HLL_PRELOAD, 3000, rows
+    else:
+        # "collisions": ~10^5 codes per taxon, so that different taxa of a clade hold EQUAL encoded hashes (a few hundred
+        # per pair out of 2^25) — the case in which a clade's union is smaller than the sum of its members
+        n_gen, glen, n_reads = (4, 150000, 5000) if case == "collisions" else (12, 3000, 1500)
+        tax = synth.make_taxonomy(n_gen, 2, 1) if case == "collisions" else synth.make_taxonomy(n_gen, 4, 2)
+        genomes = synth.random_genomes(rng, n_gen, glen, shared_frac=0.3 if case != "collisions" else 0.02)
+        km, tx = synth.label_kmers(genomes, synth.species_ids(tax), tax, K)
+        kdb, idx = synth.build_db_images(km, tx, K, 8, 2)
+        bases, offs = synth.sample_reads(rng, genomes, n_reads, 150, 0.001, 0.1, 0.02)
+        tax_rows = tax.rows
+        mode = {"all_sparse": binding.HLL_PRELOAD, "mixed": binding.HLL_PRELOAD, "dense_only": binding.HLL_DENSE_ONLY,
+                "chunked": binding.HLL_CHUNKED, "collisions": binding.HLL_PRELOAD}[case]
+        unit = {"all_sparse": 1200, "mixed": 40000, "dense_only": 500000, "chunked": 500000, "collisions": 1200}[case]
+    clf = _classifier(hll_mode=mode, work_unit_size=unit)
+    clf.stage_db(kdb, idx)
+    clf.set_taxonomy(*tax.parent_map())
+    clf.classify(bases, offs)
+    clf.finish()
+    kinds = _clade_tree_equals_per_clade(clf, tax_rows)
+    if case in ("all_sparse", "collisions"):
+        assert kinds == {"sparse"}
+    if case == "dense_only":
+        assert kinds == {"dense"}
+    # a second batch changes the state: the roll-up follows
+    clf.classify(bases[: int(offs[200])], offs[:201])
+    clf.finish()
+    _clade_tree_equals_per_clade(clf, tax_rows)
+    clf.close()
