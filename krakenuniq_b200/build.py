@@ -61,7 +61,7 @@ def build_classify(force: bool = False) -> str:
     os.makedirs(os.path.dirname(CLASSIFY), exist_ok=True)
     for out, defs in ((CLASSIFY, []), (exact, ["-DEXACT_COUNTING"])):
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-fopenmp"] + defs + [src, "-o", out, "-L" + os.path.dirname(LIB),
-               "-lkuq", "-lz", "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
+               "-lkuq", "-lz", "-ldl", "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -9,7 +9,8 @@
 //   stats / progress lines         src/classify.cpp:361-375, 555-558
 //   taxDB reader, genome sizes     src/taxdb.hpp:563-605, 850-885
 //   report (clades, sorting, cols) src/taxdb.hpp:928-1123, src/classify.cpp:286-328
-// Not supported (exit with a message): -I uid mapping, -q or -x together with several -d databases.
+// Not supported (exit with a message): -I uid mapping, -x together with several -d databases (the reference's own loop
+// for that combination queries database 0 in every pass, classify.cpp:585-632).
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
@@ -19,6 +20,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <dlfcn.h>
 #include <omp.h>
 #include <condition_variable>
 #include <deque>
@@ -183,21 +185,54 @@ struct Read {
   uint64_t seq_off, seq_len;          // into the batch's bases buffer
 };
 
-struct LineReader {     // std::ifstream + std::getline state semantics (eofbit / failbit), over zlib
+// bzip2 input (the reference reads it through bxzstr when built with libbz2, seqreader.hpp:24,48).  The image has the
+// runtime library but not its header, so the three entry points of the high-level API are bound with dlopen.
+struct Bz2Api {
+  void *(*open)(const char *, const char *) = NULL;
+  int (*read)(void *, void *, int) = NULL;
+  void (*close)(void *) = NULL;
+  bool load() {
+    if (open) return true;
+    void *h = NULL;
+    for (const char *name : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"}) if ((h = dlopen(name, RTLD_NOW))) break;
+    if (!h) return false;
+    open = (void *(*)(const char *, const char *))dlsym(h, "BZ2_bzopen");
+    read = (int (*)(void *, void *, int))dlsym(h, "BZ2_bzread");
+    close = (void (*)(void *))dlsym(h, "BZ2_bzclose");
+    return open && read && close;
+  }
+};
+static Bz2Api Bz2;
+
+static bool is_bzip2(const unsigned char *magic3) { return magic3[0] == 'B' && magic3[1] == 'Z' && magic3[2] == 'h'; }
+
+struct LineReader {     // std::ifstream + std::getline state semantics (eofbit / failbit), over zlib / libbz2
   gzFile gz = NULL;
+  void *bz = NULL;
   vector<char> buf;
   size_t pos = 0, end = 0;
   bool eofbit = false, failbit = false;
   bool open(const char *path) {
+    unsigned char magic[3] = {0, 0, 0};
+    if (FILE *f = fopen(path, "rb")) { size_t got = fread(magic, 1, 3, f); (void)got; fclose(f); }
+    buf.resize(8 << 20);
+    if (is_bzip2(magic)) {
+      if (!Bz2.load()) die(EX_UNAVAILABLE, string("bzip2 input needs libbz2.so.1.0, which could not be loaded: ") + path);
+      bz = Bz2.open(path, "rb");
+      return bz != NULL;
+    }
     gz = gzopen(path, "rb");
     if (!gz) return false;
     gzbuffer(gz, 1 << 20);
-    buf.resize(8 << 20);
     return true;
   }
-  void close() { if (gz) gzclose(gz); gz = NULL; }
+  void close() {
+    if (gz) gzclose(gz);
+    if (bz) Bz2.close(bz);
+    gz = NULL; bz = NULL;
+  }
   bool fill() {           // false at end of data
-    int n = gzread(gz, buf.data(), (unsigned)buf.size());
+    int n = bz ? Bz2.read(bz, buf.data(), (int)buf.size()) : gzread(gz, buf.data(), (unsigned)buf.size());
     if (n <= 0) return false;
     pos = 0; end = (size_t)n;
     return true;
@@ -727,7 +762,10 @@ static bool process_file_parallel(kuq_ctx *ctx0, const char *filename) {
   const char *base = (const char *)mmap(0, size, PROT_READ, MAP_PRIVATE, fd, 0);
   ::close(fd);
   if (base == MAP_FAILED) return false;
-  if ((unsigned char)base[0] == 0x1f && (unsigned char)base[1] == 0x8b) { munmap((void *)base, size); return false; }   // gzip
+  if (((unsigned char)base[0] == 0x1f && (unsigned char)base[1] == 0x8b) || (size >= 3 && is_bzip2((const unsigned char *)base))) {
+    munmap((void *)base, size);                                     // gzip / bzip2: the serial reader decompresses
+    return false;
+  }
   madvise((void *)base, size, MADV_WILLNEED);
   const char *fend = base + size;
   const bool fastq = Fastq_input = base[0] == '@';                                  // determine_input_file_type

@@ -68,6 +68,20 @@ def test_cli_ingest_paths(tmp_path, threads, serial, tag, extra, reads):
     assert _report_lines(rep) == _report_lines(os.path.join(G, f"{tag}.report.tsv"))
 
 
+def test_cli_bz2_input(tmp_path):
+    """bzip2-compressed reads (seqreader.hpp:24,48: the reference reads them through bxzstr)"""
+    import bz2
+    bz = tmp_path / "reads.fa.bz2"
+    bz.write_bytes(bz2.compress(open(os.path.join(G, "reads.fa"), "rb").read()))
+    exe = build.build_classify()
+    out = tmp_path / "o.kraken"
+    cmd = [exe, "-d", os.path.join(G, "database.kdb"), "-i", os.path.join(G, "database.idx"), "-a",
+           os.path.join(G, "taxDB"), "-M", "-o", str(out), str(bz)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, KUQ_SPARSE_SLOTS=str(1 << 22)))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == open(os.path.join(G, "preload.kraken")).read()
+
+
 def test_cli_gz_input(tmp_path):
     import gzip
     import shutil
