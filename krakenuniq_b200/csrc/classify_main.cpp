@@ -1469,6 +1469,15 @@ static void run_multi_db(kuq_ctx *ctx, const vector<Mapped> &kdbs, const vector<
     load_file_batches(argv[i], batches, true);
     for (size_t j = first; j < batches.size(); j++) batches[j].file = i;
   }
+  {
+    // the merged per-window ids of all reads stay on the host between the databases (4 bytes per base + one batch of
+    // scratch): say so instead of running into the OOM killer
+    uint64_t bytes = 0, largest = 0;
+    for (auto &b : batches) { bytes += b.bases.size() * 4; largest = std::max<uint64_t>(largest, b.bases.size() * 4); }
+    const uint64_t avail = (uint64_t)sysconf(_SC_AVPHYS_PAGES) * (uint64_t)sysconf(_SC_PAGESIZE);
+    if (bytes + largest > avail) die(EX_OSERR, "classifying against several databases needs about " + std::to_string((bytes + largest) >> 30) +
+                                               " GiB of RAM for the merged k-mer ids, " + std::to_string(avail >> 30) + " GiB are available: split the input");
+  }
   for (auto &b : batches) b.codes.assign(b.bases.size() + 1, 0);
   vector<uint32_t> tmp;
   for (size_t d = 0; d < n_db; d++) {
