@@ -7,8 +7,8 @@ echo "## k_scan: cp.async.bulk (UBLKCP) + mbarrier (SYNCS)"
 cuobjdump -sass -fun '_ZN3kuq6k_scanENS_6ParamsE' $SO 2>/dev/null | grep -E "arch =|Function|UBLKCP|SYNCS" | sort -u | head -20
 echo "## k_exact_insert: 128-bit compare-and-swap"
 cuobjdump -sass -fun '_ZN3kuq14k_exact_insertENS_6ParamsE' $SO 2>/dev/null | grep -E "Function|CAS.128" | head -4
-echo "## k_lookup<MODE_FUSED>: record flag (atomic OR on the key word), register CAS"
-cuobjdump -sass -fun '_ZN3kuq8k_lookupILi0EEEvNS_6ParamsE' $SO 2>/dev/null | grep -E "Function|REDG|ATOMG|RED\.E" | sort -u | head -8
+echo "## k_lookup<MODE_FUSED, lean>: record flag (atomic OR on the key word), register CAS"
+cuobjdump -sass -fun '_ZN3kuq8k_lookupILi0ELb1EEEvNS_6ParamsE' $SO 2>/dev/null | grep -E "Function|REDG|ATOMG|RED\.E" | sort -u | head -8
 echo "## k_signal_peers / k_wait_flags: system-scope fences + globaltimer"
 cuobjdump -sass -fun '_ZN3kuq14k_signal_peersENS_9PeerFlagsEjjy' $SO 2>/dev/null | grep -E "Function|MEMBAR|ST.E" | sort -u | head -6
 cuobjdump -sass -fun '_ZN3kuq12k_wait_flagsEPKyjyyPj' $SO 2>/dev/null | grep -E "Function|GLOBALTIMER|NANOSLEEP|LD.E" | sort -u | head -6
